@@ -1,0 +1,80 @@
+"""Seeded synthetic weights and transcripts (there is no network for checkpoints).
+
+The weight recipe is the one SURVEY.md section 8(d) fixes, shared by the oracle runs
+that produced tests/golden/ and by every GPU test / bench run: iterate the
+parameters in ``named_parameters()`` order with ONE seeded CPU generator,
+RMSNorm weights = 1, embeddings ~ N(0,1), dense kernels ~ N(0, fan_in^-1/2),
+then round every non-norm tensor to a bf16-representable fp32 value - so the
+bf16 weight stream the kernels read holds exactly the oracle's numbers.
+"""
+
+from __future__ import annotations
+
+import hashlib
+
+import torch
+
+
+def fan_in_of(name: str, shape) -> int:
+    # o_proj kernels contract (heads, head_dim); every other kernel contracts axis 0
+    return int(shape[0]) * int(shape[1]) if "o_proj" in name else int(shape[0])
+
+
+@torch.no_grad()
+def init_synthetic_(named_params, seed: int = 1234) -> None:
+    """In-place init of an iterable of (name, fp32 CPU tensor) in the given order."""
+    g = torch.Generator().manual_seed(seed)
+    for name, p in named_params:
+        if "norm" in name:
+            p.fill_(1.0)
+            continue
+        if "embedding" in name:
+            p.normal_(0.0, 1.0, generator=g)
+        else:
+            p.normal_(0.0, fan_in_of(name, p.shape) ** -0.5, generator=g)
+        p.copy_(p.to(torch.bfloat16).to(torch.float32))
+
+
+def synthetic_state_dict(shapes: dict, seed: int = 1234) -> dict:
+    """``shapes``: ordered name -> shape mapping (named_parameters order)."""
+    sd = {n: torch.empty(s, dtype=torch.float32) for n, s in shapes.items()}
+    init_synthetic_(sd.items(), seed)
+    return sd
+
+
+def weights_fingerprint(sd: dict, names=None) -> str:
+    """sha256 over the bf16 bit patterns of a few tensors - lets a GPU box
+    verify it regenerated the very weights the golden fixtures were made with."""
+    h = hashlib.sha256()
+    for n in (names or sorted(sd)):
+        t = sd[n].detach().to("cpu", torch.float32).contiguous()
+        h.update(n.encode())
+        h.update(t.to(torch.bfloat16).view(torch.int16).numpy().tobytes())
+    return h.hexdigest()
+
+
+def synthetic_transcript(i: int, min_bytes: int = 60, max_bytes: int = 200) -> str:
+    """Deterministic alternating [S1]/[S2] dialogue of 60-200 bytes (config 5)."""
+    words = ("dia is an open weights text to dialogue model you get full control over scripts and voices "
+             "the quick brown fox jumps over the lazy dog while rain keeps falling on the quiet harbor town "
+             "please remember to bring the blue notebook when we meet at the station tomorrow morning").split()
+    state = (i * 2654435761 + 12345) & 0xFFFFFFFF
+    target = min_bytes + state % (max_bytes - min_bytes + 1)
+    out, spk = "", 1
+    while True:
+        state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+        n = 4 + state % 7
+        sent = []
+        for _ in range(n):
+            state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+            sent.append(words[state % len(words)])
+        piece = f"[S{spk}] " + " ".join(sent).capitalize() + ". "
+        if out and len((out + piece).encode()) > target:
+            break
+        out += piece
+        spk = 3 - spk
+    return out.strip()
+
+
+DEFAULT_TRANSCRIPT = ("[S1] Dia is an open weights text to dialogue model. "
+                      "[S2] You get full control over scripts and voices. [S1]")

@@ -1,0 +1,162 @@
+// common.cuh - sm_100a PTX helpers shared by the Dia decode kernels.
+//
+// mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) for the weight /
+// KV stream, packed fp32x2 FMA (SASS FFMA2), L2-only loads for data other CTAs
+// wrote, watchdog-bounded waits (a hang on a shared GPU box is never acceptable:
+// every spin has a cycle budget, after which the kernel records an error code
+// and traps).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dia {
+
+constexpr int kHeadDim = 128;
+constexpr int kConsumerWarps = 8;                       // math warps per CTA
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = kConsumerThreads + 32;         // + 1 producer warp (one elected lane issues copies)
+constexpr int kSlotBytes = 8192;                        // one ring slot = one bulk copy
+constexpr int kNumSlots = 19;                           // 152 KB of weights / KV in flight per SM
+constexpr int kXsBytes = 65536;                         // activation vector [K][2] fp32, K <= 8192
+constexpr int kRedBytes = 8192;                         // cross-warp reduction scratch
+constexpr int kMiscBytes = 1024;                        // mbarriers + small shared scalars
+constexpr int kSmemBytes = kNumSlots * kSlotBytes + kXsBytes + kRedBytes + kMiscBytes;
+constexpr unsigned long long kWatchdogCycles = 4000000000ull;   // ~2 s at 1.9 GHz
+
+enum DeviceError : int {
+    kErrNone = 0,
+    kErrGridBarrierTimeout = 1,
+    kErrFullBarrierTimeout = 2,
+    kErrEmptyBarrierTimeout = 3,
+    kErrStepDoneTimeout = 4,
+    kErrBadState = 5,
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait; on timeout record `code` and trap (kills the launch, never hangs the box)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kWatchdogCycles) {
+            *reinterpret_cast<volatile int*>(err) = code;
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+// ---- bulk async copy global -> shared (TMA engine, no tensor map needed for 1-D) -------------
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---- named barrier over the consumer warps only (the producer warp never joins) --------------
+__device__ __forceinline__ void consumer_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+}
+
+// ---- loads that must observe other CTAs' writes: L2 only ---------------------------------------
+__device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float2 ldcg_f2(const float2* p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ldcg_f4(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldcg_i(const int* p) { return __ldcg(p); }
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_s32(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// ---- packed fp32x2 math (Blackwell FFMA2) -------------------------------------------------------
+typedef unsigned long long f32x2;   // two packed floats in a 64-bit register
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// two bf16 packed in a u32 -> (lo element, hi element) as exact fp32
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) {
+    return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+
+}  // namespace dia

@@ -1,0 +1,642 @@
+// engine.cu - host side of libdia_b200.so: the C ABI declared in include/dia_b200.h.
+//
+// Owns the repacked weight stream, the per-CTA tables, the scratch vectors and the
+// device-side generate state; builds StepParams and launches the persistent step kernel.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "engine_internal.h"
+
+using namespace dia;
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+std::atomic<long long> g_launches{0};
+
+#define CK(expr)                                                                           \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            g_last_cuda_error = std::string(#expr) + ": " + cudaGetErrorString(_e);        \
+            return DIA_B200_ECUDA;                                                         \
+        }                                                                                  \
+    } while (0)
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace
+
+struct dia_b200_engine {
+    dia_b200_shape shape{};
+    int device = 0;
+    int G = 0;
+    int Vpad = 0;
+    int n_groups[G_COUNT]{};
+    int Kdim[G_COUNT]{};
+    std::vector<CtaTable> tab;
+    std::vector<int> owner[G_COUNT], local[G_COUNT];
+    size_t stream_bytes = 0;          // allocation size (with alignment padding)
+    long long weight_bytes = 0;       // payload bytes = bytes streamed per step
+
+    // device
+    unsigned char* d_wstream = nullptr;
+    CtaTable* d_tab = nullptr;
+    int* d_owner[G_COUNT]{};
+    int* d_local[G_COUNT]{};
+    float* d_emb = nullptr;
+    float* d_norms = nullptr;
+    float* d_rope_sin = nullptr;
+    float* d_rope_cos = nullptr;
+    int n_pos = 0;
+    float** d_ptrs = nullptr;         // [4][L] self_k, self_v, cross_k, cross_v
+    float2 *d_x = nullptr, *d_qkv = nullptr, *d_attn = nullptr, *d_cq = nullptr, *d_cattn = nullptr,
+           *d_hidden = nullptr;
+    float* d_logits = nullptr;
+    float *d_sa_part = nullptr, *d_ca_part = nullptr;
+    unsigned* d_pair_cnt = nullptr;
+    unsigned* d_grid_bar = nullptr;
+    int* d_err = nullptr;
+    int* d_pred = nullptr;
+    int* d_tokens = nullptr;          // staging [2][C]
+    GenState* d_gs = nullptr;
+    // pinned host staging
+    float** h_ptrs = nullptr;
+    GenState* h_gs = nullptr;
+    int* h_err = nullptr;
+
+    bool weights_loaded = false, caches_bound = false, rope_set = false, gen_active = false;
+    int text_len = 0;
+    int sa_nsplit = 1, ca_nsplit = 1;
+    // generate loop
+    dia_b200_gen_params gp{};
+    int* gen_grid = nullptr;
+    int gen_pos = 0, gen_slot = 0;
+};
+
+namespace {
+
+int validate_shape(const dia_b200_shape& s) {
+    if (s.n_layer <= 0 || s.d_model <= 0 || s.n_hidden <= 0 || s.q_heads <= 0 || s.kv_heads <= 0 ||
+        s.cross_heads <= 0 || s.channels <= 0 || s.channels > DIA_B200_MAX_CHANNELS || s.vocab <= 0 ||
+        s.max_audio_len <= 0 || s.max_text_len <= 0)
+        return DIA_B200_EINVAL;
+    if (s.q_heads != 4 * s.kv_heads) return DIA_B200_EUNSUPPORTED;       // kernels are built for GQA 4:1
+    if (s.d_model % 16 || s.n_hidden % 16) return DIA_B200_EINVAL;
+    if (s.d_model > 8192 || s.n_hidden > 8192 || s.q_heads * kHeadDim > 8192 || s.cross_heads * kHeadDim > 8192)
+        return DIA_B200_EUNSUPPORTED;                                     // activation vector must fit 64 KB of smem
+    if (s.channels * s.vocab * 4 > kXsBytes) return DIA_B200_EUNSUPPORTED;
+    return DIA_B200_OK;
+}
+
+void fill_params(const dia_b200_engine* e, StepParams& p) {
+    std::memset(&p, 0, sizeof(p));
+    const dia_b200_shape& s = e->shape;
+    p.L = s.n_layer; p.D = s.d_model; p.F = s.n_hidden; p.Hq = s.q_heads; p.Hkv = s.kv_heads; p.Hc = s.cross_heads;
+    p.C = s.channels; p.V = s.vocab; p.Vpad = e->Vpad; p.Lmax = s.max_audio_len; p.Smax = s.max_text_len;
+    for (int i = 0; i < G_COUNT; ++i) p.Kdim[i] = e->Kdim[i];
+    p.eps = s.norm_eps; p.G = e->G; p.sa_nsplit = e->sa_nsplit; p.ca_nsplit = e->ca_nsplit;
+    p.wstream = e->d_wstream; p.cta_tab = e->d_tab; p.emb = e->d_emb; p.norms = e->d_norms;
+    p.rope_sin = e->d_rope_sin; p.rope_cos = e->d_rope_cos; p.n_pos = e->n_pos;
+    p.self_k = e->d_ptrs; p.self_v = e->d_ptrs + s.n_layer;
+    p.cross_k = const_cast<const float* const*>(e->d_ptrs + 2 * s.n_layer);
+    p.cross_v = const_cast<const float* const*>(e->d_ptrs + 3 * s.n_layer);
+    p.text_len = e->text_len;
+    p.x = e->d_x; p.qkv = e->d_qkv; p.attn = e->d_attn; p.cq = e->d_cq; p.cattn = e->d_cattn; p.hidden = e->d_hidden;
+    p.logits = e->d_logits; p.sa_part = e->d_sa_part; p.ca_part = e->d_ca_part; p.pair_cnt = e->d_pair_cnt;
+    p.grid_bar = e->d_grid_bar; p.err = e->d_err;
+    p.n_steps = 1;
+    p.cfg_scale = 3.0f; p.temperature = 0.0f; p.top_p = 0.95f; p.top_k = 35; p.max_tokens = s.max_audio_len;
+    p.eos = s.eos_value; p.pad = s.pad_value; p.bos = s.bos_value;
+    for (int i = 0; i < DIA_B200_MAX_CHANNELS; ++i) p.delay[i] = s.delay_pattern[i];
+    p.pred_out = e->d_pred;
+}
+
+int run_stages(dia_b200_engine* e, StepParams& p, bool cooperative, cudaStream_t st) {
+    CK(cudaMemsetAsync(e->d_grid_bar, 0, sizeof(unsigned), st));
+    CK(launch_step_kernel(p, cooperative, st));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int check_sampling_supported(float temperature, int top_k) {
+    if (temperature == 0.0f) return DIA_B200_OK;
+    if (temperature < 0.0f) return DIA_B200_EINVAL;
+    if (top_k <= 0 || top_k > 64) return DIA_B200_EUNSUPPORTED;   // fused sampler keeps <= 64 candidates
+    return DIA_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dia_b200_abi_version(void) { return DIA_B200_ABI_VERSION; }
+
+const char* dia_b200_error_string(int code) {
+    switch (code) {
+        case DIA_B200_OK: return "ok";
+        case DIA_B200_EINVAL: return "invalid argument or unsupported shape";
+        case DIA_B200_ECUDA: return "CUDA runtime error";
+        case DIA_B200_ENOMEM: return "out of memory";
+        case DIA_B200_ESTATE: return "call sequence error (weights / rope table / caches not set)";
+        case DIA_B200_EUNSUPPORTED: return "not supported by the sm_100a decode path";
+        default: return "unknown error";
+    }
+}
+
+const char* dia_b200_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+int64_t dia_b200_launch_count(void) { return g_launches.load(); }
+
+int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, dia_b200_engine** out) {
+    if (!shape || !out) return DIA_B200_EINVAL;
+    int rc = validate_shape(*shape);
+    if (rc) return rc;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { g_last_cuda_error = "device is not sm_100-class"; return DIA_B200_EUNSUPPORTED; }
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) { g_last_cuda_error = "cooperative launch unsupported"; return DIA_B200_EUNSUPPORTED; }
+
+    dia_b200_engine* e = new (std::nothrow) dia_b200_engine();
+    if (!e) return DIA_B200_ENOMEM;
+    e->shape = *shape;
+    e->device = device;
+    e->G = n_ctas > 0 ? n_ctas : prop.multiProcessorCount;
+    if (e->G > prop.multiProcessorCount) { delete e; return DIA_B200_EINVAL; }   // 1 CTA / SM must be co-resident
+    const dia_b200_shape& s = e->shape;
+    const int G = e->G;
+    if (G < 2 * s.kv_heads || G < s.cross_heads) { delete e; return DIA_B200_EINVAL; }
+    e->Vpad = (s.vocab + 7) & ~7;
+    e->sa_nsplit = G / (2 * s.kv_heads);
+    e->ca_nsplit = G / s.cross_heads;
+    {
+        int per = (s.max_audio_len + e->sa_nsplit - 1) / e->sa_nsplit;
+        int perc = (s.max_text_len + e->ca_nsplit - 1) / e->ca_nsplit;
+        if (((per + 15) & ~15) > 1024 || ((perc + 15) & ~15) > 1024) { delete e; return DIA_B200_EUNSUPPORTED; }
+    }
+
+    // ---- column-group partition of every GEMM over the CTAs --------------------------------
+    const int nq = s.q_heads * kHeadDim, nkv = s.kv_heads * kHeadDim, nc = s.cross_heads * kHeadDim;
+    const int units[G_COUNT] = {(nq + 2 * nkv) / 8, s.d_model / 8, nc / 8, s.d_model / 8, s.n_hidden / 8,
+                                s.d_model / 8, s.channels * e->Vpad / 8};
+    const int mult[G_COUNT] = {1, 1, 1, 1, 2, 1, 1};    // mlp-in: a unit is a (gate, up) pair of groups
+    const int kd[G_COUNT] = {s.d_model, nq, s.d_model, nc, s.d_model, s.n_hidden, s.d_model};
+    e->tab.assign(G, CtaTable{});
+    std::vector<long long> load(G, 0);                   // bytes per layer assigned so far (for balancing)
+    for (int t = 0; t < G_COUNT; ++t) {
+        e->Kdim[t] = kd[t];
+        e->n_groups[t] = units[t] * mult[t];
+        const int base = units[t] / G, extra = units[t] % G;
+        // the CTAs with the least bytes so far take the `extra` units
+        std::vector<int> order(G);
+        for (int c = 0; c < G; ++c) order[c] = c;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return load[a] < load[b]; });
+        std::vector<int> cnt(G, base);
+        for (int i = 0; i < extra; ++i) cnt[order[i]]++;
+        int g0 = 0;
+        e->owner[t].resize(e->n_groups[t]);
+        e->local[t].resize(e->n_groups[t]);
+        for (int c = 0; c < G; ++c) {
+            const int gc = cnt[c] * mult[t];
+            if (gc > 32) { delete e; return DIA_B200_EUNSUPPORTED; }
+            e->tab[c].g0[t] = g0;
+            e->tab[c].gc[t] = gc;
+            for (int i = 0; i < gc; ++i) { e->owner[t][g0 + i] = c; e->local[t][g0 + i] = i; }
+            g0 += gc;
+            load[c] += (long long)gc * 16 * kd[t] * (t == G_LOGITS ? 1 : 1);
+        }
+    }
+    unsigned long long off = 0;
+    for (int c = 0; c < G; ++c) {
+        CtaTable& t = e->tab[c];
+        unsigned o = 0;
+        for (int g = 0; g < G_LOGITS; ++g) { t.slab_off[g] = o; o += (unsigned)t.gc[g] * 16u * (unsigned)kd[g]; }
+        t.layer_bytes = o;
+        t.slab_off[G_LOGITS] = 0;
+        t.logits_off = (unsigned long long)o * s.n_layer;
+        const unsigned long long total = t.logits_off + (unsigned long long)t.gc[G_LOGITS] * 16ull * kd[G_LOGITS];
+        t.stream_base = off;
+        e->weight_bytes += (long long)total;
+        off += (total + 255ull) & ~255ull;
+    }
+    e->stream_bytes = off + 65536;       // slack: bulk copies never read past a slab, this is belt and braces
+
+    // ---- device allocations ---------------------------------------------------------------------
+    const size_t D = s.d_model;
+#define ALLOC(ptr, bytes)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes));                   \
+        if (_e != cudaSuccess) {                                                                  \
+            g_last_cuda_error = std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(_e);    \
+            dia_b200_engine_destroy(e);                                                           \
+            return _e == cudaErrorMemoryAllocation ? DIA_B200_ENOMEM : DIA_B200_ECUDA;            \
+        }                                                                                         \
+        cudaMemset((ptr), 0, (bytes));                                                            \
+    } while (0)
+    ALLOC(e->d_wstream, e->stream_bytes);
+    ALLOC(e->d_tab, sizeof(CtaTable) * G);
+    for (int t = 0; t < G_COUNT; ++t) {
+        ALLOC(e->d_owner[t], sizeof(int) * e->n_groups[t]);
+        ALLOC(e->d_local[t], sizeof(int) * e->n_groups[t]);
+    }
+    ALLOC(e->d_emb, sizeof(float) * (size_t)s.channels * s.vocab * D);
+    ALLOC(e->d_norms, sizeof(float) * ((size_t)s.n_layer * 3 + 1) * D);
+    ALLOC(e->d_ptrs, sizeof(float*) * 4 * s.n_layer);
+    ALLOC(e->d_x, sizeof(float2) * D);
+    ALLOC(e->d_qkv, sizeof(float2) * (nq + 2 * nkv));
+    ALLOC(e->d_attn, sizeof(float2) * nq);
+    ALLOC(e->d_cq, sizeof(float2) * nc);
+    ALLOC(e->d_cattn, sizeof(float2) * nc);
+    ALLOC(e->d_hidden, sizeof(float2) * s.n_hidden);
+    ALLOC(e->d_logits, sizeof(float) * 2 * s.channels * s.vocab);
+    ALLOC(e->d_sa_part, sizeof(float) * 2 * s.q_heads * e->sa_nsplit * 132);
+    ALLOC(e->d_ca_part, sizeof(float) * s.cross_heads * e->ca_nsplit * 132);
+    ALLOC(e->d_pair_cnt, sizeof(unsigned) * (2 * s.kv_heads + s.cross_heads));
+    ALLOC(e->d_grid_bar, sizeof(unsigned) * 4);
+    ALLOC(e->d_err, sizeof(int) * 4);
+    ALLOC(e->d_pred, sizeof(int) * DIA_B200_MAX_CHANNELS);
+    ALLOC(e->d_tokens, sizeof(int) * 2 * DIA_B200_MAX_CHANNELS);
+    ALLOC(e->d_gs, sizeof(GenState));
+#undef ALLOC
+    if (cudaMallocHost(reinterpret_cast<void**>(&e->h_ptrs), sizeof(float*) * 4 * s.n_layer) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&e->h_gs), sizeof(GenState)) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&e->h_err), sizeof(int) * 4) != cudaSuccess) {
+        dia_b200_engine_destroy(e);
+        return DIA_B200_ENOMEM;
+    }
+    CK(cudaMemcpy(e->d_tab, e->tab.data(), sizeof(CtaTable) * G, cudaMemcpyHostToDevice));
+    for (int t = 0; t < G_COUNT; ++t) {
+        CK(cudaMemcpy(e->d_owner[t], e->owner[t].data(), sizeof(int) * e->n_groups[t], cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(e->d_local[t], e->local[t].data(), sizeof(int) * e->n_groups[t], cudaMemcpyHostToDevice));
+    }
+    *out = e;
+    return DIA_B200_OK;
+}
+
+int dia_b200_engine_destroy(dia_b200_engine* e) {
+    if (!e) return DIA_B200_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    void* dev[] = {e->d_wstream, e->d_tab, e->d_emb, e->d_norms, e->d_rope_sin, e->d_rope_cos, e->d_ptrs, e->d_x,
+                   e->d_qkv, e->d_attn, e->d_cq, e->d_cattn, e->d_hidden, e->d_logits, e->d_sa_part, e->d_ca_part,
+                   e->d_pair_cnt, e->d_grid_bar, e->d_err, e->d_pred, e->d_tokens, e->d_gs};
+    for (void* p : dev) if (p) cudaFree(p);
+    for (int t = 0; t < G_COUNT; ++t) { if (e->d_owner[t]) cudaFree(e->d_owner[t]); if (e->d_local[t]) cudaFree(e->d_local[t]); }
+    if (e->h_ptrs) cudaFreeHost(e->h_ptrs);
+    if (e->h_gs) cudaFreeHost(e->h_gs);
+    if (e->h_err) cudaFreeHost(e->h_err);
+    delete e;
+    return DIA_B200_OK;
+}
+
+int dia_b200_engine_num_ctas(const dia_b200_engine* e) { return e ? e->G : DIA_B200_EINVAL; }
+int64_t dia_b200_engine_weight_stream_bytes(const dia_b200_engine* e) { return e ? e->weight_bytes : DIA_B200_EINVAL; }
+
+int dia_b200_load_decoder_weights(dia_b200_engine* e, const void* const* tensors, int n_tensors, int dense_dtype,
+                                  void* stream) {
+    if (!e || !tensors || (dense_dtype != 0 && dense_dtype != 1)) return DIA_B200_EINVAL;
+    const dia_b200_shape& s = e->shape;
+    const int expect = s.channels + 11 * s.n_layer + 2;
+    if (n_tensors != expect) return DIA_B200_EINVAL;
+    for (int i = 0; i < n_tensors; ++i) if (!tensors[i]) return DIA_B200_EINVAL;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = S(stream);
+    const size_t D = s.d_model;
+    int ti = 0;
+    for (int c = 0; c < s.channels; ++c, ++ti)
+        CK(cudaMemcpyAsync(e->d_emb + (size_t)c * s.vocab * D, tensors[ti], sizeof(float) * s.vocab * D,
+                           cudaMemcpyDeviceToDevice, st));
+    RepackArgs a{};
+    a.src_bf16 = dense_dtype; a.Hq = s.q_heads; a.Hkv = s.kv_heads; a.F = s.n_hidden; a.V = s.vocab; a.Vpad = e->Vpad;
+    a.C = s.channels; a.tab = e->d_tab; a.wstream = e->d_wstream;
+    auto repack = [&](int gemm, int layer, const void* s0, const void* s1, const void* s2, int N) -> int {
+        a.src[0] = s0; a.src[1] = s1; a.src[2] = s2; a.gemm = gemm; a.layer = layer; a.K = e->Kdim[gemm];
+        a.n_groups = e->n_groups[gemm]; a.N = N; a.owner = e->d_owner[gemm]; a.local = e->d_local[gemm];
+        CK(launch_repack(a, st));
+        g_launches++;
+        return DIA_B200_OK;
+    };
+    for (int l = 0; l < s.n_layer; ++l) {
+        for (int n = 0; n < 3; ++n, ++ti)
+            CK(cudaMemcpyAsync(e->d_norms + ((size_t)l * 3 + n) * D, tensors[ti], sizeof(float) * D,
+                               cudaMemcpyDeviceToDevice, st));
+        const void *q = tensors[ti], *k = tensors[ti + 1], *v = tensors[ti + 2], *o = tensors[ti + 3];
+        const void *cq = tensors[ti + 4], *co = tensors[ti + 5], *wi = tensors[ti + 6], *wo = tensors[ti + 7];
+        ti += 8;
+        int rc;
+        if ((rc = repack(G_QKV, l, q, k, v, 0))) return rc;
+        if ((rc = repack(G_SO, l, o, nullptr, nullptr, s.d_model))) return rc;
+        if ((rc = repack(G_CQ, l, cq, nullptr, nullptr, s.cross_heads * kHeadDim))) return rc;
+        if ((rc = repack(G_CO, l, co, nullptr, nullptr, s.d_model))) return rc;
+        if ((rc = repack(G_WI, l, wi, nullptr, nullptr, 0))) return rc;
+        if ((rc = repack(G_WO, l, wo, nullptr, nullptr, s.d_model))) return rc;
+    }
+    CK(cudaMemcpyAsync(e->d_norms + (size_t)s.n_layer * 3 * D, tensors[ti], sizeof(float) * D, cudaMemcpyDeviceToDevice,
+                       st));
+    ++ti;
+    int rc = repack(G_LOGITS, 0, tensors[ti], nullptr, nullptr, 0);
+    if (rc) return rc;
+    e->weights_loaded = true;
+    return DIA_B200_OK;
+}
+
+int dia_b200_set_rope_table(dia_b200_engine* e, const float* sin_host, const float* cos_host, int n_pos) {
+    if (!e || !sin_host || !cos_host || n_pos <= 0) return DIA_B200_EINVAL;
+    CK(cudaSetDevice(e->device));
+    if (e->d_rope_sin) { cudaFree(e->d_rope_sin); e->d_rope_sin = nullptr; }
+    if (e->d_rope_cos) { cudaFree(e->d_rope_cos); e->d_rope_cos = nullptr; }
+    const size_t bytes = sizeof(float) * (size_t)n_pos * (kHeadDim / 2);
+    CK(cudaMalloc(reinterpret_cast<void**>(&e->d_rope_sin), bytes));
+    CK(cudaMalloc(reinterpret_cast<void**>(&e->d_rope_cos), bytes));
+    CK(cudaMemcpy(e->d_rope_sin, sin_host, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_rope_cos, cos_host, bytes, cudaMemcpyHostToDevice));
+    e->n_pos = n_pos;
+    e->rope_set = true;
+    return DIA_B200_OK;
+}
+
+int dia_b200_bind_caches(dia_b200_engine* e, void* const* self_k, void* const* self_v, const void* const* cross_k,
+                         const void* const* cross_v, int n_layer, int text_len, void* stream) {
+    if (!e || !self_k || !self_v || !cross_k || !cross_v) return DIA_B200_EINVAL;
+    if (n_layer != e->shape.n_layer || text_len < 0 || text_len > e->shape.max_text_len) return DIA_B200_EINVAL;
+    CK(cudaSetDevice(e->device));
+    const int L = n_layer;
+    // the pinned staging buffer is reused: make sure the previous async copy has drained
+    CK(cudaStreamSynchronize(S(stream)));
+    for (int l = 0; l < L; ++l) {
+        if (!self_k[l] || !self_v[l] || !cross_k[l] || !cross_v[l]) return DIA_B200_EINVAL;
+        if ((reinterpret_cast<uintptr_t>(self_k[l]) | reinterpret_cast<uintptr_t>(self_v[l]) |
+             reinterpret_cast<uintptr_t>(cross_k[l]) | reinterpret_cast<uintptr_t>(cross_v[l])) & 15)
+            return DIA_B200_EINVAL;                      // bulk copies need 16-byte aligned rows
+        e->h_ptrs[l] = static_cast<float*>(self_k[l]);
+        e->h_ptrs[L + l] = static_cast<float*>(self_v[l]);
+        e->h_ptrs[2 * L + l] = const_cast<float*>(static_cast<const float*>(cross_k[l]));
+        e->h_ptrs[3 * L + l] = const_cast<float*>(static_cast<const float*>(cross_v[l]));
+    }
+    CK(cudaMemcpyAsync(e->d_ptrs, e->h_ptrs, sizeof(float*) * 4 * L, cudaMemcpyHostToDevice, S(stream)));
+    e->text_len = text_len;
+    e->caches_bound = true;
+    e->gen_active = false;
+    return DIA_B200_OK;
+}
+
+static int ready(const dia_b200_engine* e, bool need_caches) {
+    if (!e) return DIA_B200_EINVAL;
+    if (!e->weights_loaded || !e->rope_set) return DIA_B200_ESTATE;
+    if (need_caches && !e->caches_bound) return DIA_B200_ESTATE;
+    return DIA_B200_OK;
+}
+
+int dia_b200_decode_step(dia_b200_engine* e, const int32_t* tokens, int pos, int slot, float* logits, void* stream) {
+    int rc = ready(e, true);
+    if (rc) return rc;
+    if (!tokens || !logits || pos < 0 || slot < 0 || slot >= e->shape.max_audio_len) return DIA_B200_EINVAL;
+    CK(cudaSetDevice(e->device));
+    StepParams p;
+    fill_params(e, p);
+    p.tokens = tokens;
+    p.stage_begin = 0;
+    p.stage_end = 8 * p.L + 2;          // embed .. logits (no sampling)
+    p.pos0 = pos; p.slot0 = slot;
+    p.logits = logits;
+    return run_stages(e, p, true, S(stream));
+}
+
+int dia_b200_decoder_layer_step(dia_b200_engine* e, int layer, const float* x_in, float* x_out, int pos, int slot,
+                                void* stream) {
+    int rc = ready(e, true);
+    if (rc) return rc;
+    if (!x_in || !x_out || layer < 0 || layer >= e->shape.n_layer || pos < 0 || slot < 0 ||
+        slot >= e->shape.max_audio_len)
+        return DIA_B200_EINVAL;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = S(stream);
+    CK(launch_interleave(x_in, e->d_x, e->shape.d_model, st));
+    g_launches++;
+    StepParams p;
+    fill_params(e, p);
+    p.stage_begin = 1 + 8 * layer;
+    p.stage_end = p.stage_begin + 8;
+    p.pos0 = pos; p.slot0 = slot;
+    rc = run_stages(e, p, true, st);
+    if (rc) return rc;
+    CK(launch_deinterleave(e->d_x, x_out, e->shape.d_model, st));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_embed_sum(dia_b200_engine* e, const int32_t* tokens, int n_rows, float* x, void* stream) {
+    if (!e || !tokens || !x || n_rows < 0) return DIA_B200_EINVAL;
+    if (!e->weights_loaded) return DIA_B200_ESTATE;
+    CK(cudaSetDevice(e->device));
+    CK(launch_embed_sum(e->d_emb, tokens, n_rows, e->shape.channels, e->shape.vocab, e->shape.d_model, x, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_head_sample(dia_b200_engine* e, const float* logits, float cfg_scale, float temperature, float top_p,
+                         int top_k, uint64_t seed, uint64_t draw, int32_t* pred, float* probs, void* stream) {
+    if (!e || !logits || !pred) return DIA_B200_EINVAL;
+    int rc = check_sampling_supported(temperature, top_k);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    StepParams p;
+    fill_params(e, p);
+    p.cfg_scale = cfg_scale; p.temperature = temperature; p.top_p = top_p; p.top_k = top_k; p.seed = seed;
+    CK(launch_head_sample(p, logits, draw, pred, probs, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_generate_begin(dia_b200_engine* e, int32_t* grid, const dia_b200_gen_params* gp, void* stream) {
+    int rc = ready(e, true);
+    if (rc) return rc;
+    if (!grid || !gp) return DIA_B200_EINVAL;
+    if (gp->prefill_step < 1 || gp->max_tokens < 1 || gp->max_tokens > e->shape.max_audio_len ||
+        gp->first_slot < 0 || gp->first_slot >= e->shape.max_audio_len)
+        return DIA_B200_EINVAL;
+    rc = check_sampling_supported(gp->temperature, gp->top_k);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(S(stream)));     // h_gs staging reuse
+    int dmax = 0;
+    for (int c = 0; c < e->shape.channels; ++c) dmax = std::max(dmax, (int)e->shape.delay_pattern[c]);
+    std::memset(e->h_gs, 0, sizeof(GenState));
+    e->h_gs->dec_step = gp->prefill_step - 1;          // dia/model.py:736
+    e->h_gs->bos_countdown = dmax;                     // :739
+    e->h_gs->eos_countdown = -1;                       // :741
+    e->h_gs->finished = (e->h_gs->dec_step >= gp->max_tokens - 1) ? 1 : 0;
+    CK(cudaMemcpyAsync(e->d_gs, e->h_gs, sizeof(GenState), cudaMemcpyHostToDevice, S(stream)));
+    CK(cudaMemsetAsync(e->d_err, 0, sizeof(int), S(stream)));
+    e->gp = *gp;
+    e->gen_grid = grid;
+    e->gen_pos = gp->prefill_step;                     // first iteration: cur = dec_step + 1
+    e->gen_slot = gp->first_slot;                      // KVCache.current_idx after the (optional) prefill
+    e->gen_active = true;
+    return DIA_B200_OK;
+}
+
+int dia_b200_generate_steps(dia_b200_engine* e, int n_steps, void* stream) {
+    int rc = ready(e, true);
+    if (rc) return rc;
+    if (!e->gen_active) return DIA_B200_ESTATE;
+    if (n_steps < 0) return DIA_B200_EINVAL;
+    // never run past the cache / grid: the device loop is finished by then anyway
+    n_steps = std::min(n_steps, e->shape.max_audio_len - e->gen_slot);
+    n_steps = std::min(n_steps, e->shape.max_audio_len - e->gen_pos);
+    if (n_steps <= 0) return DIA_B200_OK;
+    CK(cudaSetDevice(e->device));
+    StepParams p;
+    fill_params(e, p);
+    p.stage_begin = 0;
+    p.stage_end = 8 * p.L + 3;
+    p.n_steps = n_steps;
+    p.pos0 = e->gen_pos; p.slot0 = e->gen_slot;
+    p.grid = e->gen_grid; p.gs = e->d_gs;
+    p.cfg_scale = e->gp.cfg_scale; p.temperature = e->gp.temperature; p.top_p = e->gp.top_p; p.top_k = e->gp.top_k;
+    p.max_tokens = e->gp.max_tokens; p.seed = e->gp.seed;
+    rc = run_stages(e, p, true, S(stream));
+    if (rc) return rc;
+    e->gen_pos += n_steps;
+    e->gen_slot += n_steps;
+    return DIA_B200_OK;
+}
+
+int dia_b200_generate_status(dia_b200_engine* e, dia_b200_gen_status* out, void* stream) {
+    if (!e || !out) return DIA_B200_EINVAL;
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(e->h_gs, e->d_gs, sizeof(GenState), cudaMemcpyDeviceToHost, S(stream)));
+    CK(cudaMemcpyAsync(e->h_err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    CK(cudaStreamSynchronize(S(stream)));
+    out->dec_step = e->h_gs->dec_step;
+    out->finished = e->h_gs->finished;
+    out->eos_detected = e->h_gs->eos_detected;
+    out->eos_countdown = e->h_gs->eos_countdown;
+    out->bos_countdown = e->h_gs->bos_countdown;
+    out->steps_run = e->h_gs->steps_run;
+    out->device_error = e->h_err[0];
+    out->reserved = 0;
+    return DIA_B200_OK;
+}
+
+int dia_b200_delay_apply_i32(const int32_t* in, int32_t* out, int B, int T, int C, const int32_t* delay_host,
+                             int32_t pad_value, int32_t bos_value, void* stream) {
+    if (B < 0 || T < 0 || C < 0 || C > DIA_B200_MAX_CHANNELS || !delay_host) return DIA_B200_EINVAL;
+    if ((long long)B * T * C == 0) return DIA_B200_OK;
+    if (!in || !out || in == out) return DIA_B200_EINVAL;
+    CK(launch_delay_apply(in, out, B, T, C, delay_host, pad_value, bos_value, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_delay_revert_i32(const int32_t* in, int32_t* out, int B, int T, int C, const int32_t* delay_host,
+                              int32_t pad_value, int T_orig, void* stream) {
+    if (B < 0 || T < 0 || C < 0 || C > DIA_B200_MAX_CHANNELS || !delay_host) return DIA_B200_EINVAL;
+    if ((long long)B * T * C == 0) return DIA_B200_OK;
+    if (!in || !out || in == out) return DIA_B200_EINVAL;
+    CK(launch_delay_revert(in, out, B, T, C, delay_host, pad_value, T_orig, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_finalize_codes_i32(const int32_t* in, int32_t* out, int T, int C, const int32_t* delay_host,
+                                int32_t pad_value, int codebook_size, void* stream) {
+    if (T < 0 || C <= 0 || C > DIA_B200_MAX_CHANNELS || !delay_host || codebook_size <= 0) return DIA_B200_EINVAL;
+    int dmax = 0;
+    for (int i = 0; i < C; ++i) dmax = std::max(dmax, (int)delay_host[i]);
+    if (T - dmax <= 0) return DIA_B200_OK;
+    if (!in || !out || in == out) return DIA_B200_EINVAL;
+    CK(launch_finalize_codes(in, out, T, C, delay_host, pad_value, codebook_size, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_build_delay_indices(int32_t* t_idx, int64_t* indices, int B, int T, int C, const int32_t* delay_host,
+                                 void* stream) {
+    if (B < 0 || T < 0 || C < 0 || C > DIA_B200_MAX_CHANNELS || !delay_host) return DIA_B200_EINVAL;
+    if ((long long)B * T * C == 0) return DIA_B200_OK;
+    if (!t_idx || !indices) return DIA_B200_EINVAL;
+    CK(launch_build_delay_indices(t_idx, reinterpret_cast<long long*>(indices), B, T, C, delay_host, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_build_revert_indices(int64_t* t_idx, int64_t* indices, int B, int T, int C, const int32_t* delay_host,
+                                  void* stream) {
+    if (B < 0 || T < 0 || C < 0 || C > DIA_B200_MAX_CHANNELS || !delay_host) return DIA_B200_EINVAL;
+    if ((long long)B * T * C == 0) return DIA_B200_OK;
+    if (!t_idx || !indices) return DIA_B200_EINVAL;
+    CK(launch_build_revert_indices(reinterpret_cast<long long*>(t_idx), reinterpret_cast<long long*>(indices), B, T,
+                                   C, delay_host, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_debug_run_stages(dia_b200_engine* e, const int32_t* tokens, int stage_begin, int stage_end, int pos,
+                              int slot, int cooperative, void* stream) {
+    int rc = ready(e, true);
+    if (rc) return rc;
+    const int S_total = 8 * e->shape.n_layer + 3;
+    if (stage_begin < 0 || stage_end > S_total || stage_begin >= stage_end) return DIA_B200_EINVAL;
+    if (!cooperative && stage_end - stage_begin != 1) return DIA_B200_EINVAL;   // no grid barrier without co-residency
+    if (stage_begin == 0 && !tokens) return DIA_B200_EINVAL;
+    CK(cudaSetDevice(e->device));
+    StepParams p;
+    fill_params(e, p);
+    p.tokens = tokens;
+    p.stage_begin = stage_begin; p.stage_end = stage_end;
+    p.pos0 = pos; p.slot0 = slot;
+    return run_stages(e, p, cooperative != 0, S(stream));
+}
+
+static int buffer_of(dia_b200_engine* e, int which, void** ptr, size_t* bytes) {
+    const dia_b200_shape& s = e->shape;
+    const size_t nq = (size_t)s.q_heads * kHeadDim, nkv = (size_t)s.kv_heads * kHeadDim,
+                 nc = (size_t)s.cross_heads * kHeadDim;
+    switch (which) {
+        case DIA_B200_BUF_X: *ptr = e->d_x; *bytes = 8 * (size_t)s.d_model; break;
+        case DIA_B200_BUF_QKV: *ptr = e->d_qkv; *bytes = 8 * (nq + 2 * nkv); break;
+        case DIA_B200_BUF_ATTN: *ptr = e->d_attn; *bytes = 8 * nq; break;
+        case DIA_B200_BUF_CQ: *ptr = e->d_cq; *bytes = 8 * nc; break;
+        case DIA_B200_BUF_CATTN: *ptr = e->d_cattn; *bytes = 8 * nc; break;
+        case DIA_B200_BUF_HIDDEN: *ptr = e->d_hidden; *bytes = 8 * (size_t)s.n_hidden; break;
+        case DIA_B200_BUF_LOGITS: *ptr = e->d_logits; *bytes = 4 * 2 * (size_t)s.channels * s.vocab; break;
+        case DIA_B200_BUF_PRED: *ptr = e->d_pred; *bytes = 4 * (size_t)s.channels; break;
+        default: return DIA_B200_EINVAL;
+    }
+    return DIA_B200_OK;
+}
+
+int dia_b200_debug_read(dia_b200_engine* e, int which, void* host_dst, size_t nbytes, void* stream) {
+    if (!e || !host_dst) return DIA_B200_EINVAL;
+    void* p; size_t b;
+    int rc = buffer_of(e, which, &p, &b);
+    if (rc) return rc;
+    if (nbytes > b) return DIA_B200_EINVAL;
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(host_dst, p, nbytes, cudaMemcpyDeviceToHost, S(stream)));
+    CK(cudaStreamSynchronize(S(stream)));
+    return DIA_B200_OK;
+}
+
+int dia_b200_debug_write(dia_b200_engine* e, int which, const void* host_src, size_t nbytes, void* stream) {
+    if (!e || !host_src) return DIA_B200_EINVAL;
+    void* p; size_t b;
+    int rc = buffer_of(e, which, &p, &b);
+    if (rc) return rc;
+    if (nbytes > b) return DIA_B200_EINVAL;
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(p, host_src, nbytes, cudaMemcpyHostToDevice, S(stream)));
+    CK(cudaStreamSynchronize(S(stream)));
+    return DIA_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+// engine_internal.h - structures shared between the host engine and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dia_b200.h"
+
+namespace dia {
+
+// GEMM families inside one decoder layer (+ the logits head); index into CtaTable
+enum GemmType : int { G_QKV = 0, G_SO = 1, G_CQ = 2, G_CO = 3, G_WI = 4, G_WO = 5, G_LOGITS = 6, G_COUNT = 7 };
+
+// stage kinds of one decode step
+enum StageKind : int {
+    S_EMBED = 0,
+    S_QKV, S_SATTN, S_SO, S_CQ, S_CATTN, S_CO, S_WI, S_WO,   // 8 per layer
+    S_LOGITS, S_SAMPLE
+};
+
+// Per-CTA slice of every GEMM: a CTA owns `gc` groups of 8 output columns starting at group `g0`
+// and streams its [K x gc*8] bf16 slab (k-major, 16 B per (k, group)) from `stream_base`.
+struct CtaTable {
+    unsigned long long stream_base;    // byte offset of this CTA's weight stream
+    unsigned long long logits_off;     // byte offset of the logits slab inside the stream
+    unsigned layer_bytes;              // bytes of one layer in this CTA's stream
+    unsigned slab_off[G_COUNT];        // byte offset of each slab inside a layer block
+    int g0[G_COUNT];
+    int gc[G_COUNT];
+};
+
+struct GenState {                      // device-resident Dia.generate loop state (dia/model.py:736-807)
+    int dec_step;
+    int finished;
+    int eos_detected;
+    int eos_countdown;
+    int bos_countdown;
+    int steps_run;
+    int device_error;
+    int reserved;
+};
+
+struct StepParams {
+    // geometry
+    int L, D, F, Hq, Hkv, Hc, C, V, Vpad, Lmax, Smax;
+    int Kdim[G_COUNT];                 // contraction length per GEMM family
+    float eps;
+    int G;                             // CTAs the tables were built for
+    int sa_nsplit, ca_nsplit;          // max key splits per (row, kv head) / per cross head
+    // weights
+    const unsigned char* wstream;
+    const CtaTable* cta_tab;
+    const float* emb;                  // [C][V][D] fp32
+    const float* norms;                // [L][3][D] then final [D]
+    const float* rope_sin;             // [n_pos][64]
+    const float* rope_cos;
+    int n_pos;
+    // caches (device arrays of L pointers)
+    float* const* self_k;
+    float* const* self_v;
+    const float* const* cross_k;
+    const float* const* cross_v;
+    int text_len;
+    // scratch (all fp32; vectors interleaved [n][2] = (uncond row, cond row))
+    float2* x;
+    float2* qkv;
+    float2* attn;
+    float2* cq;
+    float2* cattn;
+    float2* hidden;
+    float* logits;                     // [2][C][V]
+    float* sa_part;                    // [2*Hq][sa_nsplit][132]
+    float* ca_part;                    // [Hc][ca_nsplit][132]
+    unsigned* pair_cnt;                // last-arriver counters, [2*Hkv + Hc]
+    unsigned* grid_bar;                // grid barrier counter (zeroed before each launch)
+    int* err;
+    // run control
+    int stage_begin, stage_end;        // stages of a step to execute, [begin, end)
+    int n_steps;
+    int pos0, slot0;                   // RoPE position / cache slot of the first step
+    const int* tokens;                 // [2][C] explicit input tokens (API mode) or nullptr (generate mode)
+    // generate mode
+    int* grid;                         // [Lmax][C] token grid
+    GenState* gs;
+    float cfg_scale, temperature, top_p;
+    int top_k;
+    int max_tokens;
+    unsigned long long seed;
+    int eos, pad, bos;
+    int delay[DIA_B200_MAX_CHANNELS];
+    int* pred_out;                     // [C] raw prediction of the last executed step
+    float* probs_out;                  // optional [C][V]
+};
+
+// ---- launchers (each returns the cudaError_t of the launch) --------------------------------
+cudaError_t launch_step_kernel(const StepParams& p, bool cooperative, cudaStream_t st);
+int step_kernel_smem_bytes();
+cudaError_t launch_head_sample(const StepParams& p, const float* logits, unsigned long long draw, int* pred,
+                               float* probs, cudaStream_t st);
+struct RepackArgs {
+    const void* src[3];     // QKV: q, k, v kernels; otherwise src[0]
+    int src_bf16;
+    int K;
+    int gemm;
+    int layer;
+    int n_groups;
+    int Hq, Hkv, F, V, Vpad, C, N;
+    const int* owner;       // [n_groups] CTA owning each column group
+    const int* local;       // [n_groups] index of the group inside its CTA's slab
+    const CtaTable* tab;
+    unsigned char* wstream;
+};
+cudaError_t launch_repack(const RepackArgs& a, cudaStream_t st);
+cudaError_t launch_embed_sum(const float* emb, const int* tokens, int n_rows, int C, int V, int D, float* x,
+                             cudaStream_t st);
+cudaError_t launch_interleave(const float* x_rows, float2* x_il, int D, cudaStream_t st);
+cudaError_t launch_deinterleave(const float2* x_il, float* x_rows, int D, cudaStream_t st);
+cudaError_t launch_delay_apply(const int* in, int* out, int B, int T, int C, const int* delay, int pad, int bos,
+                               cudaStream_t st);
+cudaError_t launch_delay_revert(const int* in, int* out, int B, int T, int C, const int* delay, int pad, int T_orig,
+                                cudaStream_t st);
+cudaError_t launch_finalize_codes(const int* in, int* out, int T, int C, const int* delay, int pad, int codebook,
+                                  cudaStream_t st);
+cudaError_t launch_build_delay_indices(int* t_idx, long long* idx, int B, int T, int C, const int* delay,
+                                       cudaStream_t st);
+cudaError_t launch_build_revert_indices(long long* t_idx, long long* idx, int B, int T, int C, const int* delay,
+                                        cudaStream_t st);
+
+struct DelayArg { int d[DIA_B200_MAX_CHANNELS]; };
+
+}  // namespace dia

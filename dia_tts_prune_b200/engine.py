@@ -1,0 +1,233 @@
+"""Python face of the C ABI: one ``DecodeEngine`` per GPU wraps ``dia_b200_engine``.
+
+Pure plumbing: tensors are handed over as ``data_ptr()`` + the current CUDA stream.  All
+arithmetic happens in ``csrc/`` kernels; there is no eager / CPU fallback here.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .config import DiaConfig
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr())
+
+
+def rope_tables(config: DiaConfig, n_pos: int, head_dim: int = 128) -> tuple[torch.Tensor, torch.Tensor]:
+    """sin/cos of ``int32 position * inv_freq`` computed with the reference's own CPU expressions
+    (RotaryEmbedding, dia/layers.py:126-132,146,161-162) so that the table equals what the fp32
+    CPU reference uses, bit for bit."""
+    half = head_dim // 2
+    fraction = (2.0 * torch.arange(0, half)) / head_dim
+    m = config.model
+    inv_freq = (1.0 / (m.rope_min_timescale * (m.rope_max_timescale / m.rope_min_timescale) ** fraction)).to(torch.float32)
+    pos = torch.arange(n_pos, dtype=torch.int32).unsqueeze(-1)
+    freqs = (pos * inv_freq).to(torch.float32)
+    return torch.sin(freqs).contiguous(), torch.cos(freqs).contiguous()
+
+
+def decoder_tensor_names(config: DiaConfig) -> list[str]:
+    """Names (relative to the Decoder module) in the order ``dia_b200_load_decoder_weights`` expects."""
+    names = [f"embeddings.{c}.weight" for c in range(config.data.channels)]
+    for i in range(config.model.decoder.n_layer):
+        p = f"layers.{i}."
+        names += [p + "pre_sa_norm.weight", p + "pre_ca_norm.weight", p + "pre_mlp_norm.weight",
+                  p + "self_attention.q_proj.weight", p + "self_attention.k_proj.weight",
+                  p + "self_attention.v_proj.weight", p + "self_attention.o_proj.weight",
+                  p + "cross_attention.q_proj.weight", p + "cross_attention.o_proj.weight",
+                  p + "mlp.wi_fused.weight", p + "mlp.wo.weight"]
+    return names + ["norm.weight", "logits_dense.weight"]
+
+
+class DecodeEngine:
+    def __init__(self, config: DiaConfig, device: torch.device | str | int = "cuda", n_ctas: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dia_tts_prune_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.config = config
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        d, dt = config.model.decoder, config.data
+        if d.gqa_head_dim != 128 or d.cross_head_dim != 128:
+            raise NotImplementedError("kernels are specialised for head_dim 128")
+        sh = _lib.Shape()
+        sh.n_layer, sh.d_model, sh.n_hidden = d.n_layer, d.n_embd, d.n_hidden
+        sh.q_heads, sh.kv_heads, sh.cross_heads = d.gqa_query_heads, d.kv_heads, d.cross_query_heads
+        sh.channels, sh.vocab = dt.channels, config.model.tgt_vocab_size
+        sh.max_audio_len, sh.max_text_len = dt.audio_length, dt.text_length
+        sh.eos_value, sh.pad_value, sh.bos_value = dt.audio_eos_value, dt.audio_pad_value, dt.audio_bos_value
+        for i, v in enumerate(dt.delay_pattern):
+            sh.delay_pattern[i] = v
+        sh.norm_eps = config.model.normalization_layer_epsilon
+        self._h = C.c_void_p()
+        _lib.check(self.lib.dia_b200_engine_create(C.byref(sh), self.device.index, n_ctas, C.byref(self._h)),
+                   "engine_create")
+        self.C, self.V, self.D, self.L = dt.channels, config.model.tgt_vocab_size, d.n_embd, d.n_layer
+        self.n_ctas = self.lib.dia_b200_engine_num_ctas(self._h)
+        self.weight_stream_bytes = int(self.lib.dia_b200_engine_weight_stream_bytes(self._h))
+        sin, cos = rope_tables(config, max(dt.audio_length, dt.text_length) + 1)
+        _lib.check(self.lib.dia_b200_set_rope_table(self._h, _ptr(sin), _ptr(cos), sin.shape[0]), "set_rope_table")
+        self._keep = []        # tensors whose memory the engine points into
+        self._bound = None
+        self.weights_version = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.dia_b200_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights -----------------------------------------------------------------------------
+    def load_weights(self, tensors: dict[str, torch.Tensor]) -> None:
+        """``tensors``: Decoder-relative name -> CUDA tensor (dense kernels all fp32 or all bf16)."""
+        names = decoder_tensor_names(self.config)
+        dense = [n for n in names if "proj" in n or "mlp" in n or "logits" in n]
+        dts = {tensors[n].dtype for n in dense}
+        if len(dts) != 1 or next(iter(dts)) not in (torch.float32, torch.bfloat16):
+            raise ValueError(f"dense kernels must be uniformly float32 or bfloat16, got {dts}")
+        dense_dtype = 1 if next(iter(dts)) == torch.bfloat16 else 0
+        staged = []
+        for n in names:
+            t = tensors[n].detach()
+            if n not in dense:
+                t = t.to(torch.float32)
+            t = t.to(self.device).contiguous()
+            staged.append(t)
+        arr = (C.c_void_p * len(staged))(*[t.data_ptr() for t in staged])
+        _lib.check(self.lib.dia_b200_load_decoder_weights(self._h, arr, len(staged), dense_dtype, _stream(self.device)),
+                   "load_decoder_weights")
+        torch.cuda.current_stream(self.device).synchronize()    # sources may be freed after this
+
+    # ---- per-utterance binding -------------------------------------------------------------------
+    def bind(self, self_caches, cross_caches, text_len: int) -> None:
+        L = self.L
+        if len(self_caches) != L or len(cross_caches) != L:
+            raise ValueError("cache lists must have one entry per decoder layer")
+        keep = []
+        ptrs = [[], [], [], []]
+        d = self.config.model.decoder
+        for sc, cc in zip(self_caches, cross_caches):
+            for t, shape in ((sc.k, (2, d.kv_heads, self.config.data.audio_length, 128)), (sc.v, None)):
+                if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                    raise ValueError("self KV cache tensors must be contiguous float32 CUDA tensors")
+                if shape is not None and tuple(t.shape) != shape:
+                    raise ValueError(f"self KV cache shape {tuple(t.shape)} != {shape}")
+            ck, cv = cc.k, cc.v
+            if ck.dtype != torch.float32 or not ck.is_contiguous():
+                ck = ck.to(torch.float32).contiguous()
+            if cv.dtype != torch.float32 or not cv.is_contiguous():
+                cv = cv.to(torch.float32).contiguous()
+            if tuple(ck.shape) != (2, d.cross_query_heads, self.config.data.text_length, 128):
+                raise ValueError(f"cross KV cache shape {tuple(ck.shape)} unexpected")
+            keep += [sc.k, sc.v, ck, cv]
+            for lst, t in zip(ptrs, (sc.k, sc.v, ck, cv)):
+                lst.append(t.data_ptr())
+        arrs = [(C.c_void_p * L)(*p) for p in ptrs]
+        _lib.check(self.lib.dia_b200_bind_caches(self._h, arrs[0], arrs[1], arrs[2], arrs[3], L, int(text_len),
+                                                 _stream(self.device)), "bind_caches")
+        self._keep = keep
+        self._bound = tuple(ptrs[0] + ptrs[2]) + (int(text_len),)
+
+    def bound_key(self):
+        return self._bound
+
+    # ---- operator boundaries -----------------------------------------------------------------------
+    def decode_step(self, tokens_2xC: torch.Tensor, pos: int, slot: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        tok = tokens_2xC.to(device=self.device, dtype=torch.int32).contiguous()
+        if out is None:
+            out = torch.empty((2, self.C, self.V), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dia_b200_decode_step(self._h, _ptr(tok), int(pos), int(slot), _ptr(out),
+                                                 _stream(self.device)), "decode_step")
+        return out
+
+    def layer_step(self, layer: int, x_2xD: torch.Tensor, pos: int, slot: int) -> torch.Tensor:
+        x = x_2xD.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(x)
+        _lib.check(self.lib.dia_b200_decoder_layer_step(self._h, int(layer), _ptr(x), _ptr(out), int(pos), int(slot),
+                                                        _stream(self.device)), "decoder_layer_step")
+        return out
+
+    def embed_sum(self, tokens_NxC: torch.Tensor) -> torch.Tensor:
+        tok = tokens_NxC.to(device=self.device, dtype=torch.int32).contiguous()
+        n = tok.shape[0]
+        out = torch.empty((n, self.D), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dia_b200_embed_sum(self._h, _ptr(tok), n, _ptr(out), _stream(self.device)), "embed_sum")
+        return out
+
+    def head_sample(self, logits_2xCxV: torch.Tensor, cfg_scale: float, temperature: float, top_p: float, top_k: int,
+                    seed: int = 0, draw: int = 0, want_probs: bool = False):
+        lg = logits_2xCxV.to(device=self.device, dtype=torch.float32).contiguous()
+        pred = torch.empty((self.C,), dtype=torch.int32, device=self.device)
+        probs = torch.empty((self.C, self.V), dtype=torch.float32, device=self.device) if want_probs else None
+        _lib.check(self.lib.dia_b200_head_sample(self._h, _ptr(lg), float(cfg_scale), float(temperature), float(top_p),
+                                                 int(top_k or 0), int(seed) & (2 ** 64 - 1), int(draw), _ptr(pred),
+                                                 _ptr(probs) if want_probs else None, _stream(self.device)),
+                   "head_sample")
+        return (pred, probs) if want_probs else pred
+
+    # ---- the device-resident generate loop ---------------------------------------------------------------
+    def generate_begin(self, grid: torch.Tensor, prefill_step: int, first_slot: int, max_tokens: int, cfg_scale: float,
+                       temperature: float, top_p: float, top_k: int, seed: int) -> None:
+        if grid.dtype != torch.int32 or not grid.is_contiguous() or grid.device != self.device:
+            raise ValueError("token grid must be a contiguous int32 CUDA tensor")
+        gp = _lib.GenParams(float(cfg_scale), float(temperature), float(top_p), int(top_k or 0), int(max_tokens),
+                            int(prefill_step), int(first_slot), 0, int(seed) & (2 ** 64 - 1))
+        _lib.check(self.lib.dia_b200_generate_begin(self._h, _ptr(grid), C.byref(gp), _stream(self.device)),
+                   "generate_begin")
+        self._keep.append(grid)
+
+    def generate_steps(self, n_steps: int) -> None:
+        _lib.check(self.lib.dia_b200_generate_steps(self._h, int(n_steps), _stream(self.device)), "generate_steps")
+
+    def status(self) -> _lib.GenStatus:
+        st = _lib.GenStatus()
+        _lib.check(self.lib.dia_b200_generate_status(self._h, C.byref(st), _stream(self.device)), "generate_status")
+        if st.device_error:
+            raise RuntimeError(f"device-side watchdog / state error code {st.device_error}")
+        return st
+
+    # ---- debugging hooks used by the parity tests -----------------------------------------------------------
+    def run_stages(self, tokens_2xC, stage_begin: int, stage_end: int, pos: int, slot: int, cooperative: bool = True):
+        tok = None if tokens_2xC is None else tokens_2xC.to(device=self.device, dtype=torch.int32).contiguous()
+        _lib.check(self.lib.dia_b200_debug_run_stages(self._h, _ptr(tok) if tok is not None else None, stage_begin,
+                                                      stage_end, pos, slot, 1 if cooperative else 0,
+                                                      _stream(self.device)), "debug_run_stages")
+
+    def read_buffer(self, which: int) -> torch.Tensor:
+        d = self.config.model.decoder
+        n = {_lib.BUF_X: self.D, _lib.BUF_QKV: (d.gqa_query_heads + 2 * d.kv_heads) * 128,
+             _lib.BUF_ATTN: d.gqa_query_heads * 128, _lib.BUF_CQ: d.cross_query_heads * 128,
+             _lib.BUF_CATTN: d.cross_query_heads * 128, _lib.BUF_HIDDEN: d.n_hidden}
+        if which == _lib.BUF_LOGITS:
+            out = torch.empty((2, self.C, self.V), dtype=torch.float32)
+        elif which == _lib.BUF_PRED:
+            out = torch.empty((self.C,), dtype=torch.int32)
+        else:
+            out = torch.empty((n[which], 2), dtype=torch.float32)
+        _lib.check(self.lib.dia_b200_debug_read(self._h, which, _ptr(out), out.numel() * out.element_size(),
+                                                _stream(self.device)), "debug_read")
+        return out if which in (_lib.BUF_LOGITS, _lib.BUF_PRED) else out.t().contiguous()   # -> [2, n]
+
+    def write_buffer(self, which: int, rows_2xN: torch.Tensor) -> None:
+        t = rows_2xN.to("cpu", torch.float32).t().contiguous()
+        _lib.check(self.lib.dia_b200_debug_write(self._h, which, _ptr(t), t.numel() * 4, _stream(self.device)),
+                   "debug_write")
+
+
+def launch_count() -> int:
+    return int(_lib.load().dia_b200_launch_count())

@@ -1,0 +1,100 @@
+"""Weight producers for the pruned variants (drop-in for the reference's ``dia/pruning_utils.py``).
+
+Thin wrappers over ``torch.nn.utils.prune`` applied to every ``DenseGeneral`` - masks only, shapes
+never change (dia/pruning_utils.py:13-179) - plus the 2:4 mask the reference does not have
+(SURVEY.md 8(d), config 4).  Pruned zeros stream through the decode kernels like any other value;
+after ``make_pruning_permanent`` the Decoder's repacked weight copy is invalidated.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.utils.prune as prune
+
+from .layers import DenseGeneral
+
+DEFAULT_PRUNABLE_MODULES = (DenseGeneral,)
+
+
+def get_prunable_modules(model: nn.Module, module_types=DEFAULT_PRUNABLE_MODULES, parameter_name: str = "weight"):
+    """[(module, parameter_name)] for every module of the given types that owns the parameter."""
+    out = []
+    for _, m in model.named_modules():
+        if isinstance(m, tuple(module_types)) and getattr(m, parameter_name, None) is not None:
+            out.append((m, parameter_name))
+    if not out:
+        print(f"Warning: no prunable modules of types {module_types} with parameter '{parameter_name}'")
+    return out
+
+
+def apply_unstructured_pruning(model: nn.Module, amount: float, module_types=DEFAULT_PRUNABLE_MODULES):
+    """Global L1-magnitude pruning over all selected kernels (dia/pruning_utils.py:42-62)."""
+    if not 0.0 <= amount <= 1.0:
+        raise ValueError("amount must be in [0, 1]")
+    params = get_prunable_modules(model, module_types)
+    if params and amount > 0:
+        prune.global_unstructured(params, pruning_method=prune.L1Unstructured, amount=amount)
+    return model
+
+
+def apply_structured_pruning(model: nn.Module, amount: float, dim: int = 0, n: int = 2,
+                             module_types=DEFAULT_PRUNABLE_MODULES):
+    """Per-module Ln structured pruning along ``dim`` (dia/pruning_utils.py:64-119).  With the
+    [in..., out...] kernel layout dim=0 zeroes INPUT slices: hidden neurons for ``mlp.wo``."""
+    if not 0.0 <= amount <= 1.0:
+        raise ValueError("amount must be in [0, 1]")
+    for m, name in get_prunable_modules(model, module_types):
+        w = getattr(m, name)
+        if dim >= w.ndim:
+            print(f"Warning: skipping module with {w.ndim}-D weight for dim={dim}")
+            continue
+        if amount > 0:
+            prune.ln_structured(m, name=name, amount=amount, n=n, dim=dim)
+    return model
+
+
+@torch.no_grad()
+def apply_2to4_pruning(model: nn.Module, module_types=DEFAULT_PRUNABLE_MODULES):
+    """Keep the 2 largest-magnitude of every 4 consecutive K (input) entries per output column of each
+    kernel viewed as [K, N]; applied as a custom mask so that
+    ``make_pruning_permanent`` / ``check_pruning_sparsity`` treat it like the other modes."""
+    for m, name in get_prunable_modules(model, module_types):
+        w = getattr(m, name)
+        n_in = len(m.in_shapes)
+        K = 1
+        for s in w.shape[:n_in]:
+            K *= s
+        if K % 4:
+            continue
+        w2 = w.detach().reshape(K // 4, 4, -1).abs().float()
+        keep = w2.topk(2, dim=1).indices
+        mask = torch.zeros_like(w2, dtype=torch.bool).scatter_(1, keep, True).reshape(w.shape)
+        prune.custom_from_mask(m, name=name, mask=mask.to(w.dtype))
+    return model
+
+
+def make_pruning_permanent(model: nn.Module, module_types=DEFAULT_PRUNABLE_MODULES):
+    """Fold masks into the weights and drop the reparametrisation (dia/pruning_utils.py:122-151)."""
+    for m, name in get_prunable_modules(model, module_types, parameter_name="weight"):
+        if prune.is_pruned(m):
+            try:
+                prune.remove(m, name)
+            except ValueError:
+                pass
+    for m in model.modules():
+        if hasattr(m, "invalidate_engine"):
+            m.invalidate_engine()
+    return model
+
+
+def check_pruning_sparsity(model: nn.Module, module_types=DEFAULT_PRUNABLE_MODULES) -> float:
+    """Global fraction of exact zeros over the selected kernels (dia/pruning_utils.py:153-179)."""
+    zeros = total = 0
+    for m, name in get_prunable_modules(model, module_types):
+        w = getattr(m, name)
+        zeros += int((w == 0).sum().item())
+        total += w.numel()
+    sparsity = zeros / total if total else 0.0
+    print(f"Global sparsity: {100.0 * sparsity:.2f}% ({zeros}/{total})")
+    return sparsity

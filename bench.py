@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py - decoded audio frames/s of the Dia-1.6B decode path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): Dia-1.6B, bf16 weights, ONE transcript, CFG batch 2, a full
+3072-token generation = 3071 autoregressive decode steps.  A bench "step" is one such generation.
+With N > 1 GPUs every rank runs its own utterance (replicas, no collective on the data path:
+SURVEY.md 8(e)); `value` is the sum over ranks divided by the slowest rank's time (weak scaling).
+
+  value  frames/s of the decode loop with everything already resident in HBM (encoder output,
+         cross-KV, token grid), timed on the device with CUDA events on the launching stream.
+  e2e    frames/s through the public API, `Dia.generate(text, output="codes")` + `.cpu()`: text in host
+         memory in, codes in host memory out; encoder, cross-KV precompute, H2D/D2H inside the region.
+  roofline     the step kernel: algorithmic bytes of the steps in a launch / event-timed launch duration,
+               against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline the CPU port of the reference's own algorithm (oracle/, kind "port": the reference is
+               Python and cannot travel to the GPU box) timed on this box's host cores.
+
+`--impl reference` times that CPU port alone (rank 0 only).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "decoded_audio_frames_per_s"
+UNIT = "frames/s"
+MAX_TOKENS = 3072
+WEIGHT_SEED = 5
+FRAME_RATE = 44100 / 512          # 86.13 frames per second of audio
+
+
+def algorithmic_bytes(cfg, slot: int, text_len: int, kv_elem: int = 4) -> int:
+    """bf16 weights of the 18 layers + logits head, fp32 norm weights, 9 embedding rows,
+    plus self-KV rows read / appended and the valid cross-KV rows of the conditional row."""
+    d, e = cfg.model.decoder, cfg.model.encoder
+    D, F, hd = d.n_embd, d.n_hidden, 128
+    nq, nkv, nc = d.gqa_query_heads * hd, d.kv_heads * hd, d.cross_query_heads * hd
+    per_layer = D * (nq + 2 * nkv) + nq * D + D * nc + nc * D + D * 2 * F + F * D
+    w = 2 * (d.n_layer * per_layer + D * cfg.data.channels * cfg.model.tgt_vocab_size)
+    w += 4 * (3 * d.n_layer + 1) * D + 4 * cfg.data.channels * D
+    kv_row = d.n_layer * 2 * 2 * nkv * kv_elem            # K and V, both CFG rows, all layers, one slot
+    cross = d.n_layer * 2 * nc * kv_elem * text_len       # K and V, conditional row only
+    return w + kv_row * (slot + 1) + cross
+
+
+class ClockSampler:
+    """nvidia-smi sampled during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        load = [x for x in sm if mx and x > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak() -> tuple[float, str]:
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_cpu_model(seed: int, suppress_eos: bool):
+    """fp32 CPU DiaModel with the shared synthetic recipe; returns (Dia, state dict clone or None)."""
+    import torch
+    from dia_tts_prune_b200.config import dia_1_6b_config
+    from dia_tts_prune_b200.model import Dia
+    from dia_tts_prune_b200 import synthetic as SY
+    cfg = dia_1_6b_config()
+    dia = Dia(cfg, "float32", torch.device("cpu"))
+    SY.init_synthetic_(dia.model.named_parameters(), seed)
+    if suppress_eos:
+        # random weights would emit EOS on channel 0 within ~1000 steps and end the utterance early;
+        # a zero EOS column keeps all 3071 steps running
+        with torch.no_grad():
+            dia.model.decoder.logits_dense.weight[:, 0, cfg.data.audio_eos_value] = 0.0
+    return dia, cfg
+
+
+def cpu_port_frames_per_s(sd, cfg, text: str, n_steps: int, threads: int) -> dict:
+    """The oracle port of the reference's decode loop, timed on the host (dead cross-attention K/V
+    re-projection kept, as shipped: dia/layers.py:274-275)."""
+    import torch
+    from oracle import dia_oracle as O
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    tr = O.generate(sd, cfg, text, max_tokens=1 + n_steps, temperature=0.0, cfg_scale=3.0, dead_cross_kv=True,
+                    time_steps=True)
+    total = time.perf_counter() - t0
+    loop = sum(tr.step_seconds)
+    return {"value": len(tr.step_seconds) / loop, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{len(tr.step_seconds)} greedy decode steps of the same Dia-1.6B fp32 workload on the host "
+                      f"(CFG batch 2, dead cross-K/V projection kept as shipped), loop {loop:.1f}s; one-time "
+                      f"encoder+cross-KV prepare {total - loop:.1f}s excluded"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from dia_tts_prune_b200 import synthetic as SY
+    threads = os.cpu_count() or 1
+    dia, cfg = build_cpu_model(WEIGHT_SEED, suppress_eos=True)
+    sd = {k: v.detach() for k, v in dia.model.named_parameters()}
+    per_step = max(2, args.ref_decode_steps)
+    vals, t_all = [], time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        r = cpu_port_frames_per_s(sd, cfg, SY.DEFAULT_TRANSCRIPT, per_step, threads)
+        if i >= args.warmup:
+            vals.append(r)
+    v = statistics.mean(x["value"] for x in vals)
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * per_step / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Dia-1.6B single transcript, CFG batch 2, greedy; bounded sample of the 3072-token "
+                                   f"generation: {per_step} decode steps per bench step on the host CPU"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "rtfx": v / FRAME_RATE, "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+    from dia_tts_prune_b200 import synthetic as SY
+    from dia_tts_prune_b200.engine import launch_count
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
+
+    dia, cfg = build_cpu_model(WEIGHT_SEED, suppress_eos=True)
+    sd_cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        sd_cpu = {k: v.detach().clone() for k, v in dia.model.named_parameters()}
+    # configs[1]: bf16 weights.  Values are bf16-representable, so this cast is exact.
+    for n, p in dia.model.named_parameters():
+        if "proj" in n or "mlp" in n or "logits" in n:
+            p.data = p.data.to(torch.bfloat16)
+    dia.compute_dtype = torch.bfloat16
+    dia.device = dev
+    dia.model.to(dev)
+    dia.model.eval()
+    text = SY.DEFAULT_TRANSCRIPT if world == 1 else SY.synthetic_transcript(rank)
+    sampling = dict(cfg_scale=3.0, temperature=1.3, top_p=0.95, top_k=35)
+
+    # ---- resident inputs for the device-timed loop --------------------------------------------------
+    eff = dia._effective_text(text, None)
+    with torch.inference_mode():
+        dec_state, dec_out = dia._prepare_generation(eff, None, False)
+    pristine = dec_out.generated_tokens.clone()
+    text_len = dec_state.text_len
+
+    def one_generation(profile=None) -> int:
+        dec_out.generated_tokens.copy_(pristine)
+        for c in dec_state.self_attn_cache:
+            c.current_idx = 0
+        with torch.inference_mode():
+            last = dia._run_loop(dec_state, dec_out, MAX_TOKENS, sampling["cfg_scale"], sampling["temperature"],
+                                 sampling["top_p"], sampling["top_k"], 1234, False, profile=profile)
+        return last + 1 - (dec_out.prefill_step - 1)        # loop iterations executed (the loop ends by `break`)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_generation()
+    sampler = ClockSampler(local)
+    sync_all()
+    sampler.start()
+    launches0 = launch_count()
+    profile: list = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps_run = 0
+    for _ in range(args.steps):
+        steps_run += one_generation(profile)
+    e1.record()
+    sync_all()
+    launches = launch_count() - launches0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    frames_dev = steps_run                                     # one decode step = one frame (9 codes)
+
+    # roofline of the step kernel: per-launch algorithmic bytes / event-timed duration
+    k_bytes = k_ms = 0.0
+    for (a, b, slot0, n) in profile:
+        k_ms += a.elapsed_time(b)
+        k_bytes += sum(algorithmic_bytes(cfg, slot0 + i, text_len) for i in range(n))
+    peak, peak_src = measured_peak()
+    achieved = k_bytes / (k_ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API, host buffers in and out ---------------------------------------
+    def one_e2e():
+        codes = dia.generate(text, max_tokens=MAX_TOKENS, seed=1234, output="codes", **{
+            "cfg_scale": sampling["cfg_scale"], "temperature": sampling["temperature"], "top_p": sampling["top_p"],
+            "cfg_filter_top_k": sampling["top_k"]})
+        host = codes.cpu()
+        return dia.last_stats["steps"], host
+    for _ in range(min(args.warmup, 2)):
+        one_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps, d2h = 0, 0
+    for _ in range(args.steps):
+        n, host = one_e2e()
+        e2e_steps += n
+        d2h = host.numel() * host.element_size()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    h2d = 2 * cfg.data.text_length * 8 + 4                     # [2, text_length] int64 text tokens (+ seed)
+
+    # ---- reduce over ranks: max time, sum frames ------------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_s, float(frames_dev), float(e2e_steps), k_ms, k_bytes, float(launches)],
+                     dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s = tmax[0].item(), tmax[1].item()
+        frames_dev, e2e_steps, launches = tsum[2].item(), tsum[3].item(), tsum[6].item()
+    value = frames_dev / (dev_ms * 1e-3)
+    e2e_value = e2e_steps / e2e_s
+
+    cpu_base = None
+    if sd_cpu is not None:
+        cpu_base = cpu_port_frames_per_s(sd_cpu, cfg, SY.DEFAULT_TRANSCRIPT, args.cpu_decode_steps, os.cpu_count() or 1)
+
+    if rank == 0:
+        traffic = None
+        try:   # per-launch DRAM bytes from the committed `ncu --set full` capture, if present
+            with open(os.path.join(REPO, "profiles", "step_kernel_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Dia-1.6B bf16 weights, single transcript per GPU, CFG batch 2, full 3072-token "
+                                   "generation (3071 decode steps), reference default sampling T=1.3 top_p=0.95 top_k=35",
+                       "precision": "bf16 weights; fp32 activations, accumulation, softmax and KV cache",
+                       "weights": f"random-init seed {WEIGHT_SEED}, channel-0 EOS column zeroed so no early EOS",
+                       "l2": "inputs larger than L2: 2.53 GB of weights streamed per decode step",
+                       "frame": "1 frame = 1 decode step = 9 codes = 512 samples @ 44.1 kHz",
+                       "text_len": text_len, "parallelism": f"replicas x{world}, no data-path collective"},
+            "decode_ms_per_frame": dev_ms / (frames_dev / world),
+            "rtfx": value / world / FRAME_RATE,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1000.0 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "dia_step_kernel",
+                         "launches_timed": len(profile),
+                         "algorithmic_bytes_per_launch": k_bytes / max(1, len(profile))},
+            "cpu_baseline": cpu_base,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-decode-steps", type=int, default=12, help="decode steps of the cpu_baseline sample")
+    ap.add_argument("--ref-decode-steps", type=int, default=4, help="decode steps per reference-arm bench step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

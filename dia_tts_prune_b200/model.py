@@ -311,6 +311,9 @@ class Dia:
             raise ValueError("`audio_prompt_text` is required when `audio_prompt` is provided.")
         if output not in ("audio", "codes"):
             raise ValueError("output must be 'audio' or 'codes'")
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            # loud, before the reference's catch-all: this path has no CPU implementation
+            raise RuntimeError("Dia.generate needs the model on a CUDA device (sm_100a); there is no CPU fallback")
         if seed is not None:
             torch.manual_seed(seed)
             np.random.seed(seed)
@@ -355,8 +358,10 @@ class Dia:
             return None
 
     def _run_loop(self, dec_state: DecoderInferenceState, dec_output: DecoderOutput, max_tokens: int, cfg_scale: float,
-                  temperature: float, top_p: float, top_k: int, seed: int, verbose: bool) -> int:
-        """The while-loop of dia/model.py:748-815, executed on the device in blocks of steps."""
+                  temperature: float, top_p: float, top_k: int, seed: int, verbose: bool,
+                  profile: list | None = None) -> int:
+        """The while-loop of dia/model.py:748-815, executed on the device in blocks of steps.
+        ``profile``: optional list receiving (start_event, end_event, first_slot, n_steps) per launch."""
         eng = self.model.decoder._engine_for(dec_state)
         first_slot = dec_state.self_attn_cache[0].current_idx
         P = dec_output.prefill_step
@@ -364,10 +369,19 @@ class Dia:
                            top_k, seed)
         remaining = max(0, max_tokens - P)
         # all launches are queued back to back; a launch that starts after the loop finished is a no-op
+        slot = first_slot
         while remaining > 0:
             n = min(_STEPS_PER_LAUNCH, remaining)
-            eng.generate_steps(n)
+            if profile is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                eng.generate_steps(n)
+                e1.record()
+                profile.append((e0, e1, slot, n))
+            else:
+                eng.generate_steps(n)
             remaining -= n
+            slot += n
         st = eng.status()                                  # the only host <-> device sync of the loop
         for c in dec_state.self_attn_cache:
             c.current_idx = first_slot + st.steps_run

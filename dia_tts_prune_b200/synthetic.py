@@ -59,21 +59,22 @@ def synthetic_transcript(i: int, min_bytes: int = 60, max_bytes: int = 200) -> s
              "the quick brown fox jumps over the lazy dog while rain keeps falling on the quiet harbor town "
              "please remember to bring the blue notebook when we meet at the station tomorrow morning").split()
     state = (i * 2654435761 + 12345) & 0xFFFFFFFF
-    target = min_bytes + state % (max_bytes - min_bytes + 1)
-    out, spk = "", 1
-    while True:
+
+    def nxt():
+        nonlocal state
         state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
-        n = 4 + state % 7
-        sent = []
-        for _ in range(n):
-            state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
-            sent.append(words[state % len(words)])
-        piece = f"[S{spk}] " + " ".join(sent).capitalize() + ". "
-        if out and len((out + piece).encode()) > target:
-            break
-        out += piece
-        spk = 3 - spk
-    return out.strip()
+        return state >> 8
+
+    target = min_bytes + nxt() % (max_bytes - 12 - min_bytes + 1)      # a word adds at most 11 bytes
+    out, spk, left = "[S1]", 1, 4 + nxt() % 6
+    while len(out.encode()) < target:
+        if left == 0:
+            spk = 3 - spk
+            out += f". [S{spk}]"
+            left = 4 + nxt() % 6
+        out += " " + words[nxt() % len(words)]
+        left -= 1
+    return out + "."
 
 
 DEFAULT_TRANSCRIPT = ("[S1] Dia is an open weights text to dialogue model. "

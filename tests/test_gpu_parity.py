@@ -1,0 +1,387 @@
+"""GPU suite (`-m gpu`): the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs, against the golden fixtures the reference produced, and - at BASELINE.json's full sizes -
+through size-independent properties.
+
+Bars (BASELINE.json north_star): integer / index work and greedy code streams bit-exact; teacher-forced
+logits within 2e-2 max-abs of the fp32 reference (we assert a far tighter 5e-4).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_dia
+from dia_tts_prune_b200 import _lib, audio, synthetic as SY
+from dia_tts_prune_b200.config import dia_1_6b_config, tiny_config
+from oracle import delay_oracle, dia_oracle as O
+
+pytestmark = pytest.mark.gpu
+DELAYS = [0, 8, 9, 10, 11, 12, 13, 14, 15]
+LOGIT_TOL = 2e-2          # the north-star bar
+LOGIT_TIGHT = 5e-4        # what the fp32-activation design actually achieves (~2.4e-5)
+
+
+def test_native_library_is_loaded_and_device_is_blackwell():
+    lib = _lib.load()
+    assert lib.dia_b200_abi_version() == 1
+    assert torch.cuda.get_device_capability(0)[0] >= 10
+
+
+# ---- K13: delay / revert gathers, bit-exact -----------------------------------------------------------------
+@pytest.mark.parametrize("B,T,C,dl", [(1, 6, 3, [0, 1, 2]), (1, 1, 9, DELAYS), (1, 5, 9, DELAYS), (1, 16, 9, DELAYS),
+                                      (2, 40, 9, DELAYS), (3, 3088, 9, DELAYS), (1, 3072, 9, DELAYS),
+                                      (2, 17, 4, [3, 0, 7, 1]), (64, 3088, 9, DELAYS)])
+def test_delay_kernels_bit_exact(B, T, C, dl):
+    rng = np.random.default_rng(B * 7 + T)
+    x = rng.integers(0, 1024, size=(B, T, C), dtype=np.int32)
+    xt = torch.from_numpy(x).cuda()
+    pre = audio.build_delay_indices(B, T, C, dl)
+    ot, oi = delay_oracle.build_delay_indices(B, T, C, dl)
+    assert pre[0].dtype == torch.int32 and pre[1].dtype == torch.int64
+    assert np.array_equal(pre[0].cpu().numpy(), ot) and np.array_equal(pre[1].cpu().numpy(), oi)
+    got = audio.apply_audio_delay(xt, 1025, 1026, pre)
+    assert got.dtype == torch.int32 and got.is_cuda
+    assert np.array_equal(got.cpu().numpy(), delay_oracle.apply_audio_delay(x, 1025, 1026, dl))
+    rpre = audio.build_revert_indices(B, T, C, dl)
+    rt, ri = delay_oracle.build_revert_indices(B, T, C, dl)
+    assert rpre[0].dtype == torch.int64
+    assert np.array_equal(rpre[0].cpu().numpy(), rt) and np.array_equal(rpre[1].cpu().numpy(), ri)
+    got = audio.revert_audio_delay(xt, 1025, rpre, T)
+    assert np.array_equal(got.cpu().numpy(), delay_oracle.revert_audio_delay(x, 1025, dl, T))
+    # revert o apply is the identity away from the clamped tail
+    rt2 = audio.revert_audio_delay(audio.apply_audio_delay(xt, 1025, 1026, pre), 1025, rpre, T)
+    keep = max(T - max(dl), 0)
+    assert torch.equal(rt2[:, :keep], xt[:, :keep])
+
+
+def test_delay_kernels_golden_and_dtypes(gold_delay):
+    g = gold_delay
+    x = torch.tensor(g["input"], dtype=torch.int32)
+    pre = audio.build_delay_indices(g["B"], g["T"], g["C"], g["delay"])
+    ap = audio.apply_audio_delay(x, g["pad"], g["bos"], pre)          # CPU tensor in -> CPU tensor out
+    assert not ap.is_cuda and ap.tolist() == g["apply"]
+    rv = audio.revert_audio_delay(ap, g["pad"], audio.build_revert_indices(g["B"], g["T"], g["C"], g["delay"]), g["T"])
+    assert rv.tolist() == g["revert"]
+    x9 = torch.tensor(g["input9"], dtype=torch.int64).cuda()          # other integer dtypes are preserved
+    ap9 = audio.apply_audio_delay(x9, 1025, 1026, audio.build_delay_indices(2, 24, 9, DELAYS))
+    assert ap9.dtype == torch.int64 and ap9.tolist() == g["apply9"]
+    rv9 = audio.revert_audio_delay(x9, 1025, audio.build_revert_indices(2, 24, 9, DELAYS), 24)
+    assert rv9.tolist() == g["revert9"]
+    e = torch.zeros((0, 4, 9), dtype=torch.int32).cuda()              # empty grid
+    assert audio.apply_audio_delay(e, 1025, 1026, audio.build_delay_indices(0, 4, 9, DELAYS)).shape == (0, 4, 9)
+    with pytest.raises(ValueError):
+        audio.apply_audio_delay(x9, 1025, 1026, audio.build_delay_indices(2, 23, 9, DELAYS))
+
+
+def test_finalize_codes_kernel():
+    cfg = tiny_config()
+    rng = np.random.default_rng(3)
+    for T in (16, 17, 100, 3070):
+        codes = torch.from_numpy(rng.integers(-1, 1028, size=(T, 9), dtype=np.int32))
+        got = audio.finalize_codes(codes.cuda(), DELAYS, 1025, 1024)
+        want = O.finalize_codes(cfg, codes)
+        assert got.shape == want.shape and torch.equal(got.cpu(), want.to(torch.int32))
+    assert audio.finalize_codes(torch.zeros((10, 9), dtype=torch.int32).cuda(), DELAYS, 1025).shape == (1, 9, 0)
+
+
+# ---- K1: embedding gather-sum ---------------------------------------------------------------------------------
+def test_embed_sum_matches_reference_order(tiny_gpu):
+    dia, sd = tiny_gpu
+    eng = dia.model.decoder.engine()
+    g = torch.Generator().manual_seed(0)
+    tok = torch.randint(0, 1028, (37, 9), generator=g, dtype=torch.int32)
+    got = eng.embed_sum(tok.cuda()).cpu()
+    want = O.embed_sum(sd, dia.config, tok.long())
+    assert torch.equal(got, want)                                     # same fp32 adds in the same order
+    assert eng.embed_sum(tok[:0].cuda()).shape == (0, eng.D)
+
+
+# ---- tiny config: every boundary against the oracle ---------------------------------------------------------------
+def _prepared(dia, text):
+    with torch.inference_mode():
+        return dia._prepare_generation(dia._effective_text(text, None), None, False)
+
+
+def test_tiny_teacher_forced_logits_and_kv(tiny_gpu, gold_tiny):
+    dia, sd = tiny_gpu
+    cfg = dia.config
+    text = str(gold_tiny["text"])
+    grid = torch.from_numpy(gold_tiny["grid"])
+    steps = [int(s) for s in gold_tiny["logits_steps"]]
+    st, out = _prepared(dia, text)
+    st_o, _, _ = O.prepare_generation(sd, cfg, O.effective_text(text, None), None, dead_cross_kv=False)
+    worst = 0.0
+    for cur in range(1, max(steps) + 1):
+        st.prepare_step(cur)
+        toks = grid[cur - 1].cuda().unsqueeze(0).unsqueeze(0).expand(2, 1, -1)
+        with torch.inference_mode():
+            lg = dia.model.decoder.decode_step(toks, st)
+        assert lg.shape == (2, 1, 9, 1028) and lg.dtype == torch.float32
+        st_o.prepare_step(cur)
+        with torch.inference_mode():
+            lo = O.decoder_forward(sd, cfg, grid[cur - 1].unsqueeze(0).unsqueeze(0).expand(2, 1, -1), st_o,
+                                   prefill=False, dead_cross_kv=False)
+        worst = max(worst, (lg.cpu() - lo).abs().max().item())
+        if cur in steps:
+            assert np.abs(lg[:, 0].cpu().numpy() - gold_tiny["logits"][steps.index(cur)]).max() < LOGIT_TIGHT
+    assert worst < LOGIT_TIGHT, worst
+    n = max(steps)
+    for i, (c, co) in enumerate(zip(st.self_attn_cache, st_o.self_cache)):
+        assert c.current_idx == co.current_idx == n
+        assert (c.k[:, :, :n].cpu() - co.k[:, :, :n]).abs().max() < 1e-4
+        assert (c.v[:, :, :n].cpu() - co.v[:, :, :n]).abs().max() < 1e-4
+        assert (c.k[:, :, n:] == 0).all()                              # nothing written past the current slot
+
+
+def test_tiny_decoder_layer_boundary(tiny_gpu):
+    dia, sd = tiny_gpu
+    cfg = dia.config
+    text = "[S1] Layer boundary. [S2] Check."
+    st, out = _prepared(dia, text)
+    st_o, _, _ = O.prepare_generation(sd, cfg, O.effective_text(text, None), None, dead_cross_kv=False)
+    g = torch.Generator().manual_seed(4)
+    for cur in (1, 2, 3):
+        st.prepare_step(cur)
+        st_o.prepare_step(cur)
+        x = torch.randn(2, 1, cfg.model.decoder.n_embd, generator=g)
+        xo = x.clone()
+        xg = x.cuda()
+        with torch.inference_mode():
+            for i, layer in enumerate(dia.model.decoder.layers):
+                xg = layer(xg, st, self_attn_cache=st.self_attn_cache[i], cross_attn_cache=st.cross_attn_cache[i])
+                xo = O.decoder_layer(sd, cfg, i, xo, st_o, prefill=False, dead_cross_kv=False)
+                assert (xg.cpu() - xo).abs().max() < 1e-4, (cur, i)
+
+
+def test_tiny_greedy_stream_bit_exact(tiny_gpu, gold_tiny):
+    dia, sd = tiny_gpu
+    codes = dia.generate(str(gold_tiny["text"]), max_tokens=40, temperature=0.0, output="codes")
+    assert torch.equal(dia.last_codes.cpu(), torch.from_numpy(gold_tiny["codes"]))
+    assert gold_tiny["margins"].min() > 1e-4
+    want = O.finalize_codes(dia.config, torch.from_numpy(gold_tiny["codes"]))
+    assert torch.equal(codes.cpu(), want.to(torch.int32))
+    # deterministic: a second run is bit-identical; blocks of launches give the same stream as one launch
+    dia.generate(str(gold_tiny["text"]), max_tokens=40, temperature=0.0, output="codes")
+    assert torch.equal(dia.last_codes.cpu(), torch.from_numpy(gold_tiny["codes"]))
+
+
+def test_tiny_voice_clone_path_bit_exact(tiny_gpu, gold_tiny):
+    """Prompt prefill + the slot-clobber / skipped-position / discarded-prediction quirks (Appendix C Q1-Q3)."""
+    dia, sd = tiny_gpu
+    prompt = torch.from_numpy(gold_tiny["clone_prompt"])
+    dia.generate(str(gold_tiny["clone_text"]), max_tokens=int(gold_tiny["clone_max_tokens"]), temperature=0.0,
+                 audio_prompt=prompt, audio_prompt_text=str(gold_tiny["clone_prompt_text"]), output="codes")
+    assert gold_tiny["clone_margins"].min() > 1e-4
+    assert torch.equal(dia.last_codes.cpu(), torch.from_numpy(gold_tiny["clone_codes"]))
+    with pytest.raises(ValueError):
+        dia.generate("x", audio_prompt=prompt)
+
+
+def test_tiny_stage_modes_agree(tiny_gpu):
+    """One cooperative launch over all stages == one launch per stage (no grid barrier, cold ring)."""
+    dia, sd = tiny_gpu
+    st, out = _prepared(dia, "[S1] Modes. [S2] Agree.")
+    eng = dia.model.decoder._engine_for(st)
+    tok = torch.full((2, 9), 1026, dtype=torch.int32).cuda()
+    L = dia.config.model.decoder.n_layer
+    a = eng.decode_step(tok, 1, 0).clone()
+    for s in range(8 * L + 2):
+        eng.run_stages(tok, s, s + 1, 1, 0, cooperative=False)
+    b = eng.read_buffer(_lib.BUF_LOGITS)
+    assert torch.equal(a.cpu(), b)
+
+
+def test_tiny_eos_state_machine_matches_reference_loop(gold_tiny):
+    """The end-of-budget EOS countdown: forced EOS/PAD per delay, the break, the returned row count."""
+    cfg = tiny_config()
+    dia, sd = build_dia(cfg, 7)
+    with torch.no_grad():     # keep a natural channel-0 EOS out of the way so only the forced path fires
+        w = dict(dia.model.named_parameters())["decoder.logits_dense.weight"]
+        w[:, 0, 1024] = 0
+        sd["decoder.logits_dense.weight"] = w.detach().clone()
+    dia.device = torch.device("cuda:0")
+    dia.model.to(dia.device)
+    for mt in (20, 33, 40):
+        tr = O.generate(sd, cfg, "[S1] End. [S2] Now.", max_tokens=mt, temperature=0.0, dead_cross_kv=False)
+        dia.generate("[S1] End. [S2] Now.", max_tokens=mt, temperature=0.0, output="codes")
+        assert torch.equal(dia.last_codes.cpu(), tr.codes), mt
+        assert dia.last_codes.shape[0] == tr.codes.shape[0]
+    # forced EOS/PAD pattern at the end of the budget (dia/model.py:779-804); channel 8 never gets EOS (Q6)
+    tail = dia.last_codes.cpu()
+    assert tail[-14, 0] == 1024 and (tail[-13:, 0] == 1025).all() and (tail[:, 8] != 1024).all()
+
+
+# ---- sampling head ------------------------------------------------------------------------------------------------
+def test_head_sample_filtered_probs_and_argmax(tiny_gpu, gold_sampling):
+    dia, sd = tiny_gpu
+    eng = dia.model.decoder.engine()
+    cfg = dia.config
+    g = torch.Generator().manual_seed(9)
+    for scale in (1.0, 3.0, 8.0):
+        logits = torch.randn(2, 9, 1028, generator=g) * scale
+        guided = O.cfg_combine_and_mask(cfg, logits.clone(), 3.0)
+        assert torch.equal(eng.head_sample(logits, 3.0, 0.0, 0.95, 35).cpu().long(), torch.argmax(guided, -1))
+        for (T, p, k) in ((1.3, 0.95, 35), (1.0, 0.75, 4), (0.7, 0.5, 10), (2.0, 1.0, 64), (1.0, 0.9, 1)):
+            pred, probs = eng.head_sample(logits, 3.0, T, p, k, seed=1, draw=0, want_probs=True)
+            want = O.filtered_probs(guided.clone(), T, p, k)
+            assert torch.equal(probs.cpu() > 0, want > 0), (scale, T, p, k)          # the same survivors
+            assert (probs.cpu() - want).abs().max() < 1e-6
+            assert (want[torch.arange(9), pred.cpu().long()] > 0).all()               # draws come from the survivors
+    # ties on the maximum: lowest index wins (torch.argmax on CPU)
+    lg = torch.zeros(2, 9, 1028)
+    lg[1, :, 5] = 1.0
+    lg[1, :, 9] = 1.0
+    assert eng.head_sample(lg, 3.0, 0.0, 0.95, 35).tolist() == [5] * 9
+    with pytest.raises(NotImplementedError):
+        eng.head_sample(lg, 3.0, 1.0, 0.95, 0)                                        # top-k disabled: unsupported
+
+
+def test_head_sample_distribution_chi2(tiny_gpu):
+    dia, sd = tiny_gpu
+    eng = dia.model.decoder.engine()
+    base = torch.full((1028,), -1000.0)
+    vals = torch.tensor([2.0, 1.5, 1.0, 0.5, 0.0, -0.5])
+    base[[3, 100, 500, 777, 1000, 1027]] = vals
+    logits = torch.zeros(2, 9, 1028)
+    logits[1] = base                                                   # cond; uncond = 0 -> guided = 4 * base
+    guided = O.cfg_combine_and_mask(dia.config, logits.clone(), 3.0)
+    want = O.filtered_probs(guided.clone(), 1.3, 0.999, 35)[0]
+    counts = torch.zeros(1028)
+    n_draws = 1500
+    for d in range(n_draws):
+        pred = eng.head_sample(logits, 3.0, 1.3, 0.999, 35, seed=77, draw=d)
+        counts += torch.bincount(pred.cpu().long(), minlength=1028).float()
+    n = n_draws * 9
+    sup = want > 0
+    assert counts[~sup].sum() == 0
+    exp = want[sup] * n
+    m = exp > 5
+    chi2 = (((counts[sup] - exp) ** 2 / exp)[m]).sum().item()
+    assert chi2 < 30.0, chi2                                            # <= 5 dof: p ~ 1e-5
+
+
+def test_tiny_sampled_generation_is_seed_deterministic(tiny_gpu):
+    dia, sd = tiny_gpu
+    a = dia.generate("[S1] Sampling. [S2] Twice.", max_tokens=48, seed=11, output="codes").cpu()
+    b = dia.generate("[S1] Sampling. [S2] Twice.", max_tokens=48, seed=11, output="codes").cpu()
+    c = dia.generate("[S1] Sampling. [S2] Twice.", max_tokens=48, seed=12, output="codes").cpu()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert ((a >= 0) & (a <= 1023)).all()
+
+
+# ---- pruned weights (config 4) on the tiny config --------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["structured", "2to4"])
+def test_tiny_pruned_variants_match_oracle(mode):
+    from dia_tts_prune_b200 import pruning_utils as PU
+    cfg = tiny_config()
+    dia, _ = build_dia(cfg, 7)
+    if mode == "structured":
+        PU.apply_structured_pruning(dia.model, 0.25, dim=0, n=2)
+    else:
+        PU.apply_2to4_pruning(dia.model)
+    PU.make_pruning_permanent(dia.model)
+    assert PU.check_pruning_sparsity(dia.model) > 0.2
+    sd = {k: v.detach().clone() for k, v in dia.model.named_parameters()}
+    dia.device = torch.device("cuda:0")
+    dia.model.to(dia.device)
+    text = "[S1] Pruned. [S2] Weights."
+    tr = O.generate(sd, cfg, text, max_tokens=30, temperature=0.0, dead_cross_kv=False, keep_logits_at={1, 20})
+    st, out = _prepared(dia, text)
+    st.prepare_step(1)
+    with torch.inference_mode():
+        lg = dia.model.decoder.decode_step(out.get_tokens_at(0).unsqueeze(0).unsqueeze(0).expand(2, 1, -1), st)
+    assert (lg[:, 0].cpu() - tr.logits[1]).abs().max() < LOGIT_TIGHT
+    dia.generate(text, max_tokens=30, temperature=0.0, output="codes")
+    if torch.stack(tr.margins).min() > 1e-4:
+        assert torch.equal(dia.last_codes.cpu(), tr.codes)
+
+
+# ---- Dia-1.6B (BASELINE.json configs) ----------------------------------------------------------------------------------
+def test_full_weights_are_the_golden_ones(full_gpu, gold_full):
+    dia, sd = full_gpu
+    sub = [n for n in sd if "layers.0." in n or "logits" in n]
+    assert SY.weights_fingerprint(sd, sub) == str(gold_full["fingerprint"])
+    eng = dia.model.decoder.engine()
+    assert eng.n_ctas == torch.cuda.get_device_properties(0).multi_processor_count
+    assert abs(eng.weight_stream_bytes - 2_529_312_768) < 1_000_000    # 18 layers + logits head in bf16
+
+
+def test_full_config1_greedy_stream_bit_exact(full_gpu, gold_full):
+    """configs[0]/[1]: the reference's own greedy run (256 steps) reproduced bit for bit from bf16 weights."""
+    dia, sd = full_gpu
+    codes = dia.generate(str(gold_full["text"]), max_tokens=int(gold_full["max_tokens"]), temperature=0.0,
+                         cfg_scale=float(gold_full["cfg_scale"]), output="codes")
+    want = torch.from_numpy(gold_full["codes"])
+    got = dia.last_codes.cpu()
+    if not torch.equal(got, want):
+        d = (got != want).nonzero()[0].tolist()
+        pytest.fail(f"first divergence at returned row {d[0]} channel {d[1]}; oracle margin there "
+                    f"{gold_full['margins'][d[0], d[1]]:.3e}")
+    assert torch.equal(codes.cpu(), torch.from_numpy(gold_full["finalized"]).to(torch.int32))
+
+
+def test_full_teacher_forced_logits_within_tolerance(full_gpu, gold_full):
+    dia, sd = full_gpu
+    grid = torch.from_numpy(gold_full["grid"]).cuda()
+    steps = gold_full["logits_steps"].tolist()
+    st, out = _prepared(dia, str(gold_full["text"]))
+    worst = 0.0
+    for cur in range(1, max(steps) + 1):
+        st.prepare_step(cur)
+        with torch.inference_mode():
+            lg = dia.model.decoder.decode_step(grid[cur - 1].unsqueeze(0).unsqueeze(0).expand(2, 1, -1), st)
+        if cur in steps:
+            err = np.abs(lg[:, 0].cpu().numpy() - gold_full["logits"][steps.index(cur)]).max()
+            worst = max(worst, float(err))
+    print(f"max-abs logits error over {len(steps)} golden steps: {worst:.3e}")
+    assert worst < LOGIT_TOL and worst < LOGIT_TIGHT
+    k = st.self_attn_cache[0].k[:, :, :4].cpu().numpy()
+    assert np.abs(k - gold_full["self_k_probe"][0]).max() < 1e-4
+    k = st.self_attn_cache[-1].k[:, :, :4].cpu().numpy()
+    assert np.abs(k - gold_full["self_k_probe"][1]).max() < 1e-4
+
+
+def test_full_config3_voice_clone(full_gpu, gold_clone):
+    """configs[2]: 861-frame prompt prefilled into the KV cache, then decode; codes bit-exact vs the reference."""
+    dia, sd = full_gpu
+    g = gold_clone
+    prompt = torch.from_numpy(g["prompt"])
+    dia.generate(str(g["text"]), max_tokens=int(g["max_tokens"]), temperature=0.0, audio_prompt=prompt,
+                 audio_prompt_text=str(g["prompt_text"]), output="codes")
+    want = torch.from_numpy(g["codes"])
+    got = dia.last_codes.cpu()
+    assert got.shape == want.shape
+    if not torch.equal(got, want):
+        d = (got != want).nonzero()[0].tolist()
+        pytest.fail(f"first divergence at row {d[0]} ch {d[1]}, margin {g['margins'][d[0], d[1]]:.3e}")
+
+
+def test_full_size_properties_3072_steps(full_gpu):
+    """configs[1] at full length: 3071 steps; determinism, value ranges, the forced-EOS tail, slot bookkeeping."""
+    dia, sd = full_gpu
+    text = SY.synthetic_transcript(3)
+    a = dia.generate(text, max_tokens=3072, temperature=0.0, output="codes")
+    raw_a = dia.last_codes.clone()
+    steps = dia.last_stats["steps"]
+    b = dia.generate(text, max_tokens=3072, temperature=0.0, output="codes")
+    assert torch.equal(a, b) and torch.equal(raw_a, dia.last_codes)     # run-to-run bit-identical
+    assert a.shape[1] == 9 and ((a >= 0) & (a <= 1023)).all()
+    t = raw_a.cpu()
+    if steps == 3071:                                                   # no natural EOS: the budget forced it
+        assert t.shape[0] == 3070 and a.shape[2] == 3055
+        assert t[-14, 0] == 1024 and (t[-13:, 0] == 1025).all()
+    assert (t[:7, 1] == 1026).all()                                     # delayed channels still emit BOS early on
+    s = dia.generate(text, max_tokens=3072, seed=3, output="codes")     # reference default sampling
+    assert s.shape[1] == 9 and ((s >= 0) & (s <= 1023)).all()
+
+
+def test_full_sequential_utterances_on_one_engine(full_gpu, gold_full):
+    """configs[4] on one GPU: rebinding caches per utterance leaves no state behind."""
+    dia, sd = full_gpu
+    first = dia.generate(str(gold_full["text"]), max_tokens=40, temperature=0.0, output="codes").cpu()
+    for i in range(2):
+        dia.generate(SY.synthetic_transcript(i), max_tokens=24, temperature=0.0, output="codes")
+    again = dia.generate(str(gold_full["text"]), max_tokens=40, temperature=0.0, output="codes").cpu()
+    assert torch.equal(first, again)
+    assert torch.equal(dia.last_codes.cpu(), torch.from_numpy(gold_full["codes"][:39]))

@@ -187,9 +187,7 @@ def run_ours(args) -> None:
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         sd_cpu = {k: v.detach().clone() for k, v in dia.model.named_parameters()}
     # configs[1]: bf16 weights.  Values are bf16-representable, so this cast is exact.
-    for n, p in dia.model.named_parameters():
-        if "proj" in n or "mlp" in n or "logits" in n:
-            p.data = p.data.to(torch.bfloat16)
+    SY.cast_dense_kernels_(dia.model, torch.bfloat16)
     dia.compute_dtype = torch.bfloat16
     dia.device = dev
     dia.model.to(dev)
@@ -205,10 +203,10 @@ def run_ours(args) -> None:
     text_len = dec_state.text_len
 
     def one_generation(profile=None) -> int:
-        dec_out.generated_tokens.copy_(pristine)
         for c in dec_state.self_attn_cache:
             c.current_idx = 0
         with torch.inference_mode():
+            dec_out.generated_tokens.copy_(pristine)
             last = dia._run_loop(dec_state, dec_out, MAX_TOKENS, sampling["cfg_scale"], sampling["temperature"],
                                  sampling["top_p"], sampling["top_k"], 1234, False, profile=profile)
         return last + 1 - (dec_out.prefill_step - 1)        # loop iterations executed (the loop ends by `break`)

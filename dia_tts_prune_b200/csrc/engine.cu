@@ -23,8 +23,9 @@ std::atomic<long long> g_launches{0};
 #define CK(expr)                                                                           \
     do {                                                                                   \
         cudaError_t _e = (expr);                                                           \
-        if (_e != cudaSuccess) {                                                           \
+ if (_e != cudaSuccess) {                                                           \
             g_last_cuda_error = std::string(#expr) + ": " + cudaGetErrorString(_e);        \
+            (void)cudaGetLastError(); /* non-sticky errors must not poison the next launch */ \
             return DIA_B200_ECUDA;                                                         \
         }                                                                                  \
     } while (0)
@@ -434,7 +435,9 @@ int dia_b200_decoder_layer_step(dia_b200_engine* e, int layer, const float* x_in
 }
 
 int dia_b200_embed_sum(dia_b200_engine* e, const int32_t* tokens, int n_rows, float* x, void* stream) {
-    if (!e || !tokens || !x || n_rows < 0) return DIA_B200_EINVAL;
+    if (!e || n_rows < 0) return DIA_B200_EINVAL;
+    if (n_rows == 0) return DIA_B200_OK;
+    if (!tokens || !x) return DIA_B200_EINVAL;
     if (!e->weights_loaded) return DIA_B200_ESTATE;
     CK(cudaSetDevice(e->device));
     CK(launch_embed_sum(e->d_emb, tokens, n_rows, e->shape.channels, e->shape.vocab, e->shape.d_model, x, S(stream)));

@@ -667,7 +667,12 @@ __device__ void embed_stage(Ctx& c, int pos) {
     float s0 = 0.f, s1 = 0.f;
     for (int ch = 0; ch < p.C; ++ch) {
         int a = ldcg_i(t0 + ch), b = ldcg_i(t1 + ch);
-        if (a < 0 || a >= p.V || b < 0 || b >= p.V) { *p.err = kErrBadState; a = 0; b = 0; }
+        if (a < 0 || a >= p.V || b < 0 || b >= p.V) {
+            // steps executed after the utterance finished read unwritten (-1) grid rows: harmless no-ops
+            const bool dead = p.tokens == nullptr && p.gs != nullptr && ldcg_i(&p.gs->finished) != 0;
+            if (!dead) *p.err = kErrBadState;
+            a = 0; b = 0;
+        }
         const float* tab = p.emb + (size_t)ch * p.V * p.D;
         const float e0 = __ldg(tab + (size_t)a * p.D + d), e1 = __ldg(tab + (size_t)b * p.D + d);
         s0 = ch == 0 ? e0 : s0 + e0;

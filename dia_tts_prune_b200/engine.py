@@ -12,6 +12,7 @@ import torch
 
 from . import _lib
 from .config import DiaConfig
+from .synthetic import is_dense_kernel
 
 
 def _stream(device) -> C.c_void_p:
@@ -96,7 +97,7 @@ class DecodeEngine:
     def load_weights(self, tensors: dict[str, torch.Tensor]) -> None:
         """``tensors``: Decoder-relative name -> CUDA tensor (dense kernels all fp32 or all bf16)."""
         names = decoder_tensor_names(self.config)
-        dense = [n for n in names if "proj" in n or "mlp" in n or "logits" in n]
+        dense = [n for n in names if is_dense_kernel(n)]
         dts = {tensors[n].dtype for n in dense}
         if len(dts) != 1 or next(iter(dts)) not in (torch.float32, torch.bfloat16):
             raise ValueError(f"dense kernels must be uniformly float32 or bfloat16, got {dts}")

@@ -15,6 +15,18 @@ import hashlib
 import torch
 
 
+def is_dense_kernel(name: str) -> bool:
+    """True for DenseGeneral kernels (the tensors that may be stored bf16); norms and embeddings stay fp32."""
+    return name.endswith(("_proj.weight", "mlp.wi_fused.weight", "mlp.wo.weight", "logits_dense.weight"))
+
+
+def cast_dense_kernels_(model, dtype) -> None:
+    """Store every DenseGeneral kernel of ``model`` in ``dtype`` (what Dia(config, "bfloat16") does)."""
+    for n, p in model.named_parameters():
+        if is_dense_kernel(n):
+            p.data = p.data.to(dtype)
+
+
 def fan_in_of(name: str, shape) -> int:
     # o_proj kernels contract (heads, head_dim); every other kernel contracts axis 0
     return int(shape[0]) * int(shape[1]) if "o_proj" in name else int(shape[0])

@@ -52,9 +52,7 @@ def build_dia(cfg, seed, device=None, bf16=False):
     sd = {k: v.detach().clone() for k, v in dia.model.named_parameters()}
     if device is not None:
         if bf16:
-            for n, p in dia.model.named_parameters():
-                if "proj" in n or "mlp" in n or "logits" in n:
-                    p.data = p.data.to(torch.bfloat16)
+            SY.cast_dense_kernels_(dia.model, torch.bfloat16)
             dia.compute_dtype = torch.bfloat16
         dia.device = torch.device(device)
         dia.model.to(dia.device)

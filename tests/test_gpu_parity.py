@@ -384,4 +384,5 @@ def test_full_sequential_utterances_on_one_engine(full_gpu, gold_full):
         dia.generate(SY.synthetic_transcript(i), max_tokens=24, temperature=0.0, output="codes")
     again = dia.generate(str(gold_full["text"]), max_tokens=40, temperature=0.0, output="codes").cpu()
     assert torch.equal(first, again)
-    assert torch.equal(dia.last_codes.cpu(), torch.from_numpy(gold_full["codes"][:39]))
+    # rows before the end-of-budget EOS countdown (cur >= 40 - 16) equal the reference's 256-step stream
+    assert torch.equal(dia.last_codes.cpu()[:22], torch.from_numpy(gold_full["codes"][:22]))

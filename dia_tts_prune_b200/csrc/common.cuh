@@ -18,7 +18,7 @@ constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;         // + 1 producer warp (one elected lane issues copies)
 constexpr int kSlotBytes = 8192;                        // one ring slot = one bulk copy
 constexpr int kNumSlots = 19;                           // 152 KB of weights / KV in flight per SM
-constexpr int kXsBytes = 65536;                         // activation vector [K][2] fp32, K <= 8192
+constexpr int kXsBytes = 65536;                         // per-warp B-fragment staging (GEMM), attention / sampler scratch
 constexpr int kRedBytes = 8192;                         // cross-warp reduction scratch
 constexpr int kMiscBytes = 1024;                        // mbarriers + small shared scalars
 constexpr int kSmemBytes = kNumSlots * kSlotBytes + kXsBytes + kRedBytes + kMiscBytes;
@@ -116,6 +116,12 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

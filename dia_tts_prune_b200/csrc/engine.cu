@@ -17,6 +17,7 @@ using namespace dia;
 
 namespace {
 
+constexpr int kTimingSteps = 16;
 thread_local std::string g_last_cuda_error;
 std::atomic<long long> g_launches{0};
 
@@ -60,6 +61,8 @@ struct dia_b200_engine {
     float2 *d_x = nullptr, *d_qkv = nullptr, *d_attn = nullptr, *d_cq = nullptr, *d_cattn = nullptr,
            *d_hidden = nullptr;
     float* d_logits = nullptr;
+    unsigned short *d_xparts = nullptr, *d_attn_parts = nullptr, *d_cattn_parts = nullptr, *d_hidden_parts = nullptr;
+    float* d_ssq = nullptr;
     float *d_sa_part = nullptr, *d_ca_part = nullptr;
     unsigned* d_pair_cnt = nullptr;
     unsigned* d_grid_bar = nullptr;
@@ -67,6 +70,8 @@ struct dia_b200_engine {
     int* d_pred = nullptr;
     int* d_tokens = nullptr;          // staging [2][C]
     GenState* d_gs = nullptr;
+    long long* d_timing = nullptr;    // [kTimingSteps][S][2], debug only
+    bool timing_on = false;
     // pinned host staging
     float** h_ptrs = nullptr;
     GenState* h_gs = nullptr;
@@ -89,7 +94,7 @@ int validate_shape(const dia_b200_shape& s) {
         s.max_audio_len <= 0 || s.max_text_len <= 0)
         return DIA_B200_EINVAL;
     if (s.q_heads != 4 * s.kv_heads) return DIA_B200_EUNSUPPORTED;       // kernels are built for GQA 4:1
-    if (s.d_model % 16 || s.n_hidden % 16) return DIA_B200_EINVAL;
+    if (s.d_model % 16 || s.n_hidden % 16) return DIA_B200_EINVAL;                // MMA k-blocks of 16 rows
     if (s.d_model > 8192 || s.n_hidden > 8192 || s.q_heads * kHeadDim > 8192 || s.cross_heads * kHeadDim > 8192)
         return DIA_B200_EUNSUPPORTED;                                     // activation vector must fit 64 KB of smem
     if (s.channels * s.vocab * 4 > kXsBytes) return DIA_B200_EUNSUPPORTED;
@@ -110,6 +115,8 @@ void fill_params(const dia_b200_engine* e, StepParams& p) {
     p.cross_v = const_cast<const float* const*>(e->d_ptrs + 3 * s.n_layer);
     p.text_len = e->text_len;
     p.x = e->d_x; p.qkv = e->d_qkv; p.attn = e->d_attn; p.cq = e->d_cq; p.cattn = e->d_cattn; p.hidden = e->d_hidden;
+    p.xparts = e->d_xparts; p.attn_parts = e->d_attn_parts; p.cattn_parts = e->d_cattn_parts;
+    p.hidden_parts = e->d_hidden_parts; p.ssq = e->d_ssq;
     p.logits = e->d_logits; p.sa_part = e->d_sa_part; p.ca_part = e->d_ca_part; p.pair_cnt = e->d_pair_cnt;
     p.grid_bar = e->d_grid_bar; p.err = e->d_err;
     p.n_steps = 1;
@@ -117,9 +124,11 @@ void fill_params(const dia_b200_engine* e, StepParams& p) {
     p.eos = s.eos_value; p.pad = s.pad_value; p.bos = s.bos_value;
     for (int i = 0; i < DIA_B200_MAX_CHANNELS; ++i) p.delay[i] = s.delay_pattern[i];
     p.pred_out = e->d_pred;
+    p.timing = e->timing_on ? e->d_timing : nullptr;
 }
 
 int run_stages(dia_b200_engine* e, StepParams& p, bool cooperative, cudaStream_t st) {
+    if (p.n_steps > kTimingSteps) p.timing = nullptr;
     CK(cudaMemsetAsync(e->d_grid_bar, 0, sizeof(unsigned), st));
     CK(launch_step_kernel(p, cooperative, st));
     g_launches++;
@@ -207,7 +216,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
         e->local[t].resize(e->n_groups[t]);
         for (int c = 0; c < G; ++c) {
             const int gc = cnt[c] * mult[t];
-            if (gc > 32) { delete e; return DIA_B200_EUNSUPPORTED; }
+            if (gc > 16) { delete e; return DIA_B200_EUNSUPPORTED; }          // <= 8 MMA tiles per CTA and GEMM
             e->tab[c].g0[t] = g0;
             e->tab[c].gc[t] = gc;
             for (int i = 0; i < gc; ++i) { e->owner[t][g0 + i] = c; e->local[t][g0 + i] = i; }
@@ -258,6 +267,11 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     ALLOC(e->d_cattn, sizeof(float2) * nc);
     ALLOC(e->d_hidden, sizeof(float2) * s.n_hidden);
     ALLOC(e->d_logits, sizeof(float) * 2 * s.channels * s.vocab);
+    ALLOC(e->d_xparts, (size_t)(s.d_model / 16) * 256);          // zero-filled: MMA columns 3 and 7 stay zero
+    ALLOC(e->d_attn_parts, (size_t)(nq / 16) * 256);
+    ALLOC(e->d_cattn_parts, (size_t)(nc / 16) * 256);            // row 0 (unconditional) is never written: exact zeros
+    ALLOC(e->d_hidden_parts, (size_t)(s.n_hidden / 16) * 256);
+    ALLOC(e->d_ssq, sizeof(float) * 2 * G);
     ALLOC(e->d_sa_part, sizeof(float) * 2 * s.q_heads * e->sa_nsplit * 132);
     ALLOC(e->d_ca_part, sizeof(float) * s.cross_heads * e->ca_nsplit * 132);
     ALLOC(e->d_pair_cnt, sizeof(unsigned) * (2 * s.kv_heads + s.cross_heads));
@@ -266,6 +280,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     ALLOC(e->d_pred, sizeof(int) * DIA_B200_MAX_CHANNELS);
     ALLOC(e->d_tokens, sizeof(int) * 2 * DIA_B200_MAX_CHANNELS);
     ALLOC(e->d_gs, sizeof(GenState));
+    ALLOC(e->d_timing, sizeof(long long) * 8 * kTimingSteps * (8 * s.n_layer + 3));
 #undef ALLOC
     if (cudaMallocHost(reinterpret_cast<void**>(&e->h_ptrs), sizeof(float*) * 4 * s.n_layer) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&e->h_gs), sizeof(GenState)) != cudaSuccess ||
@@ -288,7 +303,8 @@ int dia_b200_engine_destroy(dia_b200_engine* e) {
     cudaDeviceSynchronize();
     void* dev[] = {e->d_wstream, e->d_tab, e->d_emb, e->d_norms, e->d_rope_sin, e->d_rope_cos, e->d_ptrs, e->d_x,
                    e->d_qkv, e->d_attn, e->d_cq, e->d_cattn, e->d_hidden, e->d_logits, e->d_sa_part, e->d_ca_part,
-                   e->d_pair_cnt, e->d_grid_bar, e->d_err, e->d_pred, e->d_tokens, e->d_gs};
+                   e->d_pair_cnt, e->d_grid_bar, e->d_err, e->d_pred, e->d_tokens, e->d_gs, e->d_timing,
+                   e->d_xparts, e->d_attn_parts, e->d_cattn_parts, e->d_hidden_parts, e->d_ssq};
     for (void* p : dev) if (p) cudaFree(p);
     for (int t = 0; t < G_COUNT; ++t) { if (e->d_owner[t]) cudaFree(e->d_owner[t]); if (e->d_local[t]) cudaFree(e->d_local[t]); }
     if (e->h_ptrs) cudaFreeHost(e->h_ptrs);
@@ -420,7 +436,8 @@ int dia_b200_decoder_layer_step(dia_b200_engine* e, int layer, const float* x_in
         return DIA_B200_EINVAL;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = S(stream);
-    CK(launch_interleave(x_in, e->d_x, e->shape.d_model, st));
+    CK(launch_xprep(x_in, e->d_x, e->d_xparts, e->d_ssq, e->d_norms + (size_t)layer * 3 * e->shape.d_model,
+                    e->shape.d_model, e->G, st));
     g_launches++;
     StepParams p;
     fill_params(e, p);
@@ -613,8 +630,15 @@ static int buffer_of(dia_b200_engine* e, int which, void** ptr, size_t* bytes) {
         case DIA_B200_BUF_HIDDEN: *ptr = e->d_hidden; *bytes = 8 * (size_t)s.n_hidden; break;
         case DIA_B200_BUF_LOGITS: *ptr = e->d_logits; *bytes = 4 * 2 * (size_t)s.channels * s.vocab; break;
         case DIA_B200_BUF_PRED: *ptr = e->d_pred; *bytes = 4 * (size_t)s.channels; break;
+        case DIA_B200_BUF_TIMING: *ptr = e->d_timing; *bytes = 64 * (size_t)kTimingSteps * (8 * s.n_layer + 3); break;
         default: return DIA_B200_EINVAL;
     }
+    return DIA_B200_OK;
+}
+
+int dia_b200_debug_enable_timing(dia_b200_engine* e, int enable) {
+    if (!e) return DIA_B200_EINVAL;
+    e->timing_on = enable != 0;
     return DIA_B200_OK;
 }
 
@@ -626,18 +650,6 @@ int dia_b200_debug_read(dia_b200_engine* e, int which, void* host_dst, size_t nb
     if (nbytes > b) return DIA_B200_EINVAL;
     CK(cudaSetDevice(e->device));
     CK(cudaMemcpyAsync(host_dst, p, nbytes, cudaMemcpyDeviceToHost, S(stream)));
-    CK(cudaStreamSynchronize(S(stream)));
-    return DIA_B200_OK;
-}
-
-int dia_b200_debug_write(dia_b200_engine* e, int which, const void* host_src, size_t nbytes, void* stream) {
-    if (!e || !host_src) return DIA_B200_EINVAL;
-    void* p; size_t b;
-    int rc = buffer_of(e, which, &p, &b);
-    if (rc) return rc;
-    if (nbytes > b) return DIA_B200_EINVAL;
-    CK(cudaSetDevice(e->device));
-    CK(cudaMemcpyAsync(p, host_src, nbytes, cudaMemcpyHostToDevice, S(stream)));
     CK(cudaStreamSynchronize(S(stream)));
     return DIA_B200_OK;
 }

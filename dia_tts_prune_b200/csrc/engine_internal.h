@@ -69,6 +69,12 @@ struct StepParams {
     float2* cattn;
     float2* hidden;
     float* logits;                     // [2][C][V]
+    // the same vectors as MMA B fragments: bf16 hi/lo/lo2 split, [k/16][8 cols][4 kq][4] (see step_kernel.cu)
+    unsigned short* xparts;            // x * w_norm of the next consumer
+    unsigned short* attn_parts;
+    unsigned short* cattn_parts;
+    unsigned short* hidden_parts;
+    float* ssq;                        // [2][G] per-CTA partial sums of x^2 (for the consumer's RMSNorm)
     float* sa_part;                    // [2*Hq][sa_nsplit][132]
     float* ca_part;                    // [Hc][ca_nsplit][132]
     unsigned* pair_cnt;                // last-arriver counters, [2*Hkv + Hc]
@@ -90,6 +96,7 @@ struct StepParams {
     int delay[DIA_B200_MAX_CHANNELS];
     int* pred_out;                     // [C] raw prediction of the last executed step
     float* probs_out;                  // optional [C][V]
+    long long* timing;                 // optional [n_steps][S][8] clock64 stamps of CTA 0 (see tools/stage_profile.py)
 };
 
 // ---- launchers (each returns the cudaError_t of the launch) --------------------------------
@@ -113,7 +120,8 @@ struct RepackArgs {
 cudaError_t launch_repack(const RepackArgs& a, cudaStream_t st);
 cudaError_t launch_embed_sum(const float* emb, const int* tokens, int n_rows, int C, int V, int D, float* x,
                              cudaStream_t st);
-cudaError_t launch_interleave(const float* x_rows, float2* x_il, int D, cudaStream_t st);
+cudaError_t launch_xprep(const float* x_rows, float2* x_il, unsigned short* xparts, float* ssq, const float* normw,
+                         int D, int G, cudaStream_t st);
 cudaError_t launch_deinterleave(const float2* x_il, float* x_rows, int D, cudaStream_t st);
 cudaError_t launch_delay_apply(const int* in, int* out, int B, int T, int C, const int* delay, int pad, int bos,
                                cudaStream_t st);

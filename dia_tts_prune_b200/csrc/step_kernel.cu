@@ -26,15 +26,29 @@
 //
 // Reference semantics: dia/layers.py:671-720 (decode_step), :530-584 (DecoderLayer),
 // :238-346 (Attention), :92-105 (MlpBlock); dia/model.py:429-488, 32-82, 748-807.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "engine_internal.h"
 
 namespace dia {
 
+// per-GEMM constants of this CTA, computed once per launch (no integer divisions in the stage loop)
+struct GemmCfg {
+    int gc, g0, K;
+    int row_bytes;     // gc * 16
+    int rpc;           // rows of the slab per ring slot (multiple of 16 = one MMA k-block)
+    int n_chunks;
+    int n_mt;          // 16-column MMA tiles = ceil(gc / 2)
+};
+
 struct SharedMisc {
     uint64_t full[kNumSlots];
     uint64_t empty[kNumSlots];
     CtaTable tab;
+    GemmCfg gcfg[G_COUNT];
+    float ssq_part[kConsumerWarps][2];   // per-warp sums of x_new^2 of a residual stage (published at the barrier)
+    float inv_rms[2];                    // 1/rms of the stage input, per batch row
     float stat[32];
     int stages_done;     // consumer -> producer progress (global stage index + 1)
     int flag;
@@ -50,6 +64,7 @@ struct Ctx {
     int tid, warp, lane;
     unsigned cbase;      // ring chunk index at the start of the current stage
     unsigned nbar;       // grid barriers passed so far in this launch
+    long long* tstamp;   // debug: 8 clock64 slots of the current stage (CTA 0, thread 0 only)
 };
 
 __device__ __forceinline__ void decode_stage(int s, int L, int& kind, int& layer) {
@@ -69,13 +84,6 @@ __device__ __forceinline__ int gemm_of_kind(int kind) {
         case S_LOGITS: return G_LOGITS;
         default: return -1;
     }
-}
-
-// rows of a slab that fit one ring slot, rounded down to a multiple of the rows a warp
-// covers per iteration (R = 32 / gc lanes-groups)
-__device__ __forceinline__ int rows_per_chunk(int gc, int R) {
-    int rpc = kSlotBytes / (gc * 16);
-    return rpc - rpc % R;
 }
 
 struct AttnWork {
@@ -122,17 +130,28 @@ __device__ __forceinline__ AttnWork cross_attn_work(const StepParams& p, int cta
 // ------------------------------------------------------------------------------------------
 // grid barrier (consumer warps only)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(Ctx& c) {
+// thread 0, after a consumer_sync: this CTA's share of sum(x^2) of the new residual stream (fixed order)
+__device__ __forceinline__ void publish_ssq_partials(Ctx& c) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; ++w) { s0 += c.misc->ssq_part[w][0]; s1 += c.misc->ssq_part[w][1]; }
+    c.p->ssq[blockIdx.x] = s0;
+    c.p->ssq[gridDim.x + blockIdx.x] = s1;
+}
+
+__device__ __forceinline__ void grid_barrier(Ctx& c, bool publish_ssq) {
     const StepParams& p = *c.p;
-    consumer_sync();
+    consumer_sync();                       // every consumer thread's stage output is issued
     c.nbar++;
     if (c.tid == 0) {
-        __threadfence();
+        if (publish_ssq) publish_ssq_partials(c);
+        // release: orders the whole CTA's prior writes (bar.sync above makes them visible to this
+        // thread, the release is cumulative) before the arrival becomes visible at gpu scope
         red_release_add_u32(p.grid_bar, 1u);
         const unsigned target = c.nbar * gridDim.x;
-        if (ld_acquire_u32(p.grid_bar) < target) {
+        if (ld_relaxed_u32(p.grid_bar) < target) {
             const unsigned long long t0 = clock64();
-            while (ld_acquire_u32(p.grid_bar) < target) {
+            while (ld_relaxed_u32(p.grid_bar) < target) {
                 if (clock64() - t0 > kWatchdogCycles) {
                     *reinterpret_cast<volatile int*>(p.err) = kErrGridBarrierTimeout;
                     __threadfence_system();
@@ -140,7 +159,9 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
                 }
             }
         }
-        __threadfence();
+        // acquire side: every read of data another CTA produced goes to L2 (ld.global.cg / bulk copies),
+        // never through L1, and is issued after this loop exits (GPUs do not speculate past the branch),
+        // so no L1 invalidation / fence is needed here.  The named barrier below orders the other threads.
     }
     consumer_sync();
 }
@@ -179,18 +200,15 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
             decode_stage(s, p.L, kind, layer);
             const int gt = gemm_of_kind(kind);
             if (gt >= 0) {
-                const int gc = tab.gc[gt];
-                if (gc == 0) continue;
-                const int K = p.Kdim[gt];
-                const int R = gc > 16 ? 1 : 32 / gc;
-                const int rpc = rows_per_chunk(gc, R);
-                const uint32_t row_bytes = gc * 16;
+                const GemmCfg& g = misc->gcfg[gt];
+                if (g.gc == 0) continue;
                 const unsigned char* base = p.wstream + tab.stream_base +
                     (gt == G_LOGITS ? tab.logits_off
                                     : (unsigned long long)layer * tab.layer_bytes + tab.slab_off[gt]);
-                for (int r0 = 0; r0 < K; r0 += rpc) {
-                    const int rows = min(rpc, K - r0);
-                    pr.issue(base + (size_t)r0 * row_bytes, rows * row_bytes, false);
+                for (int r0 = 0; r0 < g.K; r0 += g.rpc) {
+                    const int rows = min(g.rpc, g.K - r0);
+                    pr.issue(base + (size_t)r0 * g.row_bytes, rows * g.row_bytes, false);
+                    if (r0 == 0 && p.timing != nullptr && cta == 0) p.timing[((size_t)n * S + s) * 8 + 7] = clock64();
                 }
             } else if (kind == S_SATTN || kind == S_CATTN) {
                 const bool self = kind == S_SATTN;
@@ -236,190 +254,285 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
 }
 
 // ------------------------------------------------------------------------------------------
-// GEMM stage: y[2][N_cta] = xs[2][K] . W_slab, fp32 accumulate, fused prologue / epilogue
+// GEMM stage: y[2][N_cta] = x[2][K] . W_slab on the tensor cores (mma.sync m16n8k16, bf16 x bf16 ->
+// fp32).  Swap-AB: the 16 rows of the MMA are 16 OUTPUT COLUMNS (two 8-column groups of the slab,
+// fed from the ring with ldmatrix.trans - the slab is [k][n], n contiguous), the 8 columns of the MMA
+// carry the two batch rows, each split into three bf16 terms  x = hi + lo + lo2  (exact to 24 bits),
+// so the product keeps fp32-activation accuracy while the weights stay bf16.
+//   MMA column n: 0,1,2 = row 0 (hi, lo, lo2)   4,5,6 = row 1 (hi, lo, lo2)   3,7 = zero
+// Activation vectors live in global memory ALREADY split and laid out as B fragments ("parts"):
+// k-block kb (16 rows) = 256 B, the 8-byte word of lane l = n*4 + kq holds the bf16 of rows
+// {2kq, 2kq+1, 8+2kq, 9+2kq} of column n.  The epilogue that produces a vector writes it in this form
+// once (pre-multiplied by the consumer's RMSNorm weight), so a consumer warp fetches exactly the
+// fragments of the k-range it owns straight from L2 - no staging pass, no block sync before the MMAs.
+// The 1/rms factor commutes with the GEMM and is applied in the epilogue from per-CTA partial sums.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fma_row(f32x2 (&accA)[4], f32x2 (&accB)[4], const uint4& w, const float2& x) {
-    const f32x2 xa = pack2(x.x, x.x), xb = pack2(x.y, x.y);
-    const f32x2 w0 = bf16x2_to_f32x2(w.x), w1 = bf16x2_to_f32x2(w.y), w2 = bf16x2_to_f32x2(w.z),
-                w3 = bf16x2_to_f32x2(w.w);
-    accA[0] = ffma2(xa, w0, accA[0]); accB[0] = ffma2(xb, w0, accB[0]);
-    accA[1] = ffma2(xa, w1, accA[1]); accB[1] = ffma2(xb, w1, accB[1]);
-    accA[2] = ffma2(xa, w2, accA[2]); accB[2] = ffma2(xb, w2, accB[2]);
-    accA[3] = ffma2(xa, w3, accA[3]); accB[3] = ffma2(xb, w3, accB[3]);
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t smem_addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// x = hi + lo + lo2 with each term bf16 (round-to-nearest at every level; the residuals are exact)
+__device__ __forceinline__ void split3(float x, unsigned short (&t)[3]) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(l);
+    const __nv_bfloat16 l2 = __float2bfloat16_rn(r2);
+    t[0] = __bfloat16_as_ushort(h); t[1] = __bfloat16_as_ushort(l); t[2] = __bfloat16_as_ushort(l2);
+}
+// write element (k, batch row r) of a vector into its parts buffer
+__device__ __forceinline__ void store_parts(unsigned short* parts, int k, int r, float v) {
+    unsigned short t[3];
+    split3(v, t);
+    const int kk = k & 15;
+    unsigned short* base = parts + (size_t)(k >> 4) * 128 + ((kk & 7) >> 1) * 4 + (kk & 1) + ((kk >> 3) << 1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) base[(r * 4 + i) * 16] = t[i];
 }
 
-// load the stage's input vector [K][2] into xs, optionally RMS-normalised (fp32, eps, weight)
-__device__ void load_vector(Ctx& c, const float2* src, int K, const float* normw) {
-    const StepParams& p = *c.p;
-    float4* xs4 = reinterpret_cast<float4*>(c.xs);
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    const int n4 = K >> 1;
-    float ss0 = 0.f, ss1 = 0.f;
-    for (int i = c.tid; i < n4; i += kConsumerThreads) {
-        const float4 v = ldcg_f4(s4 + i);
-        xs4[i] = v;
-        ss0 = fmaf(v.x, v.x, ss0); ss0 = fmaf(v.z, v.z, ss0);
-        ss1 = fmaf(v.y, v.y, ss1); ss1 = fmaf(v.w, v.w, ss1);
-    }
-    if (normw != nullptr) {
-        ss0 = warp_sum(ss0);
-        ss1 = warp_sum(ss1);
-        if (c.lane == 0) { c.misc->stat[c.warp] = ss0; c.misc->stat[8 + c.warp] = ss1; }
-        consumer_sync();
-        float t0 = 0.f, t1 = 0.f;
+constexpr int kMaxTiles = 8;     // <= 16 column groups per CTA and GEMM
+constexpr int kMaxKb = 16;       // k-blocks per ring slot (slot rows are capped at 256)
+constexpr int kBStageBytes = kMaxKb * 256;   // B fragments of one slot; two such buffers per warp
+
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// L2 -> this warp's staging buffer: the B fragments of rows [r0, r0 + 16*nkb) (256 B per k-block;
+// half-warps take alternate k-blocks, 16 B per lane, L2-only so no stale L1 line can be read)
+__device__ __forceinline__ void stage_b_frags(uint32_t dst, const unsigned char* parts, int r0, int nkb, int lane) {
+    const unsigned char* src = parts + (size_t)(r0 >> 4) * 256 + (lane & 15) * 16;
+    const uint32_t d = dst + (lane & 15) * 16;
+    for (int kb = lane >> 4; kb < nkb; kb += 2) cp_async16_cg(d + kb * 256, src + (size_t)kb * 256);
+    cp_async_commit();
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
+// The MMAs of one ring slot.  Three compact, rolled variants (the kernel has ~150 short stages per
+// step; straight-line code that overflows the instruction caches costs more than it saves):
+//   1 tile : 4 k-blocks per iteration on 4 independent accumulator chains
+//   2 tiles: 2 k-blocks per iteration, 2 chains per tile
+//   n tiles: 1 k-block per iteration, the tiles are the independent chains
+__device__ __forceinline__ void mma_slot_1(float (&acc)[kMaxTiles][4], uint32_t a_addr, uint32_t kb_bytes, int nkb,
+                                           uint32_t b_addr) {
+    int kb = 0;
+    for (; kb + 4 <= nkb; kb += 4) {
 #pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) { t0 += c.misc->stat[w]; t1 += c.misc->stat[8 + w]; }
-        const float inv0 = 1.0f / sqrtf(t0 / (float)K + p.eps);
-        const float inv1 = 1.0f / sqrtf(t1 / (float)K + p.eps);
-        const float2* w2 = reinterpret_cast<const float2*>(normw);
-        for (int i = c.tid; i < n4; i += kConsumerThreads) {
-            float4 v = xs4[i];
-            const float2 w = __ldg(w2 + i);
-            v.x = (v.x * inv0) * w.x; v.y = (v.y * inv1) * w.x;
-            v.z = (v.z * inv0) * w.y; v.w = (v.w * inv1) * w.y;
-            xs4[i] = v;
+        for (int u = 0; u < 4; ++u) {
+            const uint2 b = lds_u2(b_addr + (kb + u) * 256);
+            uint32_t a[4];
+            ldmatrix_x4_trans(a, a_addr + (kb + u) * kb_bytes);
+            mma_bf16_16816(acc[u], a, b.x, b.y);
         }
     }
-    consumer_sync();
+    for (; kb < nkb; ++kb) {
+        const uint2 b = lds_u2(b_addr + kb * 256);
+        uint32_t a[4];
+        ldmatrix_x4_trans(a, a_addr + kb * kb_bytes);
+        mma_bf16_16816(acc[0], a, b.x, b.y);
+    }
+}
+__device__ __forceinline__ void mma_slot_2(float (&acc)[kMaxTiles][4], uint32_t a_addr, uint32_t kb_bytes, int nkb,
+                                           uint32_t b_addr) {
+    int kb = 0;
+    for (; kb + 2 <= nkb; kb += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint2 b = lds_u2(b_addr + (kb + u) * 256);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t a[4];
+                ldmatrix_x4_trans(a, a_addr + (kb + u) * kb_bytes + mt * 32);
+                mma_bf16_16816(acc[u * 2 + mt], a, b.x, b.y);
+            }
+        }
+    }
+    if (kb < nkb) {
+        const uint2 b = lds_u2(b_addr + kb * 256);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            uint32_t a[4];
+            ldmatrix_x4_trans(a, a_addr + kb * kb_bytes + mt * 32);
+            mma_bf16_16816(acc[mt], a, b.x, b.y);
+        }
+    }
+}
+__device__ __forceinline__ void mma_slot_n(float (&acc)[kMaxTiles][4], uint32_t a_addr, uint32_t kb_bytes, int nkb,
+                                           uint32_t b_addr, int n_mt) {
+    for (int kb = 0; kb < nkb; ++kb) {
+        const uint2 b = lds_u2(b_addr + kb * 256);
+#pragma unroll
+        for (int mt = 0; mt < kMaxTiles; ++mt) {
+            if (mt < n_mt) {
+                uint32_t a[4];
+                ldmatrix_x4_trans(a, a_addr + kb * kb_bytes + mt * 32);
+                mma_bf16_16816(acc[mt], a, b.x, b.y);
+            }
+        }
+    }
 }
 
 __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     const StepParams& p = *c.p;
-    const CtaTable& tab = c.misc->tab;
-    const int gc = tab.gc[gt];
+    const GemmCfg& g = c.misc->gcfg[gt];
+    const int gc = g.gc, g0 = g.g0, K = g.K, n_mt = g.n_mt;
+    const int lane = c.lane;
+    const bool resid = (gt == G_SO || gt == G_CO || gt == G_WO);
+    if (resid && lane == 0) { c.misc->ssq_part[c.warp][0] = 0.f; c.misc->ssq_part[c.warp][1] = 0.f; }
     if (gc == 0) return;
-    const int g0 = tab.g0[gt];
-    const int K = p.Kdim[gt];
 
-    const float2* src;
-    const float* normw = nullptr;
+    const unsigned char* parts;
+    bool normed = false;
     switch (gt) {
-        case G_QKV: src = p.x; normw = p.norms + ((size_t)layer * 3 + 0) * p.D; break;
-        case G_SO: src = p.attn; break;
-        case G_CQ: src = p.x; normw = p.norms + ((size_t)layer * 3 + 1) * p.D; break;
-        case G_CO: src = p.cattn; break;
-        case G_WI: src = p.x; normw = p.norms + ((size_t)layer * 3 + 2) * p.D; break;
-        case G_WO: src = p.hidden; break;
-        default: src = p.x; normw = p.norms + (size_t)p.L * 3 * p.D; break;   // logits: final norm
+        case G_SO: parts = reinterpret_cast<const unsigned char*>(p.attn_parts); break;
+        case G_CO: parts = reinterpret_cast<const unsigned char*>(p.cattn_parts); break;
+        case G_WO: parts = reinterpret_cast<const unsigned char*>(p.hidden_parts); break;
+        default: parts = reinterpret_cast<const unsigned char*>(p.xparts); normed = true; break;
     }
-    load_vector(c, src, K, normw);
+    const int n_chunks = g.n_chunks, rpc = g.rpc;
+    // this warp's slots are ci = warp, warp + 8, ...; the B fragments of its first slot start moving now
+    const uint32_t bstage = smem_u32(c.xs) + c.warp * (2 * kBStageBytes);
+    if (c.warp < n_chunks) stage_b_frags(bstage, parts, c.warp * rpc, min(rpc, K - c.warp * rpc) >> 4, lane);
 
-    const int R = gc > 16 ? 1 : 32 / gc;
-    const int rpc = rows_per_chunk(gc, R);
-    const int row_bytes = gc * 16;
-    const int n_chunks = (K + rpc - 1) / rpc;
-    const int j = c.lane / gc, g = c.lane - j * gc;
-    const bool lane_active = j < R;
-    const int lane_off = j * row_bytes + g * 16;
-    const int it_bytes = R * row_bytes;
+    // epilogue role of this thread: (tile, row, column-in-tile); its residual is fetched now, used last
+    const int e_mt = c.tid >> 5, e_r = (c.tid >> 4) & 1, e_m = c.tid & 15;
+    const int e_group = 2 * e_mt + (e_m >> 3);
+    const bool e_valid = e_mt < n_mt && e_group < gc;
+    const int e_n = (g0 + e_group) * 8 + (e_m & 7);
+    float resid_v = 0.f;
+    if (resid && e_valid) resid_v = ldcg_f(reinterpret_cast<const float*>(p.x) + (size_t)e_n * 2 + e_r);
 
-    f32x2 accA[4], accB[4];
+    if (normed && c.warp == kConsumerWarps - 1) {
+        // 1/rms of the input from the per-CTA partial sums its producers published (fixed order)
+        float s0 = 0.f, s1 = 0.f;
+        for (int i = lane; i < (int)gridDim.x; i += 32) { s0 += ldcg_f(p.ssq + i); s1 += ldcg_f(p.ssq + gridDim.x + i); }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0) {   // torch.nn.RMSNorm: x * rsqrt(mean(x^2) + eps) * w
+            c.misc->inv_rms[0] = 1.0f / sqrtf(s0 / (float)K + p.eps);
+            c.misc->inv_rms[1] = 1.0f / sqrtf(s1 / (float)K + p.eps);
+        }
+    }
+
+    float acc[kMaxTiles][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { accA[i] = 0ull; accB[i] = 0ull; }
+    for (int i = 0; i < kMaxTiles; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
 
-    for (int ci = c.warp; ci < n_chunks; ci += kConsumerWarps) {
+    // ldmatrix row address of this lane inside a k-block: tile t = lane/8 -> (k half = t/2, group = t%2)
+    const uint32_t lm_off = (uint32_t)((((lane >> 4) << 3) + (lane & 7)) * g.row_bytes + ((lane >> 3) & 1) * 16);
+    const uint32_t ring_base = smem_u32(c.ring) + lm_off;
+    const uint32_t kb_bytes = 16u * g.row_bytes;
+    if (c.tstamp) c.tstamp[1] = clock64();
+
+    int buf = 0;
+    for (int ci = c.warp; ci < n_chunks; ci += kConsumerWarps, buf ^= 1) {
+        const int cn = ci + kConsumerWarps;
+        if (cn < n_chunks) stage_b_frags(bstage + (buf ^ 1) * kBStageBytes, parts, cn * rpc, min(rpc, K - cn * rpc) >> 4, lane);
         const unsigned idx = c.cbase + ci;
         const unsigned slot = idx % kNumSlots;
         mbar_wait(&c.misc->full[slot], (idx / kNumSlots) & 1u, p.err, kErrFullBarrierTimeout);
-        const int rows = min(rpc, K - ci * rpc);
-        if (lane_active) {
-            const unsigned char* sp = c.ring + slot * kSlotBytes + lane_off;
-            const float2* xp = c.xs + ci * rpc + j;
-            const int full = rows / R;
-            int it = 0;
-            for (; it + 4 <= full; it += 4) {
-                const uint4 w0 = *reinterpret_cast<const uint4*>(sp + (it + 0) * it_bytes);
-                const uint4 w1 = *reinterpret_cast<const uint4*>(sp + (it + 1) * it_bytes);
-                const uint4 w2 = *reinterpret_cast<const uint4*>(sp + (it + 2) * it_bytes);
-                const uint4 w3 = *reinterpret_cast<const uint4*>(sp + (it + 3) * it_bytes);
-                const float2 x0 = xp[(it + 0) * R], x1 = xp[(it + 1) * R], x2 = xp[(it + 2) * R],
-                             x3 = xp[(it + 3) * R];
-                fma_row(accA, accB, w0, x0);
-                fma_row(accA, accB, w1, x1);
-                fma_row(accA, accB, w2, x2);
-                fma_row(accA, accB, w3, x3);
-            }
-            for (; it < full; ++it) {
-                const uint4 w0 = *reinterpret_cast<const uint4*>(sp + it * it_bytes);
-                fma_row(accA, accB, w0, xp[it * R]);
-            }
-            if (j < rows - full * R) {
-                const uint4 w0 = *reinterpret_cast<const uint4*>(sp + full * it_bytes);
-                fma_row(accA, accB, w0, xp[full * R]);
-            }
-        }
+        if (cn < n_chunks) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.misc->empty[slot]);
+        if (c.tstamp && ci == c.warp) c.tstamp[6] = clock64();
+        const int nkb = min(rpc, K - ci * rpc) >> 4;
+        const uint32_t a_addr = ring_base + slot * kSlotBytes;
+        const uint32_t b_addr = bstage + buf * kBStageBytes + lane * 8;
+        if (n_mt == 1) mma_slot_1(acc, a_addr, kb_bytes, nkb, b_addr);
+        else if (n_mt == 2) mma_slot_2(acc, a_addr, kb_bytes, nkb, b_addr);
+        else mma_slot_n(acc, a_addr, kb_bytes, nkb, b_addr, n_mt);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c.misc->empty[slot]);
     }
     c.cbase += n_chunks;
-
-    // ---- reduce: over the R row-lanes of a warp by shuffles, then over warps through smem ----
-    float v[16];   // e = row*8 + col
+    if (n_mt == 1) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        unpack2(accA[i], v[2 * i], v[2 * i + 1]);
-        unpack2(accB[i], v[8 + 2 * i], v[8 + 2 * i + 1]);
+        for (int j = 0; j < 4; ++j) acc[0][j] = (acc[0][j] + acc[1][j]) + (acc[2][j] + acc[3][j]);
+    } else if (n_mt == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[0][j] += acc[2][j]; acc[1][j] += acc[3][j]; }
     }
-    if (R > 1) {
-        int off = 1;
-        while (off * 2 < R) off *= 2;
-        for (; off >= 1; off >>= 1) {
-            const int delta = off * gc;
-            const bool ok = c.lane + delta < 32;
+    if (c.tstamp) c.tstamp[2] = clock64();
+
+    // ---- sum the three bf16 terms (MMA columns) of each batch row, then the 8 warps through smem ----
+    // C fragment: c0,c1 = D[m][2q], D[m][2q+1]; c2,c3 = D[m+8][..] with m = lane/4, q = lane%4.
+    // q = 0,1 hold row 0 (hi+lo | lo2+0), q = 2,3 hold row 1.
+    const int q = lane & 3, m = lane >> 2;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const float t = __shfl_down_sync(0xffffffffu, v[e], delta);
-                if (ok) v[e] += t;
+    for (int mt = 0; mt < kMaxTiles; ++mt) {
+        if (mt < n_mt) {
+            float lo = acc[mt][0] + acc[mt][1], hi = acc[mt][2] + acc[mt][3];
+            lo += __shfl_xor_sync(0xffffffffu, lo, 1);
+            hi += __shfl_xor_sync(0xffffffffu, hi, 1);
+            if ((q & 1) == 0) {
+                float* r = c.red + ((size_t)c.warp * n_mt + mt) * 32 + (q >> 1) * 16;
+                r[m] = lo;
+                r[m + 8] = hi;
             }
         }
     }
-    if (c.lane < gc) {
-        float4* r4 = reinterpret_cast<float4*>(c.red + ((size_t)c.warp * gc + c.lane) * 16);
-        r4[0] = make_float4(v[0], v[1], v[2], v[3]);
-        r4[1] = make_float4(v[4], v[5], v[6], v[7]);
-        r4[2] = make_float4(v[8], v[9], v[10], v[11]);
-        r4[3] = make_float4(v[12], v[13], v[14], v[15]);
-    }
     consumer_sync();
+    if (c.tstamp) c.tstamp[3] = clock64();
 
-    // ---- epilogue ----------------------------------------------------------------------------
-    if (gt == G_WI) {
-        // groups alternate (gate, up) of the same 8 hidden units: h = silu(gate) * up (dia/layers.py:95-101)
-        const int n_out = (gc >> 1) * 16;
-        for (int t = c.tid; t < n_out; t += kConsumerThreads) {
-            const int hg = t >> 4, e = t & 15;
-            float gate = 0.f, up = 0.f;
+    const float inv = normed ? c.misc->inv_rms[e_r] : 1.0f;
+    auto total = [&](int mm) {
+        float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < kConsumerWarps; ++w) {
-                gate += c.red[((size_t)w * gc + 2 * hg) * 16 + e];
-                up += c.red[((size_t)w * gc + 2 * hg + 1) * 16 + e];
-            }
-            const float h = (gate / (1.0f + expf(-gate))) * up;
-            const int n = ((g0 >> 1) + hg) * 8 + (e & 7);
-            reinterpret_cast<float*>(p.hidden)[(size_t)n * 2 + (e >> 3)] = h;
+        for (int w = 0; w < kConsumerWarps; ++w) s += c.red[((size_t)w * n_mt + e_mt) * 32 + e_r * 16 + mm];
+        return s;
+    };
+    if (gt == G_WI) {
+        // a tile = (gate group, up group) of the same 8 hidden units: h = silu(gate) * up (dia/layers.py:95-101)
+        if (!e_valid || e_m >= 8) return;
+        const float gate = total(e_m) * inv, up = total(e_m + 8) * inv;
+        const float h = (gate / (1.0f + expf(-gate))) * up;
+        const int n = ((g0 >> 1) + e_mt) * 8 + e_m;
+        reinterpret_cast<float*>(p.hidden)[(size_t)n * 2 + e_r] = h;
+        store_parts(p.hidden_parts, n, e_r, h);
+        return;
+    }
+    if (!resid) {
+        if (!e_valid) return;
+        const float y = total(e_m) * inv;
+        if (gt == G_QKV) {
+            reinterpret_cast<float*>(p.qkv)[(size_t)e_n * 2 + e_r] = y;
+        } else if (gt == G_CQ) {
+            reinterpret_cast<float*>(p.cq)[(size_t)e_n * 2 + e_r] = y;
+        } else {
+            const int ch = e_n / p.Vpad, vv = e_n - ch * p.Vpad;
+            if (ch < p.C && vv < p.V) p.logits[((size_t)e_r * p.C + ch) * p.V + vv] = y;
         }
         return;
     }
-    const int n_out = gc * 16;
-    for (int t = c.tid; t < n_out; t += kConsumerThreads) {
-        const int gg = t >> 4, e = t & 15;
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) s += c.red[((size_t)w * gc + gg) * 16 + e];
-        const int n = (g0 + gg) * 8 + (e & 7);
-        const int r = e >> 3;
-        if (gt == G_QKV) {
-            reinterpret_cast<float*>(p.qkv)[(size_t)n * 2 + r] = s;
-        } else if (gt == G_CQ) {
-            reinterpret_cast<float*>(p.cq)[(size_t)n * 2 + r] = s;
-        } else if (gt == G_LOGITS) {
-            const int ch = n / p.Vpad, vv = n - ch * p.Vpad;
-            if (ch < p.C && vv < p.V) p.logits[((size_t)r * p.C + ch) * p.V + vv] = s;
-        } else {   // residual add (dia/layers.py:555,574,582)
-            float* xp = reinterpret_cast<float*>(p.x) + (size_t)n * 2 + r;
-            *xp = ldcg_f(xp) + s;
-        }
+    // residual add (dia/layers.py:555,574,582); the new stream is also written as the parts of
+    // x * w_norm for the NEXT consumer, and its sum of squares is collected for that consumer's RMSNorm
+    float xn = 0.f;
+    if (e_valid) {
+        xn = resid_v + total(e_m);
+        reinterpret_cast<float*>(p.x)[(size_t)e_n * 2 + e_r] = xn;
+        const float* wn = gt == G_SO ? p.norms + ((size_t)layer * 3 + 1) * p.D
+                        : gt == G_CO ? p.norms + ((size_t)layer * 3 + 2) * p.D
+                                     : p.norms + ((size_t)(layer + 1) * 3) * p.D;   // next layer's pre_sa_norm, or
+        store_parts(p.xparts, e_n, e_r, xn * __ldg(wn + e_n));                      // the final norm after layer L-1
     }
+    float sq = xn * xn;                                                // half-warps = batch rows
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((lane & 15) == 0) c.misc->ssq_part[c.warp][e_r] = sq;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -603,6 +716,7 @@ __device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
     consumer_sync();
 
     float* outf = reinterpret_cast<float*>(kSelf ? p.attn : p.cattn);
+    unsigned short* oparts = kSelf ? p.attn_parts : p.cattn_parts;
     float* part = kSelf ? p.sa_part : p.ca_part;
     for (int i = c.tid; i < HPK * kHeadDim; i += kConsumerThreads) {
         const int h = i >> 7, d = i & 127;
@@ -615,6 +729,7 @@ __device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
             const float val = l > 0.f ? o / l : 0.f;
             if (kSelf) outf[((size_t)head * kHeadDim + d) * 2 + r] = val;
             else reinterpret_cast<float2*>(outf)[(size_t)head * kHeadDim + d] = make_float2(0.f, val);
+            store_parts(oparts, head * kHeadDim + d, r, val);      // row 0 of the cross output stays all-zero
         } else {
             float* pp = part + (((size_t)(kSelf ? r * p.Hq + head : head)) * nsplit + w.split) * 132;
             pp[4 + d] = o;
@@ -650,6 +765,7 @@ __device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
         const float val = Lsum > 0.f ? O / Lsum : 0.f;
         if (kSelf) outf[((size_t)head * kHeadDim + d) * 2 + r] = val;
         else reinterpret_cast<float2*>(outf)[(size_t)head * kHeadDim + d] = make_float2(0.f, val);
+        store_parts(oparts, head * kHeadDim + d, r, val);
     }
 }
 
@@ -659,26 +775,32 @@ __device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
 __device__ void embed_stage(Ctx& c, int pos) {
     const StepParams& p = *c.p;
     const int d = blockIdx.x * kConsumerThreads + c.tid;
-    if (d >= p.D) return;
-    const int* t0;
-    const int* t1;
-    if (p.tokens != nullptr) { t0 = p.tokens; t1 = p.tokens + p.C; }
-    else { t0 = t1 = p.grid + (size_t)(pos - 1) * p.C; }
     float s0 = 0.f, s1 = 0.f;
-    for (int ch = 0; ch < p.C; ++ch) {
-        int a = ldcg_i(t0 + ch), b = ldcg_i(t1 + ch);
-        if (a < 0 || a >= p.V || b < 0 || b >= p.V) {
-            // steps executed after the utterance finished read unwritten (-1) grid rows: harmless no-ops
-            const bool dead = p.tokens == nullptr && p.gs != nullptr && ldcg_i(&p.gs->finished) != 0;
-            if (!dead) *p.err = kErrBadState;
-            a = 0; b = 0;
+    if (d < p.D) {
+        const int* t0;
+        const int* t1;
+        if (p.tokens != nullptr) { t0 = p.tokens; t1 = p.tokens + p.C; }
+        else { t0 = t1 = p.grid + (size_t)(pos - 1) * p.C; }
+        for (int ch = 0; ch < p.C; ++ch) {
+            int a = ldcg_i(t0 + ch), b = ldcg_i(t1 + ch);
+            if (a < 0 || a >= p.V || b < 0 || b >= p.V) {
+                // steps executed after the utterance finished read unwritten (-1) grid rows: harmless no-ops
+                const bool dead = p.tokens == nullptr && p.gs != nullptr && ldcg_i(&p.gs->finished) != 0;
+                if (!dead) *p.err = kErrBadState;
+                a = 0; b = 0;
+            }
+            const float* tab = p.emb + (size_t)ch * p.V * p.D;
+            const float e0 = __ldg(tab + (size_t)a * p.D + d), e1 = __ldg(tab + (size_t)b * p.D + d);
+            s0 = ch == 0 ? e0 : s0 + e0;
+            s1 = ch == 0 ? e1 : s1 + e1;
         }
-        const float* tab = p.emb + (size_t)ch * p.V * p.D;
-        const float e0 = __ldg(tab + (size_t)a * p.D + d), e1 = __ldg(tab + (size_t)b * p.D + d);
-        s0 = ch == 0 ? e0 : s0 + e0;
-        s1 = ch == 0 ? e1 : s1 + e1;
+        p.x[d] = make_float2(s0, s1);
+        const float w = __ldg(p.norms + d);                 // layer 0 pre_sa_norm: the first consumer of x
+        store_parts(p.xparts, d, 0, s0 * w);
+        store_parts(p.xparts, d, 1, s1 * w);
     }
-    p.x[d] = make_float2(s0, s1);
+    const float q0 = warp_sum(s0 * s0), q1 = warp_sum(s1 * s1);
+    if (c.lane == 0) { c.misc->ssq_part[c.warp][0] = q0; c.misc->ssq_part[c.warp][1] = q1; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -901,6 +1023,15 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
         for (int i = tid; i < (int)(sizeof(CtaTable) / 4); i += kThreads) dst[i] = src[i];
     }
     __syncthreads();
+    if (tid < G_COUNT) {
+        GemmCfg& g = misc->gcfg[tid];
+        g.gc = misc->tab.gc[tid]; g.g0 = misc->tab.g0[tid]; g.K = p.Kdim[tid];
+        g.row_bytes = g.gc * 16;
+        g.rpc = g.gc > 0 ? min(kMaxKb * 16, (kSlotBytes / (g.gc * 16)) & ~15) : 16;
+        g.n_chunks = g.gc > 0 ? (g.K + g.rpc - 1) / g.rpc : 0;
+        g.n_mt = (g.gc + 1) >> 1;
+    }
+    __syncthreads();
 
     if (tid >= kConsumerThreads) {
         if (tid == kConsumerThreads) producer_loop(p, ring, misc);
@@ -918,6 +1049,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
         for (int s = p.stage_begin; s < p.stage_end; ++s) {
             int kind, layer;
             decode_stage(s, p.L, kind, layer);
+            c.tstamp = (p.timing != nullptr && blockIdx.x == 0 && tid == 0) ? p.timing + ((size_t)n * S + s) * 8 : nullptr;
+            if (c.tstamp) c.tstamp[0] = clock64();
             switch (kind) {
                 case S_EMBED: embed_stage(c, pos); break;
                 case S_SATTN: attn_stage<4, true>(c, layer, pos, slot); break;
@@ -926,7 +1059,12 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
                 default: gemm_stage(c, gemm_of_kind(kind), layer); break;
             }
             const bool last = (n == p.n_steps - 1) && (s == p.stage_end - 1);
-            if (!last) grid_barrier(c);
+            const bool tm = p.timing != nullptr && blockIdx.x == 0 && tid == 0;
+            if (tm) p.timing[((size_t)n * S + s) * 8 + 4] = clock64();
+            const bool publish = kind == S_EMBED || kind == S_SO || kind == S_CO || kind == S_WO;
+            if (!last) grid_barrier(c, publish);
+            else if (publish) { consumer_sync(); if (tid == 0) publish_ssq_partials(c); }
+            if (tm) p.timing[((size_t)n * S + s) * 8 + 5] = clock64();
             if (tid == 0) st_release_cta_s32(&misc->stages_done, n * S + s + 1);
         }
     }

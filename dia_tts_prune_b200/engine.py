@@ -224,10 +224,18 @@ class DecodeEngine:
                                                 _stream(self.device)), "debug_read")
         return out if which in (_lib.BUF_LOGITS, _lib.BUF_PRED) else out.t().contiguous()   # -> [2, n]
 
-    def write_buffer(self, which: int, rows_2xN: torch.Tensor) -> None:
-        t = rows_2xN.to("cpu", torch.float32).t().contiguous()
-        _lib.check(self.lib.dia_b200_debug_write(self._h, which, _ptr(t), t.numel() * 4, _stream(self.device)),
-                   "debug_write")
+    def enable_timing(self, on: bool = True) -> None:
+        _lib.check(self.lib.dia_b200_debug_enable_timing(self._h, 1 if on else 0), "debug_enable_timing")
+
+    def read_timing(self, n_steps: int) -> torch.Tensor:
+        """int64 [n_steps, stages, 8] SM-clock stamps of CTA 0, thread 0: 0 stage start, 1 input vector
+        loaded, 2 main loop done, 3 cross-warp reduce done, 4 work done, 5 grid barrier passed, 6 first ring
+        slot ready (GEMM stages only)."""
+        S = 8 * self.L + 3
+        out = torch.empty((16, S, 8), dtype=torch.int64)
+        _lib.check(self.lib.dia_b200_debug_read(self._h, _lib.BUF_TIMING, _ptr(out), out.numel() * 8,
+                                                _stream(self.device)), "debug_read")
+        return out[:n_steps]
 
 
 def launch_count() -> int:

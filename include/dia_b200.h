@@ -187,14 +187,16 @@ enum dia_b200_buffer {
     DIA_B200_BUF_CATTN = 4,  /* [cross_heads*128][2]                     */
     DIA_B200_BUF_HIDDEN = 5, /* [n_hidden][2]                            */
     DIA_B200_BUF_LOGITS = 6, /* [2][C][V]                                */
-    DIA_B200_BUF_PRED = 7    /* int32 [C] raw prediction of the last step */
+    DIA_B200_BUF_PRED = 7,   /* int32 [C] raw prediction of the last step */
+    DIA_B200_BUF_TIMING = 8  /* int64 [16][stages][8]: SM-clock stamps of CTA 0 inside each stage */
 };
 /* stage ids inside one decode step: 0 = embed, 1+8*l+{0..7} = qkv, self-attn, self-o, cross-q,
  * cross-attn, cross-o, mlp-in, mlp-out of layer l, 1+8*L = logits, 2+8*L = sample */
 int dia_b200_debug_run_stages(dia_b200_engine *e, const int32_t *tokens, int stage_begin, int stage_end, int pos,
                               int slot, int cooperative, void *stream);
+/* per-stage timestamps for launches of <= 16 steps (profiling aid; a persistent kernel is opaque to ncu) */
+int dia_b200_debug_enable_timing(dia_b200_engine *e, int enable);
 int dia_b200_debug_read(dia_b200_engine *e, int which, void *host_dst, size_t nbytes, void *stream);
-int dia_b200_debug_write(dia_b200_engine *e, int which, const void *host_src, size_t nbytes, void *stream);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 int64_t dia_b200_launch_count(void);
 

@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Per-stage time breakdown of the persistent step kernel (in-kernel SM-clock stamps of CTA 0).
+
+    python tools/stage_profile.py [--slot 0] [--steps 8] [--tiny]
+Prints, per stage kind, the mean work time and the mean barrier wait of CTA 0, in microseconds.
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from dia_tts_prune_b200 import synthetic as SY                              # noqa: E402
+from dia_tts_prune_b200.config import dia_1_6b_config, tiny_config          # noqa: E402
+from dia_tts_prune_b200.model import Dia                                    # noqa: E402
+
+NAMES = ["qkv", "sattn", "so", "cq", "cattn", "co", "wi", "wo"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--slot", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--tiny", action="store_true")
+    ap.add_argument("--greedy", action="store_true")
+    a = ap.parse_args()
+    cfg = tiny_config() if a.tiny else dia_1_6b_config()
+    dev = torch.device("cuda:0")
+    dia = Dia(cfg, "float32", torch.device("cpu"))
+    SY.init_synthetic_(dia.model.named_parameters(), 5)
+    with torch.no_grad():
+        dia.model.decoder.logits_dense.weight[:, 0, 1024] = 0.0
+    SY.cast_dense_kernels_(dia.model, torch.bfloat16)
+    dia.device = dev
+    dia.model.to(dev).eval()
+    with torch.inference_mode():
+        st, out = dia._prepare_generation(dia._effective_text(SY.DEFAULT_TRANSCRIPT, None), None, False)
+        eng = dia.model.decoder._engine_for(st)
+        mhz = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 1965
+        L = cfg.model.decoder.n_layer
+        S = 8 * L + 3
+        # fill the grid so that any starting slot has a valid input row
+        out.generated_tokens[: a.slot + a.steps + 2] = 7
+        for it in range(2):
+            eng.enable_timing(it == 1)
+            eng.generate_begin(out.generated_tokens, a.slot + 1, a.slot, cfg.data.audio_length, 3.0,
+                               0.0 if a.greedy else 1.3, 0.95, 35, 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.generate_steps(a.steps)
+            e1.record()
+            torch.cuda.synchronize()
+        t = eng.read_timing(a.steps).double()
+        print(f"launch of {a.steps} steps from slot {a.slot}: {e0.elapsed_time(e1) * 1000 / a.steps:.1f} us/step (event)")
+        t = t[1:]                                                      # skip the cold first step
+        us = 1.0 / mhz
+        tot = ((t[:, -1, 5] - t[:, 0, 0]).mean()) * us
+        print(f"clock {mhz} MHz; per-step total from stamps {tot:.1f} us (steps 1..{a.steps - 1})")
+        print(f"{'stage':8s} {'prod lead':>9s} {'load x':>7s} {'1st slot':>8s} {'loop':>7s} {'reduce':>7s} {'epi':>7s} {'work':>7s} "
+              f"{'barrier':>8s} {'x/step':>6s} {'total':>8s}")
+        rows = [("embed", [0])] + [(NAMES[j], [1 + 8 * l + j for l in range(L)]) for j in range(8)] + \
+               [("logits", [8 * L + 1]), ("sample", [8 * L + 2])]
+        for name, idx in rows:
+            x = t[:, idx, :]
+            d = lambda i, j: ((x[..., i] - x[..., j]).mean().item() * us)     # noqa: E731
+            gemm = name not in ("embed", "sattn", "cattn", "sample")
+            work, bar = d(4, 0), d(5, 4)
+            if gemm:
+                print(f"{name:8s} {d(0, 7):9.2f} {d(1, 0):7.2f} {d(6, 1):8.2f} {d(2, 1):7.2f} {d(3, 2):7.2f} {d(4, 3):7.2f} {work:7.2f} "
+                      f"{bar:8.2f} {len(idx):6d} {(work + bar) * len(idx):8.1f}")
+            else:
+                print(f"{name:8s} {'':9s} {'':7s} {'':8s} {'':7s} {'':7s} {'':7s} {work:7.2f} {bar:8.2f} {len(idx):6d} "
+                      f"{(work + bar) * len(idx):8.1f}")
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,7 @@ from . import build as _build
 MAX_CHANNELS = 16
 
 # enum dia_b200_buffer
-BUF_X, BUF_QKV, BUF_ATTN, BUF_CQ, BUF_CATTN, BUF_HIDDEN, BUF_LOGITS, BUF_PRED, BUF_TIMING = range(9)
+BUF_X, BUF_LOGITS, BUF_PRED, BUF_TIMING, BUF_CTA_TIMING = 0, 6, 7, 8, 9
 E_OK, E_INVAL, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 
@@ -65,6 +65,7 @@ _SIGNATURES = {
     "dia_b200_build_revert_indices": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _vp]),
     "dia_b200_debug_run_stages": (_i, [_vp, _i32p, _i, _i, _i, _i, _i, _vp]),
     "dia_b200_debug_enable_timing": (_i, [_vp, _i]),
+    "dia_b200_debug_last_device_error": (_i, [_vp, C.POINTER(C.c_int32), _i]),
     "dia_b200_debug_read": (_i, [_vp, _i, _vp, C.c_size_t, _vp]),
 }
 

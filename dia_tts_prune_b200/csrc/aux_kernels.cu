@@ -95,51 +95,16 @@ cudaError_t launch_embed_sum(const float* emb, const int* tokens, int n_rows, in
 // ------------------------------------------------------------------------------------------
 // [2][D] rows <-> interleaved [D][2]
 // ------------------------------------------------------------------------------------------
-// API rows [2][D] -> engine form: interleaved fp32 [D][2], the bf16-split MMA fragments of x * w_norm,
-// and sum(x^2) per row (published in slot 0 of the per-CTA partials, the other slots zeroed)
-__device__ __forceinline__ void xprep_split3(float x, unsigned short (&t)[3]) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(h);
-    const __nv_bfloat16 l = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(l);
-    t[0] = __bfloat16_as_ushort(h); t[1] = __bfloat16_as_ushort(l);
-    t[2] = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
-}
-__global__ void xprep_kernel(const float* __restrict__ rows, float2* __restrict__ il, unsigned short* __restrict__ parts,
-                             float* __restrict__ ssq, const float* __restrict__ normw, int D, int G) {
-    __shared__ float red[2][32];
-    float s0 = 0.f, s1 = 0.f;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        const float a = rows[d], b = rows[D + d], w = normw[d];
-        il[d] = make_float2(a, b);
-        s0 = fmaf(a, a, s0); s1 = fmaf(b, b, s1);
-        const int kk = d & 15;
-        unsigned short* base = parts + (size_t)(d >> 4) * 128 + ((kk & 7) >> 1) * 4 + (kk & 1) + ((kk >> 3) << 1);
-        unsigned short t[3];
-        xprep_split3(a * w, t);
-        for (int i = 0; i < 3; ++i) base[i * 16] = t[i];
-        xprep_split3(b * w, t);
-        for (int i = 0; i < 3; ++i) base[(4 + i) * 16] = t[i];
-    }
-    s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) ssq[i] = 0.f;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t0 = 0.f, t1 = 0.f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t0 += red[0][w]; t1 += red[1][w]; }
-        ssq[0] = t0;
-        ssq[G] = t1;
-    }
+__global__ void interleave_kernel(const float* __restrict__ rows, float2* __restrict__ il, int D) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) il[d] = make_float2(rows[d], rows[D + d]);
 }
 __global__ void deinterleave_kernel(const float2* __restrict__ il, float* __restrict__ rows, int D) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d < D) { const float2 v = il[d]; rows[d] = v.x; rows[D + d] = v.y; }
 }
-cudaError_t launch_xprep(const float* x_rows, float2* x_il, unsigned short* xparts, float* ssq, const float* normw,
-                         int D, int G, cudaStream_t st) {
-    xprep_kernel<<<1, 512, 0, st>>>(x_rows, x_il, xparts, ssq, normw, D, G);
+cudaError_t launch_interleave(const float* x_rows, float2* x_il, int D, cudaStream_t st) {
+    interleave_kernel<<<(D + 255) / 256, 256, 0, st>>>(x_rows, x_il, D);
     return cudaGetLastError();
 }
 cudaError_t launch_deinterleave(const float2* x_il, float* x_rows, int D, cudaStream_t st) {

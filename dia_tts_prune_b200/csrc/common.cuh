@@ -15,13 +15,15 @@ namespace dia {
 constexpr int kHeadDim = 128;
 constexpr int kConsumerWarps = 8;                       // math warps per CTA
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = kConsumerThreads + 32;         // + 1 producer warp (one elected lane issues copies)
+constexpr int kProducerWarp = 9;                        // on another scheduler than warp 0 (warp 8 exits at once)
+constexpr int kThreads = (kProducerWarp + 1) * 32;      // 8 math warps + the producer warp (one elected lane issues copies)
 constexpr int kSlotBytes = 8192;                        // one ring slot = one bulk copy
-constexpr int kNumSlots = 19;                           // 152 KB of weights / KV in flight per SM
-constexpr int kXsBytes = 65536;                         // per-warp B-fragment staging (GEMM), attention / sampler scratch
-constexpr int kRedBytes = 8192;                         // cross-warp reduction scratch
+constexpr int kNumSlots = 20;                           // 160 KB of weights / KV in flight per SM
+constexpr int kBStageBytes = 4096;                      // per-warp B-fragment staging of one ring slot (16 k-blocks)
+constexpr int kXsBytes = 49152;                         // B staging (GEMM), attention / sampler scratch
+constexpr int kRedBytes = 8192;                         // cross-warp reduction scratch (two of these, ping-pong)
 constexpr int kMiscBytes = 1024;                        // mbarriers + small shared scalars
-constexpr int kSmemBytes = kNumSlots * kSlotBytes + kXsBytes + kRedBytes + kMiscBytes;
+constexpr int kSmemBytes = kNumSlots * kSlotBytes + kXsBytes + 2 * kRedBytes + kMiscBytes;
 constexpr unsigned long long kWatchdogCycles = 4000000000ull;   // ~2 s at 1.9 GHz
 
 enum DeviceError : int {
@@ -31,7 +33,9 @@ enum DeviceError : int {
     kErrEmptyBarrierTimeout = 3,
     kErrStepDoneTimeout = 4,
     kErrBadState = 5,
+    kErrFlagTimeout = 6,
 };
+constexpr unsigned kMaxSpins = 1u << 23;                        // polls of one flag word before the watchdog fires
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -58,17 +62,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait; on timeout record `code` and trap (kills the launch, never hangs the box)
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    const unsigned long long t0 = clock64();
+static __device__ __noinline__ void ll_timeout(int* err, int code, unsigned info = 0);
+__device__ __forceinline__ void ll_check_abort(int* err, unsigned spins, int site, unsigned info);
+// the same with a suspend-time hint: the warp sleeps in hardware until the phase completes or ~`ns` elapse,
+// instead of burning the issue slots of the scheduler it shares with two math warps
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait; on timeout record `code` and trap (kills the launch, never hangs the box).  The slow path is
+// out of line and sleeps in hardware between polls.
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* err, int code, unsigned info) {
+    unsigned polls = 0;
+#ifdef DIA_NO_WAIT_HINT
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > kWatchdogCycles) {
-            *reinterpret_cast<volatile int*>(err) = code;
-            __threadfence_system();
-            __trap();
-        }
+#else
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+#endif
+        if (++polls > 4000000u) ll_timeout(err, code, info);   // seconds, even if a poll returns in a microsecond
+        ll_check_abort(err, polls, 100 + code, info);
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code, unsigned info = 0) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err, code, info);
 }
 
 // ---- bulk async copy global -> shared (TMA engine, no tensor map needed for 1-D) -------------
@@ -132,6 +155,70 @@ __device__ __forceinline__ int ld_acquire_cta_s32(const int* p) {
 }
 __device__ __forceinline__ void st_release_cta_s32(int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// ---- flag-in-data words ("LL" protocol): one aligned 8-byte word carries payload + sequence flag, is
+// written with one strong store and read with one strong load, so a reader that sees the flag has the
+// payload - no fence, no barrier, no separate counter between a producing and a consuming CTA.
+__device__ __forceinline__ void ll_st(unsigned long long* p, uint32_t lo, uint32_t hi) {
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint2 ll_ld(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    uint2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r.x), "=r"(r.y) : "l"(v));
+    return r;
+}
+// two adjacent words with one 16-byte load (each 8-byte half carries its own flag)
+__device__ __forceinline__ uint4 ll_ld2(const void* p) {
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    uint4 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r.x), "=r"(r.y) : "l"(a));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r.z), "=r"(r.w) : "l"(b));
+    return r;
+}
+// Watchdog plumbing.  `err` is mapped pinned HOST memory (readable after the context died):
+//   [0..7]  first failure: code, block, thread, info, 4 site-specific words
+//   [16 + 2 * (block * 10 + warp)]  where every other waiting warp was stuck when it noticed the failure
+static __device__ __noinline__ void ll_report(int* err, int site, unsigned info) {
+    volatile int* e = reinterpret_cast<volatile int*>(err);
+    const int slot = 16 + (blockIdx.x * 10 + (threadIdx.x >> 5)) * 2;
+    e[slot] = site;
+    e[slot + 1] = (int)info;
+    __threadfence_system();
+}
+static __device__ __noinline__ void ll_timeout(int* err, int code, unsigned info) {
+    volatile int* e = reinterpret_cast<volatile int*>(err);
+    if (e[0] == 0) { e[0] = code; e[1] = blockIdx.x; e[2] = threadIdx.x; e[3] = (int)info; }
+    ll_report(err, code, info);
+    for (int i = 0; i < 100; ++i) __nanosleep(1000000);         // let the other waiters report before the context dies
+    __trap();
+}
+// called from spin loops every few thousand polls: has somebody else's watchdog fired?
+__device__ __forceinline__ void ll_check_abort(int* err, unsigned spins, int site, unsigned info) {
+    if ((spins & 0x3fffu) == 0x3fffu && reinterpret_cast<volatile int*>(err)[0] != 0) {
+        ll_report(err, site, info);
+        for (;;) __nanosleep(1000000);
+    }
+}
+// one thread spins on one word until its 32-bit flag matches; returns the payload
+static __device__ __noinline__ uint32_t ll_wait32_slow(const unsigned long long* p, uint32_t flag, int* err) {
+    unsigned spins = 0;
+    uint2 w = ll_ld(p);
+    while (w.y != flag) {
+        if (++spins > kMaxSpins) ll_timeout(err, kErrFlagTimeout + 3, flag);
+        ll_check_abort(err, spins, 100 + kErrFlagTimeout + 3, flag);
+        w = ll_ld(p);
+    }
+    return w.x;
+}
+__device__ __forceinline__ uint32_t ll_wait32(const unsigned long long* p, uint32_t flag, int* err) {
+    const uint2 w = ll_ld(p);
+    return w.y == flag ? w.x : ll_wait32_slow(p, flag, err);
 }
 
 // ---- packed fp32x2 math (Blackwell FFMA2) -------------------------------------------------------

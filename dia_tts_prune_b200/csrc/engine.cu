@@ -18,6 +18,7 @@ using namespace dia;
 namespace {
 
 constexpr int kTimingSteps = 16;
+constexpr int kErrWords = 16 + 2 * 10 * 160;        // watchdog record + one (site, info) pair per warp of every CTA
 thread_local std::string g_last_cuda_error;
 std::atomic<long long> g_launches{0};
 
@@ -42,6 +43,7 @@ struct dia_b200_engine {
     int Vpad = 0;
     int n_groups[G_COUNT]{};
     int Kdim[G_COUNT]{};
+    int tclass[G_COUNT]{};
     std::vector<CtaTable> tab;
     std::vector<int> owner[G_COUNT], local[G_COUNT];
     size_t stream_bytes = 0;          // allocation size (with alignment padding)
@@ -58,19 +60,16 @@ struct dia_b200_engine {
     float* d_rope_cos = nullptr;
     int n_pos = 0;
     float** d_ptrs = nullptr;         // [4][L] self_k, self_v, cross_k, cross_v
-    float2 *d_x = nullptr, *d_qkv = nullptr, *d_attn = nullptr, *d_cq = nullptr, *d_cattn = nullptr,
-           *d_hidden = nullptr;
+    float2* d_x = nullptr;
     float* d_logits = nullptr;
-    unsigned short *d_xparts = nullptr, *d_attn_parts = nullptr, *d_cattn_parts = nullptr, *d_hidden_parts = nullptr;
-    float* d_ssq = nullptr;
-    float *d_sa_part = nullptr, *d_ca_part = nullptr;
-    unsigned* d_pair_cnt = nullptr;
-    unsigned* d_grid_bar = nullptr;
-    int* d_err = nullptr;
+    unsigned long long* d_ll = nullptr;   // the flag-in-data region (zeroed before every launch)
+    size_t ll_bytes = 0;
+    int* d_err = nullptr;             // device alias of h_err (mapped pinned memory: survives a trapped kernel)
     int* d_pred = nullptr;
     int* d_tokens = nullptr;          // staging [2][C]
     GenState* d_gs = nullptr;
-    long long* d_timing = nullptr;    // [kTimingSteps][S][2], debug only
+    long long* d_timing = nullptr;    // [kTimingSteps][S][8], debug only
+    unsigned long long* d_cta_timing = nullptr;   // [S][G], debug only
     bool timing_on = false;
     // pinned host staging
     float** h_ptrs = nullptr;
@@ -80,10 +79,12 @@ struct dia_b200_engine {
     bool weights_loaded = false, caches_bound = false, rope_set = false, gen_active = false;
     int text_len = 0;
     int sa_nsplit = 1, ca_nsplit = 1;
+    int n_res = 0;                    // CTAs [0, n_res) own residual-stream columns
     // generate loop
     dia_b200_gen_params gp{};
     int* gen_grid = nullptr;
     int gen_pos = 0, gen_slot = 0;
+    long long gen_steps = 0;          // decode steps launched since generate_begin (RNG draw index)
 };
 
 namespace {
@@ -95,9 +96,7 @@ int validate_shape(const dia_b200_shape& s) {
         return DIA_B200_EINVAL;
     if (s.q_heads != 4 * s.kv_heads) return DIA_B200_EUNSUPPORTED;       // kernels are built for GQA 4:1
     if (s.d_model % 16 || s.n_hidden % 16) return DIA_B200_EINVAL;                // MMA k-blocks of 16 rows
-    if (s.d_model > 8192 || s.n_hidden > 8192 || s.q_heads * kHeadDim > 8192 || s.cross_heads * kHeadDim > 8192)
-        return DIA_B200_EUNSUPPORTED;                                     // activation vector must fit 64 KB of smem
-    if (s.channels * s.vocab * 4 > kXsBytes) return DIA_B200_EUNSUPPORTED;
+    if (s.vocab > 5 * kConsumerThreads) return DIA_B200_EUNSUPPORTED;     // sampler: <= 5 entries of a channel per thread
     return DIA_B200_OK;
 }
 
@@ -106,30 +105,41 @@ void fill_params(const dia_b200_engine* e, StepParams& p) {
     const dia_b200_shape& s = e->shape;
     p.L = s.n_layer; p.D = s.d_model; p.F = s.n_hidden; p.Hq = s.q_heads; p.Hkv = s.kv_heads; p.Hc = s.cross_heads;
     p.C = s.channels; p.V = s.vocab; p.Vpad = e->Vpad; p.Lmax = s.max_audio_len; p.Smax = s.max_text_len;
-    for (int i = 0; i < G_COUNT; ++i) p.Kdim[i] = e->Kdim[i];
-    p.eps = s.norm_eps; p.G = e->G; p.sa_nsplit = e->sa_nsplit; p.ca_nsplit = e->ca_nsplit;
+    for (int i = 0; i < G_COUNT; ++i) { p.Kdim[i] = e->Kdim[i]; p.tclass[i] = e->tclass[i]; }
+    p.eps = s.norm_eps; p.G = e->G; p.n_res = e->n_res; p.sa_nsplit = e->sa_nsplit; p.ca_nsplit = e->ca_nsplit;
     p.wstream = e->d_wstream; p.cta_tab = e->d_tab; p.emb = e->d_emb; p.norms = e->d_norms;
     p.rope_sin = e->d_rope_sin; p.rope_cos = e->d_rope_cos; p.n_pos = e->n_pos;
     p.self_k = e->d_ptrs; p.self_v = e->d_ptrs + s.n_layer;
     p.cross_k = const_cast<const float* const*>(e->d_ptrs + 2 * s.n_layer);
     p.cross_v = const_cast<const float* const*>(e->d_ptrs + 3 * s.n_layer);
     p.text_len = e->text_len;
-    p.x = e->d_x; p.qkv = e->d_qkv; p.attn = e->d_attn; p.cq = e->d_cq; p.cattn = e->d_cattn; p.hidden = e->d_hidden;
-    p.xparts = e->d_xparts; p.attn_parts = e->d_attn_parts; p.cattn_parts = e->d_cattn_parts;
-    p.hidden_parts = e->d_hidden_parts; p.ssq = e->d_ssq;
-    p.logits = e->d_logits; p.sa_part = e->d_sa_part; p.ca_part = e->d_ca_part; p.pair_cnt = e->d_pair_cnt;
-    p.grid_bar = e->d_grid_bar; p.err = e->d_err;
+    p.x = e->d_x;
+    p.logits = e->d_logits;
+    ll_layout(p, &p, e->d_ll);
+    p.err = e->d_err;
     p.n_steps = 1;
     p.cfg_scale = 3.0f; p.temperature = 0.0f; p.top_p = 0.95f; p.top_k = 35; p.max_tokens = s.max_audio_len;
     p.eos = s.eos_value; p.pad = s.pad_value; p.bos = s.bos_value;
     for (int i = 0; i < DIA_B200_MAX_CHANNELS; ++i) p.delay[i] = s.delay_pattern[i];
     p.pred_out = e->d_pred;
     p.timing = e->timing_on ? e->d_timing : nullptr;
+    p.cta_timing = e->timing_on ? e->d_cta_timing : nullptr;
+}
+
+// stage ranges a launch may cover: it starts at the embedding, a layer or the logits head (the residual stream is
+// handed over in d_x) and ends after the embedding, a layer, the logits head or the sampler
+bool stage_range_ok(const dia_b200_engine* e, int b, int en) {
+    const int L = e->shape.n_layer;
+    auto boundary = [&](int s) { return s == 0 || s == 8 * L + 2 || s == 8 * L + 3 || (s >= 1 && s <= 8 * L + 1 && (s - 1) % 8 == 0); };
+    return b >= 0 && b < en && en <= 8 * L + 3 && boundary(b) && b != 8 * L + 3 && b != 8 * L + 2 && boundary(en);
 }
 
 int run_stages(dia_b200_engine* e, StepParams& p, bool cooperative, cudaStream_t st) {
-    if (p.n_steps > kTimingSteps) p.timing = nullptr;
-    CK(cudaMemsetAsync(e->d_grid_bar, 0, sizeof(unsigned), st));
+    if (!stage_range_ok(e, p.stage_begin, p.stage_end)) return DIA_B200_EINVAL;
+    if (p.n_steps > kTimingSteps) { p.timing = nullptr; p.cta_timing = nullptr; }
+    // sequence flags restart at 1 in every launch: 16-bit flags bound the stages of one launch
+    if ((long long)p.n_steps * (8 * p.L + 3) + 1 > 65535) return DIA_B200_EINVAL;
+    CK(cudaMemsetAsync(e->d_ll, 0, e->ll_bytes, st));
     CK(launch_step_kernel(p, cooperative, st));
     g_launches++;
     return DIA_B200_OK;
@@ -191,26 +201,36 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
         int per = (s.max_audio_len + e->sa_nsplit - 1) / e->sa_nsplit;
         int perc = (s.max_text_len + e->ca_nsplit - 1) / e->ca_nsplit;
         if (((per + 15) & ~15) > 1024 || ((perc + 15) & ~15) > 1024) { delete e; return DIA_B200_EUNSUPPORTED; }
+        if ((s.max_text_len + 127) / 128 > e->ca_nsplit) { delete e; return DIA_B200_EUNSUPPORTED; }
     }
 
     // ---- column-group partition of every GEMM over the CTAs --------------------------------
+    // The three residual GEMMs (self-o, cross-o, mlp-out) share ONE partition, so each element of the residual
+    // stream has a fixed owner thread and never leaves its register; the other GEMMs are balanced against the
+    // bytes a CTA already streams per layer.
     const int nq = s.q_heads * kHeadDim, nkv = s.kv_heads * kHeadDim, nc = s.cross_heads * kHeadDim;
     const int units[G_COUNT] = {(nq + 2 * nkv) / 8, s.d_model / 8, nc / 8, s.d_model / 8, s.n_hidden / 8,
                                 s.d_model / 8, s.channels * e->Vpad / 8};
     const int mult[G_COUNT] = {1, 1, 1, 1, 2, 1, 1};    // mlp-in: a unit is a (gate, up) pair of groups
     const int kd[G_COUNT] = {s.d_model, nq, s.d_model, nc, s.d_model, s.n_hidden, s.d_model};
+    if (s.d_model / 8 > 2 * G) { delete e; return DIA_B200_EUNSUPPORTED; }   // residual columns: one MMA tile per CTA
     e->tab.assign(G, CtaTable{});
     std::vector<long long> load(G, 0);                   // bytes per layer assigned so far (for balancing)
-    for (int t = 0; t < G_COUNT; ++t) {
+    const int order_t[G_COUNT] = {G_SO, G_CO, G_WO, G_WI, G_QKV, G_CQ, G_LOGITS};
+    for (int oi = 0; oi < G_COUNT; ++oi) {
+        const int t = order_t[oi];
         e->Kdim[t] = kd[t];
         e->n_groups[t] = units[t] * mult[t];
-        const int base = units[t] / G, extra = units[t] % G;
-        // the CTAs with the least bytes so far take the `extra` units
-        std::vector<int> order(G);
-        for (int c = 0; c < G; ++c) order[c] = c;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return load[a] < load[b]; });
-        std::vector<int> cnt(G, base);
-        for (int i = 0; i < extra; ++i) cnt[order[i]]++;
+        std::vector<int> cnt(G, units[t] / G);
+        if (t == G_CO || t == G_WO) {
+            for (int c = 0; c < G; ++c) cnt[c] = e->tab[c].gc[G_SO];
+        } else {
+            // the CTAs with the least bytes so far take the `extra` units
+            std::vector<int> order(G);
+            for (int c = 0; c < G; ++c) order[c] = c;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return load[a] < load[b]; });
+            for (int i = 0; i < units[t] % G; ++i) cnt[order[i]]++;
+        }
         int g0 = 0;
         e->owner[t].resize(e->n_groups[t]);
         e->local[t].resize(e->n_groups[t]);
@@ -221,9 +241,21 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
             e->tab[c].gc[t] = gc;
             for (int i = 0; i < gc; ++i) { e->owner[t][g0 + i] = c; e->local[t][g0 + i] = i; }
             g0 += gc;
-            load[c] += (long long)gc * 16 * kd[t] * (t == G_LOGITS ? 1 : 1);
+            if (t != G_LOGITS) load[c] += (long long)gc * 16 * kd[t];
         }
     }
+    for (int t = 0; t < G_COUNT; ++t) {
+        int mx = 1;
+        for (int c = 0; c < G; ++c) mx = std::max(mx, (e->tab[c].gc[t] + 1) / 2);
+        e->tclass[t] = mx <= 1 ? 1 : mx <= 2 ? 2 : mx <= 4 ? 4 : 8;
+    }
+    for (int c = 0; c < G; ++c) {
+        if (e->tab[c].gc[G_SO] > 0) {
+            if (c != e->n_res) { delete e; return DIA_B200_EUNSUPPORTED; }   // owners must be CTAs 0 .. n_res-1
+            e->n_res = c + 1;
+        }
+    }
+    if (e->n_res > 160) { delete e; return DIA_B200_EUNSUPPORTED; }          // sum(x^2) partials: 5 per lane of one warp
     unsigned long long off = 0;
     for (int c = 0; c < G; ++c) {
         CtaTable& t = e->tab[c];
@@ -261,33 +293,29 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     ALLOC(e->d_norms, sizeof(float) * ((size_t)s.n_layer * 3 + 1) * D);
     ALLOC(e->d_ptrs, sizeof(float*) * 4 * s.n_layer);
     ALLOC(e->d_x, sizeof(float2) * D);
-    ALLOC(e->d_qkv, sizeof(float2) * (nq + 2 * nkv));
-    ALLOC(e->d_attn, sizeof(float2) * nq);
-    ALLOC(e->d_cq, sizeof(float2) * nc);
-    ALLOC(e->d_cattn, sizeof(float2) * nc);
-    ALLOC(e->d_hidden, sizeof(float2) * s.n_hidden);
     ALLOC(e->d_logits, sizeof(float) * 2 * s.channels * s.vocab);
-    ALLOC(e->d_xparts, (size_t)(s.d_model / 16) * 256);          // zero-filled: MMA columns 3 and 7 stay zero
-    ALLOC(e->d_attn_parts, (size_t)(nq / 16) * 256);
-    ALLOC(e->d_cattn_parts, (size_t)(nc / 16) * 256);            // row 0 (unconditional) is never written: exact zeros
-    ALLOC(e->d_hidden_parts, (size_t)(s.n_hidden / 16) * 256);
-    ALLOC(e->d_ssq, sizeof(float) * 2 * G);
-    ALLOC(e->d_sa_part, sizeof(float) * 2 * s.q_heads * e->sa_nsplit * 132);
-    ALLOC(e->d_ca_part, sizeof(float) * s.cross_heads * e->ca_nsplit * 132);
-    ALLOC(e->d_pair_cnt, sizeof(unsigned) * (2 * s.kv_heads + s.cross_heads));
-    ALLOC(e->d_grid_bar, sizeof(unsigned) * 4);
-    ALLOC(e->d_err, sizeof(int) * 4);
+    {
+        StepParams geom;
+        std::memset(&geom, 0, sizeof(geom));
+        geom.D = s.d_model; geom.F = s.n_hidden; geom.Hq = s.q_heads; geom.Hkv = s.kv_heads; geom.Hc = s.cross_heads;
+        geom.C = s.channels; geom.V = s.vocab; geom.G = G; geom.sa_nsplit = e->sa_nsplit; geom.ca_nsplit = e->ca_nsplit;
+        e->ll_bytes = ll_layout(geom, nullptr, nullptr);
+    }
+    ALLOC(e->d_ll, e->ll_bytes);
     ALLOC(e->d_pred, sizeof(int) * DIA_B200_MAX_CHANNELS);
     ALLOC(e->d_tokens, sizeof(int) * 2 * DIA_B200_MAX_CHANNELS);
     ALLOC(e->d_gs, sizeof(GenState));
     ALLOC(e->d_timing, sizeof(long long) * 8 * kTimingSteps * (8 * s.n_layer + 3));
+    ALLOC(e->d_cta_timing, sizeof(unsigned long long) * G * (8 * s.n_layer + 3));
 #undef ALLOC
     if (cudaMallocHost(reinterpret_cast<void**>(&e->h_ptrs), sizeof(float*) * 4 * s.n_layer) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&e->h_gs), sizeof(GenState)) != cudaSuccess ||
-        cudaMallocHost(reinterpret_cast<void**>(&e->h_err), sizeof(int) * 4) != cudaSuccess) {
+        cudaHostAlloc(reinterpret_cast<void**>(&e->h_err), sizeof(int) * kErrWords, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->d_err), e->h_err, 0) != cudaSuccess) {
         dia_b200_engine_destroy(e);
         return DIA_B200_ENOMEM;
     }
+    std::memset(e->h_err, 0, sizeof(int) * kErrWords);
     CK(cudaMemcpy(e->d_tab, e->tab.data(), sizeof(CtaTable) * G, cudaMemcpyHostToDevice));
     for (int t = 0; t < G_COUNT; ++t) {
         CK(cudaMemcpy(e->d_owner[t], e->owner[t].data(), sizeof(int) * e->n_groups[t], cudaMemcpyHostToDevice));
@@ -302,9 +330,7 @@ int dia_b200_engine_destroy(dia_b200_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     void* dev[] = {e->d_wstream, e->d_tab, e->d_emb, e->d_norms, e->d_rope_sin, e->d_rope_cos, e->d_ptrs, e->d_x,
-                   e->d_qkv, e->d_attn, e->d_cq, e->d_cattn, e->d_hidden, e->d_logits, e->d_sa_part, e->d_ca_part,
-                   e->d_pair_cnt, e->d_grid_bar, e->d_err, e->d_pred, e->d_tokens, e->d_gs, e->d_timing,
-                   e->d_xparts, e->d_attn_parts, e->d_cattn_parts, e->d_hidden_parts, e->d_ssq};
+                   e->d_logits, e->d_ll, e->d_pred, e->d_tokens, e->d_gs, e->d_timing, e->d_cta_timing};
     for (void* p : dev) if (p) cudaFree(p);
     for (int t = 0; t < G_COUNT; ++t) { if (e->d_owner[t]) cudaFree(e->d_owner[t]); if (e->d_local[t]) cudaFree(e->d_local[t]); }
     if (e->h_ptrs) cudaFreeHost(e->h_ptrs);
@@ -436,8 +462,7 @@ int dia_b200_decoder_layer_step(dia_b200_engine* e, int layer, const float* x_in
         return DIA_B200_EINVAL;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = S(stream);
-    CK(launch_xprep(x_in, e->d_x, e->d_xparts, e->d_ssq, e->d_norms + (size_t)layer * 3 * e->shape.d_model,
-                    e->shape.d_model, e->G, st));
+    CK(launch_interleave(x_in, e->d_x, e->shape.d_model, st));
     g_launches++;
     StepParams p;
     fill_params(e, p);
@@ -495,11 +520,12 @@ int dia_b200_generate_begin(dia_b200_engine* e, int32_t* grid, const dia_b200_ge
     e->h_gs->eos_countdown = -1;                       // :741
     e->h_gs->finished = (e->h_gs->dec_step >= gp->max_tokens - 1) ? 1 : 0;
     CK(cudaMemcpyAsync(e->d_gs, e->h_gs, sizeof(GenState), cudaMemcpyHostToDevice, S(stream)));
-    CK(cudaMemsetAsync(e->d_err, 0, sizeof(int), S(stream)));
+    std::memset(e->h_err, 0, sizeof(int) * kErrWords);         // the stream is idle (synchronised above)
     e->gp = *gp;
     e->gen_grid = grid;
     e->gen_pos = gp->prefill_step;                     // first iteration: cur = dec_step + 1
     e->gen_slot = gp->first_slot;                      // KVCache.current_idx after the (optional) prefill
+    e->gen_steps = 0;
     e->gen_active = true;
     return DIA_B200_OK;
 }
@@ -514,19 +540,25 @@ int dia_b200_generate_steps(dia_b200_engine* e, int n_steps, void* stream) {
     n_steps = std::min(n_steps, e->shape.max_audio_len - e->gen_pos);
     if (n_steps <= 0) return DIA_B200_OK;
     CK(cudaSetDevice(e->device));
-    StepParams p;
-    fill_params(e, p);
-    p.stage_begin = 0;
-    p.stage_end = 8 * p.L + 3;
-    p.n_steps = n_steps;
-    p.pos0 = e->gen_pos; p.slot0 = e->gen_slot;
-    p.grid = e->gen_grid; p.gs = e->d_gs;
-    p.cfg_scale = e->gp.cfg_scale; p.temperature = e->gp.temperature; p.top_p = e->gp.top_p; p.top_k = e->gp.top_k;
-    p.max_tokens = e->gp.max_tokens; p.seed = e->gp.seed;
-    rc = run_stages(e, p, true, S(stream));
-    if (rc) return rc;
-    e->gen_pos += n_steps;
-    e->gen_slot += n_steps;
+    const int max_per_launch = 65534 / (8 * e->shape.n_layer + 3);      // 16-bit sequence flags
+    while (n_steps > 0) {
+        const int n = std::min(n_steps, max_per_launch);
+        StepParams p;
+        fill_params(e, p);
+        p.stage_begin = 0;
+        p.stage_end = 8 * p.L + 3;
+        p.n_steps = n;
+        p.pos0 = e->gen_pos; p.slot0 = e->gen_slot;
+        p.grid = e->gen_grid; p.gs = e->d_gs;
+        p.cfg_scale = e->gp.cfg_scale; p.temperature = e->gp.temperature; p.top_p = e->gp.top_p; p.top_k = e->gp.top_k;
+        p.max_tokens = e->gp.max_tokens; p.seed = e->gp.seed; p.draw0 = (unsigned long long)e->gen_steps;
+        rc = run_stages(e, p, true, S(stream));
+        if (rc) return rc;
+        e->gen_pos += n;
+        e->gen_slot += n;
+        e->gen_steps += n;
+        n_steps -= n;
+    }
     return DIA_B200_OK;
 }
 
@@ -534,7 +566,6 @@ int dia_b200_generate_status(dia_b200_engine* e, dia_b200_gen_status* out, void*
     if (!e || !out) return DIA_B200_EINVAL;
     CK(cudaSetDevice(e->device));
     CK(cudaMemcpyAsync(e->h_gs, e->d_gs, sizeof(GenState), cudaMemcpyDeviceToHost, S(stream)));
-    CK(cudaMemcpyAsync(e->h_err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
     CK(cudaStreamSynchronize(S(stream)));
     out->dec_step = e->h_gs->dec_step;
     out->finished = e->h_gs->finished;
@@ -604,9 +635,7 @@ int dia_b200_debug_run_stages(dia_b200_engine* e, const int32_t* tokens, int sta
                               int slot, int cooperative, void* stream) {
     int rc = ready(e, true);
     if (rc) return rc;
-    const int S_total = 8 * e->shape.n_layer + 3;
-    if (stage_begin < 0 || stage_end > S_total || stage_begin >= stage_end) return DIA_B200_EINVAL;
-    if (!cooperative && stage_end - stage_begin != 1) return DIA_B200_EINVAL;   // no grid barrier without co-residency
+    if (!stage_range_ok(e, stage_begin, stage_end) || stage_end > 8 * e->shape.n_layer + 2) return DIA_B200_EINVAL;
     if (stage_begin == 0 && !tokens) return DIA_B200_EINVAL;
     CK(cudaSetDevice(e->device));
     StepParams p;
@@ -619,20 +648,20 @@ int dia_b200_debug_run_stages(dia_b200_engine* e, const int32_t* tokens, int sta
 
 static int buffer_of(dia_b200_engine* e, int which, void** ptr, size_t* bytes) {
     const dia_b200_shape& s = e->shape;
-    const size_t nq = (size_t)s.q_heads * kHeadDim, nkv = (size_t)s.kv_heads * kHeadDim,
-                 nc = (size_t)s.cross_heads * kHeadDim;
     switch (which) {
         case DIA_B200_BUF_X: *ptr = e->d_x; *bytes = 8 * (size_t)s.d_model; break;
-        case DIA_B200_BUF_QKV: *ptr = e->d_qkv; *bytes = 8 * (nq + 2 * nkv); break;
-        case DIA_B200_BUF_ATTN: *ptr = e->d_attn; *bytes = 8 * nq; break;
-        case DIA_B200_BUF_CQ: *ptr = e->d_cq; *bytes = 8 * nc; break;
-        case DIA_B200_BUF_CATTN: *ptr = e->d_cattn; *bytes = 8 * nc; break;
-        case DIA_B200_BUF_HIDDEN: *ptr = e->d_hidden; *bytes = 8 * (size_t)s.n_hidden; break;
+        case DIA_B200_BUF_CTA_TIMING: *ptr = e->d_cta_timing; *bytes = 8 * (size_t)e->G * (8 * s.n_layer + 3); break;
         case DIA_B200_BUF_LOGITS: *ptr = e->d_logits; *bytes = 4 * 2 * (size_t)s.channels * s.vocab; break;
         case DIA_B200_BUF_PRED: *ptr = e->d_pred; *bytes = 4 * (size_t)s.channels; break;
         case DIA_B200_BUF_TIMING: *ptr = e->d_timing; *bytes = 64 * (size_t)kTimingSteps * (8 * s.n_layer + 3); break;
         default: return DIA_B200_EINVAL;
     }
+    return DIA_B200_OK;
+}
+
+int dia_b200_debug_last_device_error(dia_b200_engine* e, int32_t* out, int n_words) {
+    if (!e || !out || n_words < 0) return DIA_B200_EINVAL;
+    for (int i = 0; i < n_words && i < kErrWords; ++i) out[i] = reinterpret_cast<volatile int*>(e->h_err)[i];
     return DIA_B200_OK;
 }
 

@@ -44,8 +44,10 @@ struct StepParams {
     // geometry
     int L, D, F, Hq, Hkv, Hc, C, V, Vpad, Lmax, Smax;
     int Kdim[G_COUNT];                 // contraction length per GEMM family
+    int tclass[G_COUNT];               // MMA tiles every CTA computes per k-block: 1, 2, 4 or 8 (>= its real tiles)
     float eps;
     int G;                             // CTAs the tables were built for
+    int n_res;                         // CTAs [0, n_res) own columns of the residual stream (and publish sum(x^2))
     int sa_nsplit, ca_nsplit;          // max key splits per (row, kv head) / per cross head
     // weights
     const unsigned char* wstream;
@@ -61,24 +63,23 @@ struct StepParams {
     const float* const* cross_k;
     const float* const* cross_v;
     int text_len;
-    // scratch (all fp32; vectors interleaved [n][2] = (uncond row, cond row))
-    float2* x;
-    float2* qkv;
-    float2* attn;
-    float2* cq;
-    float2* cattn;
-    float2* hidden;
+    // plain buffers at the launch boundary
+    float2* x;                         // residual stream, interleaved [D][2] (read when stage_begin > 0, always written)
     float* logits;                     // [2][C][V]
-    // the same vectors as MMA B fragments: bf16 hi/lo/lo2 split, [k/16][8 cols][4 kq][4] (see step_kernel.cu)
-    unsigned short* xparts;            // x * w_norm of the next consumer
-    unsigned short* attn_parts;
-    unsigned short* cattn_parts;
-    unsigned short* hidden_parts;
-    float* ssq;                        // [2][G] per-CTA partial sums of x^2 (for the consumer's RMSNorm)
-    float* sa_part;                    // [2*Hq][sa_nsplit][132]
-    float* ca_part;                    // [Hc][ca_nsplit][132]
-    unsigned* pair_cnt;                // last-arriver counters, [2*Hkv + Hc]
-    unsigned* grid_bar;                // grid barrier counter (zeroed before each launch)
+    // flag-in-data buffers (zeroed before every launch; see step_kernel.cu).  Activation vectors feeding a GEMM
+    // are stored as [k/16][2 rows][16] words of (bf16 hi, lo, lo2, flag16); the rest as (fp32, flag32).
+    unsigned long long* ll_x;          // RMSNorm-weighted residual stream for the next projection   [D]
+    unsigned long long* ll_attn;       // self-attention output                                     [Hq*128]
+    unsigned long long* ll_cattn;      // cross-attention output (row 0 = exact zeros)             [Hc*128]
+    unsigned long long* ll_hidden;     // silu(gate) * up                                           [F]
+    unsigned long long* ll_qkv;        // [(Hq + 2 Hkv) * 128][2]
+    unsigned long long* ll_cq;         // [Hc * 128][2]
+    unsigned long long* ll_ssq;        // [G][2] per-CTA partial sums of x^2 (for the consumer's RMSNorm)
+    unsigned long long* ll_sa_part;    // [2*Hkv][sa_nsplit][4][132] split-KV partials (m, l, -, -, o[128])
+    unsigned long long* ll_ca_part;    // [Hc][ca_nsplit][132]
+    unsigned long long* ll_glog;       // [C][V] guided + masked logits
+    unsigned long long* ll_pred;       // [C] raw prediction per channel
+    unsigned long long* ll_tok;        // [C] input tokens of the next step
     int* err;
     // run control
     int stage_begin, stage_end;        // stages of a step to execute, [begin, end)
@@ -92,11 +93,12 @@ struct StepParams {
     int top_k;
     int max_tokens;
     unsigned long long seed;
+    unsigned long long draw0;          // RNG draw index of the first step of this launch
     int eos, pad, bos;
     int delay[DIA_B200_MAX_CHANNELS];
     int* pred_out;                     // [C] raw prediction of the last executed step
-    float* probs_out;                  // optional [C][V]
     long long* timing;                 // optional [n_steps][S][8] clock64 stamps of CTA 0 (see tools/stage_profile.py)
+    unsigned long long* cta_timing;    // optional [S][G] globaltimer at the end of each stage of step 1, per CTA
 };
 
 // ---- launchers (each returns the cudaError_t of the launch) --------------------------------
@@ -104,6 +106,7 @@ cudaError_t launch_step_kernel(const StepParams& p, bool cooperative, cudaStream
 int step_kernel_smem_bytes();
 cudaError_t launch_head_sample(const StepParams& p, const float* logits, unsigned long long draw, int* pred,
                                float* probs, cudaStream_t st);
+size_t ll_layout(const StepParams& geom, StepParams* out, unsigned long long* base);   // carve the LL region
 struct RepackArgs {
     const void* src[3];     // QKV: q, k, v kernels; otherwise src[0]
     int src_bf16;
@@ -120,8 +123,7 @@ struct RepackArgs {
 cudaError_t launch_repack(const RepackArgs& a, cudaStream_t st);
 cudaError_t launch_embed_sum(const float* emb, const int* tokens, int n_rows, int C, int V, int D, float* x,
                              cudaStream_t st);
-cudaError_t launch_xprep(const float* x_rows, float2* x_il, unsigned short* xparts, float* ssq, const float* normw,
-                         int D, int G, cudaStream_t st);
+cudaError_t launch_interleave(const float* x_rows, float2* x_il, int D, cudaStream_t st);
 cudaError_t launch_deinterleave(const float2* x_il, float* x_rows, int D, cudaStream_t st);
 cudaError_t launch_delay_apply(const int* in, int* out, int B, int T, int C, const int* delay, int pad, int bos,
                                cudaStream_t st);

@@ -1,28 +1,37 @@
 // step_kernel.cu - the persistent Dia decode-step kernel for sm_100a.
 //
-// One CTA per SM (148 on B200), launched cooperatively.  A decode step is a chain of
-// ~147 strictly dependent stages (embed, 8 per decoder layer, logits, sample) over a
-// batch of 2 rows (CFG uncond/cond) - 2 FLOP per weight byte, i.e. bound by streaming
-// 2.53 GB of bf16 weights from HBM3e, not by math.  The design follows from that:
+// One CTA per SM (148 on B200), launched cooperatively (co-residency is required: CTAs wait on each
+// other's data).  A decode step is a chain of ~147 strictly dependent stages (embed, 8 per decoder
+// layer, logits, sample) over a batch of 2 rows (CFG uncond/cond) - 2 FLOP per weight byte, i.e. bound
+// by streaming 2.53 GB of bf16 weights from HBM3e, and after that by the LATENCY of the stage chain
+// (386 us of HBM time per step leaves 2.6 us per stage).  The design follows from those two facts:
 //
-//  * every CTA owns a fixed slice of the output columns of every GEMM, and the host
-//    repacks the weights ONCE into one contiguous bf16 byte stream per CTA in exactly
-//    the order that CTA consumes them;
+//  * every CTA owns a fixed slice of the output columns of every GEMM, and the host repacks the
+//    weights ONCE into one contiguous bf16 byte stream per CTA in exactly the order that CTA
+//    consumes them;
 //  * a producer warp (one elected lane) walks that stream with 1-D bulk async copies
-//    (cp.async.bulk, the TMA engine) into a 19 x 8 KB shared-memory ring guarded by
-//    full/empty mbarriers.  It never joins the grid barriers, so it keeps prefetching
-//    the NEXT stages' weights while the math warps sit in a barrier or in a
-//    latency-bound attention stage - HBM stays busy across all 147 stage boundaries;
-//  * 8 math warps consume ring slots (one slot per warp at a time), convert bf16 pairs
-//    with two ALU ops and accumulate in fp32 with packed FFMA2; activations, residual
-//    stream, norms, softmax and the KV cache stay fp32 (required for
-//    the 2e-2 / bit-exact-greedy bar), reductions run in a fixed order (deterministic);
-//  * stages are separated by a counter-based grid barrier (one atomic + an acquire poll);
-//  * self-attention streams its K/V tiles through the same ring (split-KV over CTAs,
-//    4 query heads share each KV tile, RoPE fused, K/V append fused, last-arriver
-//    combine), cross-attention reads only the valid keys of the conditional row;
-//  * the sampling stage (CFG combine, masks, argmax / top-k / top-p / Philox draw) and the
-//    EOS state machine run on the device, so a whole run of steps needs no host sync.
+//    (cp.async.bulk, the TMA engine) into a 20 x 8 KB shared-memory ring guarded by full/empty
+//    mbarriers.  It never waits for the math warps' dependencies, so it keeps prefetching the NEXT
+//    stages' weights while they sit in a latency-bound stage - HBM stays busy across stage boundaries;
+//  * there is NO grid barrier.  Every vector that crosses CTAs (normalised residual stream, q/k/v,
+//    attention outputs, MLP hidden, split-KV partials, logits, tokens) is written as 8-byte words that
+//    carry their own sequence flag ("LL" words: one strong store, one strong load, the reader re-polls
+//    until the flag is the producing stage's number).  A stage boundary therefore costs one L2 write
+//    plus one L2 read instead of fence + atomic + poll + read;
+//  * the residual stream never leaves the SM: the three residual GEMMs (self-o, cross-o, mlp-out) share
+//    one column partition, so each element of x lives in a register of the thread that owns its column;
+//  * 8 math warps consume ring slots (one slot per warp at a time) on the tensor cores (mma.sync
+//    m16n8k16, swap-AB: 16 output columns x the 2 batch rows split into three bf16 terms, exact to
+//    24 bits, so the product has fp32-activation accuracy - SURVEY.md 8(c)); residual stream, norms,
+//    softmax and the KV cache stay fp32, reductions run in a fixed order (deterministic);
+//  * the code is deliberately compact and rolled: the L1.5 instruction cache is 32 KB and every stage
+//    runs once per layer, so straight-line code is fetched cold from L2 at ~30 cycles/instruction;
+//  * self-attention streams its K/V tiles through the same ring (split-KV over CTAs, 4 query heads
+//    share each KV tile, RoPE fused, K/V append fused), the splits exchange partials as LL words and
+//    each combines a slice; cross-attention reads only the valid keys of the conditional row;
+//  * sampling runs on 9 CTAs (one codebook each: CFG combine fused into the logits epilogue, radix
+//    select for top-k, top-p, Philox draw), the EOS state machine on CTA 0; a whole run of steps needs
+//    no host sync.
 //
 // Reference semantics: dia/layers.py:671-720 (decode_step), :530-584 (DecoderLayer),
 // :238-346 (Attention), :92-105 (MlpBlock); dia/model.py:429-488, 32-82, 748-807.
@@ -32,6 +41,8 @@
 #include "engine_internal.h"
 
 namespace dia {
+
+typedef unsigned long long u64;
 
 // per-GEMM constants of this CTA, computed once per launch (no integer divisions in the stage loop)
 struct GemmCfg {
@@ -47,25 +58,34 @@ struct SharedMisc {
     uint64_t empty[kNumSlots];
     CtaTable tab;
     GemmCfg gcfg[G_COUNT];
-    float ssq_part[kConsumerWarps][2];   // per-warp sums of x_new^2 of a residual stage (published at the barrier)
-    float inv_rms[2];                    // 1/rms of the stage input, per batch row
-    float stat[32];
-    int stages_done;     // consumer -> producer progress (global stage index + 1)
-    int flag;
+    float inv_rms[2][2];                 // [stage parity][batch row]: 1/rms of the stage input
+    float stat[16];
+    int bcast[8];
+    int stages_done;                     // consumer -> producer progress (global stage index + 1)
 };
 static_assert(sizeof(SharedMisc) <= kMiscBytes, "misc region too small");
 
 struct Ctx {
     const StepParams* p;
     unsigned char* ring;
-    float2* xs;
+    unsigned char* xs;
     float* red;
     SharedMisc* misc;
     int tid, warp, lane;
     unsigned cbase;      // ring chunk index at the start of the current stage
-    unsigned nbar;       // grid barriers passed so far in this launch
-    long long* tstamp;   // debug: 8 clock64 slots of the current stage (CTA 0, thread 0 only)
+    unsigned seq;        // sequence number of the current stage inside this launch (>= 1)
+    float xres;          // warp 0: this lane's element of the residual stream (lane = row * 16 + column)
+    long long* ts;       // debug: 8 clock64 slots of the current stage (CTA 0, thread 0 only)
 };
+
+// A math warp waits for generation g of a ring slot.  Successive generations of one slot are consumed by
+// DIFFERENT warps, so the waiting warp has not observed generation g-1 complete and the one-bit phase parity
+// would alias (a wait for g passes while g-1 is still in flight).  Waiting first for the RELEASE of g-1 (the
+// empty barrier, which needs g-1 filled and consumed) pins the full barrier to generation g.
+__device__ __forceinline__ void ring_wait_full(SharedMisc* misc, unsigned slot, unsigned parity, int* err, unsigned info) {
+    mbar_wait(&misc->empty[slot], parity ^ 1u, err, kErrEmptyBarrierTimeout, info);
+    mbar_wait(&misc->full[slot], parity, err, kErrFullBarrierTimeout, info);
+}
 
 __device__ __forceinline__ void decode_stage(int s, int L, int& kind, int& layer) {
     if (s == 0) { kind = S_EMBED; layer = 0; }
@@ -90,7 +110,7 @@ struct AttnWork {
     int active, pair, split, k_lo, k_hi, n_active, has_new;
 };
 // self-attention: (row, kv head) pairs x key splits over the CTAs.  Old keys are cache
-// slots [0, slot); the key/value of THIS step is taken from the qkv scratch by split 0.
+// slots [0, slot); the key/value of THIS step is taken from the qkv words by split 0.
 __device__ __forceinline__ AttnWork self_attn_work(const StepParams& p, int cta, int slot) {
     AttnWork w;
     const int nsplit = p.sa_nsplit, pairs = 2 * p.Hkv, n_old = slot;
@@ -108,7 +128,8 @@ __device__ __forceinline__ AttnWork self_attn_work(const StepParams& p, int cta,
     w.has_new = (w.split == 0);
     return w;
 }
-// cross-attention: conditional row only, one query head per KV head, keys [0, text_len)
+// cross-attention: conditional row only, one query head per KV head, keys [0, text_len); a CTA takes
+// at least 128 keys so that typical transcripts need no split at all
 __device__ __forceinline__ AttnWork cross_attn_work(const StepParams& p, int cta) {
     AttnWork w;
     const int nsplit = p.ca_nsplit, n = p.text_len;
@@ -116,7 +137,7 @@ __device__ __forceinline__ AttnWork cross_attn_work(const StepParams& p, int cta
     w.split = cta - w.pair * nsplit;
     int per = (n + nsplit - 1) / nsplit;
     per = (per + 15) & ~15;
-    if (per < 32) per = 32;
+    if (per < 128) per = 128;
     w.n_active = (n + per - 1) / per;
     if (w.n_active < 1) w.n_active = 1;
     w.active = (w.pair < p.Hc) && (w.split < w.n_active);
@@ -128,45 +149,6 @@ __device__ __forceinline__ AttnWork cross_attn_work(const StepParams& p, int cta
 }
 
 // ------------------------------------------------------------------------------------------
-// grid barrier (consumer warps only)
-// ------------------------------------------------------------------------------------------
-// thread 0, after a consumer_sync: this CTA's share of sum(x^2) of the new residual stream (fixed order)
-__device__ __forceinline__ void publish_ssq_partials(Ctx& c) {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int w = 0; w < kConsumerWarps; ++w) { s0 += c.misc->ssq_part[w][0]; s1 += c.misc->ssq_part[w][1]; }
-    c.p->ssq[blockIdx.x] = s0;
-    c.p->ssq[gridDim.x + blockIdx.x] = s1;
-}
-
-__device__ __forceinline__ void grid_barrier(Ctx& c, bool publish_ssq) {
-    const StepParams& p = *c.p;
-    consumer_sync();                       // every consumer thread's stage output is issued
-    c.nbar++;
-    if (c.tid == 0) {
-        if (publish_ssq) publish_ssq_partials(c);
-        // release: orders the whole CTA's prior writes (bar.sync above makes them visible to this
-        // thread, the release is cumulative) before the arrival becomes visible at gpu scope
-        red_release_add_u32(p.grid_bar, 1u);
-        const unsigned target = c.nbar * gridDim.x;
-        if (ld_relaxed_u32(p.grid_bar) < target) {
-            const unsigned long long t0 = clock64();
-            while (ld_relaxed_u32(p.grid_bar) < target) {
-                if (clock64() - t0 > kWatchdogCycles) {
-                    *reinterpret_cast<volatile int*>(p.err) = kErrGridBarrierTimeout;
-                    __threadfence_system();
-                    __trap();
-                }
-            }
-        }
-        // acquire side: every read of data another CTA produced goes to L2 (ld.global.cg / bulk copies),
-        // never through L1, and is issued after this loop exits (GPUs do not speculate past the branch),
-        // so no L1 invalidation / fence is needed here.  The named barrier below orders the other threads.
-    }
-    consumer_sync();
-}
-
-// ------------------------------------------------------------------------------------------
 // producer: walks this CTA's byte stream
 // ------------------------------------------------------------------------------------------
 struct Producer {
@@ -174,11 +156,12 @@ struct Producer {
     SharedMisc* misc;
     int* err;
     unsigned pc;
+    unsigned seq;
     uint64_t pol_stream, pol_keep;
     __device__ __forceinline__ void issue(const void* src, uint32_t bytes, bool keep) {
         const unsigned slot = pc % kNumSlots;
         const unsigned ph = (pc / kNumSlots) & 1u;
-        mbar_wait(&misc->empty[slot], ph ^ 1u, err, kErrEmptyBarrierTimeout);
+        mbar_wait(&misc->empty[slot], ph ^ 1u, err, kErrEmptyBarrierTimeout, (seq << 8) | slot);
         mbar_arrive_expect_tx(&misc->full[slot], bytes);
         bulk_g2s_hint(ring + slot * kSlotBytes, src, bytes, &misc->full[slot], keep ? pol_keep : pol_stream);
         pc++;
@@ -193,11 +176,14 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
     const CtaTable& tab = misc->tab;
     const int cta = blockIdx.x;
     const int S = 8 * p.L + 3;
+#pragma unroll 1
     for (int n = 0; n < p.n_steps; ++n) {
         const int slot = p.slot0 + n;
+#pragma unroll 1
         for (int s = p.stage_begin; s < p.stage_end; ++s) {
             int kind, layer;
             decode_stage(s, p.L, kind, layer);
+            pr.seq = 1u + (unsigned)(n * S + s);
             const int gt = gemm_of_kind(kind);
             if (gt >= 0) {
                 const GemmCfg& g = misc->gcfg[gt];
@@ -205,27 +191,25 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
                 const unsigned char* base = p.wstream + tab.stream_base +
                     (gt == G_LOGITS ? tab.logits_off
                                     : (unsigned long long)layer * tab.layer_bytes + tab.slab_off[gt]);
+#pragma unroll 1
                 for (int r0 = 0; r0 < g.K; r0 += g.rpc) {
                     const int rows = min(g.rpc, g.K - r0);
                     pr.issue(base + (size_t)r0 * g.row_bytes, rows * g.row_bytes, false);
-                    if (r0 == 0 && p.timing != nullptr && cta == 0) p.timing[((size_t)n * S + s) * 8 + 7] = clock64();
                 }
             } else if (kind == S_SATTN || kind == S_CATTN) {
                 const bool self = kind == S_SATTN;
                 const AttnWork w = self ? self_attn_work(p, cta, slot) : cross_attn_work(p, cta);
                 if (!w.active || w.k_hi <= w.k_lo) continue;
                 if (self && n > 0) {
-                    // rows < slot were written by other CTAs during the same stage of step n-1:
-                    // do not run ahead of that (never blocks at Dia-1.6B sizes)
-                    const int need = (n - 1) * S + s + 1;
+                    // row slot-1 was appended by another CTA during this stage of step n-1; that CTA fenced the
+                    // append before publishing its output, and this CTA's math warps consumed the self-o stage of
+                    // step n-1 (which needs every such output) once stages_done passes it.  The ring holds a
+                    // fraction of one layer, so this never blocks.
+                    const int need = (n - 1) * S + s + 2;
                     if (ld_acquire_cta_s32(&misc->stages_done) < need) {
                         const unsigned long long t0 = clock64();
                         while (ld_acquire_cta_s32(&misc->stages_done) < need) {
-                            if (clock64() - t0 > kWatchdogCycles) {
-                                *reinterpret_cast<volatile int*>(p.err) = kErrStepDoneTimeout;
-                                __threadfence_system();
-                                __trap();
-                            }
+                            if (clock64() - t0 > kWatchdogCycles) ll_timeout(p.err, kErrStepDoneTimeout);
                         }
                     }
                     fence_proxy_async();
@@ -241,8 +225,10 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
                     kb = p.cross_k[layer] + off;
                     vb = p.cross_v[layer] + off;
                 }
+#pragma unroll 1
                 for (int pass = 0; pass < 2; ++pass) {
                     const float* b = pass == 0 ? kb : vb;
+#pragma unroll 1
                     for (int k0 = w.k_lo; k0 < w.k_hi; k0 += 16) {
                         const int nk = min(16, w.k_hi - k0);
                         pr.issue(b + (size_t)k0 * kHeadDim, nk * kHeadDim * 4, !self);
@@ -254,18 +240,33 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
 }
 
 // ------------------------------------------------------------------------------------------
+// activation vectors as LL words
+// ------------------------------------------------------------------------------------------
+// x = hi + lo + lo2 with each term bf16 (round-to-nearest at every level; the residuals are exact)
+__device__ __forceinline__ void ll_store_parts(u64* dst, int k, int r, float x, uint32_t f16) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(l);
+    const __nv_bfloat16 l2 = __float2bfloat16_rn(r2);
+    const uint32_t lo = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+    const uint32_t hi = (uint32_t)__bfloat16_as_ushort(l2) | (f16 << 16);
+    ll_st(dst + (size_t)(k >> 4) * 32 + r * 16 + (k & 15), lo, hi);
+}
+
+// ------------------------------------------------------------------------------------------
 // GEMM stage: y[2][N_cta] = x[2][K] . W_slab on the tensor cores (mma.sync m16n8k16, bf16 x bf16 ->
 // fp32).  Swap-AB: the 16 rows of the MMA are 16 OUTPUT COLUMNS (two 8-column groups of the slab,
 // fed from the ring with ldmatrix.trans - the slab is [k][n], n contiguous), the 8 columns of the MMA
-// carry the two batch rows, each split into three bf16 terms  x = hi + lo + lo2  (exact to 24 bits),
-// so the product keeps fp32-activation accuracy while the weights stay bf16.
+// carry the two batch rows, each split into three bf16 terms  x = hi + lo + lo2:
 //   MMA column n: 0,1,2 = row 0 (hi, lo, lo2)   4,5,6 = row 1 (hi, lo, lo2)   3,7 = zero
-// Activation vectors live in global memory ALREADY split and laid out as B fragments ("parts"):
-// k-block kb (16 rows) = 256 B, the 8-byte word of lane l = n*4 + kq holds the bf16 of rows
-// {2kq, 2kq+1, 8+2kq, 9+2kq} of column n.  The epilogue that produces a vector writes it in this form
-// once (pre-multiplied by the consumer's RMSNorm weight), so a consumer warp fetches exactly the
-// fragments of the k-range it owns straight from L2 - no staging pass, no block sync before the MMAs.
-// The 1/rms factor commutes with the GEMM and is applied in the epilogue from per-CTA partial sums.
+// The k index of the MMA is a free permutation as long as A and B agree; it is chosen so that the four
+// k values of lane q are the four CONSECUTIVE slab rows 4q..4q+3 (see lm_off below).
+// The input vector arrives as LL words [k/16][row][16] = (hi, lo, lo2, flag16) written by the epilogue
+// that produced it (pre-multiplied by the consumer's RMSNorm weight).  A warp fetches the words of the
+// k-range of its ring slot with up to 8 16-byte loads per lane, re-polls until every flag carries the
+// producing stage's number, and transposes them into B fragments in its private staging buffer.  The
+// 1/rms factor commutes with the GEMM and is applied in the epilogue from per-CTA partial sums.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t smem_addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -279,109 +280,58 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// x = hi + lo + lo2 with each term bf16 (round-to-nearest at every level; the residuals are exact)
-__device__ __forceinline__ void split3(float x, unsigned short (&t)[3]) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(h);
-    const __nv_bfloat16 l = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(l);
-    const __nv_bfloat16 l2 = __float2bfloat16_rn(r2);
-    t[0] = __bfloat16_as_ushort(h); t[1] = __bfloat16_as_ushort(l); t[2] = __bfloat16_as_ushort(l2);
-}
-// write element (k, batch row r) of a vector into its parts buffer
-__device__ __forceinline__ void store_parts(unsigned short* parts, int k, int r, float v) {
-    unsigned short t[3];
-    split3(v, t);
-    const int kk = k & 15;
-    unsigned short* base = parts + (size_t)(k >> 4) * 128 + ((kk & 7) >> 1) * 4 + (kk & 1) + ((kk >> 3) << 1);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) base[(r * 4 + i) * 16] = t[i];
-}
-
-constexpr int kMaxTiles = 8;     // <= 16 column groups per CTA and GEMM
-constexpr int kMaxKb = 16;       // k-blocks per ring slot (slot rows are capped at 256)
-constexpr int kBStageBytes = kMaxKb * 256;   // B fragments of one slot; two such buffers per warp
-
-__device__ __forceinline__ void cp_async16_cg(uint32_t dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// L2 -> this warp's staging buffer: the B fragments of rows [r0, r0 + 16*nkb) (256 B per k-block;
-// half-warps take alternate k-blocks, 16 B per lane, L2-only so no stale L1 line can be read)
-__device__ __forceinline__ void stage_b_frags(uint32_t dst, const unsigned char* parts, int r0, int nkb, int lane) {
-    const unsigned char* src = parts + (size_t)(r0 >> 4) * 256 + (lane & 15) * 16;
-    const uint32_t d = dst + (lane & 15) * 16;
-    for (int kb = lane >> 4; kb < nkb; kb += 2) cp_async16_cg(d + kb * 256, src + (size_t)kb * 256);
-    cp_async_commit();
-}
 __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
-// The MMAs of one ring slot.  Three compact, rolled variants (the kernel has ~150 short stages per
-// step; straight-line code that overflows the instruction caches costs more than it saves):
-//   1 tile : 4 k-blocks per iteration on 4 independent accumulator chains
-//   2 tiles: 2 k-blocks per iteration, 2 chains per tile
-//   n tiles: 1 k-block per iteration, the tiles are the independent chains
-__device__ __forceinline__ void mma_slot_1(float (&acc)[kMaxTiles][4], uint32_t a_addr, uint32_t kb_bytes, int nkb,
-                                           uint32_t b_addr) {
-    int kb = 0;
-    for (; kb + 4 <= nkb; kb += 4) {
+constexpr int kMaxTiles = 8;     // <= 16 column groups per CTA and GEMM
+constexpr int kMaxKb = 16;       // k-blocks per ring slot (slot rows are capped at 256)
+constexpr int kLLW = 8;          // 16-byte LL loads per lane for one slot: 16 k-blocks x 2 rows x 16 words / 2 / 32
+
+// the LL words of rows [row0, row0 + 16 * nkb) of `src`: lane takes the 16-byte pairs lane, lane + 32, ...
+__device__ __forceinline__ void ll_fetch(uint4 (&w)[kLLW], const u64* src, int row0, int nkb, int lane, uint32_t f16) {
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(src) + (size_t)row0 * 16 + lane * 16;
+    const int pairs = nkb * 16;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint2 b = lds_u2(b_addr + (kb + u) * 256);
-            uint32_t a[4];
-            ldmatrix_x4_trans(a, a_addr + (kb + u) * kb_bytes);
-            mma_bf16_16816(acc[u], a, b.x, b.y);
-        }
-    }
-    for (; kb < nkb; ++kb) {
-        const uint2 b = lds_u2(b_addr + kb * 256);
-        uint32_t a[4];
-        ldmatrix_x4_trans(a, a_addr + kb * kb_bytes);
-        mma_bf16_16816(acc[0], a, b.x, b.y);
+    for (int i = 0; i < kLLW; ++i) {
+        if (lane + 32 * i < pairs) w[i] = ll_ld2(base + i * 512);
+        else w[i] = make_uint4(0u, f16 << 16, 0u, f16 << 16);
     }
 }
-__device__ __forceinline__ void mma_slot_2(float (&acc)[kMaxTiles][4], uint32_t a_addr, uint32_t kb_bytes, int nkb,
-                                           uint32_t b_addr) {
-    int kb = 0;
-    for (; kb + 2 <= nkb; kb += 2) {
+__device__ __forceinline__ bool ll_stale(const uint4 (&w)[kLLW], uint32_t f16) {
+    uint32_t bad = 0;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const uint2 b = lds_u2(b_addr + (kb + u) * 256);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                uint32_t a[4];
-                ldmatrix_x4_trans(a, a_addr + (kb + u) * kb_bytes + mt * 32);
-                mma_bf16_16816(acc[u * 2 + mt], a, b.x, b.y);
-            }
-        }
-    }
-    if (kb < nkb) {
-        const uint2 b = lds_u2(b_addr + kb * 256);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            uint32_t a[4];
-            ldmatrix_x4_trans(a, a_addr + kb * kb_bytes + mt * 32);
-            mma_bf16_16816(acc[mt], a, b.x, b.y);
-        }
-    }
+    for (int i = 0; i < kLLW; ++i) bad |= ((w[i].y >> 16) ^ f16) | ((w[i].w >> 16) ^ f16);
+    return bad != 0;
 }
-__device__ __forceinline__ void mma_slot_n(float (&acc)[kMaxTiles][4], uint32_t a_addr, uint32_t kb_bytes, int nkb,
-                                           uint32_t b_addr, int n_mt) {
-    for (int kb = 0; kb < nkb; ++kb) {
-        const uint2 b = lds_u2(b_addr + kb * 256);
+
+// The MMAs of one ring slot for a compile-time tile count NT (a CTA with fewer real tiles computes the padding
+// tiles on whatever follows its columns in the slot; their accumulators are never read).  Few tiles -> several
+// k-blocks in flight on independent accumulator chains (the legacy HMMA path has ~21 cycles of latency).
+template <int NT>
+__device__ __forceinline__ void mma_chunk(float (&acc)[kMaxTiles][4], uint32_t a_addr, uint32_t kb_bytes, int nkb,
+                                          uint32_t bst, uint32_t b_off0, uint32_t b_off1, uint32_t bmask) {
+    constexpr int U = NT == 1 ? 4 : (NT == 2 ? 2 : 1);
+#pragma unroll 1
+    for (int kb = 0; kb < nkb; kb += U) {
 #pragma unroll
-        for (int mt = 0; mt < kMaxTiles; ++mt) {
-            if (mt < n_mt) {
-                uint32_t a[4];
-                ldmatrix_x4_trans(a, a_addr + kb * kb_bytes + mt * 32);
-                mma_bf16_16816(acc[mt], a, b.x, b.y);
+        for (int u = 0; u < U; ++u) {
+            const int k = kb + u;
+            if (U == 1 || k < nkb) {
+                const uint32_t boff = U == 1 ? ((k & 1) ? b_off1 : b_off0) : ((u & 1) ? b_off1 : b_off0);
+                uint2 b = lds_u2(bst + (k >> 1) * 512 + boff);
+                b.x &= bmask; b.y &= bmask;
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt) {
+                    uint32_t a[4];
+                    ldmatrix_x4_trans(a, a_addr + k * kb_bytes + mt * 32);
+                    mma_bf16_16816(acc[U > 1 ? u * NT + mt : mt], a, b.x, b.y);
+                }
             }
         }
     }
@@ -391,148 +341,254 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     const StepParams& p = *c.p;
     const GemmCfg& g = c.misc->gcfg[gt];
     const int gc = g.gc, g0 = g.g0, K = g.K, n_mt = g.n_mt;
-    const int lane = c.lane;
-    const bool resid = (gt == G_SO || gt == G_CO || gt == G_WO);
-    if (resid && lane == 0) { c.misc->ssq_part[c.warp][0] = 0.f; c.misc->ssq_part[c.warp][1] = 0.f; }
     if (gc == 0) return;
+    const int lane = c.lane, warp = c.warp;
+    const bool resid = (gt == G_SO || gt == G_CO || gt == G_WO);
+    const bool normed = !resid;
+    const uint32_t fprev = c.seq - 1;                  // the producing stage
+    const uint32_t f16 = fprev & 0xffffu;
+    const int par = c.seq & 1;
+    float* red = c.red + par * (kRedBytes / 4);
 
-    const unsigned char* parts;
-    bool normed = false;
-    switch (gt) {
-        case G_SO: parts = reinterpret_cast<const unsigned char*>(p.attn_parts); break;
-        case G_CO: parts = reinterpret_cast<const unsigned char*>(p.cattn_parts); break;
-        case G_WO: parts = reinterpret_cast<const unsigned char*>(p.hidden_parts); break;
-        default: parts = reinterpret_cast<const unsigned char*>(p.xparts); normed = true; break;
-    }
+    const u64* src = gt == G_SO ? p.ll_attn : gt == G_CO ? p.ll_cattn : gt == G_WO ? p.ll_hidden : p.ll_x;
     const int n_chunks = g.n_chunks, rpc = g.rpc;
-    // this warp's slots are ci = warp, warp + 8, ...; the B fragments of its first slot start moving now
-    const uint32_t bstage = smem_u32(c.xs) + c.warp * (2 * kBStageBytes);
-    if (c.warp < n_chunks) stage_b_frags(bstage, parts, c.warp * rpc, min(rpc, K - c.warp * rpc) >> 4, lane);
 
-    // epilogue role of this thread: (tile, row, column-in-tile); its residual is fetched now, used last
-    const int e_mt = c.tid >> 5, e_r = (c.tid >> 4) & 1, e_m = c.tid & 15;
+    uint4 w[kLLW];
+
+    // RMSNorm of the input: the per-CTA partial sums of x^2 are fetched now by the last warp and used in the epilogue
+    constexpr int kSsqPerLane = 5;                     // <= 160 CTAs
+    uint4 sq[kSsqPerLane];
+    const bool ssq_warp = normed && warp == kConsumerWarps - 1;
+    if (ssq_warp) {
+#pragma unroll
+        for (int i = 0; i < kSsqPerLane; ++i) {
+            const int j = lane + 32 * i;
+            sq[i] = j < p.n_res ? ll_ld2(p.ll_ssq + 2 * j) : make_uint4(0u, fprev, 0u, fprev);
+        }
+    }
+
+    // epilogue role of this thread: (tile, row, column-in-tile)
+    const int e_mt = warp, e_r = lane >> 4, e_m = lane & 15;
     const int e_group = 2 * e_mt + (e_m >> 3);
     const bool e_valid = e_mt < n_mt && e_group < gc;
     const int e_n = (g0 + e_group) * 8 + (e_m & 7);
-    float resid_v = 0.f;
-    if (resid && e_valid) resid_v = ldcg_f(reinterpret_cast<const float*>(p.x) + (size_t)e_n * 2 + e_r);
-
-    if (normed && c.warp == kConsumerWarps - 1) {
-        // 1/rms of the input from the per-CTA partial sums its producers published (fixed order)
-        float s0 = 0.f, s1 = 0.f;
-        for (int i = lane; i < (int)gridDim.x; i += 32) { s0 += ldcg_f(p.ssq + i); s1 += ldcg_f(p.ssq + gridDim.x + i); }
-        s0 = warp_sum(s0);
-        s1 = warp_sum(s1);
-        if (lane == 0) {   // torch.nn.RMSNorm: x * rsqrt(mean(x^2) + eps) * w
-            c.misc->inv_rms[0] = 1.0f / sqrtf(s0 / (float)K + p.eps);
-            c.misc->inv_rms[1] = 1.0f / sqrtf(s1 / (float)K + p.eps);
-        }
+    float wn_v = 0.f;
+    if (resid && e_valid) {
+        // weight of the RMSNorm that consumes the new stream: pre_ca / pre_mlp of this layer, or the next
+        // layer's pre_sa (the final norm after the last layer) - a cold line, so it is fetched up front
+        const float* wn = gt == G_SO ? p.norms + ((size_t)layer * 3 + 1) * p.D
+                        : gt == G_CO ? p.norms + ((size_t)layer * 3 + 2) * p.D
+                                     : p.norms + ((size_t)(layer + 1) * 3) * p.D;
+        wn_v = __ldg(wn + e_n);
     }
 
     float acc[kMaxTiles][4];
 #pragma unroll
     for (int i = 0; i < kMaxTiles; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
 
-    // ldmatrix row address of this lane inside a k-block: tile t = lane/8 -> (k half = t/2, group = t%2)
-    const uint32_t lm_off = (uint32_t)((((lane >> 4) << 3) + (lane & 7)) * g.row_bytes + ((lane >> 3) & 1) * 16);
+    // ---- lane constants ---------------------------------------------------------------------------------
+    // A (ldmatrix.trans): matrix i = lane / 8 covers k rows 8*(i/2).. and columns 8*(i%2).. of the k-block
+    const uint32_t lm_off = (uint32_t)(((lane & 7) + 8 * (lane >> 4)) * g.row_bytes + ((lane >> 3) & 1) * 16);
     const uint32_t ring_base = smem_u32(c.ring) + lm_off;
     const uint32_t kb_bytes = 16u * g.row_bytes;
-    if (c.tstamp) c.tstamp[1] = clock64();
+    // B: lane (n = lane / 4, q = lane % 4) holds rows {2q, 2q+1} and {2q+8, 2q+9} of MMA column n = 4 * row + term.
+    // Staging: per k-block 64 words [row r][term t ^ s][q][2], s = 2 * (kb & 1) + r (bank swizzle)
+    const uint32_t bst = smem_u32(c.xs) + warp * kBStageBytes;
+    const int bq = lane & 3, bt = (lane >> 2) & 3, br = lane >> 4;
+    const uint32_t b_off0 = (uint32_t)(br * 128 + (((bt ^ br) << 3) + bq * 2) * 4);
+    const uint32_t b_off1 = (uint32_t)(256 + br * 128 + (((bt ^ (2 + br)) << 3) + bq * 2) * 4);
+    const uint32_t bmask = bt == 3 ? 0u : 0xffffffffu;
+    // store side: word pair p = lane + 32 i is (k-block (lane / 16) + 2 i, row (lane / 8) % 2, rows 2 kp, 2 kp + 1
+    // with kp = lane % 8), i.e. register kp / 4 of the lanes with q = kp % 4
+    const int ss = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    const uint32_t s_base = bst + (uint32_t)((lane >> 4) * 256 + ((lane >> 3) & 1) * 128 +
+                                             ((lane & 3) * 2 + ((lane >> 2) & 1)) * 4);
+    const uint32_t s_t0 = s_base + ((0 ^ ss) << 5), s_t1 = s_base + ((1 ^ ss) << 5), s_t2 = s_base + ((2 ^ ss) << 5);
+    const int tclass = p.tclass[gt];
+    if (c.ts) c.ts[1] = clock64();
 
-    int buf = 0;
-    for (int ci = c.warp; ci < n_chunks; ci += kConsumerWarps, buf ^= 1) {
+    // software pipeline over this warp's slots: the words of slot cn are requested before the MMAs of slot ci
+#pragma unroll 1
+    for (int ci = warp - kConsumerWarps;;) {
         const int cn = ci + kConsumerWarps;
-        if (cn < n_chunks) stage_b_frags(bstage + (buf ^ 1) * kBStageBytes, parts, cn * rpc, min(rpc, K - cn * rpc) >> 4, lane);
-        const unsigned idx = c.cbase + ci;
-        const unsigned slot = idx % kNumSlots;
-        mbar_wait(&c.misc->full[slot], (idx / kNumSlots) & 1u, p.err, kErrFullBarrierTimeout);
-        if (cn < n_chunks) cp_async_wait<1>(); else cp_async_wait<0>();
+        const int row0 = cn * rpc;
+        const int nkb_n = min(rpc, K - row0) >> 4;
+        if (cn < n_chunks) ll_fetch(w, src, row0, nkb_n, lane, f16);
+        if (ci >= 0) {
+            const unsigned idx = c.cbase + ci;
+            const unsigned slot = idx % kNumSlots;
+            ring_wait_full(c.misc, slot, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | slot);
+            const uint32_t a_addr = ring_base + slot * kSlotBytes;
+            const int nkb = min(rpc, K - ci * rpc) >> 4;
+            if (tclass == 1) mma_chunk<1>(acc, a_addr, kb_bytes, nkb, bst, b_off0, b_off1, bmask);
+            else if (tclass == 2) mma_chunk<2>(acc, a_addr, kb_bytes, nkb, bst, b_off0, b_off1, bmask);
+            else if (tclass == 4) mma_chunk<4>(acc, a_addr, kb_bytes, nkb, bst, b_off0, b_off1, bmask);
+            else mma_chunk<8>(acc, a_addr, kb_bytes, nkb, bst, b_off0, b_off1, bmask);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&c.misc->empty[slot]);
+        }
+        if (cn >= n_chunks) break;
+        // ---- the input words of slot cn: wait until the producing stage has written all of them
+        unsigned spins = 0;
+        while (__any_sync(0xffffffffu, ll_stale(w, f16))) {
+            if (lane == 0) {
+                const u64* sentinel = src + (size_t)row0 * 2;
+                while ((ll_ld(sentinel).y >> 16) != f16) {
+                    if (++spins > kMaxSpins) {
+                        volatile int* e = reinterpret_cast<volatile int*>(p.err);
+                        e[4] = 1 + row0 * 2; e[5] = (int)(ll_ld(sentinel).y >> 16); e[6] = (int)f16; e[7] = cn;
+                        ll_timeout(p.err, kErrFlagTimeout, c.seq * 16 + gt);
+                    }
+                    ll_check_abort(p.err, spins, 100 + kErrFlagTimeout, c.seq * 16 + gt);
+                }
+            }
+            __syncwarp();
+            if (++spins > kMaxSpins) {
+                // debug: which word is stale, and what flag does it carry (older = never written, newer = overwritten)
+                volatile int* e = reinterpret_cast<volatile int*>(p.err);
+                for (int i = 0; i < kLLW; ++i) {
+                    const bool b0 = (w[i].y >> 16) != f16, b1 = (w[i].w >> 16) != f16;
+                    if ((b0 || b1) && e[4] == 0) {
+                        e[4] = 1 + row0 * 2 + (lane + 32 * i) * 2 + (b0 ? 0 : 1);      // word index + 1
+                        e[5] = (int)(b0 ? w[i].y >> 16 : w[i].w >> 16);                 // flag found
+                        e[6] = (int)f16;
+                        e[7] = cn;
+                    }
+                }
+                ll_timeout(p.err, kErrFlagTimeout + 1, c.seq * 16 + gt);
+            }
+            ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 1, c.seq * 16 + gt);
+            ll_fetch(w, src, row0, nkb_n, lane, f16);
+        }
+        if (c.ts && cn == warp) c.ts[6] = clock64();
+        // ---- transpose into B fragments: word pair (k, k+1) of one row -> (hi|hi), (lo|lo), (lo2|lo2)
+        const int pairs = nkb_n * 16;
+#pragma unroll
+        for (int i = 0; i < kLLW; ++i) {
+            if (lane + 32 * i < pairs) {
+                sts_u32(s_t0 + i * 512, __byte_perm(w[i].x, w[i].z, 0x5410));
+                sts_u32(s_t1 + i * 512, __byte_perm(w[i].x, w[i].z, 0x7632));
+                sts_u32(s_t2 + i * 512, __byte_perm(w[i].y, w[i].w, 0x5410));
+            }
+        }
         __syncwarp();
-        if (c.tstamp && ci == c.warp) c.tstamp[6] = clock64();
-        const int nkb = min(rpc, K - ci * rpc) >> 4;
-        const uint32_t a_addr = ring_base + slot * kSlotBytes;
-        const uint32_t b_addr = bstage + buf * kBStageBytes + lane * 8;
-        if (n_mt == 1) mma_slot_1(acc, a_addr, kb_bytes, nkb, b_addr);
-        else if (n_mt == 2) mma_slot_2(acc, a_addr, kb_bytes, nkb, b_addr);
-        else mma_slot_n(acc, a_addr, kb_bytes, nkb, b_addr, n_mt);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&c.misc->empty[slot]);
+        ci = cn;
     }
-    c.cbase += n_chunks;
-    if (n_mt == 1) {
+    // fold the independent accumulator chains of the small tile classes (fixed order)
+    if (tclass == 1) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[0][j] = (acc[0][j] + acc[1][j]) + (acc[2][j] + acc[3][j]);
-    } else if (n_mt == 2) {
+    } else if (tclass == 2) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[0][j] += acc[2][j]; acc[1][j] += acc[3][j]; }
     }
-    if (c.tstamp) c.tstamp[2] = clock64();
+    c.cbase += n_chunks;
+    if (c.ts) c.ts[2] = clock64();
+
+    if (ssq_warp) {
+        // 1/rms of the input from the per-CTA partial sums its producers published (fixed order)
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSsqPerLane; ++i) {
+            const int j = lane + 32 * i;
+            if (j < p.n_res) {
+                uint32_t v0 = sq[i].x, v1 = sq[i].z;
+                if (sq[i].y != fprev) v0 = ll_wait32(p.ll_ssq + 2 * j, fprev, p.err);
+                if (sq[i].w != fprev) v1 = ll_wait32(p.ll_ssq + 2 * j + 1, fprev, p.err);
+                s0 += __uint_as_float(v0);
+                s1 += __uint_as_float(v1);
+            }
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0) {   // torch.nn.RMSNorm: x * rsqrt(mean(x^2) + eps) * w
+            c.misc->inv_rms[par][0] = 1.0f / sqrtf(s0 / (float)K + p.eps);
+            c.misc->inv_rms[par][1] = 1.0f / sqrtf(s1 / (float)K + p.eps);
+        }
+    }
 
     // ---- sum the three bf16 terms (MMA columns) of each batch row, then the 8 warps through smem ----
     // C fragment: c0,c1 = D[m][2q], D[m][2q+1]; c2,c3 = D[m+8][..] with m = lane/4, q = lane%4.
     // q = 0,1 hold row 0 (hi+lo | lo2+0), q = 2,3 hold row 1.
-    const int q = lane & 3, m = lane >> 2;
+    {
+        const int q = lane & 3, m = lane >> 2;
 #pragma unroll
-    for (int mt = 0; mt < kMaxTiles; ++mt) {
-        if (mt < n_mt) {
-            float lo = acc[mt][0] + acc[mt][1], hi = acc[mt][2] + acc[mt][3];
-            lo += __shfl_xor_sync(0xffffffffu, lo, 1);
-            hi += __shfl_xor_sync(0xffffffffu, hi, 1);
-            if ((q & 1) == 0) {
-                float* r = c.red + ((size_t)c.warp * n_mt + mt) * 32 + (q >> 1) * 16;
-                r[m] = lo;
-                r[m + 8] = hi;
+        for (int mt = 0; mt < kMaxTiles; ++mt) {
+            if (mt < n_mt) {
+                float lo = acc[mt][0] + acc[mt][1], hi = acc[mt][2] + acc[mt][3];
+                lo += __shfl_xor_sync(0xffffffffu, lo, 1);
+                hi += __shfl_xor_sync(0xffffffffu, hi, 1);
+                if ((q & 1) == 0) {
+                    float* r = red + ((size_t)warp * n_mt + mt) * 32 + (q >> 1) * 16;
+                    r[m] = lo;
+                    r[m + 8] = hi;
+                }
             }
         }
     }
     consumer_sync();
-    if (c.tstamp) c.tstamp[3] = clock64();
+    if (c.ts) c.ts[3] = clock64();
+    if (e_mt >= n_mt) return;                          // whole warps without a tile are done
 
-    const float inv = normed ? c.misc->inv_rms[e_r] : 1.0f;
-    auto total = [&](int mm) {
-        float s = 0.f;
+    const float inv = normed ? c.misc->inv_rms[par][e_r] : 1.0f;
+    float y = 0.f, y8 = 0.f;                           // column e_m and (mlp-in only) its partner e_m + 8
+    {
+        const float* rb = red + (size_t)e_mt * 32 + e_r * 16 + (gt == G_WI ? (e_m & 7) : e_m);
 #pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) s += c.red[((size_t)w * n_mt + e_mt) * 32 + e_r * 16 + mm];
-        return s;
-    };
+        for (int ww = 0; ww < kConsumerWarps; ++ww) {
+            y += rb[(size_t)ww * n_mt * 32];
+            if (gt == G_WI) y8 += rb[(size_t)ww * n_mt * 32 + 8];
+        }
+    }
+    const uint32_t f16n = c.seq & 0xffffu;
+    if (c.ts) c.ts[5] = clock64();
     if (gt == G_WI) {
         // a tile = (gate group, up group) of the same 8 hidden units: h = silu(gate) * up (dia/layers.py:95-101)
         if (!e_valid || e_m >= 8) return;
-        const float gate = total(e_m) * inv, up = total(e_m + 8) * inv;
+        const float gate = y * inv, up = y8 * inv;
         const float h = (gate / (1.0f + expf(-gate))) * up;
         const int n = ((g0 >> 1) + e_mt) * 8 + e_m;
-        reinterpret_cast<float*>(p.hidden)[(size_t)n * 2 + e_r] = h;
-        store_parts(p.hidden_parts, n, e_r, h);
+        ll_store_parts(p.ll_hidden, n, e_r, h, f16n);
         return;
     }
-    if (!resid) {
-        if (!e_valid) return;
-        const float y = total(e_m) * inv;
-        if (gt == G_QKV) {
-            reinterpret_cast<float*>(p.qkv)[(size_t)e_n * 2 + e_r] = y;
-        } else if (gt == G_CQ) {
-            reinterpret_cast<float*>(p.cq)[(size_t)e_n * 2 + e_r] = y;
-        } else {
-            const int ch = e_n / p.Vpad, vv = e_n - ch * p.Vpad;
-            if (ch < p.C && vv < p.V) p.logits[((size_t)e_r * p.C + ch) * p.V + vv] = y;
+    y *= inv;
+    if (gt == G_QKV) {
+        if (e_valid) ll_st(p.ll_qkv + (size_t)e_n * 2 + e_r, __float_as_uint(y), c.seq);
+        return;
+    }
+    if (gt == G_CQ) {
+        if (e_valid) ll_st(p.ll_cq + (size_t)e_n * 2 + e_r, __float_as_uint(y), c.seq);
+        return;
+    }
+    if (gt == G_LOGITS) {
+        // logits [2][C][V] (dia/layers.py:717-720) and, fused, the guided + masked logits the sampler draws from:
+        // cond + s * (cond - uncond), then the -inf masks (dia/model.py:450-478).  Lanes 16..31 hold the cond row.
+        const float un = __shfl_xor_sync(0xffffffffu, y, 16);
+        const int ch = e_n / p.Vpad, vv = e_n - ch * p.Vpad;
+        if (e_valid && ch < p.C && vv < p.V) {
+            p.logits[((size_t)e_r * p.C + ch) * p.V + vv] = y;
+            if (e_r == 1) {
+                float gv = __fadd_rn(y, __fmul_rn(p.cfg_scale, __fsub_rn(y, un)));
+                if ((ch > 0 && vv == p.eos) || vv == p.pad || vv == p.bos) gv = -INFINITY;
+                ll_st(p.ll_glog + (size_t)ch * p.V + vv, __float_as_uint(gv), c.seq);
+            }
         }
         return;
     }
-    // residual add (dia/layers.py:555,574,582); the new stream is also written as the parts of
-    // x * w_norm for the NEXT consumer, and its sum of squares is collected for that consumer's RMSNorm
+    // residual add (dia/layers.py:555,574,582): the stream stays in this lane's register; the new stream is
+    // published as the words of x * w_norm for the NEXT consumer, with this CTA's share of sum(x^2)
     float xn = 0.f;
     if (e_valid) {
-        xn = resid_v + total(e_m);
+        xn = c.xres + y;
+        c.xres = xn;
         reinterpret_cast<float*>(p.x)[(size_t)e_n * 2 + e_r] = xn;
-        const float* wn = gt == G_SO ? p.norms + ((size_t)layer * 3 + 1) * p.D
-                        : gt == G_CO ? p.norms + ((size_t)layer * 3 + 2) * p.D
-                                     : p.norms + ((size_t)(layer + 1) * 3) * p.D;   // next layer's pre_sa_norm, or
-        store_parts(p.xparts, e_n, e_r, xn * __ldg(wn + e_n));                      // the final norm after layer L-1
+        ll_store_parts(p.ll_x, e_n, e_r, xn * wn_v, f16n);
     }
-    float sq = xn * xn;                                                // half-warps = batch rows
+    if (c.ts) c.ts[7] = clock64();
+    float sqv = xn * xn;                                               // half-warps = batch rows
 #pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((lane & 15) == 0) c.misc->ssq_part[c.warp][e_r] = sq;
+    for (int o = 8; o >= 1; o >>= 1) sqv += __shfl_xor_sync(0xffffffffu, sqv, o);
+    if ((lane & 15) == 0) ll_st(p.ll_ssq + 2 * blockIdx.x + e_r, __float_as_uint(sqv), c.seq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -563,57 +619,74 @@ __device__ __forceinline__ void transpose_reduce(float (&v)[NV], int lane) {
     }
 }
 
-template <int HPK, bool kSelf>
-__device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
+// One instantiation serves both attentions (instruction footprint matters more than FMAs here): the K/V
+// passes always carry 4 query heads per KV tile.  Self-attention uses all four (GQA 4:1); cross-attention has
+// one query head per KV head, so its heads 1..3 are zero queries whose outputs are never stored.
+constexpr int HPK = 4;
+
+__device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot) {
     const StepParams& p = *c.p;
     const int cta = blockIdx.x;
-    const AttnWork w = kSelf ? self_attn_work(p, cta, slot) : cross_attn_work(p, cta);
+    const AttnWork w = self ? self_attn_work(p, cta, slot) : cross_attn_work(p, cta);
     if (!w.active) return;
-    const int r = kSelf ? w.pair / p.Hkv : 1;
-    const int kvh = kSelf ? w.pair - r * p.Hkv : w.pair;
-    const int head0 = kSelf ? kvh * HPK : w.pair;
-    const int nsplit = kSelf ? p.sa_nsplit : p.ca_nsplit;
+    const int r = self ? w.pair / p.Hkv : 1;
+    const int kvh = self ? w.pair - r * p.Hkv : w.pair;
+    const int head0 = self ? kvh * HPK : w.pair;
+    const int nh = self ? HPK : 1;                       // real query heads
+    const int nsplit = self ? p.sa_nsplit : p.ca_nsplit;
+    const uint32_t fprev = c.seq - 1;
+    const bool has_new = self && w.has_new;
 
     float* qs = reinterpret_cast<float*>(c.xs);          // [HPK][128] rotated, pre-scaled queries
     float* kn = qs + HPK * kHeadDim;                     // [128] rotated key of this step
     float* vn = kn + kHeadDim;                           // [128] value of this step
     float* stat = vn + kHeadDim;                         // m[HPK] at 0.., l[HPK] at 8..
     float* sc = stat + 16;                               // [(n_keys + 1)][HPK] scores -> probabilities
-    float* racc = reinterpret_cast<float*>(c.xs) + 8192; // [warps][HPK][128]
-    const float2* qsrc = kSelf ? p.qkv : p.cq;
-    const int pclamp = min(pos, p.n_pos - 1);
-    const float* sinr = p.rope_sin + (size_t)pclamp * 64;
-    const float* cosr = p.rope_cos + (size_t)pclamp * 64;
-    const float scale = 0.08838834764831845f;           // 1/sqrt(128)
+    float* racc = reinterpret_cast<float*>(c.xs) + 5120; // [warps][HPK][128]   (sc holds <= 1025 x 4 floats)
+    const u64* qsrc = self ? p.ll_qkv : p.ll_cq;
 
-    for (int i = c.tid; i < HPK * 64; i += kConsumerThreads) {
-        const int h = i >> 6, d = i & 63;
-        const float* q2 = reinterpret_cast<const float*>(qsrc + (size_t)(head0 + h) * kHeadDim);
-        const float a = ldcg_f(q2 + 2 * d + r), b = ldcg_f(q2 + 2 * (d + 64) + r);
-        const float sn = __ldg(sinr + d), cs = __ldg(cosr + d);
-        qs[h * kHeadDim + d] = (a * cs - b * sn) * scale;
-        qs[h * kHeadDim + d + 64] = (a * sn + b * cs) * scale;
-    }
-    if (kSelf && w.has_new) {
-        for (int d = c.tid; d < 64; d += kConsumerThreads) {
-            const float* k2 = reinterpret_cast<const float*>(p.qkv + (size_t)(p.Hq + kvh) * kHeadDim);
-            const float* v2 = reinterpret_cast<const float*>(p.qkv + (size_t)(p.Hq + p.Hkv + kvh) * kHeadDim);
-            const float a = ldcg_f(k2 + 2 * d + r), b = ldcg_f(k2 + 2 * (d + 64) + r);
-            const float sn = __ldg(sinr + d), cs = __ldg(cosr + d);
-            kn[d] = a * cs - b * sn;
-            kn[d + 64] = a * sn + b * cs;
-            vn[d] = ldcg_f(v2 + 2 * d + r);
-            vn[d + 64] = ldcg_f(v2 + 2 * (d + 64) + r);
+    // ---- inputs: wait for the projection that produced q (and k, v of this step), RoPE, scale ---------
+    if (c.tid == 0) ll_wait32(qsrc + ((size_t)head0 * kHeadDim) * 2 + r, fprev, p.err);
+    consumer_sync();
+    {
+        const int pclamp = min(pos, p.n_pos - 1);
+        const float* sinr = p.rope_sin + (size_t)pclamp * 64;
+        const float* cosr = p.rope_cos + (size_t)pclamp * 64;
+        const float scale = 0.08838834764831845f;           // 1/sqrt(128)
+        const int n_items = (HPK + 2) * 64;                  // 4 query heads, then k, then v of this step
+#pragma unroll 1
+        for (int i = c.tid; i < n_items; i += kConsumerThreads) {
+            const int hh = i >> 6, d = i & 63;
+            float o0 = 0.f, o1 = 0.f;
+            if (hh < nh || (hh >= HPK && has_new)) {
+                const int col = hh < HPK ? (head0 + hh) * kHeadDim
+                                         : (hh == HPK ? (p.Hq + kvh) * kHeadDim : (p.Hq + p.Hkv + kvh) * kHeadDim);
+                const u64* pa = qsrc + ((size_t)col + d) * 2 + r;
+                uint2 wa = ll_ld(pa), wb = ll_ld(pa + 128);
+                if (wa.y != fprev) wa.x = ll_wait32(pa, fprev, p.err);
+                if (wb.y != fprev) wb.x = ll_wait32(pa + 128, fprev, p.err);
+                const float a = __uint_as_float(wa.x), b = __uint_as_float(wb.x);
+                o0 = a; o1 = b;
+                if (hh <= HPK) {                             // RotaryEmbedding (dia/layers.py:161-173)
+                    const float sn = __ldg(sinr + d), cs = __ldg(cosr + d);
+                    o0 = a * cs - b * sn;
+                    o1 = a * sn + b * cs;
+                    if (hh < HPK) { o0 *= scale; o1 *= scale; }
+                }
+            }
+            qs[hh * kHeadDim + d] = o0;
+            qs[hh * kHeadDim + d + 64] = o1;
         }
     }
     consumer_sync();
-    if (kSelf && w.has_new) {
-        // KVCache.update (dia/state.py:99-103): append this step's K/V at `slot`
+    if (c.ts) c.ts[1] = clock64();
+    if (has_new && c.tid < kHeadDim) {
+        // KVCache.update (dia/state.py:99-103): append this step's K/V at `slot`.  The fence makes the row
+        // visible device-wide before this CTA publishes anything that lets another CTA's copy engine read it.
         const size_t row = ((size_t)w.pair * p.Lmax + slot) * kHeadDim;
-        for (int d = c.tid; d < kHeadDim; d += kConsumerThreads) {
-            p.self_k[layer][row + d] = kn[d];
-            p.self_v[layer][row + d] = vn[d];
-        }
+        p.self_k[layer][row + c.tid] = kn[c.tid];
+        p.self_v[layer][row + c.tid] = vn[c.tid];
+        __threadfence();
     }
     float4 q[HPK];
 #pragma unroll
@@ -621,53 +694,54 @@ __device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
 
     const int nk = w.k_hi - w.k_lo;
     const int nkc = (nk + 15) >> 4;
+    const int nvc = nkc + (has_new ? 1 : 0);             // the key of this step is one more (virtual) tile
 
     // ---- K pass: scores --------------------------------------------------------------------
-    for (int ci = c.warp; ci < nkc; ci += kConsumerWarps) {
-        const unsigned idx = c.cbase + ci;
-        const unsigned sl = idx % kNumSlots;
-        mbar_wait(&c.misc->full[sl], (idx / kNumSlots) & 1u, p.err, kErrFullBarrierTimeout);
-        const int keys_in = min(16, nk - ci * 16);
-        const float4* kt = reinterpret_cast<const float4*>(c.ring + sl * kSlotBytes) + c.lane;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+    for (int ci = c.warp; ci < nvc; ci += kConsumerWarps) {
+        const bool in_ring = ci < nkc;
+        unsigned sl = 0;
+        const float4* kt = reinterpret_cast<const float4*>(kn) + c.lane;
+        int keys_in = 1, key0 = nk;
+        if (in_ring) {
+            const unsigned idx = c.cbase + ci;
+            sl = idx % kNumSlots;
+            ring_wait_full(c.misc, sl, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | 0x40 | sl);
+            kt = reinterpret_cast<const float4*>(c.ring + sl * kSlotBytes) + c.lane;
+            keys_in = min(16, nk - ci * 16);
+            key0 = ci * 16;
+        }
+#pragma unroll 1
+        for (int half = 0; half < 16; half += 8) {
+            if (half >= keys_in) break;
             float v[8 * HPK];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int key = half * 8 + i;
                 float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (key < keys_in) kv = kt[key * 32];
+                if (half + i < keys_in) kv = kt[(half + i) * 32];
 #pragma unroll
                 for (int h = 0; h < HPK; ++h)
                     v[i * HPK + h] = kv.x * q[h].x + kv.y * q[h].y + kv.z * q[h].z + kv.w * q[h].w;
             }
-            transpose_reduce<8 * HPK>(v, c.lane);
-            // HPK = 4: lane l holds (key l/4, head l%4); HPK = 1: lanes 4k..4k+3 hold key k
-            const int key = half * 8 + (HPK == 4 ? (c.lane >> 2) : (c.lane >> 2));
-            const int h = HPK == 4 ? (c.lane & 3) : 0;
-            const bool writer = HPK == 4 ? true : ((c.lane & 3) == 0);
-            if (writer && key < keys_in) sc[(ci * 16 + key) * HPK + h] = v[0];
+            transpose_reduce<8 * HPK>(v, c.lane);            // lane l now holds (key l/4, head l%4)
+            const int key = half + (c.lane >> 2);
+            if (key < keys_in) sc[(key0 + key) * HPK + (c.lane & 3)] = v[0];
         }
-        __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
-    }
-    if (kSelf && w.has_new && c.warp == 0) {
-        const float4 kv = reinterpret_cast<const float4*>(kn)[c.lane];
-#pragma unroll
-        for (int h = 0; h < HPK; ++h) {
-            float s = kv.x * q[h].x + kv.y * q[h].y + kv.z * q[h].z + kv.w * q[h].w;
-            s = warp_sum(s);
-            if (c.lane == 0) sc[nk * HPK + h] = s;
+        if (in_ring) {
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
         }
     }
     consumer_sync();
-    const int n_tot = nk + ((kSelf && w.has_new) ? 1 : 0);
-    if (c.warp < HPK) {
+    const int n_tot = nk + (has_new ? 1 : 0);
+    if (c.warp < nh) {
         const int h = c.warp;
         float m = -INFINITY;
+#pragma unroll 1
         for (int i = c.lane; i < n_tot; i += 32) m = fmaxf(m, sc[i * HPK + h]);
         m = warp_max(m);
         float l = 0.f;
+#pragma unroll 1
         for (int i = c.lane; i < n_tot; i += 32) {
             const float e = expf(sc[i * HPK + h] - m);
             sc[i * HPK + h] = e;
@@ -682,132 +756,177 @@ __device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
     float4 acc[HPK];
 #pragma unroll
     for (int h = 0; h < HPK; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int ci = c.warp; ci < nkc; ci += kConsumerWarps) {
-        const unsigned idx = c.cbase + nkc + ci;
-        const unsigned sl = idx % kNumSlots;
-        mbar_wait(&c.misc->full[sl], (idx / kNumSlots) & 1u, p.err, kErrFullBarrierTimeout);
-        const int keys_in = min(16, nk - ci * 16);
-        const float4* vt = reinterpret_cast<const float4*>(c.ring + sl * kSlotBytes) + c.lane;
+#pragma unroll 1
+    for (int ci = c.warp; ci < nvc; ci += kConsumerWarps) {
+        const bool in_ring = ci < nkc;
+        unsigned sl = 0;
+        const float4* vt = reinterpret_cast<const float4*>(vn) + c.lane;
+        int keys_in = 1, key0 = nk;
+        if (in_ring) {
+            const unsigned idx = c.cbase + nkc + ci;
+            sl = idx % kNumSlots;
+            ring_wait_full(c.misc, sl, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | 0x80 | sl);
+            vt = reinterpret_cast<const float4*>(c.ring + sl * kSlotBytes) + c.lane;
+            keys_in = min(16, nk - ci * 16);
+            key0 = ci * 16;
+        }
+#pragma unroll 2
         for (int key = 0; key < keys_in; ++key) {
             const float4 vv = vt[key * 32];
-#pragma unroll
-            for (int h = 0; h < HPK; ++h) {
-                const float pr = sc[(ci * 16 + key) * HPK + h];
-                acc[h].x = fmaf(pr, vv.x, acc[h].x); acc[h].y = fmaf(pr, vv.y, acc[h].y);
-                acc[h].z = fmaf(pr, vv.z, acc[h].z); acc[h].w = fmaf(pr, vv.w, acc[h].w);
-            }
+            const float4 pr = *reinterpret_cast<const float4*>(sc + (key0 + key) * HPK);
+            acc[0].x = fmaf(pr.x, vv.x, acc[0].x); acc[0].y = fmaf(pr.x, vv.y, acc[0].y);
+            acc[0].z = fmaf(pr.x, vv.z, acc[0].z); acc[0].w = fmaf(pr.x, vv.w, acc[0].w);
+            acc[1].x = fmaf(pr.y, vv.x, acc[1].x); acc[1].y = fmaf(pr.y, vv.y, acc[1].y);
+            acc[1].z = fmaf(pr.y, vv.z, acc[1].z); acc[1].w = fmaf(pr.y, vv.w, acc[1].w);
+            acc[2].x = fmaf(pr.z, vv.x, acc[2].x); acc[2].y = fmaf(pr.z, vv.y, acc[2].y);
+            acc[2].z = fmaf(pr.z, vv.z, acc[2].z); acc[2].w = fmaf(pr.z, vv.w, acc[2].w);
+            acc[3].x = fmaf(pr.w, vv.x, acc[3].x); acc[3].y = fmaf(pr.w, vv.y, acc[3].y);
+            acc[3].z = fmaf(pr.w, vv.z, acc[3].z); acc[3].w = fmaf(pr.w, vv.w, acc[3].w);
         }
-        __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
+        if (in_ring) {
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
+        }
     }
     c.cbase += 2 * nkc;
-    if (kSelf && w.has_new && c.warp == 0) {
-        const float4 vv = reinterpret_cast<const float4*>(vn)[c.lane];
-#pragma unroll
-        for (int h = 0; h < HPK; ++h) {
-            const float pr = sc[nk * HPK + h];
-            acc[h].x = fmaf(pr, vv.x, acc[h].x); acc[h].y = fmaf(pr, vv.y, acc[h].y);
-            acc[h].z = fmaf(pr, vv.z, acc[h].z); acc[h].w = fmaf(pr, vv.w, acc[h].w);
-        }
-    }
 #pragma unroll
     for (int h = 0; h < HPK; ++h)
         reinterpret_cast<float4*>(racc + ((size_t)c.warp * HPK + h) * kHeadDim)[c.lane] = acc[h];
     consumer_sync();
+    if (c.ts) c.ts[2] = clock64();
 
-    float* outf = reinterpret_cast<float*>(kSelf ? p.attn : p.cattn);
-    unsigned short* oparts = kSelf ? p.attn_parts : p.cattn_parts;
-    float* part = kSelf ? p.sa_part : p.ca_part;
-    for (int i = c.tid; i < HPK * kHeadDim; i += kConsumerThreads) {
+    u64* oparts = self ? p.ll_attn : p.ll_cattn;
+    u64* part = (self ? p.ll_sa_part : p.ll_ca_part) + ((size_t)w.pair * nsplit) * (nh * 132);
+    const uint32_t f16n = c.seq & 0xffffu;
+#pragma unroll 1
+    for (int i = c.tid; i < nh * kHeadDim; i += kConsumerThreads) {
         const int h = i >> 7, d = i & 127;
         float o = 0.f;
 #pragma unroll
         for (int ww = 0; ww < kConsumerWarps; ++ww) o += racc[((size_t)ww * HPK + h) * kHeadDim + d];
-        const int head = head0 + h;
         if (w.n_active == 1) {
             const float l = stat[8 + h];
             const float val = l > 0.f ? o / l : 0.f;
-            if (kSelf) outf[((size_t)head * kHeadDim + d) * 2 + r] = val;
-            else reinterpret_cast<float2*>(outf)[(size_t)head * kHeadDim + d] = make_float2(0.f, val);
-            store_parts(oparts, head * kHeadDim + d, r, val);      // row 0 of the cross output stays all-zero
+            const int k = (head0 + h) * kHeadDim + d;
+            ll_store_parts(oparts, k, r, val, f16n);
+            if (!self) ll_store_parts(oparts, k, 0, 0.f, f16n);       // the unconditional row attends nothing
         } else {
-            float* pp = part + (((size_t)(kSelf ? r * p.Hq + head : head)) * nsplit + w.split) * 132;
-            pp[4 + d] = o;
-            if (d == 0) { pp[0] = stat[h]; pp[1] = stat[8 + h]; }
+            u64* pp = part + ((size_t)w.split * nh + h) * 132;
+            ll_st(pp + 4 + d, __float_as_uint(o), c.seq);
+            if (d == 0) { ll_st(pp, __float_as_uint(stat[h]), c.seq); ll_st(pp + 1, __float_as_uint(stat[8 + h]), c.seq); }
         }
     }
+    consumer_sync();                                      // the scratch is reused by the next stage
     if (w.n_active == 1) return;
 
-    // ---- last-arriving split of this pair combines all splits (fixed order => deterministic) ----
-    __threadfence();
-    consumer_sync();
-    unsigned* cnt = p.pair_cnt + (kSelf ? w.pair : 2 * p.Hkv + w.pair);
-    if (c.tid == 0) {
-        const unsigned old = atomicAdd(cnt, 1u);
-        const int last = old == (unsigned)(w.n_active - 1);
-        if (last) { *cnt = 0u; __threadfence(); }
-        c.misc->flag = last;
+    // ---- every split combines a slice of the outputs from all splits' partials (fixed order) -------------
+    const int E = nh * kHeadDim;
+    const int per = (E + w.n_active - 1) / w.n_active;
+    const int e0 = w.split * per, e1 = min(E, e0 + per);
+    if (e0 >= e1) return;                                 // (CTA-uniform)
+    const int ne = e1 - e0, na = w.n_active;
+    const int h_lo = e0 >> 7, nhh = ((e1 - 1) >> 7) - h_lo + 1;
+    float* cw = sc;                                       // [ne][na] outputs, then [nhh][na][2] (m, l)
+    float* cml = cw + ne * na;
+#pragma unroll 1
+    for (int i = c.tid; i < ne * na + nhh * na * 2; i += kConsumerThreads) {
+        const u64* src;
+        if (i < ne * na) {
+            const int e = e0 + i / na, s = i - (i / na) * na;
+            src = part + ((size_t)s * nh + (e >> 7)) * 132 + 4 + (e & 127);
+        } else {
+            const int j = i - ne * na;
+            const int hh = j / (na * 2), rem = j - hh * (na * 2);
+            src = part + ((size_t)(rem >> 1) * nh + h_lo + hh) * 132 + (rem & 1);
+        }
+        uint2 v = ll_ld(src);
+        unsigned spins = 0;
+        while (v.y != c.seq) {
+            if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 2, c.seq);
+            ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 2, c.seq);
+            __nanosleep(64);
+            v = ll_ld(src);
+        }
+        cw[i] = __uint_as_float(v.x);
     }
     consumer_sync();
-    if (!c.misc->flag) return;
-    for (int i = c.tid; i < HPK * kHeadDim; i += kConsumerThreads) {
-        const int h = i >> 7, d = i & 127;
-        const int head = head0 + h;
-        const float* pb = part + ((size_t)(kSelf ? r * p.Hq + head : head)) * nsplit * 132;
+#pragma unroll 1
+    for (int i = c.tid; i < ne; i += kConsumerThreads) {
+        const int e = e0 + i, h = e >> 7, d = e & 127;
+        const float* ml = cml + (size_t)(h - h_lo) * na * 2;
         float M = -INFINITY;
-        for (int s = 0; s < w.n_active; ++s) M = fmaxf(M, ldcg_f(pb + (size_t)s * 132));
+#pragma unroll 1
+        for (int s = 0; s < na; ++s) M = fmaxf(M, ml[2 * s]);
         float Lsum = 0.f, O = 0.f;
-        for (int s = 0; s < w.n_active; ++s) {
-            const float f = expf(ldcg_f(pb + (size_t)s * 132) - M);
-            Lsum = fmaf(ldcg_f(pb + (size_t)s * 132 + 1), f, Lsum);
-            O = fmaf(ldcg_f(pb + (size_t)s * 132 + 4 + d), f, O);
+#pragma unroll 1
+        for (int s = 0; s < na; ++s) {
+            const float f = expf(ml[2 * s] - M);
+            Lsum = fmaf(ml[2 * s + 1], f, Lsum);
+            O = fmaf(cw[i * na + s], f, O);
         }
         const float val = Lsum > 0.f ? O / Lsum : 0.f;
-        if (kSelf) outf[((size_t)head * kHeadDim + d) * 2 + r] = val;
-        else reinterpret_cast<float2*>(outf)[(size_t)head * kHeadDim + d] = make_float2(0.f, val);
-        store_parts(oparts, head * kHeadDim + d, r, val);
+        const int k = (head0 + h) * kHeadDim + d;
+        ll_store_parts(oparts, k, r, val, f16n);
+        if (!self) ll_store_parts(oparts, k, 0, 0.f, f16n);
     }
+    consumer_sync();
 }
 
 // ------------------------------------------------------------------------------------------
-// embedding gather-sum (dia/layers.py:691-696): x = ((e0 + e1) + e2) ... + e8, both CFG rows
+// residual stream entry: embedding gather-sum (dia/layers.py:691-696: x = ((e0 + e1) + e2) ... + e8, both
+// CFG rows), or - when a launch starts in the middle of a step - the stream a previous launch left in p.x.
+// Warp 0 only: lane = row * 16 + column of this CTA's residual columns.
 // ------------------------------------------------------------------------------------------
-__device__ void embed_stage(Ctx& c, int pos) {
-    const StepParams& p = *c.p;
-    const int d = blockIdx.x * kConsumerThreads + c.tid;
-    float s0 = 0.f, s1 = 0.f;
-    if (d < p.D) {
-        const int* t0;
-        const int* t1;
-        if (p.tokens != nullptr) { t0 = p.tokens; t1 = p.tokens + p.C; }
-        else { t0 = t1 = p.grid + (size_t)(pos - 1) * p.C; }
-        for (int ch = 0; ch < p.C; ++ch) {
-            int a = ldcg_i(t0 + ch), b = ldcg_i(t1 + ch);
-            if (a < 0 || a >= p.V || b < 0 || b >= p.V) {
-                // steps executed after the utterance finished read unwritten (-1) grid rows: harmless no-ops
-                const bool dead = p.tokens == nullptr && p.gs != nullptr && ldcg_i(&p.gs->finished) != 0;
-                if (!dead) *p.err = kErrBadState;
-                a = 0; b = 0;
-            }
-            const float* tab = p.emb + (size_t)ch * p.V * p.D;
-            const float e0 = __ldg(tab + (size_t)a * p.D + d), e1 = __ldg(tab + (size_t)b * p.D + d);
-            s0 = ch == 0 ? e0 : s0 + e0;
-            s1 = ch == 0 ? e1 : s1 + e1;
+__device__ __noinline__ float enter_stream(const StepParams& p, unsigned char* xs, const SharedMisc* misc, int tid,
+                                           bool embed, int pos, int step, const float* wnorm, uint32_t seq_out) {
+    const GemmCfg& g = misc->gcfg[G_SO];
+    if (g.gc == 0) return 0.f;                                // this CTA owns no residual columns
+    const int lane = tid & 31, warp = tid >> 5, e_r = lane >> 4, e_m = lane & 15;
+    const bool valid = (e_m >> 3) < g.gc;
+    const int n = (g.g0 + (e_m >> 3)) * 8 + (e_m & 7);
+    float x = 0.f;
+    if (embed) {
+        int* toks = reinterpret_cast<int*>(xs);             // [2][16] tokens, then [16][32] embedding rows
+        float* part = reinterpret_cast<float*>(xs) + 32;
+        if (warp == 0 && lane < p.C) {
+            int t0, t1;
+            if (p.tokens != nullptr && step == 0) { t0 = ldcg_i(p.tokens + lane); t1 = ldcg_i(p.tokens + p.C + lane); }
+            else if (step == 0) { t0 = t1 = ldcg_i(p.grid + (size_t)(pos - 1) * p.C + lane); }
+            else { t0 = t1 = (int)ll_wait32(p.ll_tok + lane, seq_out - 1, p.err); }
+            if (t0 < 0 || t0 >= p.V || t1 < 0 || t1 >= p.V) { *p.err = kErrBadState; t0 = 0; t1 = 0; }
+            toks[lane] = t0;
+            toks[16 + lane] = t1;
         }
-        p.x[d] = make_float2(s0, s1);
-        const float w = __ldg(p.norms + d);                 // layer 0 pre_sa_norm: the first consumer of x
-        store_parts(p.xparts, d, 0, s0 * w);
-        store_parts(p.xparts, d, 1, s1 * w);
+        consumer_sync();
+        // warp w gathers channels w, w + 8: all rows of the tables are in flight at once
+#pragma unroll 1
+        for (int ch = warp; ch < p.C; ch += kConsumerWarps)
+            part[ch * 32 + lane] = valid ? __ldg(p.emb + ((size_t)ch * p.V + toks[e_r * 16 + ch]) * p.D + n) : 0.f;
+        consumer_sync();
+        if (warp != 0) return 0.f;
+        x = part[lane];
+#pragma unroll 1
+        for (int ch = 1; ch < p.C; ++ch) x += part[ch * 32 + lane];
+    } else {
+        if (warp != 0) return 0.f;
+        if (valid) x = ldcg_f(reinterpret_cast<const float*>(p.x) + (size_t)n * 2 + e_r);
     }
-    const float q0 = warp_sum(s0 * s0), q1 = warp_sum(s1 * s1);
-    if (c.lane == 0) { c.misc->ssq_part[c.warp][0] = q0; c.misc->ssq_part[c.warp][1] = q1; }
+    if (valid) {
+        reinterpret_cast<float*>(p.x)[(size_t)n * 2 + e_r] = x;
+        ll_store_parts(p.ll_x, n, e_r, x * __ldg(wnorm + n), seq_out & 0xffffu);
+    }
+    float sqv = valid ? x * x : 0.f;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) sqv += __shfl_xor_sync(0xffffffffu, sqv, o);
+    if ((lane & 15) == 0) ll_st(p.ll_ssq + 2 * blockIdx.x + e_r, __float_as_uint(sqv), seq_out);
+    return x;
 }
 
 // ------------------------------------------------------------------------------------------
-// sampling: CFG + masks + argmax / top-k / top-p / multinomial (dia/model.py:447-488, 32-82)
+// sampling: argmax / top-k / top-p / multinomial (dia/model.py:32-82) for ONE channel by one CTA
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 10; ++i) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
@@ -818,183 +937,284 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, u
 }
 
 constexpr int kMaxCand = 64;
+constexpr int kPerThread = 5;        // vocab <= 1280 entries per channel (Dia: 1028)
 
-// one warp, one channel.  g: guided + masked logits [V] in shared memory (scaled and consumed IN
-// PLACE on the sampling path); cv/ci: candidate lists [kMaxCand].  Returns the token id (all lanes).
-__device__ int sample_channel(float* g, int V, float temperature, float top_p, int top_k,
-                              unsigned long long seed, unsigned long long draw, int ch, float* probs_out,
-                              float* cv, int* ci, int lane) {
-    float* work = g;
+// float -> unsigned key with the same order (larger float = larger key; -inf is the smallest real key)
+__device__ __forceinline__ uint32_t order_key(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct SampleSmem {
+    uint32_t keys[kPerThread * kConsumerThreads];
+    uint32_t hist[256];
+    float cv[kMaxCand];
+    int ci[kMaxCand];
+    float sv[kMaxCand];
+    int si[kMaxCand];
+    float wv[kConsumerWarps];
+    int wi[kConsumerWarps];
+    int sel[4];                      // bin, count above, token
+};
+
+// g[i] = guided + masked logit of entry tid + 256 i (-inf past V).  All 256 threads call; returns the token id
+// (valid in every thread).  probs_out (optional): the filtered distribution the draw is made from.
+__device__ int sample_channel_cta(const float (&g)[kPerThread], int V, float temperature, float top_p, int top_k,
+                                  unsigned long long seed, unsigned long long draw, int ch, float* probs_out,
+                                  SampleSmem* sm, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
     if (temperature == 0.0f) {          // torch.argmax: first maximal index
         float bv = -INFINITY;
         int bi = 0x7fffffff;
-        for (int i = lane; i < V; i += 32) {
-            const float x = g[i];
-            if (x > bv || bi == 0x7fffffff) { bv = x; bi = i; }
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            const int idx = tid + kConsumerThreads * i;
+            if (idx < V && (g[i] > bv || bi == 0x7fffffff)) { bv = g[i]; bi = idx; }
         }
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
         }
+        if (lane == 0) { sm->wv[warp] = bv; sm->wi[warp] = bi; }
+        consumer_sync();
+        bv = sm->wv[0]; bi = sm->wi[0];
+#pragma unroll 1
+        for (int ww = 1; ww < kConsumerWarps; ++ww) {
+            const float ov = sm->wv[ww];
+            const int oi = sm->wi[ww];
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        consumer_sync();
         return bi;
     }
-    for (int i = lane; i < V; i += 32) work[i] = work[i] / temperature;
-    __syncwarp();
-    // ---- top-k: extract maxima in descending order; keep ties with the k-th value ------------
-    int ncand = 0;
-    float kth = 0.f;
-    const int k = top_k;
-    while (ncand < kMaxCand) {
-        float bv = -INFINITY;
-        int bi = 0x7fffffff;
-        for (int i = lane; i < V; i += 32) {
-            const float x = work[i];
-            if (x > bv) { bv = x; bi = i; }
-        }
+    // ---- logits / temperature as order-preserving keys (dia/model.py:43) -----------------------------------
+    uint32_t key[kPerThread];
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (bi == 0x7fffffff) break;                         // nothing finite left
-        if (ncand >= k && !(bv == kth)) break;               // past k and not tied with the k-th
-        if (lane == 0) { cv[ncand] = bv; ci[ncand] = bi; work[bi] = -INFINITY; }
-        ncand++;
-        if (ncand == k) kth = bv;
-        __syncwarp();
+    for (int i = 0; i < kPerThread; ++i) {
+        const int idx = tid + kConsumerThreads * i;
+        key[i] = idx < V ? order_key(g[i] / temperature) : 0u;
+        sm->keys[idx] = key[i];
     }
-    __syncwarp();
-    // ---- softmax over the survivors, top-p on the sorted cumulative sum -----------------------
-    const float mx = cv[0];
-    float e0 = lane < ncand ? expf(cv[lane] - mx) : 0.f;
-    float e1 = lane + 32 < ncand ? expf(cv[lane + 32] - mx) : 0.f;
-    float Z = warp_sum(e0 + e1);
-    int nkeep = ncand;
-    if (top_p < 1.0f) {
-        if (lane == 0) {
-            float cum = 0.f;
-            nkeep = 0;
-            for (int i = 0; i < ncand; ++i) {
-                // entry i is removed iff the cumulative probability BEFORE it already exceeds top_p
-                if (i > 0 && cum > top_p) break;
-                cum += expf(cv[i] - mx) / Z;
-                nkeep = i + 1;
+    // ---- top-k threshold (dia/model.py:46-52): the k-th largest key, by an 8-bit radix select -------------
+    uint32_t prefix = 0u, pmask = 0u;
+    int kk = top_k, n_gt = 0;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        sm->hist[tid] = 0u;
+        if (tid == 0) { sm->sel[0] = 0; sm->sel[1] = 0; }
+        consumer_sync();
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i)
+            if (key[i] != 0u && (key[i] & pmask) == prefix) atomicAdd(&sm->hist[(key[i] >> shift) & 255u], 1u);
+        consumer_sync();
+        if (warp == 0) {
+            // lane holds bins lane*8 .. lane*8+7; suffix sums locate the bin where the count from the top reaches kk
+            int tot = 0;
+#pragma unroll 1
+            for (int b = 0; b < 8; ++b) tot += (int)sm->hist[lane * 8 + b];
+            int suf = tot;
+#pragma unroll
+            for (int m = 1; m <= 16; m <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, suf, m);
+                if (lane + m < 32) suf += t;
+            }
+            int above = suf - tot;
+            if (above < kk && kk <= suf) {
+#pragma unroll 1
+                for (int b = 7; b >= 0; --b) {
+                    const int cb = (int)sm->hist[lane * 8 + b];
+                    if (above + cb >= kk) { sm->sel[0] = lane * 8 + b; sm->sel[1] = above; break; }
+                    above += cb;
+                }
             }
         }
-        nkeep = __shfl_sync(0xffffffffu, nkeep, 0);
+        consumer_sync();
+        prefix |= (uint32_t)sm->sel[0] << shift;
+        pmask |= 0xffu << shift;
+        n_gt += sm->sel[1];
+        kk -= sm->sel[1];
     }
-    e0 = lane < nkeep ? e0 : 0.f;
-    e1 = lane + 32 < nkeep ? e1 : 0.f;
-    const float Z2 = warp_sum(e0 + e1);
-    if (probs_out != nullptr) {
-        for (int i = lane; i < V; i += 32) probs_out[i] = 0.f;
+    const uint32_t thr = prefix;
+    // ---- survivors: everything above the k-th value plus its ties, in index order (<= 64 kept) -------------
+    if (warp == 0) {
+        int n_out = 0, ties = 0;
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+        for (int base = 0; base < V; base += 32) {
+            const int idx = base + lane;
+            const uint32_t kx = idx < V ? sm->keys[idx] : 0u;
+            const bool gtk = kx > thr, eqk = kx == thr && kx != 0u;
+            const unsigned m_eq = __ballot_sync(0xffffffffu, eqk);
+            const bool keep = gtk || (eqk && (n_gt + ties + __popc(m_eq & lt)) < kMaxCand);
+            const unsigned m_keep = __ballot_sync(0xffffffffu, keep);
+            const int posn = n_out + __popc(m_keep & lt);
+            if (keep && posn < kMaxCand) { sm->cv[posn] = key_value(kx); sm->ci[posn] = idx; }
+            n_out += __popc(m_keep);
+            ties += __popc(m_eq);
+        }
+        const int ncand = min(n_out, kMaxCand);
         __syncwarp();
-        if (lane < nkeep) probs_out[ci[lane]] = e0 / Z2;
-        if (lane + 32 < nkeep) probs_out[ci[lane + 32]] = e1 / Z2;
-    }
-    // ---- multinomial(1): inverse CDF over the survivors with a Philox uniform -------------------
-    int tok = ci[0];
-    if (lane == 0) {
-        uint32_t ctr[4] = {(uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)ch, 0x44494131u};
-        philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
-        const float u = (float)(ctr[0] >> 8) * (1.0f / 16777216.0f);   // [0, 1)
-        const float target = u * Z2;
-        float cum = 0.f;
-        tok = ci[nkeep - 1];
-        for (int i = 0; i < nkeep; ++i) {
-            cum += expf(cv[i] - mx);
-            if (cum > target) { tok = ci[i]; break; }
+        // ---- sort descending by value (ties: lower index first) with a rank sort ---------------------------
+#pragma unroll 1
+        for (int e = lane; e < ncand; e += 32) {
+            const float v = sm->cv[e];
+            int rank = 0;
+#pragma unroll 1
+            for (int j = 0; j < ncand; ++j) {
+                const float wv = sm->cv[j];
+                rank += (wv > v || (wv == v && j < e)) ? 1 : 0;
+            }
+            sm->sv[rank] = v;
+            sm->si[rank] = sm->ci[e];
+        }
+        __syncwarp();
+        // ---- softmax over the survivors, top-p on the sorted cumulative sum (dia/model.py:56-70) ------------
+        const float mx = sm->sv[0];
+        float e0 = lane < ncand ? expf(sm->sv[lane] - mx) : 0.f;
+        float e1 = lane + 32 < ncand ? expf(sm->sv[lane + 32] - mx) : 0.f;
+        const float Z = warp_sum(e0 + e1);
+        if (lane < ncand) sm->cv[lane] = e0;                   // cv now holds exp(l - max) in sorted order
+        if (lane + 32 < ncand) sm->cv[lane + 32] = e1;
+        __syncwarp();
+        int nkeep = ncand;
+        if (top_p < 1.0f) {
+            if (lane == 0) {
+                float cum = 0.f;
+                nkeep = 0;
+#pragma unroll 1
+                for (int i = 0; i < ncand; ++i) {
+                    // entry i is removed iff the cumulative probability BEFORE it already exceeds top_p
+                    if (i > 0 && cum > top_p) break;
+                    cum += sm->cv[i] / Z;
+                    nkeep = i + 1;
+                }
+            }
+            nkeep = __shfl_sync(0xffffffffu, nkeep, 0);
+        }
+        e0 = lane < nkeep ? e0 : 0.f;
+        e1 = lane + 32 < nkeep ? e1 : 0.f;
+        const float Z2 = warp_sum(e0 + e1);
+        if (probs_out != nullptr) {
+#pragma unroll 1
+            for (int i = lane; i < V; i += 32) probs_out[i] = 0.f;
+            __syncwarp();
+            if (lane < nkeep) probs_out[sm->si[lane]] = e0 / Z2;
+            if (lane + 32 < nkeep) probs_out[sm->si[lane + 32]] = e1 / Z2;
+        }
+        // ---- multinomial(1): inverse CDF over the survivors with a Philox uniform ---------------------------
+        if (lane == 0) {
+            uint32_t ctr[4] = {(uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)ch, 0x44494131u};
+            philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+            const float u = (float)(ctr[0] >> 8) * (1.0f / 16777216.0f);   // [0, 1)
+            const float target = u * Z2;
+            float cum = 0.f;
+            int tok = sm->si[nkeep - 1];
+#pragma unroll 1
+            for (int i = 0; i < nkeep; ++i) {
+                cum += sm->cv[i];
+                if (cum > target) { tok = sm->si[i]; break; }
+            }
+            sm->sel[2] = tok;
         }
     }
-    return __shfl_sync(0xffffffffu, tok, 0);
+    consumer_sync();
+    const int tok = sm->sel[2];
+    consumer_sync();
+    return tok;
 }
 
-// guided = cond + s * (cond - uncond), then the -inf masks (dia/model.py:450-478)
-__device__ __forceinline__ float guided_logit(float un, float co, float s, int ch, int v, int V, int eos, int pad,
-                                              int bos) {
-    float gv = __fadd_rn(co, __fmul_rn(s, __fsub_rn(co, un)));
-    if ((ch > 0 && v == eos) || v == pad || v == bos) gv = -INFINITY;
-    if (V <= eos + 1 && v >= V) gv = -INFINITY;
-    return gv;
-}
-
-// shared by the in-kernel sampling stage and the standalone head_sample kernel.
-// smem: gbuf [C*V] floats, candidate lists [warps][kMaxCand]; preds int[C]
-__device__ void sample_all_channels(const StepParams& p, const float* logits, unsigned long long draw, float* gbuf,
-                                    float* cv, int* ci, int* preds, float* probs_out, int tid, int warp,
-                                    int lane, int nwarps) {
-    const int CV = p.C * p.V;
-    for (int i = tid; i < CV; i += nwarps * 32) {
-        const int ch = i / p.V, v = i - ch * p.V;
-        gbuf[i] = guided_logit(ldcg_f(logits + i), ldcg_f(logits + CV + i), p.cfg_scale, ch, v, p.V, p.eos, p.pad,
-                               p.bos);
-    }
-    asm volatile("bar.sync 1, %0;" ::"r"(nwarps * 32) : "memory");
-    for (int ch = warp; ch < p.C; ch += nwarps) {
-        const int t = sample_channel(gbuf + (size_t)ch * p.V, p.V, p.temperature, p.top_p, p.top_k, p.seed, draw, ch,
-                                     probs_out ? probs_out + (size_t)ch * p.V : nullptr,
-                                     cv + warp * kMaxCand, ci + warp * kMaxCand, lane);
-        if (lane == 0) preds[ch] = t;
-    }
-    asm volatile("bar.sync 1, %0;" ::"r"(nwarps * 32) : "memory");
-}
-
+// the sampling stage: CTA ch < C draws channel ch from the guided logits; CTA 0 then runs the body of the
+// reference's while loop after _decoder_step (dia/model.py:771-807) and publishes the next step's tokens
 __device__ void sample_stage(Ctx& c, int step_index, int pos) {
     const StepParams& p = *c.p;
-    if (blockIdx.x != 0) return;
-    float* gbuf = reinterpret_cast<float*>(c.xs);                       // C*V floats (37 KB of the 64 KB)
-    float* cv = c.red;                                                  // [warps][64]
-    int* ci = reinterpret_cast<int*>(c.red + kConsumerWarps * kMaxCand);
-    int* preds = reinterpret_cast<int*>(c.red + 2 * kConsumerWarps * kMaxCand);
-    const unsigned long long draw = (unsigned long long)(p.gs ? p.gs->steps_run : step_index);
-    sample_all_channels(p, p.logits, draw, gbuf, cv, ci, preds, p.probs_out, c.tid, c.warp, c.lane,
-                        kConsumerWarps);
-    if (c.tid != 0) return;
-    for (int ch = 0; ch < p.C; ++ch) p.pred_out[ch] = preds[ch];
-    GenState* gs = p.gs;
-    if (gs == nullptr || p.grid == nullptr) return;
-    // ---- the body of the reference's while loop after _decoder_step (dia/model.py:771-807) ----
-    if (!gs->finished) {
-        if (gs->dec_step >= p.max_tokens - 1) {
-            gs->finished = 1;
-        } else {
-            int dmax = 0;
-            for (int ch = 0; ch < p.C; ++ch) dmax = max(dmax, p.delay[ch]);
-            const int cur = gs->dec_step + 1;
-            if (cur != pos) *p.err = kErrBadState;
-            int pr[DIA_B200_MAX_CHANNELS];
-            for (int ch = 0; ch < p.C; ++ch) pr[ch] = preds[ch];
-            if (!gs->eos_detected && pr[0] == p.eos) { gs->eos_detected = 1; gs->eos_countdown = dmax; }
-            if (gs->eos_countdown > 0) {
-                const int s = dmax - gs->eos_countdown;
-                for (int ch = 0; ch < p.C; ++ch) {
-                    if (s == p.delay[ch]) pr[ch] = p.eos;
-                    else if (s > p.delay[ch] && pr[ch] != p.eos) pr[ch] = p.pad;
-                }
-                gs->eos_countdown -= 1;
-            }
-            gs->bos_countdown = max(0, gs->bos_countdown - 1);
-            int* row = p.grid + (size_t)cur * p.C;
-            for (int ch = 0; ch < p.C; ++ch) {
-                if (gs->bos_countdown > 0) { if (row[ch] == -1) row[ch] = pr[ch]; }   // update_one(apply_mask=True)
-                else row[ch] = pr[ch];
-            }
-            if (gs->eos_countdown == 0) {
-                gs->finished = 1;                                   // break: dec_step is NOT advanced
-            } else {
-                if (cur >= p.max_tokens - dmax - 1 && !gs->eos_detected) {
-                    gs->eos_detected = 1;
-                    gs->eos_countdown = dmax;
-                }
-                gs->dec_step += 1;
-                if (gs->dec_step >= p.max_tokens - 1) gs->finished = 1;
-            }
+    const int ch = blockIdx.x;
+    if (ch >= p.C) return;
+    SampleSmem* sm = reinterpret_cast<SampleSmem*>(c.xs);
+    const u64* src = p.ll_glog + (size_t)ch * p.V;
+    float g[kPerThread];
+    {
+        uint2 wv[kPerThread];
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            const int idx = c.tid + kConsumerThreads * i;
+            wv[i] = idx < p.V ? ll_ld(src + idx) : make_uint2(0xff800000u, c.seq - 1);      // -inf past V
+        }
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            if (wv[i].y != c.seq - 1) wv[i].x = ll_wait32(src + c.tid + kConsumerThreads * i, c.seq - 1, p.err);
+            g[i] = __uint_as_float(wv[i].x);
         }
     }
-    gs->steps_run += 1;
+    const int tok = sample_channel_cta(g, p.V, p.temperature, p.top_p, p.top_k, p.seed, p.draw0 + step_index, ch,
+                                       nullptr, sm, c.tid);
+    if (c.tid == 0) ll_st(p.ll_pred + ch, (uint32_t)tok, c.seq);
+    if (ch != 0 || c.warp != 0) return;
+
+    // ---- CTA 0, warp 0: lane = channel ------------------------------------------------------------------
+    const int lane = c.lane;
+    int pr = 0;
+    if (lane < p.C) {
+        pr = (int)ll_wait32(p.ll_pred + lane, c.seq, p.err);
+        p.pred_out[lane] = pr;
+    }
+    GenState* gs = p.gs;
+    int next_tok = 0;
+    if (gs != nullptr && p.grid != nullptr) {
+        int dec_step = gs->dec_step, finished = gs->finished, eos_detected = gs->eos_detected;
+        int eos_cd = gs->eos_countdown, bos_cd = gs->bos_countdown, steps_run = gs->steps_run;
+        __syncwarp();
+        if (!finished) {
+            if (dec_step >= p.max_tokens - 1) {
+                finished = 1;
+            } else {
+                int dmax = 0;
+#pragma unroll 1
+                for (int i = 0; i < p.C; ++i) dmax = max(dmax, p.delay[i]);
+                const int cur = dec_step + 1;
+                if (cur != pos && lane == 0) *p.err = kErrBadState;
+                const int pr0 = __shfl_sync(0xffffffffu, pr, 0);
+                if (!eos_detected && pr0 == p.eos) { eos_detected = 1; eos_cd = dmax; }
+                if (eos_cd > 0) {
+                    const int s = dmax - eos_cd;
+                    if (lane < p.C) {
+                        if (s == p.delay[lane]) pr = p.eos;
+                        else if (s > p.delay[lane] && pr != p.eos) pr = p.pad;
+                    }
+                    eos_cd -= 1;
+                }
+                bos_cd = max(0, bos_cd - 1);
+                if (lane < p.C) {
+                    int* cell = p.grid + (size_t)cur * p.C + lane;
+                    if (bos_cd > 0) {                                  // update_one(apply_mask=True)
+                        const int old = ldcg_i(cell);
+                        if (old == -1) *cell = pr; else pr = old;
+                    } else {
+                        *cell = pr;
+                    }
+                    next_tok = pr;
+                }
+                if (eos_cd == 0) {
+                    finished = 1;                                   // break: dec_step is NOT advanced
+                } else {
+                    if (cur >= p.max_tokens - dmax - 1 && !eos_detected) { eos_detected = 1; eos_cd = dmax; }
+                    dec_step += 1;
+                    if (dec_step >= p.max_tokens - 1) finished = 1;
+                }
+            }
+        }
+        steps_run += 1;
+        if (lane == 0) {
+            gs->dec_step = dec_step; gs->finished = finished; gs->eos_detected = eos_detected;
+            gs->eos_countdown = eos_cd; gs->bos_countdown = bos_cd; gs->steps_run = steps_run;
+        }
+        if (finished) next_tok = 0;                                 // later steps of this launch are dead
+    }
+    if (lane < p.C) ll_st(p.ll_tok + lane, (uint32_t)next_tok, c.seq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1003,23 +1223,24 @@ __device__ void sample_stage(Ctx& c, int step_index, int pos) {
 extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* ring = smem;
-    float2* xs = reinterpret_cast<float2*>(smem + kNumSlots * kSlotBytes);
+    unsigned char* xs = smem + kNumSlots * kSlotBytes;
     float* red = reinterpret_cast<float*>(smem + kNumSlots * kSlotBytes + kXsBytes);
-    SharedMisc* misc = reinterpret_cast<SharedMisc*>(smem + kNumSlots * kSlotBytes + kXsBytes + kRedBytes);
+    SharedMisc* misc = reinterpret_cast<SharedMisc*>(smem + kNumSlots * kSlotBytes + kXsBytes + 2 * kRedBytes);
 
     const int tid = threadIdx.x;
-    // a launch queued behind the one that finished the utterance is a no-op.  Uniform: `finished`
-    // is only written by the sampler after >100 grid barriers, i.e. after every CTA has read it.
+    // a launch queued behind the one that finished the utterance is a no-op.  Uniform: `finished` is only
+    // written at the end of a step, which needs every CTA to have taken part in that step's stages.
     if (p.gs != nullptr && p.grid != nullptr && ldcg_i(&p.gs->finished) != 0) return;
     if (tid == 0) {
+#pragma unroll 1
         for (int i = 0; i < kNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
         misc->stages_done = 0;
-        misc->flag = 0;
         fence_mbar_init();
     }
     {   // copy this CTA's table
         const int* src = reinterpret_cast<const int*>(p.cta_tab + blockIdx.x);
         int* dst = reinterpret_cast<int*>(&misc->tab);
+#pragma unroll 1
         for (int i = tid; i < (int)(sizeof(CtaTable) / 4); i += kThreads) dst[i] = src[i];
     }
     __syncthreads();
@@ -1034,54 +1255,71 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
     __syncthreads();
 
     if (tid >= kConsumerThreads) {
-        if (tid == kConsumerThreads) producer_loop(p, ring, misc);
+        if (tid == kProducerWarp * 32) producer_loop(p, ring, misc);
         return;
     }
 
     Ctx c;
     c.p = &p; c.ring = ring; c.xs = xs; c.red = red; c.misc = misc;
     c.tid = tid; c.warp = tid >> 5; c.lane = tid & 31;
-    c.cbase = 0; c.nbar = 0;
+    c.cbase = 0; c.seq = 0; c.xres = 0.f; c.ts = nullptr;
     const int S = 8 * p.L + 3;
 
+    if (p.stage_begin > 0) {
+        // the stream a previous launch left in p.x, published as if stage_begin - 1 had just produced it
+        const int layer = (p.stage_begin - 1) >> 3;
+        c.seq = (unsigned)p.stage_begin;
+        c.xres = enter_stream(p, xs, misc, tid, false, 0, 0, p.norms + (size_t)layer * 3 * p.D, c.seq);
+    }
+#pragma unroll 1
     for (int n = 0; n < p.n_steps; ++n) {
         const int pos = p.pos0 + n, slot = p.slot0 + n;
+#pragma unroll 1
         for (int s = p.stage_begin; s < p.stage_end; ++s) {
             int kind, layer;
             decode_stage(s, p.L, kind, layer);
-            c.tstamp = (p.timing != nullptr && blockIdx.x == 0 && tid == 0) ? p.timing + ((size_t)n * S + s) * 8 : nullptr;
-            if (c.tstamp) c.tstamp[0] = clock64();
+            c.seq = 1u + (unsigned)(n * S + s);
+            c.ts = (p.timing != nullptr && blockIdx.x == 0 && tid == 0) ? p.timing + ((size_t)n * S + s) * 8 : nullptr;
+            if (c.ts) c.ts[0] = clock64();
             switch (kind) {
-                case S_EMBED: embed_stage(c, pos); break;
-                case S_SATTN: attn_stage<4, true>(c, layer, pos, slot); break;
-                case S_CATTN: attn_stage<1, false>(c, layer, pos, slot); break;
+                case S_EMBED: c.xres = enter_stream(p, xs, misc, tid, true, pos, n, p.norms, c.seq); break;
+                case S_SATTN:
+                case S_CATTN: attn_stage(c, kind == S_SATTN, layer, pos, slot); break;
                 case S_SAMPLE: sample_stage(c, n, pos); break;
                 default: gemm_stage(c, gemm_of_kind(kind), layer); break;
             }
-            const bool last = (n == p.n_steps - 1) && (s == p.stage_end - 1);
-            const bool tm = p.timing != nullptr && blockIdx.x == 0 && tid == 0;
-            if (tm) p.timing[((size_t)n * S + s) * 8 + 4] = clock64();
-            const bool publish = kind == S_EMBED || kind == S_SO || kind == S_CO || kind == S_WO;
-            if (!last) grid_barrier(c, publish);
-            else if (publish) { consumer_sync(); if (tid == 0) publish_ssq_partials(c); }
-            if (tm) p.timing[((size_t)n * S + s) * 8 + 5] = clock64();
+            if (c.ts) c.ts[4] = clock64();
+            if (p.cta_timing != nullptr && n == 1 && tid == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                p.cta_timing[(size_t)s * gridDim.x + blockIdx.x] = t;
+            }
             if (tid == 0) st_release_cta_s32(&misc->stages_done, n * S + s + 1);
         }
     }
 }
 
-// standalone head: CFG + masks + sampling on caller-provided logits (dia/model.py:447-488)
+// standalone head: CFG + masks + sampling on caller-provided logits (dia/model.py:447-488); one CTA per channel
 extern "C" __global__ void __launch_bounds__(kConsumerThreads, 1)
 dia_head_sample_kernel(const __grid_constant__ StepParams p, const float* logits, unsigned long long draw, int* pred,
                        float* probs) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    float* gbuf = reinterpret_cast<float*>(smem);
-    float* cv = gbuf + ((p.C * p.V + 3) & ~3);
-    int* ci = reinterpret_cast<int*>(cv + kConsumerWarps * kMaxCand);
-    int* preds = ci + kConsumerWarps * kMaxCand;
-    const int tid = threadIdx.x;
-    sample_all_channels(p, logits, draw, gbuf, cv, ci, preds, probs, tid, tid >> 5, tid & 31, kConsumerWarps);
-    if (tid < p.C) pred[tid] = preds[tid];
+    __shared__ SampleSmem sm;
+    const int ch = blockIdx.x, tid = threadIdx.x;
+    float g[kPerThread];
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+        const int v = tid + kConsumerThreads * i;
+        float gv = -INFINITY;
+        if (v < p.V) {
+            const float un = logits[(size_t)ch * p.V + v], co = logits[((size_t)p.C + ch) * p.V + v];
+            gv = __fadd_rn(co, __fmul_rn(p.cfg_scale, __fsub_rn(co, un)));
+            if ((ch > 0 && v == p.eos) || v == p.pad || v == p.bos) gv = -INFINITY;
+        }
+        g[i] = gv;
+    }
+    const int tok = sample_channel_cta(g, p.V, p.temperature, p.top_p, p.top_k, p.seed, draw, ch,
+                                       probs ? probs + (size_t)ch * p.V : nullptr, &sm, tid);
+    if (tid == 0) pred[ch] = tok;
 }
 
 int step_kernel_smem_bytes() { return kSmemBytes; }
@@ -1093,26 +1331,41 @@ cudaError_t launch_step_kernel(const StepParams& p, bool cooperative, cudaStream
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (cooperative) {
-        void* args[] = {const_cast<StepParams*>(&p)};
-        return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dia_step_kernel), dim3(p.G), dim3(kThreads),
-                                           args, kSmemBytes, st);
-    }
-    dia_step_kernel<<<p.G, kThreads, kSmemBytes, st>>>(p);
-    return cudaGetLastError();
+    (void)cooperative;     // CTAs wait on each other's data: co-residency is always required
+    void* args[] = {const_cast<StepParams*>(&p)};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dia_step_kernel), dim3(p.G), dim3(kThreads), args,
+                                       kSmemBytes, st);
 }
 
 cudaError_t launch_head_sample(const StepParams& p, const float* logits, unsigned long long draw, int* pred,
                                float* probs, cudaStream_t st) {
-    const int smem = ((p.C * p.V + 3) & ~3) * 4 + kConsumerWarps * kMaxCand * 8 + 64 * 4;
-    static int attr_bytes = 0;
-    if (smem > attr_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(dia_head_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_bytes = smem;
-    }
-    dia_head_sample_kernel<<<1, kConsumerThreads, smem, st>>>(p, logits, draw, pred, probs);
+    dia_head_sample_kernel<<<p.C, kConsumerThreads, 0, st>>>(p, logits, draw, pred, probs);
     return cudaGetLastError();
+}
+
+// carve the LL region: fills the ll_* pointers of `out` from `base` (may be null to only size it); returns bytes
+size_t ll_layout(const StepParams& g, StepParams* out, unsigned long long* base) {
+    size_t off = 0;
+    auto take = [&](unsigned long long*& ptr, size_t words) {
+        if (out) ptr = base ? base + off : nullptr;
+        off += (words + 15) & ~(size_t)15;
+    };
+    StepParams scratch;
+    StepParams& o = out ? *out : scratch;
+    const size_t nq = (size_t)g.Hq * kHeadDim, nkv = (size_t)g.Hkv * kHeadDim, nc = (size_t)g.Hc * kHeadDim;
+    take(o.ll_x, (size_t)g.D * 2);
+    take(o.ll_attn, nq * 2);
+    take(o.ll_cattn, nc * 2);
+    take(o.ll_hidden, (size_t)g.F * 2);
+    take(o.ll_qkv, (nq + 2 * nkv) * 2);
+    take(o.ll_cq, nc * 2);
+    take(o.ll_ssq, (size_t)g.G * 2);
+    take(o.ll_sa_part, (size_t)2 * g.Hkv * g.sa_nsplit * 4 * 132);
+    take(o.ll_ca_part, (size_t)g.Hc * g.ca_nsplit * 132);
+    take(o.ll_glog, (size_t)g.C * g.V);
+    take(o.ll_pred, DIA_B200_MAX_CHANNELS);
+    take(o.ll_tok, DIA_B200_MAX_CHANNELS);
+    return off * sizeof(unsigned long long);
 }
 
 }  // namespace dia

@@ -210,32 +210,56 @@ class DecodeEngine:
                                                       _stream(self.device)), "debug_run_stages")
 
     def read_buffer(self, which: int) -> torch.Tensor:
-        d = self.config.model.decoder
-        n = {_lib.BUF_X: self.D, _lib.BUF_QKV: (d.gqa_query_heads + 2 * d.kv_heads) * 128,
-             _lib.BUF_ATTN: d.gqa_query_heads * 128, _lib.BUF_CQ: d.cross_query_heads * 128,
-             _lib.BUF_CATTN: d.cross_query_heads * 128, _lib.BUF_HIDDEN: d.n_hidden}
         if which == _lib.BUF_LOGITS:
             out = torch.empty((2, self.C, self.V), dtype=torch.float32)
         elif which == _lib.BUF_PRED:
             out = torch.empty((self.C,), dtype=torch.int32)
+        elif which == _lib.BUF_X:
+            out = torch.empty((self.D, 2), dtype=torch.float32)
         else:
-            out = torch.empty((n[which], 2), dtype=torch.float32)
+            raise ValueError(f"unknown buffer id {which}")
         _lib.check(self.lib.dia_b200_debug_read(self._h, which, _ptr(out), out.numel() * out.element_size(),
                                                 _stream(self.device)), "debug_read")
-        return out if which in (_lib.BUF_LOGITS, _lib.BUF_PRED) else out.t().contiguous()   # -> [2, n]
+        return out.t().contiguous() if which == _lib.BUF_X else out                       # x -> [2, D]
+
+    def last_device_error(self, full: bool = False):
+        """[code, block, thread, info, 4 detail words] a kernel watchdog left in pinned host memory (works after
+        a failed launch).  full=True: also {(block, warp): (site, info)} for every warp that was waiting."""
+        n = 16 + 2 * 10 * self.n_ctas
+        out = (C.c_int32 * n)()
+        self.lib.dia_b200_debug_last_device_error(self._h, out, n)
+        head = list(out[:8])
+        if not full:
+            return head
+        where = {}
+        for b in range(self.n_ctas):
+            for w in range(10):
+                s, i = out[16 + 2 * (b * 10 + w)], out[16 + 2 * (b * 10 + w) + 1]
+                if s:
+                    where[(b, w)] = (s, i)
+        return head, where
 
     def enable_timing(self, on: bool = True) -> None:
         _lib.check(self.lib.dia_b200_debug_enable_timing(self._h, 1 if on else 0), "debug_enable_timing")
 
     def read_timing(self, n_steps: int) -> torch.Tensor:
-        """int64 [n_steps, stages, 8] SM-clock stamps of CTA 0, thread 0: 0 stage start, 1 input vector
-        loaded, 2 main loop done, 3 cross-warp reduce done, 4 work done, 5 grid barrier passed, 6 first ring
-        slot ready (GEMM stages only)."""
+        """int64 [n_steps, stages, 8] SM-clock stamps of CTA 0, thread 0: 0 stage start, 1 setup done (GEMM) /
+        inputs loaded (attention), 2 main loop done, 3 cross-warp reduce done, 4 stage done, 6 first input
+        words arrived (GEMM stages only)."""
         S = 8 * self.L + 3
         out = torch.empty((16, S, 8), dtype=torch.int64)
         _lib.check(self.lib.dia_b200_debug_read(self._h, _lib.BUF_TIMING, _ptr(out), out.numel() * 8,
                                                 _stream(self.device)), "debug_read")
         return out[:n_steps]
+
+    def read_cta_timing(self) -> torch.Tensor:
+        """int64 [stages, n_ctas]: %globaltimer (ns) at which every CTA finished each stage of step 1 of the last
+        timed launch (needs a launch of >= 2 steps)."""
+        S = 8 * self.L + 3
+        out = torch.empty((S, self.n_ctas), dtype=torch.int64)
+        _lib.check(self.lib.dia_b200_debug_read(self._h, _lib.BUF_CTA_TIMING, _ptr(out), out.numel() * 8,
+                                                _stream(self.device)), "debug_read")
+        return out
 
 
 def launch_count() -> int:

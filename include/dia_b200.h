@@ -180,23 +180,25 @@ int dia_b200_build_revert_indices(int64_t *t_idx, int64_t *indices, int B, int T
 
 /* ---- introspection for tests and the bench ------------------------------------------------- */
 enum dia_b200_buffer {
-    DIA_B200_BUF_X = 0,      /* residual stream, interleaved [D][2]      */
-    DIA_B200_BUF_QKV = 1,    /* [(q_heads+2*kv_heads)*128][2]            */
-    DIA_B200_BUF_ATTN = 2,   /* [q_heads*128][2]                         */
-    DIA_B200_BUF_CQ = 3,     /* [cross_heads*128][2]                     */
-    DIA_B200_BUF_CATTN = 4,  /* [cross_heads*128][2]                     */
-    DIA_B200_BUF_HIDDEN = 5, /* [n_hidden][2]                            */
+    DIA_B200_BUF_X = 0,      /* residual stream after the last executed stage, interleaved [D][2] */
     DIA_B200_BUF_LOGITS = 6, /* [2][C][V]                                */
     DIA_B200_BUF_PRED = 7,   /* int32 [C] raw prediction of the last step */
-    DIA_B200_BUF_TIMING = 8  /* int64 [16][stages][8]: SM-clock stamps of CTA 0 inside each stage */
+    DIA_B200_BUF_TIMING = 8, /* int64 [16][stages][8]: SM-clock stamps of CTA 0 inside each stage */
+    DIA_B200_BUF_CTA_TIMING = 9 /* uint64 [stages][n_ctas]: %globaltimer (ns) at the end of each stage of step 1 */
 };
 /* stage ids inside one decode step: 0 = embed, 1+8*l+{0..7} = qkv, self-attn, self-o, cross-q,
- * cross-attn, cross-o, mlp-in, mlp-out of layer l, 1+8*L = logits, 2+8*L = sample */
+ * cross-attn, cross-o, mlp-in, mlp-out of layer l, 1+8*L = logits, 2+8*L = sample.  A launch may begin at
+ * the embedding, at a layer or at the logits head and end after any of those (the residual stream is handed
+ * from launch to launch in DIA_B200_BUF_X); the `cooperative` argument is ignored (always cooperative). */
 int dia_b200_debug_run_stages(dia_b200_engine *e, const int32_t *tokens, int stage_begin, int stage_end, int pos,
                               int slot, int cooperative, void *stream);
 /* per-stage timestamps for launches of <= 16 steps (profiling aid; a persistent kernel is opaque to ncu) */
 int dia_b200_debug_enable_timing(dia_b200_engine *e, int enable);
 int dia_b200_debug_read(dia_b200_engine *e, int which, void *host_dst, size_t nbytes, void *stream);
+/* {code, block, thread, stage sequence number} written by a kernel watchdog into pinned host memory: readable
+ * even after the launch was killed (codes: 1-4 ring / progress barriers, 5 bad state, 6 data-flag timeout) */
+int dia_b200_debug_last_device_error(dia_b200_engine *e, int32_t *out, int n_words);
+/* words [4..7]: site-specific detail; [16 + 2*(block*10 + warp)]: (site, info) of every warp that was waiting */
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 int64_t dia_b200_launch_count(void);
 

@@ -179,17 +179,21 @@ def test_tiny_voice_clone_path_bit_exact(tiny_gpu, gold_tiny):
 
 
 def test_tiny_stage_modes_agree(tiny_gpu):
-    """One cooperative launch over all stages == one launch per stage (no grid barrier, cold ring)."""
+    """One launch over all stages == one launch per block of stages (embedding, each layer, logits head),
+    the residual stream handed from launch to launch."""
     dia, sd = tiny_gpu
     st, out = _prepared(dia, "[S1] Modes. [S2] Agree.")
     eng = dia.model.decoder._engine_for(st)
     tok = torch.full((2, 9), 1026, dtype=torch.int32).cuda()
     L = dia.config.model.decoder.n_layer
     a = eng.decode_step(tok, 1, 0).clone()
-    for s in range(8 * L + 2):
-        eng.run_stages(tok, s, s + 1, 1, 0, cooperative=False)
+    bounds = [0, 1] + [1 + 8 * (l + 1) for l in range(L)] + [8 * L + 2]
+    for s0, s1 in zip(bounds[:-1], bounds[1:]):
+        eng.run_stages(tok, s0, s1, 1, 0)
     b = eng.read_buffer(_lib.BUF_LOGITS)
     assert torch.equal(a.cpu(), b)
+    with pytest.raises(ValueError):
+        eng.run_stages(tok, 2, 5, 1, 0)                                  # not on a layer boundary
 
 
 def test_tiny_eos_state_machine_matches_reference_loop(gold_tiny):

@@ -72,13 +72,9 @@ def main():
             torch.cuda.synchronize()
             print(f"step {step} embed err", err(eng.read_buffer(_lib.BUF_X), xs_o[0][:, 0]))
             if step == 0 or not a.full:
-                names = ["qkv", "sattn", "so", "cq", "cattn", "co", "wi", "wo"]
                 for i in range(min(L, 2)):
-                    for j in range(8):
-                        eng.run_stages(tk, 0, 1 + 8 * i + j + 1, cur, slot)
-                        torch.cuda.synchronize()
-                        if j in (2, 5, 7):
-                            print(f"  L{i} after {names[j]:6s} x max {eng.read_buffer(_lib.BUF_X).abs().max():.4f}")
+                    eng.run_stages(tk, 0, 1 + 8 * (i + 1), cur, slot)
+                    torch.cuda.synchronize()
                     print(f"  layer {i} out err", err(eng.read_buffer(_lib.BUF_X), xs_o[i + 1][:, 0]))
             logits = eng.decode_step(tk, cur, slot)
             torch.cuda.synchronize()

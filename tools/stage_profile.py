@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--greedy", action="store_true")
+    ap.add_argument("--ctas", action="store_true", help="also print the per-CTA spread of stage end times")
     a = ap.parse_args()
     cfg = tiny_config() if a.tiny else dia_1_6b_config()
     dev = torch.device("cuda:0")
@@ -51,28 +52,42 @@ def main():
             e0.record()
             eng.generate_steps(a.steps)
             e1.record()
-            torch.cuda.synchronize()
+            try:
+                torch.cuda.synchronize()
+            except Exception as ex:
+                print("launch failed:", ex.__class__.__name__, "device error words", eng.last_device_error())
+                raise
         t = eng.read_timing(a.steps).double()
         print(f"launch of {a.steps} steps from slot {a.slot}: {e0.elapsed_time(e1) * 1000 / a.steps:.1f} us/step (event)")
         t = t[1:]                                                      # skip the cold first step
         us = 1.0 / mhz
-        tot = ((t[:, -1, 5] - t[:, 0, 0]).mean()) * us
+        # no barriers: a stage's cost on CTA 0 = start of the next stage - its own start
+        starts = t[:, :, 0].reshape(-1)
+        dur = torch.cat([starts[1:] - starts[:-1], (t[-1, -1, 4] - t[-1, -1, 0]).reshape(1)]).reshape(t.shape[0], S)
+        tot = dur.sum(1).mean().item() * us
         print(f"clock {mhz} MHz; per-step total from stamps {tot:.1f} us (steps 1..{a.steps - 1})")
-        print(f"{'stage':8s} {'prod lead':>9s} {'load x':>7s} {'1st slot':>8s} {'loop':>7s} {'reduce':>7s} {'epi':>7s} {'work':>7s} "
-              f"{'barrier':>8s} {'x/step':>6s} {'total':>8s}")
+        print(f"{'stage':8s} {'setup':>7s} {'wait in':>8s} {'loop':>7s} {'reduce':>7s} {'epi':>7s} {'stage':>7s} {'x/step':>6s} {'total':>8s}")
         rows = [("embed", [0])] + [(NAMES[j], [1 + 8 * l + j for l in range(L)]) for j in range(8)] + \
                [("logits", [8 * L + 1]), ("sample", [8 * L + 2])]
         for name, idx in rows:
             x = t[:, idx, :]
             d = lambda i, j: ((x[..., i] - x[..., j]).mean().item() * us)     # noqa: E731
-            gemm = name not in ("embed", "sattn", "cattn", "sample")
-            work, bar = d(4, 0), d(5, 4)
-            if gemm:
-                print(f"{name:8s} {d(0, 7):9.2f} {d(1, 0):7.2f} {d(6, 1):8.2f} {d(2, 1):7.2f} {d(3, 2):7.2f} {d(4, 3):7.2f} {work:7.2f} "
-                      f"{bar:8.2f} {len(idx):6d} {(work + bar) * len(idx):8.1f}")
+            stage = dur[:, idx].mean().item() * us
+            if name not in ("embed", "sattn", "cattn", "sample"):
+                print(f"{name:8s} {d(1, 0):7.2f} {d(6, 1):8.2f} {d(2, 6):7.2f} {d(3, 2):7.2f} {d(4, 3):7.2f} {stage:7.2f} "
+                      f"{len(idx):6d} {stage * len(idx):8.1f}   epi: sum {d(5, 3):5.2f} store {d(7, 5):5.2f} tail {d(4, 7):5.2f}")
+            elif name in ("sattn", "cattn"):
+                print(f"{name:8s} {'':7s} {d(1, 0):8.2f} {d(2, 1):7.2f} {'':7s} {d(4, 2):7.2f} {stage:7.2f} "
+                      f"{len(idx):6d} {stage * len(idx):8.1f}")
             else:
-                print(f"{name:8s} {'':9s} {'':7s} {'':8s} {'':7s} {'':7s} {'':7s} {work:7.2f} {bar:8.2f} {len(idx):6d} "
-                      f"{(work + bar) * len(idx):8.1f}")
+                print(f"{name:8s} {'':7s} {'':8s} {'':7s} {'':7s} {'':7s} {stage:7.2f} {len(idx):6d} {stage * len(idx):8.1f}")
+        if a.ctas:
+            ct = eng.read_cta_timing().double()                          # [S, G] ns, step 1
+            end = ct.max(1).values
+            print("per-stage spread over CTAs (step 1): stage, last CTA finish - first CTA finish [us], slowest CTA")
+            for name, idx in rows:
+                sp = (ct[idx].max(1).values - ct[idx].min(1).values).mean().item() / 1000
+                print(f"  {name:8s} spread {sp:6.2f}  stage-to-stage {((end[idx] - end[[max(i - 1, 0) for i in idx]]).mean().item()) / 1000:6.2f}")
 
 
 if __name__ == "__main__":

@@ -71,6 +71,7 @@ struct dia_b200_engine {
     long long* d_timing = nullptr;    // [kTimingSteps][S][8], debug only
     unsigned long long* d_cta_timing = nullptr;   // [S][G], debug only
     bool timing_on = false;
+    int timing_cta = 0;
     // pinned host staging
     float** h_ptrs = nullptr;
     GenState* h_gs = nullptr;
@@ -95,7 +96,7 @@ int validate_shape(const dia_b200_shape& s) {
         s.max_audio_len <= 0 || s.max_text_len <= 0)
         return DIA_B200_EINVAL;
     if (s.q_heads != 4 * s.kv_heads) return DIA_B200_EUNSUPPORTED;       // kernels are built for GQA 4:1
-    if (s.d_model % 16 || s.n_hidden % 16) return DIA_B200_EINVAL;                // MMA k-blocks of 16 rows
+    if (s.d_model % 64 || s.n_hidden % 64) return DIA_B200_EINVAL;                // MMA k-blocks of 16 rows, 4 in flight
     if (s.vocab > 5 * kConsumerThreads) return DIA_B200_EUNSUPPORTED;     // sampler: <= 5 entries of a channel per thread
     return DIA_B200_OK;
 }
@@ -123,6 +124,7 @@ void fill_params(const dia_b200_engine* e, StepParams& p) {
     for (int i = 0; i < DIA_B200_MAX_CHANNELS; ++i) p.delay[i] = s.delay_pattern[i];
     p.pred_out = e->d_pred;
     p.timing = e->timing_on ? e->d_timing : nullptr;
+    p.timing_cta = e->timing_cta;
     p.cta_timing = e->timing_on ? e->d_cta_timing : nullptr;
 }
 
@@ -668,6 +670,7 @@ int dia_b200_debug_last_device_error(dia_b200_engine* e, int32_t* out, int n_wor
 int dia_b200_debug_enable_timing(dia_b200_engine* e, int enable) {
     if (!e) return DIA_B200_EINVAL;
     e->timing_on = enable != 0;
+    e->timing_cta = enable > 0 ? std::min(enable - 1, e->G - 1) : 0;       // enable = 1 + CTA to observe
     return DIA_B200_OK;
 }
 

@@ -97,6 +97,7 @@ struct StepParams {
     int eos, pad, bos;
     int delay[DIA_B200_MAX_CHANNELS];
     int* pred_out;                     // [C] raw prediction of the last executed step
+    int timing_cta;                    // the CTA whose thread 0 writes `timing`
     long long* timing;                 // optional [n_steps][S][8] clock64 stamps of CTA 0 (see tools/stage_profile.py)
     unsigned long long* cta_timing;    // optional [S][G] globaltimer at the end of each stage of step 1, per CTA
 };

@@ -316,23 +316,24 @@ __device__ __forceinline__ bool ll_stale(const uint4 (&w)[kLLW], uint32_t f16) {
 template <int NT>
 __device__ __forceinline__ void mma_chunk(float (&acc)[kMaxTiles][4], uint32_t a_addr, uint32_t kb_bytes, int nkb,
                                           uint32_t bst, uint32_t b_off0, uint32_t b_off1, uint32_t bmask) {
-    constexpr int U = NT == 1 ? 4 : (NT == 2 ? 2 : 1);
+    constexpr int U = NT == 1 ? 4 : (NT == 2 ? 2 : 1);       // the host makes every slot a multiple of U k-blocks
 #pragma unroll 1
     for (int kb = 0; kb < nkb; kb += U) {
+        uint2 b[U];
+        uint32_t a[U][NT][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {                       // all operand loads first: they are independent
+            const int k = kb + u;
+            const uint32_t boff = U == 1 ? ((k & 1) ? b_off1 : b_off0) : ((u & 1) ? b_off1 : b_off0);
+            b[u] = lds_u2(bst + (k >> 1) * 512 + boff);
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt) ldmatrix_x4_trans(a[u][mt], a_addr + k * kb_bytes + mt * 32);
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int k = kb + u;
-            if (U == 1 || k < nkb) {
-                const uint32_t boff = U == 1 ? ((k & 1) ? b_off1 : b_off0) : ((u & 1) ? b_off1 : b_off0);
-                uint2 b = lds_u2(bst + (k >> 1) * 512 + boff);
-                b.x &= bmask; b.y &= bmask;
+            b[u].x &= bmask; b[u].y &= bmask;
 #pragma unroll
-                for (int mt = 0; mt < NT; ++mt) {
-                    uint32_t a[4];
-                    ldmatrix_x4_trans(a, a_addr + k * kb_bytes + mt * 32);
-                    mma_bf16_16816(acc[U > 1 ? u * NT + mt : mt], a, b.x, b.y);
-                }
-            }
+            for (int mt = 0; mt < NT; ++mt) mma_bf16_16816(acc[U > 1 ? u * NT + mt : mt], a[u][mt], b[u].x, b[u].y);
         }
     }
 }
@@ -1248,7 +1249,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
         GemmCfg& g = misc->gcfg[tid];
         g.gc = misc->tab.gc[tid]; g.g0 = misc->tab.g0[tid]; g.K = p.Kdim[tid];
         g.row_bytes = g.gc * 16;
-        g.rpc = g.gc > 0 ? min(kMaxKb * 16, (kSlotBytes / (g.gc * 16)) & ~15) : 16;
+        const int align = p.tclass[tid] == 1 ? 64 : (p.tclass[tid] == 2 ? 32 : 16);   // k-blocks come in groups of U
+        g.rpc = g.gc > 0 ? min(kMaxKb * 16, (kSlotBytes / (g.gc * 16)) & ~(align - 1)) : 16;
         g.n_chunks = g.gc > 0 ? (g.K + g.rpc - 1) / g.rpc : 0;
         g.n_mt = (g.gc + 1) >> 1;
     }
@@ -1279,7 +1281,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
             int kind, layer;
             decode_stage(s, p.L, kind, layer);
             c.seq = 1u + (unsigned)(n * S + s);
-            c.ts = (p.timing != nullptr && blockIdx.x == 0 && tid == 0) ? p.timing + ((size_t)n * S + s) * 8 : nullptr;
+            c.ts = (p.timing != nullptr && (int)blockIdx.x == p.timing_cta && tid == 0) ? p.timing + ((size_t)n * S + s) * 8 : nullptr;
             if (c.ts) c.ts[0] = clock64();
             switch (kind) {
                 case S_EMBED: c.xres = enter_stream(p, xs, misc, tid, true, pos, n, p.norms, c.seq); break;

@@ -239,8 +239,8 @@ class DecodeEngine:
                     where[(b, w)] = (s, i)
         return head, where
 
-    def enable_timing(self, on: bool = True) -> None:
-        _lib.check(self.lib.dia_b200_debug_enable_timing(self._h, 1 if on else 0), "debug_enable_timing")
+    def enable_timing(self, on: bool = True, cta: int = 0) -> None:
+        _lib.check(self.lib.dia_b200_debug_enable_timing(self._h, 1 + cta if on else 0), "debug_enable_timing")
 
     def read_timing(self, n_steps: int) -> torch.Tensor:
         """int64 [n_steps, stages, 8] SM-clock stamps of CTA 0, thread 0: 0 stage start, 1 setup done (GEMM) /

@@ -192,7 +192,8 @@ enum dia_b200_buffer {
  * from launch to launch in DIA_B200_BUF_X); the `cooperative` argument is ignored (always cooperative). */
 int dia_b200_debug_run_stages(dia_b200_engine *e, const int32_t *tokens, int stage_begin, int stage_end, int pos,
                               int slot, int cooperative, void *stream);
-/* per-stage timestamps for launches of <= 16 steps (profiling aid; a persistent kernel is opaque to ncu) */
+/* per-stage timestamps for launches of <= 16 steps (profiling aid; a persistent kernel is opaque to ncu);
+ * enable = 0 switches them off, enable = 1 + c records CTA c */
 int dia_b200_debug_enable_timing(dia_b200_engine *e, int enable);
 int dia_b200_debug_read(dia_b200_engine *e, int which, void *host_dst, size_t nbytes, void *stream);
 /* {code, block, thread, stage sequence number} written by a kernel watchdog into pinned host memory: readable

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--greedy", action="store_true")
+    ap.add_argument("--cta", type=int, default=0, help="the CTA whose stamps are shown")
     ap.add_argument("--ctas", action="store_true", help="also print the per-CTA spread of stage end times")
     a = ap.parse_args()
     cfg = tiny_config() if a.tiny else dia_1_6b_config()
@@ -45,7 +46,7 @@ def main():
         # fill the grid so that any starting slot has a valid input row
         out.generated_tokens[: a.slot + a.steps + 2] = 7
         for it in range(2):
-            eng.enable_timing(it == 1)
+            eng.enable_timing(it == 1, a.cta)
             eng.generate_begin(out.generated_tokens, a.slot + 1, a.slot, cfg.data.audio_length, 3.0,
                                0.0 if a.greedy else 1.3, 0.95, 35, 1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

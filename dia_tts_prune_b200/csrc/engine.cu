@@ -307,7 +307,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     ALLOC(e->d_pred, sizeof(int) * DIA_B200_MAX_CHANNELS);
     ALLOC(e->d_tokens, sizeof(int) * 2 * DIA_B200_MAX_CHANNELS);
     ALLOC(e->d_gs, sizeof(GenState));
-    ALLOC(e->d_timing, sizeof(long long) * 8 * kTimingSteps * (8 * s.n_layer + 3));
+    ALLOC(e->d_timing, sizeof(long long) * 16 * kTimingSteps * (8 * s.n_layer + 3));
     ALLOC(e->d_cta_timing, sizeof(unsigned long long) * G * (8 * s.n_layer + 3));
 #undef ALLOC
     if (cudaMallocHost(reinterpret_cast<void**>(&e->h_ptrs), sizeof(float*) * 4 * s.n_layer) != cudaSuccess ||
@@ -655,7 +655,7 @@ static int buffer_of(dia_b200_engine* e, int which, void** ptr, size_t* bytes) {
         case DIA_B200_BUF_CTA_TIMING: *ptr = e->d_cta_timing; *bytes = 8 * (size_t)e->G * (8 * s.n_layer + 3); break;
         case DIA_B200_BUF_LOGITS: *ptr = e->d_logits; *bytes = 4 * 2 * (size_t)s.channels * s.vocab; break;
         case DIA_B200_BUF_PRED: *ptr = e->d_pred; *bytes = 4 * (size_t)s.channels; break;
-        case DIA_B200_BUF_TIMING: *ptr = e->d_timing; *bytes = 64 * (size_t)kTimingSteps * (8 * s.n_layer + 3); break;
+        case DIA_B200_BUF_TIMING: *ptr = e->d_timing; *bytes = 128 * (size_t)kTimingSteps * (8 * s.n_layer + 3); break;
         default: return DIA_B200_EINVAL;
     }
     return DIA_B200_OK;

@@ -59,6 +59,7 @@ struct SharedMisc {
     CtaTable tab;
     GemmCfg gcfg[G_COUNT];
     float inv_rms[2][2];                 // [stage parity][batch row]: 1/rms of the stage input
+    unsigned inv_seq[2];                 // stage sequence number for which inv_rms[parity] is valid
     float stat[16];
     int bcast[8];
     int stages_done;                     // consumer -> producer progress (global stage index + 1)
@@ -356,17 +357,8 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
 
     uint4 w[kLLW];
 
-    // RMSNorm of the input: the per-CTA partial sums of x^2 are fetched now by the last warp and used in the epilogue
     constexpr int kSsqPerLane = 5;                     // <= 160 CTAs
-    uint4 sq[kSsqPerLane];
     const bool ssq_warp = normed && warp == kConsumerWarps - 1;
-    if (ssq_warp) {
-#pragma unroll
-        for (int i = 0; i < kSsqPerLane; ++i) {
-            const int j = lane + 32 * i;
-            sq[i] = j < p.n_res ? ll_ld2(p.ll_ssq + 2 * j) : make_uint4(0u, fprev, 0u, fprev);
-        }
-    }
 
     // epilogue role of this thread: (tile, row, column-in-tile)
     const int e_mt = warp, e_r = lane >> 4, e_m = lane & 15;
@@ -406,7 +398,7 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
                                              ((lane & 3) * 2 + ((lane >> 2) & 1)) * 4);
     const uint32_t s_t0 = s_base + ((0 ^ ss) << 5), s_t1 = s_base + ((1 ^ ss) << 5), s_t2 = s_base + ((2 ^ ss) << 5);
     const int tclass = p.tclass[gt];
-    if (c.ts) c.ts[1] = clock64();
+    if (c.ts && c.tid == 0) c.ts[1] = clock64();
 
     // software pipeline over this warp's slots: the words of slot cn are requested before the MMAs of slot ci
 #pragma unroll 1
@@ -461,7 +453,7 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
             ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 1, c.seq * 16 + gt);
             ll_fetch(w, src, row0, nkb_n, lane, f16);
         }
-        if (c.ts && cn == warp) c.ts[6] = clock64();
+        if (c.ts && c.tid == 0 && cn == warp) c.ts[6] = clock64();
         // ---- transpose into B fragments: word pair (k, k+1) of one row -> (hi|hi), (lo|lo), (lo2|lo2)
         const int pairs = nkb_n * 16;
 #pragma unroll
@@ -484,29 +476,9 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
         for (int j = 0; j < 4; ++j) { acc[0][j] += acc[2][j]; acc[1][j] += acc[3][j]; }
     }
     c.cbase += n_chunks;
-    if (c.ts) c.ts[2] = clock64();
+    if (c.ts && c.tid == 0) c.ts[2] = clock64();
 
-    if (ssq_warp) {
-        // 1/rms of the input from the per-CTA partial sums its producers published (fixed order)
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < kSsqPerLane; ++i) {
-            const int j = lane + 32 * i;
-            if (j < p.n_res) {
-                uint32_t v0 = sq[i].x, v1 = sq[i].z;
-                if (sq[i].y != fprev) v0 = ll_wait32(p.ll_ssq + 2 * j, fprev, p.err);
-                if (sq[i].w != fprev) v1 = ll_wait32(p.ll_ssq + 2 * j + 1, fprev, p.err);
-                s0 += __uint_as_float(v0);
-                s1 += __uint_as_float(v1);
-            }
-        }
-        s0 = warp_sum(s0);
-        s1 = warp_sum(s1);
-        if (lane == 0) {   // torch.nn.RMSNorm: x * rsqrt(mean(x^2) + eps) * w
-            c.misc->inv_rms[par][0] = 1.0f / sqrtf(s0 / (float)K + p.eps);
-            c.misc->inv_rms[par][1] = 1.0f / sqrtf(s1 / (float)K + p.eps);
-        }
-    }
+    if (c.ts && c.tid == 224) c.ts[8] = clock64();
 
     // ---- sum the three bf16 terms (MMA columns) of each batch row, then the 8 warps through smem ----
     // C fragment: c0,c1 = D[m][2q], D[m][2q+1]; c2,c3 = D[m+8][..] with m = lane/4, q = lane%4.
@@ -527,11 +499,43 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
             }
         }
     }
+    if (c.ts && c.tid == 224) c.ts[10] = clock64();
     consumer_sync();
-    if (c.ts) c.ts[3] = clock64();
+    if (c.ts && c.tid == 0) c.ts[3] = clock64();
+    if (ssq_warp) {
+        // RMSNorm of the input: 1/rms from the per-CTA partial sums of x^2 its producers published (fixed order).
+        // This is the one all-CTA dependency of the stage; it runs on the last warp AFTER the block barrier, in
+        // parallel with the other warps' cross-warp sums, and is handed over through a shared-memory flag.
+        uint4 sq[kSsqPerLane];
+#pragma unroll
+        for (int i = 0; i < kSsqPerLane; ++i) {
+            const int j = lane + 32 * i;
+            sq[i] = j < p.n_res ? ll_ld2(p.ll_ssq + 2 * j) : make_uint4(0u, fprev, 0u, fprev);
+        }
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSsqPerLane; ++i) {
+            const int j = lane + 32 * i;
+            if (j < p.n_res) {
+                if (sq[i].y != fprev) sq[i].x = ll_wait32(p.ll_ssq + 2 * j, fprev, p.err);
+                if (sq[i].w != fprev) sq[i].z = ll_wait32(p.ll_ssq + 2 * j + 1, fprev, p.err);
+                s0 += __uint_as_float(sq[i].x);
+                s1 += __uint_as_float(sq[i].z);
+            }
+        }
+        if (c.ts && c.tid == 224) c.ts[9] = clock64();
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0) {   // torch.nn.RMSNorm: x * rsqrt(mean(x^2) + eps) * w
+            volatile float* ir = c.misc->inv_rms[par];
+            ir[0] = 1.0f / sqrtf(s0 / (float)K + p.eps);
+            ir[1] = 1.0f / sqrtf(s1 / (float)K + p.eps);
+            __threadfence_block();
+            *reinterpret_cast<volatile unsigned*>(&c.misc->inv_seq[par]) = c.seq;
+        }
+    }
     if (e_mt >= n_mt) return;                          // whole warps without a tile are done
 
-    const float inv = normed ? c.misc->inv_rms[par][e_r] : 1.0f;
     float y = 0.f, y8 = 0.f;                           // column e_m and (mlp-in only) its partner e_m + 8
     {
         const float* rb = red + (size_t)e_mt * 32 + e_r * 16 + (gt == G_WI ? (e_m & 7) : e_m);
@@ -542,7 +546,17 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
         }
     }
     const uint32_t f16n = c.seq & 0xffffu;
-    if (c.ts) c.ts[5] = clock64();
+    if (c.ts && c.tid == 0) c.ts[5] = clock64();
+    float inv = 1.0f;
+    if (normed) {
+        const volatile unsigned* fl = reinterpret_cast<const volatile unsigned*>(&c.misc->inv_seq[par]);
+        unsigned spins = 0;
+        while (*fl != c.seq) {
+            if (++spins > (kMaxSpins << 3)) ll_timeout(p.err, kErrFlagTimeout + 4, c.seq);
+        }
+        __threadfence_block();
+        inv = reinterpret_cast<const volatile float*>(c.misc->inv_rms[par])[e_r];
+    }
     if (gt == G_WI) {
         // a tile = (gate group, up group) of the same 8 hidden units: h = silu(gate) * up (dia/layers.py:95-101)
         if (!e_valid || e_m >= 8) return;
@@ -585,7 +599,7 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
         reinterpret_cast<float*>(p.x)[(size_t)e_n * 2 + e_r] = xn;
         ll_store_parts(p.ll_x, e_n, e_r, xn * wn_v, f16n);
     }
-    if (c.ts) c.ts[7] = clock64();
+    if (c.ts && c.tid == 0) c.ts[7] = clock64();
     float sqv = xn * xn;                                               // half-warps = batch rows
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) sqv += __shfl_xor_sync(0xffffffffu, sqv, o);
@@ -680,7 +694,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
         }
     }
     consumer_sync();
-    if (c.ts) c.ts[1] = clock64();
+    if (c.ts && c.tid == 0) c.ts[1] = clock64();
     if (has_new && c.tid < kHeadDim) {
         // KVCache.update (dia/state.py:99-103): append this step's K/V at `slot`.  The fence makes the row
         // visible device-wide before this CTA publishes anything that lets another CTA's copy engine read it.
@@ -794,7 +808,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     for (int h = 0; h < HPK; ++h)
         reinterpret_cast<float4*>(racc + ((size_t)c.warp * HPK + h) * kHeadDim)[c.lane] = acc[h];
     consumer_sync();
-    if (c.ts) c.ts[2] = clock64();
+    if (c.ts && c.tid == 0) c.ts[2] = clock64();
 
     u64* oparts = self ? p.ll_attn : p.ll_cattn;
     u64* part = (self ? p.ll_sa_part : p.ll_ca_part) + ((size_t)w.pair * nsplit) * (nh * 132);
@@ -1236,6 +1250,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
 #pragma unroll 1
         for (int i = 0; i < kNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
         misc->stages_done = 0;
+        misc->inv_seq[0] = 0; misc->inv_seq[1] = 0;
         fence_mbar_init();
     }
     {   // copy this CTA's table
@@ -1281,8 +1296,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
             int kind, layer;
             decode_stage(s, p.L, kind, layer);
             c.seq = 1u + (unsigned)(n * S + s);
-            c.ts = (p.timing != nullptr && (int)blockIdx.x == p.timing_cta && tid == 0) ? p.timing + ((size_t)n * S + s) * 8 : nullptr;
-            if (c.ts) c.ts[0] = clock64();
+            c.ts = (p.timing != nullptr && (int)blockIdx.x == p.timing_cta && (tid == 0 || tid == 224)) ? p.timing + ((size_t)n * S + s) * 16 : nullptr;
+            if (c.ts && tid == 0) c.ts[0] = clock64();
             switch (kind) {
                 case S_EMBED: c.xres = enter_stream(p, xs, misc, tid, true, pos, n, p.norms, c.seq); break;
                 case S_SATTN:
@@ -1290,7 +1305,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
                 case S_SAMPLE: sample_stage(c, n, pos); break;
                 default: gemm_stage(c, gemm_of_kind(kind), layer); break;
             }
-            if (c.ts) c.ts[4] = clock64();
+            if (c.ts && tid == 0) c.ts[4] = clock64();
             if (p.cta_timing != nullptr && n == 1 && tid == 0) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

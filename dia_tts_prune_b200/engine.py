@@ -243,11 +243,11 @@ class DecodeEngine:
         _lib.check(self.lib.dia_b200_debug_enable_timing(self._h, 1 + cta if on else 0), "debug_enable_timing")
 
     def read_timing(self, n_steps: int) -> torch.Tensor:
-        """int64 [n_steps, stages, 8] SM-clock stamps of CTA 0, thread 0: 0 stage start, 1 setup done (GEMM) /
+        """int64 [n_steps, stages, 16] SM-clock stamps of CTA 0, thread 0: 0 stage start, 1 setup done (GEMM) /
         inputs loaded (attention), 2 main loop done, 3 cross-warp reduce done, 4 stage done, 6 first input
         words arrived (GEMM stages only)."""
         S = 8 * self.L + 3
-        out = torch.empty((16, S, 8), dtype=torch.int64)
+        out = torch.empty((16, S, 16), dtype=torch.int64)
         _lib.check(self.lib.dia_b200_debug_read(self._h, _lib.BUF_TIMING, _ptr(out), out.numel() * 8,
                                                 _stream(self.device)), "debug_read")
         return out[:n_steps]

@@ -183,7 +183,7 @@ enum dia_b200_buffer {
     DIA_B200_BUF_X = 0,      /* residual stream after the last executed stage, interleaved [D][2] */
     DIA_B200_BUF_LOGITS = 6, /* [2][C][V]                                */
     DIA_B200_BUF_PRED = 7,   /* int32 [C] raw prediction of the last step */
-    DIA_B200_BUF_TIMING = 8, /* int64 [16][stages][8]: SM-clock stamps of CTA 0 inside each stage */
+    DIA_B200_BUF_TIMING = 8, /* int64 [16][stages][16]: SM-clock stamps of CTA 0 inside each stage */
     DIA_B200_BUF_CTA_TIMING = 9 /* uint64 [stages][n_ctas]: %globaltimer (ns) at the end of each stage of step 1 */
 };
 /* stage ids inside one decode step: 0 = embed, 1+8*l+{0..7} = qkv, self-attn, self-o, cross-q,

@@ -390,3 +390,24 @@ def test_full_sequential_utterances_on_one_engine(full_gpu, gold_full):
     assert torch.equal(first, again)
     # rows before the end-of-budget EOS countdown (cur >= 40 - 16) equal the reference's 256-step stream
     assert torch.equal(dia.last_codes.cpu()[:22], torch.from_numpy(gold_full["codes"][:22]))
+
+
+def test_full_repeated_launches_do_not_hang(full_gpu):
+    """Regression for the ring phase-parity alias (a consumer passing a full-barrier wait one generation early
+    deadlocked the weight ring about once per thousand launches): many 64-step launches deep in the context;
+    a watchdog trap would surface here as a CUDA error with the stuck site in `last_device_error()`."""
+    dia, sd = full_gpu
+    cfg = dia.config
+    st, out = _prepared(dia, SY.DEFAULT_TRANSCRIPT)
+    eng = dia.model.decoder._engine_for(st)
+    slot, steps = 1500, 64
+    out.generated_tokens[: slot + steps + 2] = 7
+    for rep in range(12):
+        eng.generate_begin(out.generated_tokens, slot + 1, slot, cfg.data.audio_length, 3.0, 1.3, 0.95, 35, rep)
+        eng.generate_steps(steps)
+        try:
+            torch.cuda.synchronize()
+        except Exception as ex:                                           # pragma: no cover
+            pytest.fail(f"launch {rep} failed: {ex}; device error words {eng.last_device_error()}")
+        assert eng.status().steps_run == steps
+    assert eng.last_device_error()[0] == 0

@@ -76,7 +76,7 @@ def main():
             stage = dur[:, idx].mean().item() * us
             if name not in ("embed", "sattn", "cattn", "sample"):
                 print(f"{name:8s} {d(1, 0):7.2f} {d(6, 1):8.2f} {d(2, 6):7.2f} {d(3, 2):7.2f} {d(4, 3):7.2f} {stage:7.2f} "
-                      f"{len(idx):6d} {stage * len(idx):8.1f}   epi: sum {d(5, 3):5.2f} store {d(7, 5):5.2f} tail {d(4, 7):5.2f}")
+                      f"{len(idx):6d} {stage * len(idx):8.1f}   epi: sum {d(5, 3):5.2f}  warp7: loop end {d(8, 0):5.2f} ssq ready {d(9, 0):5.2f} at barrier {d(10, 0):5.2f} | warp0 at barrier {d(3, 0):5.2f}")
             elif name in ("sattn", "cattn"):
                 print(f"{name:8s} {'':7s} {d(1, 0):8.2f} {d(2, 1):7.2f} {'':7s} {d(4, 2):7.2f} {stage:7.2f} "
                       f"{len(idx):6d} {stage * len(idx):8.1f}")

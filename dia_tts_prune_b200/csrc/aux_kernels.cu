@@ -25,7 +25,7 @@ __global__ void repack_dense_kernel(const RepackArgs a) {
     const CtaTable& t = a.tab[cta];
     const unsigned long long slab = t.stream_base +
         (a.gemm == G_LOGITS ? t.logits_off : (unsigned long long)a.layer * t.layer_bytes + t.slab_off[a.gemm]);
-    unsigned char* dst = a.wstream + slab + ((size_t)k * t.gc[a.gemm] + gl) * 16;
+    unsigned char* dst = a.wstream + slab + ((size_t)gemm_row_position(k, t.gc[a.gemm], a.K) * t.gc[a.gemm] + gl) * 16;
 
     float v[8];
     if (a.gemm == G_QKV) {

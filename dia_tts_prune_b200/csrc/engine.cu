@@ -96,7 +96,12 @@ int validate_shape(const dia_b200_shape& s) {
         s.max_audio_len <= 0 || s.max_text_len <= 0)
         return DIA_B200_EINVAL;
     if (s.q_heads != 4 * s.kv_heads) return DIA_B200_EUNSUPPORTED;       // kernels are built for GQA 4:1
-    if (s.d_model % 64 || s.n_hidden % 64) return DIA_B200_EINVAL;                // MMA k-blocks of 16 rows, 4 in flight
+    // every contraction length splits into 8 warp slices of whole 256-row fetch units (or one shorter unit)
+    const int ks[4] = {s.d_model, s.n_hidden, s.q_heads * kHeadDim, s.cross_heads * kHeadDim};
+    for (int k : ks) {
+        const int sl = k / 8;
+        if (k % 512 || (sl > 256 && sl % 256)) return DIA_B200_EUNSUPPORTED;
+    }
     if (s.vocab > 5 * kConsumerThreads) return DIA_B200_EUNSUPPORTED;     // sampler: <= 5 entries of a channel per thread
     return DIA_B200_OK;
 }
@@ -250,6 +255,11 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
         int mx = 1;
         for (int c = 0; c < G; ++c) mx = std::max(mx, (e->tab[c].gc[t] + 1) / 2);
         e->tclass[t] = mx <= 1 ? 1 : mx <= 2 ? 2 : mx <= 4 ? 4 : 8;
+    }
+    for (int t = 0; t < G_COUNT; ++t) {
+        const int need = e->tclass[t] == 1 ? 64 : 32;       // k-blocks in flight per MMA group; slots start on even k-blocks
+        for (int c = 0; c < G; ++c)
+            if (e->tab[c].gc[t] > 0 && gemm_slot_rows(e->tab[c].gc[t], e->Kdim[t]) % need) { delete e; return DIA_B200_EUNSUPPORTED; }
     }
     for (int c = 0; c < G; ++c) {
         if (e->tab[c].gc[G_SO] > 0) {

@@ -29,6 +29,26 @@ struct CtaTable {
     int gc[G_COUNT];
 };
 
+// Rows of a slab in one ring slot.  Each of the 8 math warps owns the contiguous K/8 rows [w*K/8, (w+1)*K/8) of the
+// contraction; a slot holds `r` of them, r a power of two that divides K/8 and fits 8 KB.  Stream position ci of a
+// slab is slot j = ci / 8 of warp w = ci % 8, i.e. rows w*K/8 + j*r ..: ring order alternates between the warps
+// while every warp walks a contiguous k-range (one fetch of its input words serves up to 256 / r slots).
+__host__ __device__ inline int gemm_slot_rows(int gc, int K) {
+    const int sl = K / 8;
+    int cap = 8192 / (gc * 16);
+    if (cap > 256) cap = 256;
+    if (cap > sl) cap = sl;
+    int r = 16;
+    while (r * 2 <= cap && sl % (r * 2) == 0) r *= 2;
+    return r;
+}
+// position (row index inside the slab's stream) of contraction row k
+__host__ __device__ inline int gemm_row_position(int k, int gc, int K) {
+    const int sl = K / 8, r = gemm_slot_rows(gc, K);
+    const int w = k / sl, within = k - w * sl, j = within / r, rr = within - j * r;
+    return (w + 8 * j) * r + rr;
+}
+
 struct GenState {                      // device-resident Dia.generate loop state (dia/model.py:736-807)
     int dec_step;
     int finished;

@@ -48,8 +48,11 @@ typedef unsigned long long u64;
 struct GemmCfg {
     int gc, g0, K;
     int row_bytes;     // gc * 16
-    int rpc;           // rows of the slab per ring slot (multiple of 16 = one MMA k-block)
-    int n_chunks;
+    int rpc;           // rows of the slab per ring slot (gemm_slot_rows)
+    int n_chunks;      // ring slots of the slab = K / rpc
+    int sl;            // contraction rows owned by one warp = K / 8
+    int urows;         // rows of one input fetch unit = min(sl, 256)
+    int cpu;           // ring slots per fetch unit = urows / rpc
     int n_mt;          // 16-column MMA tiles = ceil(gc / 2)
 };
 
@@ -193,10 +196,8 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
                     (gt == G_LOGITS ? tab.logits_off
                                     : (unsigned long long)layer * tab.layer_bytes + tab.slab_off[gt]);
 #pragma unroll 1
-                for (int r0 = 0; r0 < g.K; r0 += g.rpc) {
-                    const int rows = min(g.rpc, g.K - r0);
-                    pr.issue(base + (size_t)r0 * g.row_bytes, rows * g.row_bytes, false);
-                }
+                for (int r0 = 0; r0 < g.K; r0 += g.rpc)
+                    pr.issue(base + (size_t)r0 * g.row_bytes, g.rpc * g.row_bytes, false);
             } else if (kind == S_SATTN || kind == S_CATTN) {
                 const bool self = kind == S_SATTN;
                 const AttnWork w = self ? self_attn_work(p, cta, slot) : cross_attn_work(p, cta);
@@ -227,13 +228,10 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
                     vb = p.cross_v[layer] + off;
                 }
 #pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    const float* b = pass == 0 ? kb : vb;
-#pragma unroll 1
-                    for (int k0 = w.k_lo; k0 < w.k_hi; k0 += 16) {
-                        const int nk = min(16, w.k_hi - k0);
-                        pr.issue(b + (size_t)k0 * kHeadDim, nk * kHeadDim * 4, !self);
-                    }
+                for (int k0 = w.k_lo; k0 < w.k_hi; k0 += 16) {        // K tile, then the V tile of the same keys
+                    const int nk = min(16, w.k_hi - k0);
+                    pr.issue(kb + (size_t)k0 * kHeadDim, nk * kHeadDim * 4, !self);
+                    pr.issue(vb + (size_t)k0 * kHeadDim, nk * kHeadDim * 4, !self);
                 }
             }
         }
@@ -356,7 +354,6 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     const int n_chunks = g.n_chunks, rpc = g.rpc;
 
     uint4 w[kLLW];
-
     constexpr int kSsqPerLane = 5;                     // <= 160 CTAs
     const bool ssq_warp = normed && warp == kConsumerWarps - 1;
 
@@ -400,28 +397,16 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     const int tclass = p.tclass[gt];
     if (c.ts && c.tid == 0) c.ts[1] = clock64();
 
-    // software pipeline over this warp's slots: the words of slot cn are requested before the MMAs of slot ci
+    // This warp owns contraction rows [warp * sl, (warp + 1) * sl), in fetch units of up to 256 rows (the staging
+    // buffer).  Software pipeline: the input words of unit u + 1 are requested before the MMAs of unit u; the cpu ring
+    // slots of a unit are stream positions warp + 8 * (u * cpu + jc).
+    const int units = g.sl / g.urows, cpu = g.cpu, nkb_u = g.urows >> 4, nkb = rpc >> 4;
+    const int row_w = warp * g.sl;
+    ll_fetch(w, src, row_w, nkb_u, lane, f16);
 #pragma unroll 1
-    for (int ci = warp - kConsumerWarps;;) {
-        const int cn = ci + kConsumerWarps;
-        const int row0 = cn * rpc;
-        const int nkb_n = min(rpc, K - row0) >> 4;
-        if (cn < n_chunks) ll_fetch(w, src, row0, nkb_n, lane, f16);
-        if (ci >= 0) {
-            const unsigned idx = c.cbase + ci;
-            const unsigned slot = idx % kNumSlots;
-            ring_wait_full(c.misc, slot, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | slot);
-            const uint32_t a_addr = ring_base + slot * kSlotBytes;
-            const int nkb = min(rpc, K - ci * rpc) >> 4;
-            if (tclass == 1) mma_chunk<1>(acc, a_addr, kb_bytes, nkb, bst, b_off0, b_off1, bmask);
-            else if (tclass == 2) mma_chunk<2>(acc, a_addr, kb_bytes, nkb, bst, b_off0, b_off1, bmask);
-            else if (tclass == 4) mma_chunk<4>(acc, a_addr, kb_bytes, nkb, bst, b_off0, b_off1, bmask);
-            else mma_chunk<8>(acc, a_addr, kb_bytes, nkb, bst, b_off0, b_off1, bmask);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&c.misc->empty[slot]);
-        }
-        if (cn >= n_chunks) break;
-        // ---- the input words of slot cn: wait until the producing stage has written all of them
+    for (int u = 0; u < units; ++u) {
+        const int row0 = row_w + u * g.urows;
+        // ---- wait until the producing stage has written all input words of this unit
         unsigned spins = 0;
         while (__any_sync(0xffffffffu, ll_stale(w, f16))) {
             if (lane == 0) {
@@ -429,33 +414,20 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
                 while ((ll_ld(sentinel).y >> 16) != f16) {
                     if (++spins > kMaxSpins) {
                         volatile int* e = reinterpret_cast<volatile int*>(p.err);
-                        e[4] = 1 + row0 * 2; e[5] = (int)(ll_ld(sentinel).y >> 16); e[6] = (int)f16; e[7] = cn;
+                        e[4] = 1 + row0 * 2; e[5] = (int)(ll_ld(sentinel).y >> 16); e[6] = (int)f16; e[7] = u;
                         ll_timeout(p.err, kErrFlagTimeout, c.seq * 16 + gt);
                     }
                     ll_check_abort(p.err, spins, 100 + kErrFlagTimeout, c.seq * 16 + gt);
                 }
             }
             __syncwarp();
-            if (++spins > kMaxSpins) {
-                // debug: which word is stale, and what flag does it carry (older = never written, newer = overwritten)
-                volatile int* e = reinterpret_cast<volatile int*>(p.err);
-                for (int i = 0; i < kLLW; ++i) {
-                    const bool b0 = (w[i].y >> 16) != f16, b1 = (w[i].w >> 16) != f16;
-                    if ((b0 || b1) && e[4] == 0) {
-                        e[4] = 1 + row0 * 2 + (lane + 32 * i) * 2 + (b0 ? 0 : 1);      // word index + 1
-                        e[5] = (int)(b0 ? w[i].y >> 16 : w[i].w >> 16);                 // flag found
-                        e[6] = (int)f16;
-                        e[7] = cn;
-                    }
-                }
-                ll_timeout(p.err, kErrFlagTimeout + 1, c.seq * 16 + gt);
-            }
+            if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 1, c.seq * 16 + gt);
             ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 1, c.seq * 16 + gt);
-            ll_fetch(w, src, row0, nkb_n, lane, f16);
+            ll_fetch(w, src, row0, nkb_u, lane, f16);
         }
-        if (c.ts && c.tid == 0 && cn == warp) c.ts[6] = clock64();
+        if (c.ts && c.tid == 0 && u == 0) c.ts[6] = clock64();
         // ---- transpose into B fragments: word pair (k, k+1) of one row -> (hi|hi), (lo|lo), (lo2|lo2)
-        const int pairs = nkb_n * 16;
+        const int pairs = nkb_u * 16;
 #pragma unroll
         for (int i = 0; i < kLLW; ++i) {
             if (lane + 32 * i < pairs) {
@@ -464,8 +436,23 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
                 sts_u32(s_t2 + i * 512, __byte_perm(w[i].y, w[i].w, 0x5410));
             }
         }
+        if (u + 1 < units) ll_fetch(w, src, row0 + g.urows, nkb_u, lane, f16);
         __syncwarp();
-        ci = cn;
+#pragma unroll 1
+        for (int jc = 0; jc < cpu; ++jc) {
+            const unsigned idx = c.cbase + warp + kConsumerWarps * (u * cpu + jc);
+            const unsigned slot = idx % kNumSlots;
+            ring_wait_full(c.misc, slot, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | slot);
+            const uint32_t a_addr = ring_base + slot * kSlotBytes;
+            const uint32_t b_base = bst + (uint32_t)(jc * nkb) * 256u;      // nkb is even: the parity swizzle lines up
+            if (tclass == 1) mma_chunk<1>(acc, a_addr, kb_bytes, nkb, b_base, b_off0, b_off1, bmask);
+            else if (tclass == 2) mma_chunk<2>(acc, a_addr, kb_bytes, nkb, b_base, b_off0, b_off1, bmask);
+            else if (tclass == 4) mma_chunk<4>(acc, a_addr, kb_bytes, nkb, b_base, b_off0, b_off1, bmask);
+            else mma_chunk<8>(acc, a_addr, kb_bytes, nkb, b_base, b_off0, b_off1, bmask);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&c.misc->empty[slot]);
+        }
+        __syncwarp();                                        // the staging buffer is rewritten by the next unit
     }
     // fold the independent accumulator chains of the small tile classes (fixed order)
     if (tclass == 1) {
@@ -655,9 +642,10 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     float* qs = reinterpret_cast<float*>(c.xs);          // [HPK][128] rotated, pre-scaled queries
     float* kn = qs + HPK * kHeadDim;                     // [128] rotated key of this step
     float* vn = kn + kHeadDim;                           // [128] value of this step
-    float* stat = vn + kHeadDim;                         // m[HPK] at 0.., l[HPK] at 8..
-    float* sc = stat + 16;                               // [(n_keys + 1)][HPK] scores -> probabilities
-    float* racc = reinterpret_cast<float*>(c.xs) + 5120; // [warps][HPK][128]   (sc holds <= 1025 x 4 floats)
+    float* psm = vn + kHeadDim + c.warp * 64;            // [warps][16 keys][HPK] probabilities of the current tile
+    float* wstat = vn + kHeadDim + kConsumerWarps * 64;  // [warps][8]: m[HPK], l[HPK] of each warp
+    float* cw = wstat + kConsumerWarps * 8;              // split-combine staging
+    float* racc = reinterpret_cast<float*>(c.xs) + 5120; // [warps][HPK][128]
     const u64* qsrc = self ? p.ll_qkv : p.ll_cq;
 
     // ---- inputs: wait for the projection that produced q (and k, v of this step), RoPE, scale ---------
@@ -696,12 +684,13 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     consumer_sync();
     if (c.ts && c.tid == 0) c.ts[1] = clock64();
     if (has_new && c.tid < kHeadDim) {
-        // KVCache.update (dia/state.py:99-103): append this step's K/V at `slot`.  The fence makes the row
-        // visible device-wide before this CTA publishes anything that lets another CTA's copy engine read it.
+        // KVCache.update (dia/state.py:99-103): append this step's K/V at `slot`.  The row must be visible device-wide
+        // before this CTA publishes its share of the stage OUTPUT (which is what lets, one step later, another CTA's
+        // copy engine read it): the fence sits right before that publish, off the path of the other splits.
         const size_t row = ((size_t)w.pair * p.Lmax + slot) * kHeadDim;
         p.self_k[layer][row + c.tid] = kn[c.tid];
         p.self_v[layer][row + c.tid] = vn[c.tid];
-        __threadfence();
+        if (w.n_active == 1) __threadfence();
     }
     float4 q[HPK];
 #pragma unroll
@@ -711,63 +700,10 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     const int nkc = (nk + 15) >> 4;
     const int nvc = nkc + (has_new ? 1 : 0);             // the key of this step is one more (virtual) tile
 
-    // ---- K pass: scores --------------------------------------------------------------------
-#pragma unroll 1
-    for (int ci = c.warp; ci < nvc; ci += kConsumerWarps) {
-        const bool in_ring = ci < nkc;
-        unsigned sl = 0;
-        const float4* kt = reinterpret_cast<const float4*>(kn) + c.lane;
-        int keys_in = 1, key0 = nk;
-        if (in_ring) {
-            const unsigned idx = c.cbase + ci;
-            sl = idx % kNumSlots;
-            ring_wait_full(c.misc, sl, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | 0x40 | sl);
-            kt = reinterpret_cast<const float4*>(c.ring + sl * kSlotBytes) + c.lane;
-            keys_in = min(16, nk - ci * 16);
-            key0 = ci * 16;
-        }
-#pragma unroll 1
-        for (int half = 0; half < 16; half += 8) {
-            if (half >= keys_in) break;
-            float v[8 * HPK];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (half + i < keys_in) kv = kt[(half + i) * 32];
-#pragma unroll
-                for (int h = 0; h < HPK; ++h)
-                    v[i * HPK + h] = kv.x * q[h].x + kv.y * q[h].y + kv.z * q[h].z + kv.w * q[h].w;
-            }
-            transpose_reduce<8 * HPK>(v, c.lane);            // lane l now holds (key l/4, head l%4)
-            const int key = half + (c.lane >> 2);
-            if (key < keys_in) sc[(key0 + key) * HPK + (c.lane & 3)] = v[0];
-        }
-        if (in_ring) {
-            __syncwarp();
-            if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
-        }
-    }
-    consumer_sync();
-    const int n_tot = nk + (has_new ? 1 : 0);
-    if (c.warp < nh) {
-        const int h = c.warp;
-        float m = -INFINITY;
-#pragma unroll 1
-        for (int i = c.lane; i < n_tot; i += 32) m = fmaxf(m, sc[i * HPK + h]);
-        m = warp_max(m);
-        float l = 0.f;
-#pragma unroll 1
-        for (int i = c.lane; i < n_tot; i += 32) {
-            const float e = expf(sc[i * HPK + h] - m);
-            sc[i * HPK + h] = e;
-            l += e;
-        }
-        l = warp_sum(l);
-        if (c.lane == 0) { stat[h] = m; stat[8 + h] = l; }
-    }
-    consumer_sync();
-
-    // ---- V pass ----------------------------------------------------------------------------
+    // ---- one pass over the tiles of this warp (flash-style): scores of a K tile, running max / sum per head,
+    //      then the V tile of the same keys.  Lane l owns score (key l/4 [+8], head l%4) and the running (m, l)
+    //      of head l%4; every lane accumulates output dims 4*lane..4*lane+3 of all four heads.
+    float m_run = -INFINITY, l_run = 0.f;
     float4 acc[HPK];
 #pragma unroll
     for (int h = 0; h < HPK; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -775,20 +711,67 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     for (int ci = c.warp; ci < nvc; ci += kConsumerWarps) {
         const bool in_ring = ci < nkc;
         unsigned sl = 0;
+        const float4* kt = reinterpret_cast<const float4*>(kn) + c.lane;
         const float4* vt = reinterpret_cast<const float4*>(vn) + c.lane;
-        int keys_in = 1, key0 = nk;
+        int keys_in = 1;
         if (in_ring) {
-            const unsigned idx = c.cbase + nkc + ci;
+            const unsigned idx = c.cbase + 2 * ci;
+            sl = idx % kNumSlots;
+            ring_wait_full(c.misc, sl, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | 0x40 | sl);
+            kt = reinterpret_cast<const float4*>(c.ring + sl * kSlotBytes) + c.lane;
+            keys_in = min(16, nk - ci * 16);
+        }
+        float s2[2];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float v[8 * HPK];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (half * 8 + i < keys_in) kv = kt[(half * 8 + i) * 32];
+#pragma unroll
+                for (int h = 0; h < HPK; ++h)
+                    v[i * HPK + h] = kv.x * q[h].x + kv.y * q[h].y + kv.z * q[h].z + kv.w * q[h].w;
+            }
+            transpose_reduce<8 * HPK>(v, c.lane);            // lane l now holds (key l/4, head l%4)
+            const float sv = (half * 8 + (c.lane >> 2)) < keys_in ? v[0] : -INFINITY;
+            if (half == 0) s2[0] = sv; else s2[1] = sv;
+        }
+        if (in_ring) {
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
+        }
+        float mt = fmaxf(s2[0], s2[1]);                      // tile max / sum per head: over the 8 lanes of a head
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 4));
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
+        const float m_new = fmaxf(m_run, mt);
+        const float scale = expf(m_run - m_new);             // exp(-inf) = 0 on the first tile
+        const float p0 = expf(s2[0] - m_new), p1 = expf(s2[1] - m_new);
+        float lt = p0 + p1;
+        lt += __shfl_xor_sync(0xffffffffu, lt, 4);
+        lt += __shfl_xor_sync(0xffffffffu, lt, 8);
+        lt += __shfl_xor_sync(0xffffffffu, lt, 16);
+        l_run = l_run * scale + lt;
+        m_run = m_new;
+        psm[c.lane] = p0;                                    // index = key * 4 + head = lane (keys 0..7), +32 (8..15)
+        psm[32 + c.lane] = p1;
+#pragma unroll
+        for (int h = 0; h < HPK; ++h) {
+            const float sh = __shfl_sync(0xffffffffu, scale, h);
+            acc[h].x *= sh; acc[h].y *= sh; acc[h].z *= sh; acc[h].w *= sh;
+        }
+        __syncwarp();
+        if (in_ring) {
+            const unsigned idx = c.cbase + 2 * ci + 1;
             sl = idx % kNumSlots;
             ring_wait_full(c.misc, sl, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | 0x80 | sl);
             vt = reinterpret_cast<const float4*>(c.ring + sl * kSlotBytes) + c.lane;
-            keys_in = min(16, nk - ci * 16);
-            key0 = ci * 16;
         }
 #pragma unroll 2
         for (int key = 0; key < keys_in; ++key) {
             const float4 vv = vt[key * 32];
-            const float4 pr = *reinterpret_cast<const float4*>(sc + (key0 + key) * HPK);
+            const float4 pr = *reinterpret_cast<const float4*>(psm + key * HPK);
             acc[0].x = fmaf(pr.x, vv.x, acc[0].x); acc[0].y = fmaf(pr.x, vv.y, acc[0].y);
             acc[0].z = fmaf(pr.x, vv.z, acc[0].z); acc[0].w = fmaf(pr.x, vv.w, acc[0].w);
             acc[1].x = fmaf(pr.y, vv.x, acc[1].x); acc[1].y = fmaf(pr.y, vv.y, acc[1].y);
@@ -798,12 +781,11 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
             acc[3].x = fmaf(pr.w, vv.x, acc[3].x); acc[3].y = fmaf(pr.w, vv.y, acc[3].y);
             acc[3].z = fmaf(pr.w, vv.z, acc[3].z); acc[3].w = fmaf(pr.w, vv.w, acc[3].w);
         }
-        if (in_ring) {
-            __syncwarp();
-            if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
-        }
+        __syncwarp();                                        // psm is rewritten by the next tile
+        if (in_ring && c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
     }
     c.cbase += 2 * nkc;
+    if (c.lane < HPK) { wstat[c.warp * 8 + c.lane] = m_run; wstat[c.warp * 8 + 4 + c.lane] = l_run; }
 #pragma unroll
     for (int h = 0; h < HPK; ++h)
         reinterpret_cast<float4*>(racc + ((size_t)c.warp * HPK + h) * kHeadDim)[c.lane] = acc[h];
@@ -816,11 +798,17 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
 #pragma unroll 1
     for (int i = c.tid; i < nh * kHeadDim; i += kConsumerThreads) {
         const int h = i >> 7, d = i & 127;
-        float o = 0.f;
+        float M = -INFINITY;                              // merge the warps' (m, l, o) in warp order
 #pragma unroll
-        for (int ww = 0; ww < kConsumerWarps; ++ww) o += racc[((size_t)ww * HPK + h) * kHeadDim + d];
+        for (int ww = 0; ww < kConsumerWarps; ++ww) M = fmaxf(M, wstat[ww * 8 + h]);
+        float o = 0.f, l = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < kConsumerWarps; ++ww) {
+            const float f = expf(wstat[ww * 8 + h] - M);
+            l = fmaf(wstat[ww * 8 + 4 + h], f, l);
+            o = fmaf(racc[((size_t)ww * HPK + h) * kHeadDim + d], f, o);
+        }
         if (w.n_active == 1) {
-            const float l = stat[8 + h];
             const float val = l > 0.f ? o / l : 0.f;
             const int k = (head0 + h) * kHeadDim + d;
             ll_store_parts(oparts, k, r, val, f16n);
@@ -828,9 +816,10 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
         } else {
             u64* pp = part + ((size_t)w.split * nh + h) * 132;
             ll_st(pp + 4 + d, __float_as_uint(o), c.seq);
-            if (d == 0) { ll_st(pp, __float_as_uint(stat[h]), c.seq); ll_st(pp + 1, __float_as_uint(stat[8 + h]), c.seq); }
+            if (d == 0) { ll_st(pp, __float_as_uint(M), c.seq); ll_st(pp + 1, __float_as_uint(l), c.seq); }
         }
     }
+    if (has_new && c.tid < kHeadDim) __threadfence();     // (several splits: the partials are out, now the appended row)
     consumer_sync();                                      // the scratch is reused by the next stage
     if (w.n_active == 1) return;
 
@@ -841,8 +830,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     if (e0 >= e1) return;                                 // (CTA-uniform)
     const int ne = e1 - e0, na = w.n_active;
     const int h_lo = e0 >> 7, nhh = ((e1 - 1) >> 7) - h_lo + 1;
-    float* cw = sc;                                       // [ne][na] outputs, then [nhh][na][2] (m, l)
-    float* cml = cw + ne * na;
+    float* cml = cw + ne * na;                            // cw: [ne][na] outputs, then [nhh][na][2] (m, l)
 #pragma unroll 1
     for (int i = c.tid; i < ne * na + nhh * na * 2; i += kConsumerThreads) {
         const u64* src;
@@ -1264,9 +1252,11 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
         GemmCfg& g = misc->gcfg[tid];
         g.gc = misc->tab.gc[tid]; g.g0 = misc->tab.g0[tid]; g.K = p.Kdim[tid];
         g.row_bytes = g.gc * 16;
-        const int align = p.tclass[tid] == 1 ? 64 : (p.tclass[tid] == 2 ? 32 : 16);   // k-blocks come in groups of U
-        g.rpc = g.gc > 0 ? min(kMaxKb * 16, (kSlotBytes / (g.gc * 16)) & ~(align - 1)) : 16;
-        g.n_chunks = g.gc > 0 ? (g.K + g.rpc - 1) / g.rpc : 0;
+        g.rpc = g.gc > 0 ? gemm_slot_rows(g.gc, g.K) : 16;
+        g.n_chunks = g.gc > 0 ? g.K / g.rpc : 0;
+        g.sl = g.K / kConsumerWarps;
+        g.urows = min(g.sl, kMaxKb * 16);
+        g.cpu = g.urows / g.rpc;
         g.n_mt = (g.gc + 1) >> 1;
     }
     __syncthreads();

@@ -401,7 +401,8 @@ def test_full_repeated_launches_do_not_hang(full_gpu):
     st, out = _prepared(dia, SY.DEFAULT_TRANSCRIPT)
     eng = dia.model.decoder._engine_for(st)
     slot, steps = 1500, 64
-    out.generated_tokens[: slot + steps + 2] = 7
+    with torch.inference_mode():
+        out.generated_tokens[: slot + steps + 2] = 7
     for rep in range(12):
         eng.generate_begin(out.generated_tokens, slot + 1, slot, cfg.data.audio_length, 3.0, 1.3, 0.95, 35, rep)
         eng.generate_steps(steps)

@@ -86,6 +86,14 @@ def main():
             ct = eng.read_cta_timing().double()                          # [S, G] ns, step 1
             end = ct.max(1).values
             print("per-stage spread over CTAs (step 1): stage, last CTA finish - first CTA finish [us], slowest CTA")
+            for probe in ("wi", "sattn", "wo"):
+                j = NAMES.index(probe)
+                for l in (3, 9):
+                    sidx = 1 + 8 * l + j
+                    rel = (ct[sidx] - end[sidx - 1]) / 1000.0          # finish time after the previous stage completed everywhere
+                    order = torch.argsort(rel)
+                    print(f"  {probe} layer {l}: finish after prev stage [us] min {rel.min():.2f} median {rel.median():.2f} max {rel.max():.2f};"
+                          f" slowest CTAs {order[-6:].tolist()} fastest {order[:6].tolist()}")
             for name, idx in rows:
                 sp = (ct[idx].max(1).values - ct[idx].min(1).values).mean().item() / 1000
                 print(f"  {name:8s} spread {sp:6.2f}  stage-to-stage {((end[idx] - end[[max(i - 1, 0) for i in idx]]).mean().item()) / 1000:6.2f}")

@@ -41,6 +41,17 @@ WEIGHT_SEED = 5
 FRAME_RATE = 44100 / 512          # 86.13 frames per second of audio
 
 
+def workload_config(text_len: int, world: int) -> dict:
+    """The `config` object both arms print (BASELINE.json configs[1], one utterance per GPU)."""
+    return {"workload": "Dia-1.6B bf16 weights, single transcript per GPU, CFG batch 2, full 3072-token "
+                        "generation (3071 decode steps), reference default sampling T=1.3 top_p=0.95 top_k=35",
+            "precision": "bf16 weights; fp32 activations, accumulation, softmax and KV cache",
+            "weights": f"random-init seed {WEIGHT_SEED}, channel-0 EOS column zeroed so no early EOS",
+            "l2": "inputs larger than L2: 2.53 GB of weights streamed per decode step",
+            "frame": "1 frame = 1 decode step = 9 codes = 512 samples @ 44.1 kHz",
+            "text_len": text_len, "parallelism": f"replicas x{world}, no data-path collective"}
+
+
 def algorithmic_bytes(cfg, slot: int, text_len: int, kv_elem: int = 4) -> int:
     """bf16 weights of the 18 layers + logits head, fp32 norm weights, 9 embedding rows,
     plus self-KV rows read / appended and the valid cross-KV rows of the conditional row."""
@@ -147,6 +158,8 @@ def run_reference(args) -> None:
     threads = os.cpu_count() or 1
     dia, cfg = build_cpu_model(WEIGHT_SEED, suppress_eos=True)
     sd = {k: v.detach() for k, v in dia.model.named_parameters()}
+    eff = dia._effective_text(SY.DEFAULT_TRANSCRIPT, None)                 # speaker tags are one byte each
+    text_len = len(eff.encode("utf-8").replace(b"[S1]", b"\x01").replace(b"[S2]", b"\x02"))
     per_step = max(2, args.ref_decode_steps)
     vals, t_all = [], time.perf_counter()
     for i in range(args.warmup + args.steps):
@@ -157,8 +170,9 @@ def run_reference(args) -> None:
     line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * per_step / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Dia-1.6B single transcript, CFG batch 2, greedy; bounded sample of the 3072-token "
-                                   f"generation: {per_step} decode steps per bench step on the host CPU"},
+            "config": workload_config(text_len, max(1, args.gpus)),
+            "note": f"reference arm: the CPU port of the reference's own fp32 loop; every bench step is a bounded sample of "
+                    f"{per_step} greedy decode steps of that workload (precision fp32 on the host, not bf16)",
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "rtfx": v / FRAME_RATE, "wall_s": time.perf_counter() - t_all}
@@ -292,13 +306,7 @@ def run_ours(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Dia-1.6B bf16 weights, single transcript per GPU, CFG batch 2, full 3072-token "
-                                   "generation (3071 decode steps), reference default sampling T=1.3 top_p=0.95 top_k=35",
-                       "precision": "bf16 weights; fp32 activations, accumulation, softmax and KV cache",
-                       "weights": f"random-init seed {WEIGHT_SEED}, channel-0 EOS column zeroed so no early EOS",
-                       "l2": "inputs larger than L2: 2.53 GB of weights streamed per decode step",
-                       "frame": "1 frame = 1 decode step = 9 codes = 512 samples @ 44.1 kHz",
-                       "text_len": text_len, "parallelism": f"replicas x{world}, no data-path collective"},
+            "config": workload_config(text_len, world),
             "decode_ms_per_frame": dev_ms / (frames_dev / world),
             "rtfx": value / world / FRAME_RATE,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -7,6 +7,7 @@ built) or a call fails, a ``RuntimeError`` is raised.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
 from pathlib import Path
 
@@ -84,6 +85,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB
+    override = os.environ.get("DIA_B200_LIB")            # A/B timing of two builds on one box (tools/ab.sh)
+    if override:
+        path, build_if_missing = Path(override), False
     if build_if_missing and _build.is_stale():
         try:
             _build.build()

@@ -469,6 +469,7 @@ int dia_b200_decode_step(dia_b200_engine* e, const int32_t* tokens, int pos, int
     p.stage_begin = 0;
     p.stage_end = 8 * p.L + 2;          // embed .. logits (no sampling)
     p.pos0 = pos; p.slot0 = slot;
+    p.want_x = 1;
     p.logits = logits;
     return run_stages(e, p, true, S(stream));
 }
@@ -489,6 +490,7 @@ int dia_b200_decoder_layer_step(dia_b200_engine* e, int layer, const float* x_in
     p.stage_begin = 1 + 8 * layer;
     p.stage_end = p.stage_begin + 8;
     p.pos0 = pos; p.slot0 = slot;
+    p.want_x = 1;
     rc = run_stages(e, p, true, st);
     if (rc) return rc;
     CK(launch_deinterleave(e->d_x, x_out, e->shape.d_model, st));
@@ -663,6 +665,7 @@ int dia_b200_debug_run_stages(dia_b200_engine* e, const int32_t* tokens, int sta
     p.tokens = tokens;
     p.stage_begin = stage_begin; p.stage_end = stage_end;
     p.pos0 = pos; p.slot0 = slot;
+    p.want_x = 1;
     return run_stages(e, p, cooperative != 0, S(stream));
 }
 

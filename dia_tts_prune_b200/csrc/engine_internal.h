@@ -84,7 +84,8 @@ struct StepParams {
     const float* const* cross_v;
     int text_len;
     // plain buffers at the launch boundary
-    float2* x;                         // residual stream, interleaved [D][2] (read when stage_begin > 0, always written)
+    float2* x;                         // residual stream, interleaved [D][2] (read when stage_begin > 0, written if want_x)
+    int want_x;                        // keep a plain copy of the residual stream (layer-wise API and debug launches)
     float* logits;                     // [2][C][V]
     // flag-in-data buffers (zeroed before every launch; see step_kernel.cu).  Activation vectors feeding a GEMM
     // are stored as [k/16][2 rows][16] words of (bf16 hi, lo, lo2, flag16); the rest as (fp32, flag32).

@@ -474,7 +474,7 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
         const int q = lane & 3, m = lane >> 2;
 #pragma unroll
         for (int mt = 0; mt < kMaxTiles; ++mt) {
-            if (mt < n_mt) {
+            if (mt < n_mt && mt < tclass) {               // (mt < tclass: uniform, skips the dead slots in one branch)
                 float lo = acc[mt][0] + acc[mt][1], hi = acc[mt][2] + acc[mt][3];
                 lo += __shfl_xor_sync(0xffffffffu, lo, 1);
                 hi += __shfl_xor_sync(0xffffffffu, hi, 1);
@@ -583,7 +583,7 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     if (e_valid) {
         xn = c.xres + y;
         c.xres = xn;
-        reinterpret_cast<float*>(p.x)[(size_t)e_n * 2 + e_r] = xn;
+        if (p.want_x) reinterpret_cast<float*>(p.x)[(size_t)e_n * 2 + e_r] = xn;
         ll_store_parts(p.ll_x, e_n, e_r, xn * wn_v, f16n);
     }
     if (c.ts && c.tid == 0) c.ts[7] = clock64();
@@ -649,17 +649,22 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     const u64* qsrc = self ? p.ll_qkv : p.ll_cq;
 
     // ---- inputs: wait for the projection that produced q (and k, v of this step), RoPE, scale ---------
-    if (c.tid == 0) ll_wait32(qsrc + ((size_t)head0 * kHeadDim) * 2 + r, fprev, p.err);
-    consumer_sync();
     {
         const int pclamp = min(pos, p.n_pos - 1);
-        const float* sinr = p.rope_sin + (size_t)pclamp * 64;
-        const float* cosr = p.rope_cos + (size_t)pclamp * 64;
+        const int d = c.tid & 63;                            // the same rotation pair in every iteration (256 % 64 == 0)
+        const float sn = __ldg(p.rope_sin + (size_t)pclamp * 64 + d), cs = __ldg(p.rope_cos + (size_t)pclamp * 64 + d);
         const float scale = 0.08838834764831845f;           // 1/sqrt(128)
+        // one lane per warp polls the first word the warp needs: a whole CTA spinning on its 768 input words would
+        // cost the L2 too much; once that word is there the rest arrive within a round trip
+        if ((c.warp >> 1) < nh) {
+            if (c.lane == 0)
+                ll_wait32(qsrc + ((size_t)(head0 + (c.warp >> 1)) * kHeadDim + (c.warp & 1) * 32) * 2 + r, fprev, p.err);
+            __syncwarp();
+        }
         const int n_items = (HPK + 2) * 64;                  // 4 query heads, then k, then v of this step
 #pragma unroll 1
         for (int i = c.tid; i < n_items; i += kConsumerThreads) {
-            const int hh = i >> 6, d = i & 63;
+            const int hh = i >> 6;
             float o0 = 0.f, o1 = 0.f;
             if (hh < nh || (hh >= HPK && has_new)) {
                 const int col = hh < HPK ? (head0 + hh) * kHeadDim
@@ -671,7 +676,6 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
                 const float a = __uint_as_float(wa.x), b = __uint_as_float(wb.x);
                 o0 = a; o1 = b;
                 if (hh <= HPK) {                             // RotaryEmbedding (dia/layers.py:161-173)
-                    const float sn = __ldg(sinr + d), cs = __ldg(cosr + d);
                     o0 = a * cs - b * sn;
                     o1 = a * sn + b * cs;
                     if (hh < HPK) { o0 *= scale; o1 *= scale; }
@@ -915,7 +919,7 @@ __device__ __noinline__ float enter_stream(const StepParams& p, unsigned char* x
         if (valid) x = ldcg_f(reinterpret_cast<const float*>(p.x) + (size_t)n * 2 + e_r);
     }
     if (valid) {
-        reinterpret_cast<float*>(p.x)[(size_t)n * 2 + e_r] = x;
+        if (p.want_x) reinterpret_cast<float*>(p.x)[(size_t)n * 2 + e_r] = x;
         ll_store_parts(p.ll_x, n, e_r, x * __ldg(wnorm + n), seq_out & 0xffffu);
     }
     float sqv = valid ? x * x : 0.f;
@@ -1081,8 +1085,8 @@ __device__ int sample_channel_cta(const float (&g)[kPerThread], int V, float tem
         float e0 = lane < ncand ? expf(sm->sv[lane] - mx) : 0.f;
         float e1 = lane + 32 < ncand ? expf(sm->sv[lane + 32] - mx) : 0.f;
         const float Z = warp_sum(e0 + e1);
-        if (lane < ncand) sm->cv[lane] = e0;                   // cv now holds exp(l - max) in sorted order
-        if (lane + 32 < ncand) sm->cv[lane + 32] = e1;
+        if (lane < ncand) { sm->cv[lane] = e0; sm->sv[lane] = e0 / Z; }                  // cv: exp(l - max), sv: probability
+        if (lane + 32 < ncand) { sm->cv[lane + 32] = e1; sm->sv[lane + 32] = e1 / Z; }   // (both in sorted order)
         __syncwarp();
         int nkeep = ncand;
         if (top_p < 1.0f) {
@@ -1093,7 +1097,7 @@ __device__ int sample_channel_cta(const float (&g)[kPerThread], int V, float tem
                 for (int i = 0; i < ncand; ++i) {
                     // entry i is removed iff the cumulative probability BEFORE it already exceeds top_p
                     if (i > 0 && cum > top_p) break;
-                    cum += sm->cv[i] / Z;
+                    cum += sm->sv[i];
                     nkeep = i + 1;
                 }
             }

@@ -312,6 +312,28 @@ class Decoder(nn.Module):
                 out.append(KVCache.from_kv(k, v))
         return out
 
+    def precompute_cross_attn_cache_live(self, enc_live: Tensor, text_length: int) -> list[KVCache]:
+        """Same caches as ``precompute_cross_attn_cache`` for the entries that are ever observed.  ``enc_live`` is
+        the encoder output of the valid text bytes of the conditional row, ``[1, n, E]``.  The reference projects
+        all 2 x text_length encoder positions in every layer, but the unconditional row is fully masked and so are
+        the pad positions of the conditional row (overwriting them with noise leaves the
+        logits bit-identical); here those entries are zeros and only ``n`` rows are projected."""
+        out: list[KVCache] = []
+        n = enc_live.shape[1]
+        pos = torch.arange(n, dtype=torch.float32, device=enc_live.device)[None, :]
+        with torch.no_grad(), _exact_fp32():
+            x = enc_live.float()
+            for layer in self.layers:
+                ca = layer.cross_attention
+                k_live = ca.rotary_emb(ca.k_proj(x), pos).transpose(1, 2)           # [1, H, n, d]
+                v_live = ca.v_proj(x).transpose(1, 2)
+                k = torch.zeros((2, k_live.shape[1], text_length, k_live.shape[3]), dtype=k_live.dtype, device=x.device)
+                v = torch.zeros_like(k)
+                k[1, :, :n] = k_live[0]
+                v[1, :, :n] = v_live[0]
+                out.append(KVCache.from_kv(k, v))
+        return out
+
     # ---- the hot path -------------------------------------------------------------------------------------
     def decode_step(self, tgt_ids_Bx1xC: Tensor, state: DecoderInferenceState) -> Tensor:
         B, T, C = tgt_ids_Bx1xC.shape

@@ -101,6 +101,8 @@ class Dia:
         self.dac_model = None
         self.last_codes: torch.Tensor | None = None     # raw generated rows of the last generate() call
         self.last_stats: dict = {}
+        # encode / project only the text bytes the decoder can observe (set False for the reference's full tensors)
+        self.live_text_only = True
 
     # ---- loading ---------------------------------------------------------------------------------
     @classmethod
@@ -198,13 +200,27 @@ class Dia:
         enc_state = EncoderInferenceState.new(self.config, enc_input)
         self.model.eval()
         with torch.inference_mode():
-            enc_out = self.model.encoder(enc_input, enc_state)
-            cross = self.model.decoder.precompute_cross_attn_cache(enc_out, enc_state.positions)
-            dec_state = DecoderInferenceState.new(self.config, enc_state, enc_out, cross, self.compute_dtype)
             # valid text bytes form a prefix (pad = 0 never occurs inside utf-8 text); known on the host
             n_valid = int((cond[0] != self.config.data.text_pad_value).sum().item())
             if not bool((cond[0, :n_valid] != self.config.data.text_pad_value).all().item()):
                 raise NotImplementedError("text with embedded pad bytes is not supported by the cross-attention kernel")
+            if self.live_text_only and n_valid > 0:
+                # Only the n_valid text bytes of the conditional row are ever observed by the decoder: the
+                # unconditional row and the pad positions are masked everywhere, and the
+                # encoder never mixes pad and non-pad tokens (dia/state.py:24-31).  Encode and project just those.
+                live = cond[:, :n_valid]
+                es_live = EncoderInferenceState(
+                    max_seq_len=n_valid, device=live.device,
+                    positions=torch.arange(n_valid, dtype=torch.float32, device=live.device)[None, :],
+                    padding_mask=torch.ones_like(live, dtype=torch.bool), attn_mask=None)
+                enc_live = self.model.encoder(live, es_live)
+                enc_out = torch.zeros((2, cond.shape[1], enc_live.shape[-1]), dtype=enc_live.dtype, device=live.device)
+                enc_out[1, :n_valid] = enc_live[0]
+                cross = self.model.decoder.precompute_cross_attn_cache_live(enc_live, cond.shape[1])
+            else:
+                enc_out = self.model.encoder(enc_input, enc_state)
+                cross = self.model.decoder.precompute_cross_attn_cache(enc_out, enc_state.positions)
+            dec_state = DecoderInferenceState.new(self.config, enc_state, enc_out, cross, self.compute_dtype)
             dec_state.text_len = n_valid
             dec_output = DecoderOutput.new(self.config, self.device)
             dec_output.prefill(delayed, prefill_step)

@@ -412,3 +412,27 @@ def test_full_repeated_launches_do_not_hang(full_gpu):
             pytest.fail(f"launch {rep} failed: {ex}; device error words {eng.last_device_error()}")
         assert eng.status().steps_run == steps
     assert eng.last_device_error()[0] == 0
+
+
+def test_live_text_only_prepare_matches_full(tiny_gpu):
+    """Encoding / projecting only the valid text bytes of the conditional row (the only encoder work the decoder
+    can observe) gives the same live cross-KV entries and the same logits as the
+    reference's full 2 x text_length computation."""
+    dia, sd = tiny_gpu
+    text = "[S1] Live tokens only. [S2] Same logits."
+    tok = torch.full((2, 1, 9), 1026, dtype=torch.int32).cuda()
+    got = {}
+    for live in (False, True):
+        dia.live_text_only = live
+        st, out = _prepared(dia, text)
+        n = st.text_len
+        st.prepare_step(1)
+        with torch.inference_mode():
+            lg = dia.model.decoder.decode_step(tok, st).clone()
+        got[live] = (st.enc_out[1, :n].clone(), [c.k[1, :, :n].clone() for c in st.cross_attn_cache],
+                     [c.v[1, :, :n].clone() for c in st.cross_attn_cache], lg)
+    dia.live_text_only = True
+    assert (got[True][0] - got[False][0]).abs().max() < 1e-5
+    for a, b in zip(got[True][1] + got[True][2], got[False][1] + got[False][2]):
+        assert (a - b).abs().max() < 1e-5
+    assert (got[True][3] - got[False][3]).abs().max() < LOGIT_TIGHT

@@ -40,6 +40,7 @@ def main():
     sd = {k: v.detach().clone() for k, v in dia.model.named_parameters()}
     print(f"weights ready {time.time()-t0:.1f}s fingerprint {SY.weights_fingerprint(sd, [n for n in sd if 'layers.0.' in n])[:16]}")
     dia.device = dev
+    dia.live_text_only = False           # compare the full encoder / cross-KV tensors with the oracle
     dia.model.to(dev)
     dia.model.eval()
     text = "[S1] Hello there. [S2] Hi."

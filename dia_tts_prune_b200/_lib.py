@@ -64,6 +64,9 @@ _SIGNATURES = {
     "dia_b200_finalize_codes_i32": (_i, [_i32p, _i32p, _i, _i, C.POINTER(C.c_int32), C.c_int32, _i, _vp]),
     "dia_b200_build_delay_indices": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _vp]),
     "dia_b200_build_revert_indices": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _vp]),
+    "dia_b200_dense_prepare_weight": (_i, [_vp, _i, _vp, _i, _i, _vp]),
+    "dia_b200_dense_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "dia_b200_dense_forward": (_i, [_fp, _vp, _fp, _vp, _i, _i, _i, _vp]),
     "dia_b200_debug_run_stages": (_i, [_vp, _i32p, _i, _i, _i, _i, _i, _vp]),
     "dia_b200_debug_enable_timing": (_i, [_vp, _i]),
     "dia_b200_debug_last_device_error": (_i, [_vp, C.POINTER(C.c_int32), _i]),

@@ -653,6 +653,28 @@ int dia_b200_build_revert_indices(int64_t* t_idx, int64_t* indices, int B, int T
     return DIA_B200_OK;
 }
 
+int dia_b200_dense_prepare_weight(const void* w, int src_dtype, void* wt_bf16, int K, int N, void* stream) {
+    if (!w || !wt_bf16 || K <= 0 || N <= 0 || (src_dtype != 0 && src_dtype != 1)) return DIA_B200_EINVAL;
+    CK(launch_transpose_to_bf16(w, src_dtype, wt_bf16, K, N, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+size_t dia_b200_dense_workspace_bytes(int M, int K) { return (M > 0 && K > 0) ? gemm_workspace_bytes(M, K) : 0; }
+
+int dia_b200_dense_forward(const float* x, const void* wt_bf16, float* y, void* workspace, int M, int N, int K, void* stream) {
+    if (M < 0 || N <= 0 || K <= 0) return DIA_B200_EINVAL;
+    if (M == 0) return DIA_B200_OK;
+    if (!x || !wt_bf16 || !y || !workspace) return DIA_B200_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(wt_bf16) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(y)) & 15)
+        return DIA_B200_EINVAL;
+    cudaError_t e = launch_gemm_tcgen05(x, wt_bf16, y, workspace, M, N, K, S(stream));
+    if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); return DIA_B200_EUNSUPPORTED; }
+    CK(e);
+    g_launches += 2;
+    return DIA_B200_OK;
+}
+
 int dia_b200_debug_run_stages(dia_b200_engine* e, const int32_t* tokens, int stage_begin, int stage_end, int pos,
                               int slot, int cooperative, void* stream) {
     int rc = ready(e, true);

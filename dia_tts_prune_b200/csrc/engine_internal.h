@@ -158,6 +158,11 @@ cudaError_t launch_build_delay_indices(int* t_idx, long long* idx, int B, int T,
 cudaError_t launch_build_revert_indices(long long* t_idx, long long* idx, int B, int T, int C, const int* delay,
                                         cudaStream_t st);
 
+// tcgen05 GEMM for the T > 1 dense layers (gemm_tcgen05.cu)
+size_t gemm_workspace_bytes(int M, int K);
+cudaError_t launch_transpose_to_bf16(const void* w, int src_bf16, void* wt, int K, int N, cudaStream_t st);
+cudaError_t launch_gemm_tcgen05(const float* x, const void* wt, float* y, void* workspace, int M, int N, int K, cudaStream_t st);
+
 struct DelayArg { int d[DIA_B200_MAX_CHANNELS]; };
 
 }  // namespace dia

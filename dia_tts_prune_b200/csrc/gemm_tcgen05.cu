@@ -1,0 +1,262 @@
+// gemm_tcgen05.cu - the dense contractions OFF the decode step (encoder, cross-attention K/V precompute, prompt
+// prefill: SURVEY.md 8(f) rank 1) on the 5th-generation tensor cores.
+//
+//   Y[M][N] (fp32) = X[M][K] (fp32) . W[K][N] (bf16)           DenseGeneral.forward, dia/layers.py:55-66, M = B*T rows
+//
+// The reference runs these in fp32 and the K/V a prefill writes are re-read by every later greedy step, so the
+// activations may not be rounded to bf16 (hard part 2).  X is therefore split into three bf16 terms
+// (x = hi + lo + lo2, exact to 24 bits) and each k-step issues three tcgen05.mma into the SAME fp32 accumulator in
+// tensor memory: the product has fp32-operand accuracy at bf16 tensor-core speed.
+//
+// Structure (one 128 x 128 output tile per CTA, warp-specialised):
+//   warp 0    one lane: TMA producer - cp.async.bulk.tensor loads of the three A-term tiles [128 x 64] and the B
+//             tile [128 x 64] (both K-major, 128-byte swizzle) into a 3-stage shared-memory ring (64 KB per stage)
+//   warp 1    allocates 128 TMEM columns; one lane issues tcgen05.mma (M = 128, N = 128, K = 16, kind::f16, bf16
+//             inputs, fp32 accumulate) and releases ring slots with tcgen05.commit
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> registers -> fp32 stores
+// W is kept as a K-major bf16 copy [N][K] made once per weight (transpose_to_bf16_kernel), so that A and B use the
+// same canonical UMMA layout.  Every wait is bounded (a stuck pipeline traps instead of hanging the GPU).
+#include <algorithm>
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "engine_internal.h"
+
+namespace dia {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int kTerms = 3;
+constexpr int kStages = 3;
+constexpr int kTileBytes = BM * BK * 2;                     // 16 KB: one [128 x 64] bf16 tile
+constexpr int kStageBytes = (kTerms + 1) * kTileBytes;      // 64 KB
+constexpr int kGemmThreads = 192;                           // 6 warps
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    unsigned polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++polls > 20000000u) __trap();                  // seconds: the pipeline is stuck
+    }
+}
+// K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (stride byte offset), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+}  // namespace
+
+// x = hi + lo + lo2 per element, three stacked bf16 matrices [3][M][K]
+__global__ void split3_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xs, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(h);
+        const __nv_bfloat16 l = __float2bfloat16_rn(r1);
+        const float r2 = r1 - __bfloat162float(l);
+        xs[i] = h;
+        xs[n + i] = l;
+        xs[2 * n + i] = __float2bfloat16_rn(r2);
+    }
+}
+
+// W [K][N] (fp32 or bf16, N contiguous) -> Wt [N][K] bf16 (K contiguous)
+__global__ void transpose_to_bf16_kernel(const void* __restrict__ w, int src_bf16, __nv_bfloat16* __restrict__ wt, int K, int N) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, n = n0 + threadIdx.x;
+        float v = 0.f;
+        if (k < K && n < N)
+            v = src_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(w)[(size_t)k * N + n])
+                         : reinterpret_cast<const float*>(w)[(size_t)k * N + n];
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int n = n0 + r, k = k0 + threadIdx.x;
+        if (k < K && n < N) wt[(size_t)n * K + k] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+    }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+dia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        float* __restrict__ y, int M, int N, int K) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* tmem_full = empty + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int n_kb = K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {                                        // one warp allocates (and later frees) the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1u;
+                mbar_wait_bounded(&empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full[s], kStageBytes);
+                const uint32_t base = smem_u32(smem + s * kStageBytes), bar = smem_u32(&full[s]);
+                for (int t = 0; t < kTerms; ++t)            // rows of term t start at t * M in the stacked matrix
+                    tma_load_2d(base + t * kTileBytes, &map_a, bar, kb * BK, t * M + m0);
+                tma_load_2d(base + kTerms * kTileBytes, &map_b, bar, kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait_bounded(&full[s], (kb / kStages) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + s * kStageBytes);
+                const uint64_t bdesc = umma_desc(base + kTerms * kTileBytes);
+#pragma unroll
+                for (int t = 0; t < kTerms; ++t) {
+                    const uint64_t adesc = umma_desc(base + t * kTileBytes);
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j)       // advance 16 elements = 32 bytes = 2 descriptor units along K
+                        umma_bf16(tmem_base, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | t | j) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);                     // the slot is free once these MMAs have read it
+            }
+            umma_commit(tmem_full);                         // the accumulator is complete
+        }
+    } else {
+        // ===== epilogue: a warp may touch the 32 TMEM lanes of its quarter (warp id mod 4) =====
+        const int q = warp & 3;
+        mbar_wait_bounded(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int cb = 0; cb < BN / 32; ++cb) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cb * 32;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float4* dst = reinterpret_cast<float4*>(y + (size_t)row * N + n0 + cb * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// a [rows][K] bf16 matrix, K contiguous, read in [128 rows x 64 k] boxes with the 128-byte swizzle
+static bool make_map(CUtensorMap* map, const void* base, long long rows, int K) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t gemm_workspace_bytes(int M, int K) { return (size_t)kTerms * M * K * 2; }
+
+cudaError_t launch_transpose_to_bf16(const void* w, int src_bf16, void* wt, int K, int N, cudaStream_t st) {
+    dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
+    transpose_to_bf16_kernel<<<grid, block, 0, st>>>(w, src_bf16, reinterpret_cast<__nv_bfloat16*>(wt), K, N);
+    return cudaGetLastError();
+}
+
+// returns cudaErrorNotSupported for shapes the tiling does not cover (the caller decides what to do)
+cudaError_t launch_gemm_tcgen05(const float* x, const void* wt, float* y, void* workspace, int M, int N, int K, cudaStream_t st) {
+    if (M <= 0 || N % BN || K % BK || K < BK) return cudaErrorNotSupported;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(dia_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const long long n = (long long)M * K;
+    split3_rows_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(
+        x, reinterpret_cast<__nv_bfloat16*>(workspace), n);
+    CUtensorMap ma, mb;
+    if (!make_map(&ma, workspace, (long long)kTerms * M, K) || !make_map(&mb, wt, N, K)) return cudaErrorNotSupported;
+    dim3 grid(N / BN, (M + BM - 1) / BM);
+    dia_gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, y, M, N, K);
+    return cudaGetLastError();
+}
+
+}  // namespace dia

@@ -264,3 +264,34 @@ class DecodeEngine:
 
 def launch_count() -> int:
     return int(_lib.load().dia_b200_launch_count())
+
+
+# ---- tcgen05 GEMM for dense layers with more than one row (encoder, cross-KV precompute, prefill) ---------------------
+def dense_prepare_weight(w_KxN: torch.Tensor) -> torch.Tensor:
+    """K-major bf16 copy ``[N, K]`` of a DenseGeneral kernel viewed as ``[K, N]`` (float32 or bfloat16, CUDA)."""
+    lib = _lib.load()
+    if not w_KxN.is_cuda or w_KxN.dim() != 2 or w_KxN.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("expected a 2-D float32 / bfloat16 CUDA tensor")
+    w = w_KxN.contiguous()
+    K, N = w.shape
+    wt = torch.empty((N, K), dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.dia_b200_dense_prepare_weight(_ptr(w), 1 if w.dtype == torch.bfloat16 else 0, _ptr(wt), K, N,
+                                                 _stream(w.device)), "dense_prepare_weight")
+    return wt
+
+
+def dense_supported(M: int, N: int, K: int) -> bool:
+    return M > 0 and N % 128 == 0 and K % 64 == 0
+
+
+def dense_forward(x_MxK: torch.Tensor, wt_NxK: torch.Tensor) -> torch.Tensor:
+    """``x @ W`` in float32 accuracy on the tcgen05 tensor cores; ``wt_NxK`` from :func:`dense_prepare_weight`."""
+    lib = _lib.load()
+    x = x_MxK.to(torch.float32).contiguous()
+    M, K = x.shape
+    N = wt_NxK.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    ws = torch.empty((int(lib.dia_b200_dense_workspace_bytes(M, K)),), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.dia_b200_dense_forward(_ptr(x), _ptr(wt_NxK), _ptr(y), _ptr(ws), M, N, K, _stream(x.device)),
+               "dense_forward")
+    return y

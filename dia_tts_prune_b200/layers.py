@@ -22,6 +22,7 @@ norms, softmax and KV caches are always fp32.
 from __future__ import annotations
 
 import contextlib
+import math
 import weakref
 from typing import Optional
 
@@ -70,8 +71,42 @@ class DenseGeneral(nn.Module):
     def forward(self, inputs: Tensor) -> Tensor:
         n = len(self.axis)
         x_axes = tuple(a if a >= 0 else inputs.ndim + a for a in self.axis)
+        y = self._forward_tcgen05(inputs, x_axes)
+        if y is not None:
+            return y
         out = torch.tensordot(inputs.to(torch.float32), self.weight.to(torch.float32), dims=(x_axes, tuple(range(n))))
         return out.to(inputs.dtype)
+
+    # ---- sm_100a path for more than a few rows (encoder, cross-attention K/V precompute, prompt prefill) ----------
+    def _forward_tcgen05(self, inputs: Tensor, x_axes: tuple[int, ...]) -> Tensor | None:
+        """``x @ W`` on the tcgen05 tensor cores with the activations split into three bf16 terms (float32-operand
+        accuracy).  Used when the contracted axes are the trailing ones, the shape fits the 128 x 128 x 64 tiling and
+        the kernel is bfloat16 (or float32 holding bfloat16-representable values, as every kernel that went through
+        the bf16 checkpoint path is); otherwise ``None`` and the caller runs the reference's float32 tensordot."""
+        w = self.weight
+        if not (inputs.is_cuda and w.is_cuda) or torch.is_grad_enabled() and (w.requires_grad or inputs.requires_grad):
+            return None
+        n = len(x_axes)
+        if x_axes != tuple(range(inputs.ndim - n, inputs.ndim)):
+            return None
+        K = math.prod(self.in_shapes)
+        N = math.prod(self.out_features)
+        M = inputs.numel() // K if K else 0
+        from . import engine as _engine
+        if M < 8 or not _engine.dense_supported(M, N, K):
+            return None
+        key = (w.data_ptr(), w._version, w.dtype, w.device)
+        cached = getattr(self, "_b200_wt", None)
+        if cached is None or cached[0] != key:
+            w2 = w.detach().reshape(K, N)
+            ok = w.dtype == torch.bfloat16 or (w.dtype == torch.float32 and
+                                               bool(torch.equal(w2, w2.to(torch.bfloat16).to(torch.float32))))
+            cached = (key, _engine.dense_prepare_weight(w2) if ok else None)
+            self._b200_wt = cached
+        if cached[1] is None:
+            return None
+        y = _engine.dense_forward(inputs.reshape(M, K), cached[1])
+        return y.reshape(*inputs.shape[: inputs.ndim - n], *self.out_features).to(inputs.dtype)
 
 
 class MlpBlock(nn.Module):

@@ -178,6 +178,18 @@ int dia_b200_build_delay_indices(int32_t *t_idx, int64_t *indices, int B, int T,
 int dia_b200_build_revert_indices(int64_t *t_idx, int64_t *indices, int B, int T, int C, const int32_t *delay_host,
                                   void *stream);
 
+/* ---- dense layers with more than one row (encoder, cross-attention K/V precompute, prompt prefill) ------------
+ * DenseGeneral.forward (dia/layers.py:55-66) for M = B*T > 1 rows on the tcgen05 tensor cores:
+ *   y[M][N] float32 = x[M][K] float32 . W[K][N]
+ * with W given as the K-major bfloat16 copy wt[N][K] that dia_b200_dense_prepare_weight makes once per weight
+ * (src_dtype 0 = float32 source, 1 = bfloat16).  x is split into three bf16 terms inside, so the product has
+ * fp32-operand accuracy.  workspace: dia_b200_dense_workspace_bytes(M, K) bytes of device memory, 16-byte aligned.
+ * Shapes need N % 128 == 0 and K % 64 == 0, otherwise DIA_B200_EUNSUPPORTED (the caller keeps its own path). */
+int dia_b200_dense_prepare_weight(const void *w, int src_dtype, void *wt_bf16, int K, int N, void *stream);
+size_t dia_b200_dense_workspace_bytes(int M, int K);
+int dia_b200_dense_forward(const float *x, const void *wt_bf16, float *y, void *workspace, int M, int N, int K,
+                           void *stream);
+
 /* ---- introspection for tests and the bench ------------------------------------------------- */
 enum dia_b200_buffer {
     DIA_B200_BUF_X = 0,      /* residual stream after the last executed stage, interleaved [D][2] */

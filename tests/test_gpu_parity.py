@@ -436,3 +436,23 @@ def test_live_text_only_prepare_matches_full(tiny_gpu):
     for a, b in zip(got[True][1] + got[True][2], got[False][1] + got[False][2]):
         assert (a - b).abs().max() < 1e-5
     assert (got[True][3] - got[False][3]).abs().max() < LOGIT_TIGHT
+
+
+@pytest.mark.parametrize("M,N,K", [(8, 128, 64), (200, 256, 512), (1722, 2048, 2048), (333, 512, 8192)])
+def test_tcgen05_dense_matches_fp64(M, N, K):
+    """DenseGeneral for T > 1 rows (dia/layers.py:55-66) on tcgen05: fp32-operand accuracy from the three-term bf16
+    split of the activations, against a float64 product; row tail (M % 128 != 0) included."""
+    from dia_tts_prune_b200 import engine as E
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(K, N, generator=g) * K ** -0.5).to(torch.bfloat16).cuda()
+    wt = E.dense_prepare_weight(w)
+    assert torch.equal(wt, w.t().contiguous())
+    y = E.dense_forward(x, wt)
+    ref = x.double() @ w.double()
+    err = (y.double() - ref).abs().max().item()
+    # tensor-core accumulation of K products of magnitude ~1: a few 1e-5 relative (a float32 FMA chain gives ~1e-5)
+    assert err < 2e-4 * max(1.0, (K / 2048) ** 0.5), err
+    assert not E.dense_supported(M, N + 8, K)
+    with pytest.raises(NotImplementedError):
+        E.dense_forward(x, torch.empty((N + 8, K), dtype=torch.bfloat16, device="cuda"))

@@ -466,6 +466,17 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     if (c.ts && c.tid == 0) c.ts[2] = clock64();
 
     if (c.ts && c.tid == 224) c.ts[8] = clock64();
+    // RMSNorm of the input: the last warp requests the per-CTA partial sums of x^2 as soon as its MMAs are done -
+    // asynchronously into shared memory (no registers held), so the loads fly during the reduction and the barrier
+    const uint32_t ssq_buf = smem_u32(c.xs) + kConsumerWarps * kBStageBytes + lane * 16;
+    if (ssq_warp) {
+#pragma unroll
+        for (int i = 0; i < kSsqPerLane; ++i) {
+            if (lane + 32 * i < p.n_res)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ssq_buf + i * 512), "l"(p.ll_ssq + 2 * (lane + 32 * i)) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     // ---- sum the three bf16 terms (MMA columns) of each batch row, then the 8 warps through smem ----
     // C fragment: c0,c1 = D[m][2q], D[m][2q+1]; c2,c3 = D[m+8][..] with m = lane/4, q = lane%4.
@@ -493,21 +504,22 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
         // RMSNorm of the input: 1/rms from the per-CTA partial sums of x^2 its producers published (fixed order).
         // This is the one all-CTA dependency of the stage; it runs on the last warp AFTER the block barrier, in
         // parallel with the other warps' cross-warp sums, and is handed over through a shared-memory flag.
-        uint4 sq[kSsqPerLane];
-#pragma unroll
-        for (int i = 0; i < kSsqPerLane; ++i) {
-            const int j = lane + 32 * i;
-            sq[i] = j < p.n_res ? ll_ld2(p.ll_ssq + 2 * j) : make_uint4(0u, fprev, 0u, fprev);
-        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < kSsqPerLane; ++i) {
             const int j = lane + 32 * i;
             if (j < p.n_res) {
-                if (sq[i].y != fprev) sq[i].x = ll_wait32(p.ll_ssq + 2 * j, fprev, p.err);
-                if (sq[i].w != fprev) sq[i].z = ll_wait32(p.ll_ssq + 2 * j + 1, fprev, p.err);
-                s0 += __uint_as_float(sq[i].x);
-                s1 += __uint_as_float(sq[i].z);
+                uint4 q4;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(q4.x), "=r"(q4.y), "=r"(q4.z), "=r"(q4.w) : "r"(ssq_buf + i * 512) : "memory");
+                if (q4.y != fprev || q4.w != fprev) {                 // not there yet when the snapshot was taken
+                    q4 = ll_ld2(p.ll_ssq + 2 * j);
+                    if (q4.y != fprev) q4.x = ll_wait32(p.ll_ssq + 2 * j, fprev, p.err);
+                    if (q4.w != fprev) q4.z = ll_wait32(p.ll_ssq + 2 * j + 1, fprev, p.err);
+                }
+                s0 += __uint_as_float(q4.x);
+                s1 += __uint_as_float(q4.z);
             }
         }
         if (c.ts && c.tid == 224) c.ts[9] = clock64();

@@ -114,7 +114,7 @@ struct AttnWork {
     int active, pair, split, k_lo, k_hi, n_active, has_new;
 };
 // self-attention: (row, kv head) pairs x key splits over the CTAs.  Old keys are cache
-// slots [0, slot); the key/value of THIS step is taken from the qkv words by split 0.
+// slots [0, slot); the key/value of THIS step is taken from the qkv words by the last active split.
 __device__ __forceinline__ AttnWork self_attn_work(const StepParams& p, int cta, int slot) {
     AttnWork w;
     const int nsplit = p.sa_nsplit, pairs = 2 * p.Hkv, n_old = slot;
@@ -129,7 +129,7 @@ __device__ __forceinline__ AttnWork self_attn_work(const StepParams& p, int cta,
     w.k_lo = w.split * per;
     w.k_hi = min(n_old, w.k_lo + per);
     if (w.k_hi < w.k_lo) w.k_hi = w.k_lo;
-    w.has_new = (w.split == 0);
+    w.has_new = (w.split == w.n_active - 1);      // the last split has the fewest old keys (per is rounded up)
     return w;
 }
 // cross-attention: conditional row only, one query head per KV head, keys [0, text_len); a CTA takes
@@ -204,10 +204,10 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
                 if (!w.active || w.k_hi <= w.k_lo) continue;
                 if (self && n > 0) {
                     // row slot-1 was appended by another CTA during this stage of step n-1; that CTA fenced the
-                    // append before publishing its output, and this CTA's math warps consumed the self-o stage of
-                    // step n-1 (which needs every such output) once stages_done passes it.  The ring holds a
-                    // fraction of one layer, so this never blocks.
-                    const int need = (n - 1) * S + s + 2;
+                    // append before its self-o epilogue, and this CTA's math warps consumed every self-o output
+                    // once they are past the cross-q stage of step n-1.  The ring holds a fraction of one layer,
+                    // so this never blocks.
+                    const int need = (n - 1) * S + s + 3;
                     if (ld_acquire_cta_s32(&misc->stages_done) < need) {
                         const unsigned long long t0 = clock64();
                         while (ld_acquire_cta_s32(&misc->stages_done) < need) {
@@ -706,7 +706,6 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
         const size_t row = ((size_t)w.pair * p.Lmax + slot) * kHeadDim;
         p.self_k[layer][row + c.tid] = kn[c.tid];
         p.self_v[layer][row + c.tid] = vn[c.tid];
-        if (w.n_active == 1) __threadfence();
     }
     float4 q[HPK];
 #pragma unroll
@@ -835,15 +834,23 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
             if (d == 0) { ll_st(pp, __float_as_uint(M), c.seq); ll_st(pp + 1, __float_as_uint(l), c.seq); }
         }
     }
-    if (has_new && c.tid < kHeadDim) __threadfence();     // (several splits: the partials are out, now the appended row)
     consumer_sync();                                      // the scratch is reused by the next stage
-    if (w.n_active == 1) return;
+    // The appended K/V row must be visible device-wide before another CTA's copy engine reads it one step later.  That
+    // producer waits until its own math warps are past the cross-q stage of this step, which consumed the self-o
+    // outputs of every CTA - stores this CTA issues after the fence below (see producer_loop).
+    if (w.n_active == 1) {
+        if (has_new && c.tid < kHeadDim) __threadfence();
+        return;
+    }
 
     // ---- every split combines a slice of the outputs from all splits' partials (fixed order) -------------
     const int E = nh * kHeadDim;
     const int per = (E + w.n_active - 1) / w.n_active;
     const int e0 = w.split * per, e1 = min(E, e0 + per);
-    if (e0 >= e1) return;                                 // (CTA-uniform)
+    if (e0 >= e1) {                                       // (CTA-uniform)
+        if (has_new && c.tid < kHeadDim) __threadfence();
+        return;
+    }
     const int ne = e1 - e0, na = w.n_active;
     const int h_lo = e0 >> 7, nhh = ((e1 - 1) >> 7) - h_lo + 1;
     float* cml = cw + ne * na;                            // cw: [ne][na] outputs, then [nhh][na][2] (m, l)
@@ -888,6 +895,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
         ll_store_parts(oparts, k, r, val, f16n);
         if (!self) ll_store_parts(oparts, k, 0, 0.f, f16n);
     }
+    if (has_new && c.tid < kHeadDim) __threadfence();
     consumer_sync();
 }
 

@@ -41,9 +41,18 @@ WEIGHT_SEED = 5
 FRAME_RATE = 44100 / 512          # 86.13 frames per second of audio
 
 
-def workload_config(text_len: int, world: int) -> dict:
+VARIANTS = {
+    "dense": "Dia-1.6B",
+    "mlp-pruned": "Dia-1.6B with mlp.wo structurally pruned along dim 0 (offline_prune.py --prune-dim 0, L2 norm; "
+                  "BASELINE.json configs[3] 'reduced MLP width')",
+    "2to4": "Dia-1.6B with every dense kernel 2:4-pruned along K (BASELINE.json configs[3], unstructured-sparse variant)",
+}
+
+
+def workload_config(text_len: int, world: int, variant: str = "dense", amount: float = 0.0) -> dict:
     """The `config` object both arms print (BASELINE.json configs[1], one utterance per GPU)."""
-    return {"workload": "Dia-1.6B bf16 weights, single transcript per GPU, CFG batch 2, full 3072-token "
+    model = VARIANTS[variant] + (f", amount {amount}" if variant == "mlp-pruned" else "")
+    return {"workload": f"{model} bf16 weights, single transcript per GPU, CFG batch 2, full 3072-token "
                         "generation (3071 decode steps), reference default sampling T=1.3 top_p=0.95 top_k=35",
             "precision": "bf16 weights; fp32 activations, accumulation, softmax and KV cache",
             "weights": f"random-init seed {WEIGHT_SEED}, channel-0 EOS column zeroed so no early EOS",
@@ -52,14 +61,17 @@ def workload_config(text_len: int, world: int) -> dict:
             "text_len": text_len, "parallelism": f"replicas x{world}, no data-path collective"}
 
 
-def algorithmic_bytes(cfg, slot: int, text_len: int, kv_elem: int = 4) -> int:
+def algorithmic_bytes(cfg, slot: int, text_len: int, kv_elem: int = 4, n_hidden: int | None = None,
+                      weight_scale: float = 1.0) -> int:
     """bf16 weights of the 18 layers + logits head, fp32 norm weights, 9 embedding rows,
-    plus self-KV rows read / appended and the valid cross-KV rows of the conditional row."""
+    plus self-KV rows read / appended and the valid cross-KV rows of the conditional row.  Pruned variants:
+    ``n_hidden`` = live MLP width of a structurally pruned model; ``weight_scale`` = 0.5625 for 2:4 (half the
+    values + 2 bits of metadata per kept value)."""
     d, e = cfg.model.decoder, cfg.model.encoder
-    D, F, hd = d.n_embd, d.n_hidden, 128
+    D, F, hd = d.n_embd, n_hidden or d.n_hidden, 128
     nq, nkv, nc = d.gqa_query_heads * hd, d.kv_heads * hd, d.cross_query_heads * hd
     per_layer = D * (nq + 2 * nkv) + nq * D + D * nc + nc * D + D * 2 * F + F * D
-    w = 2 * (d.n_layer * per_layer + D * cfg.data.channels * cfg.model.tgt_vocab_size)
+    w = int(2 * weight_scale * (d.n_layer * per_layer + D * cfg.data.channels * cfg.model.tgt_vocab_size))
     w += 4 * (3 * d.n_layer + 1) * D + 4 * cfg.data.channels * D
     kv_row = d.n_layer * 2 * 2 * nkv * kv_elem            # K and V, both CFG rows, all layers, one slot
     cross = d.n_layer * 2 * nc * kv_elem * text_len       # K and V, conditional row only
@@ -197,6 +209,16 @@ def run_ours(args) -> None:
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
 
     dia, cfg = build_cpu_model(WEIGHT_SEED, suppress_eos=True)
+    if args.variant != "dense":
+        # BASELINE.json configs[3]: the weight producers of dia/pruning_utils.py (+ the 2:4 mask) on the same model
+        import torch.nn.utils.prune as prune
+        from dia_tts_prune_b200 import pruning_utils as PU
+        if args.variant == "mlp-pruned":
+            for layer in dia.model.decoder.layers:
+                prune.ln_structured(layer.mlp.wo, "weight", amount=args.prune_amount, n=2, dim=0)
+        else:
+            PU.apply_2to4_pruning(dia.model.decoder)
+        PU.make_pruning_permanent(dia.model)
     sd_cpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         sd_cpu = {k: v.detach().clone() for k, v in dia.model.named_parameters()}
@@ -215,6 +237,8 @@ def run_ours(args) -> None:
         dec_state, dec_out = dia._prepare_generation(eff, None, False)
     pristine = dec_out.generated_tokens.clone()
     text_len = dec_state.text_len
+    eng_width = dia.model.decoder.engine().n_hidden           # < n_hidden when dead MLP neurons were dropped
+    w_scale = 0.5625 if args.variant == "2to4" else 1.0
 
     def one_generation(profile=None) -> int:
         for c in dec_state.self_attn_cache:
@@ -253,7 +277,8 @@ def run_ours(args) -> None:
     k_bytes = k_ms = 0.0
     for (a, b, slot0, n) in profile:
         k_ms += a.elapsed_time(b)
-        k_bytes += sum(algorithmic_bytes(cfg, slot0 + i, text_len) for i in range(n))
+        k_bytes += sum(algorithmic_bytes(cfg, slot0 + i, text_len, n_hidden=eng_width, weight_scale=w_scale)
+                       for i in range(n))
     peak, peak_src = measured_peak()
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
 
@@ -299,14 +324,15 @@ def run_ours(args) -> None:
         traffic = None
         try:   # per-launch DRAM bytes from the committed `ncu --set full` capture, if present
             with open(os.path.join(REPO, "profiles", "step_kernel_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                traffic = json.load(f).get("dram_bytes_per_launch") if args.variant == "dense" else None
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(text_len, world),
+            "config": dict(workload_config(text_len, world, args.variant, args.prune_amount),
+                           **({"engine_mlp_width": eng_width} if args.variant != "dense" else {})),
             "decode_ms_per_frame": dev_ms / (frames_dev / world),
             "rtfx": value / world / FRAME_RATE,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -333,6 +359,9 @@ def main():
     ap.add_argument("--cpu-decode-steps", type=int, default=12, help="decode steps of the cpu_baseline sample")
     ap.add_argument("--ref-decode-steps", type=int, default=4, help="decode steps per reference-arm bench step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="dense", choices=sorted(VARIANTS),
+                    help="dense = BASELINE.json configs[1] (the headline); the others are configs[3]")
+    ap.add_argument("--prune-amount", type=float, default=0.5, help="mlp-pruned: fraction of hidden neurons removed")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

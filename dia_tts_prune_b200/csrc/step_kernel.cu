@@ -239,6 +239,62 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
 }
 
 // ------------------------------------------------------------------------------------------
+// norm warp: the one all-CTA dependency of a normed projection (qkv, cross-q, mlp-in, logits) is 1/rms of its input,
+// i.e. the per-CTA partial sums of x^2 that the producing residual stage published next to x.  A warp of its own
+// gathers them (fixed order), while the math warps are in the MMA loop, and hands 1/rms over through a
+// shared-memory flag that the epilogue waits on.
+// ------------------------------------------------------------------------------------------
+constexpr int kSsqPerLane = 5;                     // <= 160 residual-owning CTAs
+
+__device__ void norm_warp_loop(const StepParams& p, SharedMisc* misc) {
+    const int lane = threadIdx.x & 31;
+    const int S = 8 * p.L + 3;
+#pragma unroll 1
+    for (int n = 0; n < p.n_steps; ++n) {
+#pragma unroll 1
+        for (int s = p.stage_begin; s < p.stage_end; ++s) {
+            int kind, layer;
+            decode_stage(s, p.L, kind, layer);
+            if (kind != S_QKV && kind != S_CQ && kind != S_WI && kind != S_LOGITS) continue;
+            if (misc->gcfg[gemm_of_kind(kind)].gc == 0) continue;         // this CTA has no columns of the GEMM
+            const unsigned seq = 1u + (unsigned)(n * S + s), fprev = seq - 1;
+            // start polling when this CTA's math warps enter the stage: the partials appear together with x
+            if (s > p.stage_begin || n > 0) {
+                const int need = s > p.stage_begin ? n * S + s : (n - 1) * S + p.stage_end;
+                unsigned long long t0 = 0;
+                while (ld_acquire_cta_s32(&misc->stages_done) < need) {
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > kWatchdogCycles) ll_timeout(p.err, kErrStepDoneTimeout, seq);
+                }
+            }
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < kSsqPerLane; ++i) {
+                const int j = lane + 32 * i;
+                if (j < p.n_res) {
+                    uint4 q4 = ll_ld2(p.ll_ssq + 2 * j);
+                    if (q4.y != fprev) q4.x = ll_wait32(p.ll_ssq + 2 * j, fprev, p.err);
+                    if (q4.w != fprev) q4.z = ll_wait32(p.ll_ssq + 2 * j + 1, fprev, p.err);
+                    s0 += __uint_as_float(q4.x);
+                    s1 += __uint_as_float(q4.z);
+                }
+            }
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
+            if (lane == 0) {   // torch.nn.RMSNorm: x * rsqrt(mean(x^2) + eps) * w
+                const int par = seq & 1;
+                volatile float* ir = misc->inv_rms[par];
+                ir[0] = 1.0f / sqrtf(s0 / (float)p.D + p.eps);
+                ir[1] = 1.0f / sqrtf(s1 / (float)p.D + p.eps);
+                __threadfence_block();
+                *reinterpret_cast<volatile unsigned*>(&misc->inv_seq[par]) = seq;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // activation vectors as LL words
 // ------------------------------------------------------------------------------------------
 // x = hi + lo + lo2 with each term bf16 (round-to-nearest at every level; the residuals are exact)
@@ -354,8 +410,6 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     const int n_chunks = g.n_chunks, rpc = g.rpc;
 
     uint4 w[kLLW];
-    constexpr int kSsqPerLane = 5;                     // <= 160 CTAs
-    const bool ssq_warp = normed && warp == kConsumerWarps - 1;
 
     // epilogue role of this thread: (tile, row, column-in-tile)
     const int e_mt = warp, e_r = lane >> 4, e_m = lane & 15;
@@ -466,17 +520,6 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     if (c.ts && c.tid == 0) c.ts[2] = clock64();
 
     if (c.ts && c.tid == 224) c.ts[8] = clock64();
-    // RMSNorm of the input: the last warp requests the per-CTA partial sums of x^2 as soon as its MMAs are done -
-    // asynchronously into shared memory (no registers held), so the loads fly during the reduction and the barrier
-    const uint32_t ssq_buf = smem_u32(c.xs) + kConsumerWarps * kBStageBytes + lane * 16;
-    if (ssq_warp) {
-#pragma unroll
-        for (int i = 0; i < kSsqPerLane; ++i) {
-            if (lane + 32 * i < p.n_res)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ssq_buf + i * 512), "l"(p.ll_ssq + 2 * (lane + 32 * i)) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
 
     // ---- sum the three bf16 terms (MMA columns) of each batch row, then the 8 warps through smem ----
     // C fragment: c0,c1 = D[m][2q], D[m][2q+1]; c2,c3 = D[m+8][..] with m = lane/4, q = lane%4.
@@ -500,39 +543,6 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     if (c.ts && c.tid == 224) c.ts[10] = clock64();
     consumer_sync();
     if (c.ts && c.tid == 0) c.ts[3] = clock64();
-    if (ssq_warp) {
-        // RMSNorm of the input: 1/rms from the per-CTA partial sums of x^2 its producers published (fixed order).
-        // This is the one all-CTA dependency of the stage; it runs on the last warp AFTER the block barrier, in
-        // parallel with the other warps' cross-warp sums, and is handed over through a shared-memory flag.
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < kSsqPerLane; ++i) {
-            const int j = lane + 32 * i;
-            if (j < p.n_res) {
-                uint4 q4;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(q4.x), "=r"(q4.y), "=r"(q4.z), "=r"(q4.w) : "r"(ssq_buf + i * 512) : "memory");
-                if (q4.y != fprev || q4.w != fprev) {                 // not there yet when the snapshot was taken
-                    q4 = ll_ld2(p.ll_ssq + 2 * j);
-                    if (q4.y != fprev) q4.x = ll_wait32(p.ll_ssq + 2 * j, fprev, p.err);
-                    if (q4.w != fprev) q4.z = ll_wait32(p.ll_ssq + 2 * j + 1, fprev, p.err);
-                }
-                s0 += __uint_as_float(q4.x);
-                s1 += __uint_as_float(q4.z);
-            }
-        }
-        if (c.ts && c.tid == 224) c.ts[9] = clock64();
-        s0 = warp_sum(s0);
-        s1 = warp_sum(s1);
-        if (lane == 0) {   // torch.nn.RMSNorm: x * rsqrt(mean(x^2) + eps) * w
-            volatile float* ir = c.misc->inv_rms[par];
-            ir[0] = 1.0f / sqrtf(s0 / (float)K + p.eps);
-            ir[1] = 1.0f / sqrtf(s1 / (float)K + p.eps);
-            __threadfence_block();
-            *reinterpret_cast<volatile unsigned*>(&c.misc->inv_seq[par]) = c.seq;
-        }
-    }
     if (e_mt >= n_mt) return;                          // whole warps without a tile are done
 
     float y = 0.f, y8 = 0.f;                           // column e_m and (mlp-in only) its partner e_m + 8
@@ -548,6 +558,7 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     if (c.ts && c.tid == 0) c.ts[5] = clock64();
     float inv = 1.0f;
     if (normed) {
+        // 1/rms of the stage input: gathered from the producers' partial sums by the norm warp while the MMAs ran
         const volatile unsigned* fl = reinterpret_cast<const volatile unsigned*>(&c.misc->inv_seq[par]);
         unsigned spins = 0;
         while (*fl != c.seq) {
@@ -1287,6 +1298,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
 
     if (tid >= kConsumerThreads) {
         if (tid == kProducerWarp * 32) producer_loop(p, ring, misc);
+        else if ((tid >> 5) == kNormWarp) norm_warp_loop(p, misc);
         return;
     }
 

@@ -50,7 +50,10 @@ def decoder_tensor_names(config: DiaConfig) -> list[str]:
 
 
 class DecodeEngine:
-    def __init__(self, config: DiaConfig, device: torch.device | str | int = "cuda", n_ctas: int = 0):
+    def __init__(self, config: DiaConfig, device: torch.device | str | int = "cuda", n_ctas: int = 0,
+                 n_hidden: int | None = None):
+        """``n_hidden``: MLP width of the weights that will be loaded, when a structurally pruned checkpoint was
+        compacted (``pruning_utils.plan_mlp_compaction``); defaults to the configuration's."""
         if not torch.cuda.is_available():
             raise RuntimeError("dia_tts_prune_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -62,7 +65,8 @@ class DecodeEngine:
         if d.gqa_head_dim != 128 or d.cross_head_dim != 128:
             raise NotImplementedError("kernels are specialised for head_dim 128")
         sh = _lib.Shape()
-        sh.n_layer, sh.d_model, sh.n_hidden = d.n_layer, d.n_embd, d.n_hidden
+        self.n_hidden = int(n_hidden) if n_hidden else d.n_hidden
+        sh.n_layer, sh.d_model, sh.n_hidden = d.n_layer, d.n_embd, self.n_hidden
         sh.q_heads, sh.kv_heads, sh.cross_heads = d.gqa_query_heads, d.kv_heads, d.cross_query_heads
         sh.channels, sh.vocab = dt.channels, config.model.tgt_vocab_size
         sh.max_audio_len, sh.max_text_len = dt.audio_length, dt.text_length

@@ -283,6 +283,7 @@ class Decoder(nn.Module):
             layer._owner, layer._index = weakref.ref(self), i
         self._engine = None
         self._engine_sig = None
+        self.compact_pruned_mlp = True      # drop exactly-dead MLP neurons from the engine's weight stream
         self.register_load_state_dict_post_hook(lambda m, k: m.invalidate_engine())
 
     # ---- engine management -------------------------------------------------------------------------
@@ -305,15 +306,21 @@ class Decoder(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("the Dia decode path needs the model on a CUDA device (sm_100a); no CPU fallback")
         sig = self._weights_signature()
-        if self._engine is None or self._engine.device != dev:
+        if self._engine is not None and self._engine_sig == sig and self._engine.device == dev:
+            return self._engine
+        # (re)pack: a checkpoint whose MLP was structurally pruned (zero hidden neurons) gets a narrower engine
+        from .pruning_utils import compact_mlp, plan_mlp_compaction
+        sd = dict(self.named_parameters())
+        tensors = {n: sd[n].detach() for n in decoder_tensor_names(self.config)}
+        d = self.config.model.decoder
+        plan = plan_mlp_compaction(tensors, d.n_layer, d.n_hidden) if self.compact_pruned_mlp else None
+        width = plan[0] if plan is not None else d.n_hidden
+        if self._engine is None or self._engine.device != dev or self._engine.n_hidden != width:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = DecodeEngine(self.config, dev)
-            self._engine_sig = None
-        if self._engine_sig != sig:
-            sd = dict(self.named_parameters())
-            self._engine.load_weights({n: sd[n] for n in decoder_tensor_names(self.config)})
-            self._engine_sig = sig
+            self._engine = DecodeEngine(self.config, dev, n_hidden=width)
+        self._engine.load_weights(compact_mlp(tensors, plan) if plan is not None else tensors)
+        self._engine_sig = sig
         return self._engine
 
     def _engine_for(self, state: DecoderInferenceState):

@@ -2,8 +2,11 @@
 
 Thin wrappers over ``torch.nn.utils.prune`` applied to every ``DenseGeneral`` - masks only, shapes
 never change (dia/pruning_utils.py:13-179) - plus the 2:4 mask the reference does not have
-(SURVEY.md 8(d), config 4).  Pruned zeros stream through the decode kernels like any other value;
-after ``make_pruning_permanent`` the Decoder's repacked weight copy is invalidated.
+(SURVEY.md 8(d), config 4).  After ``make_pruning_permanent`` the Decoder's repacked weight copy is invalidated and rebuilt on the next
+decode call.  The rebuild physically drops MLP hidden neurons whose contribution is exactly zero
+(:func:`plan_mlp_compaction` - the "reduced MLP width" of a ``--prune-dim 0`` checkpoint, offline_prune.py:43):
+the decode kernels then stream (and the roofline counts) only the live part of ``wi_fused`` / ``wo``.  Other
+pruned zeros stream through the decode kernels like any other value.
 """
 
 from __future__ import annotations
@@ -98,3 +101,60 @@ def check_pruning_sparsity(model: nn.Module, module_types=DEFAULT_PRUNABLE_MODUL
     sparsity = zeros / total if total else 0.0
     print(f"Global sparsity: {100.0 * sparsity:.2f}% ({zeros}/{total})")
     return sparsity
+
+
+# ---- physical compaction of the MLP for the decode engine ---------------------------------------------------------------
+def engine_mlp_width(n_live: int) -> int:
+    """Smallest hidden width >= ``n_live`` the step kernel accepts (every contraction length splits into 8 warp
+    slices of whole 256-row fetch units, or one shorter unit that is a multiple of 64 rows)."""
+    n_live = max(int(n_live), 1)
+    if n_live <= 2048:
+        return -(-n_live // 512) * 512
+    return -(-n_live // 2048) * 2048
+
+
+@torch.no_grad()
+def mlp_live_neurons(wi_fused: torch.Tensor, wo: torch.Tensor) -> torch.Tensor:
+    """bool [F]: hidden neuron j of ``wo(silu(gate) * up)`` (dia/layers.py:92-105) can be non-zero.  It is dead when
+    row j of ``wo`` is all zeros (what structured ``dim=0`` pruning of ``mlp.wo`` produces), or when its gate or
+    up column of ``wi_fused [D, 2, F]`` is all zeros (silu(0) * up = gate * 0 = 0)."""
+    live_o = (wo != 0).any(dim=1)
+    live_g = (wi_fused[:, 0, :] != 0).any(dim=0)
+    live_u = (wi_fused[:, 1, :] != 0).any(dim=0)
+    return live_o & live_g & live_u
+
+
+@torch.no_grad()
+def plan_mlp_compaction(params: dict[str, torch.Tensor], n_layer: int, n_hidden: int,
+                        prefix: str = "layers.") -> tuple[int, list[torch.Tensor]] | None:
+    """Decide the hidden width the decode engine is built with.  Returns ``(F_eff, [index tensor per layer])`` -
+    the neurons each layer keeps, ascending, padded with dead ones up to the common width - or ``None`` when
+    nothing can be dropped.  Dropping a dead neuron removes terms that are exactly zero, so the layer output is
+    unchanged up to fp32 summation order."""
+    lives = []
+    for i in range(n_layer):
+        lives.append(mlp_live_neurons(params[f"{prefix}{i}.mlp.wi_fused.weight"], params[f"{prefix}{i}.mlp.wo.weight"]))
+    width = engine_mlp_width(max(int(l.sum().item()) for l in lives))
+    if width >= n_hidden:
+        return None
+    keep = []
+    for live in lives:
+        idx_live = torch.nonzero(live, as_tuple=False).flatten()
+        idx_dead = torch.nonzero(~live, as_tuple=False).flatten()
+        idx = torch.cat([idx_live, idx_dead[: width - idx_live.numel()]])
+        keep.append(torch.sort(idx).values)
+    return width, keep
+
+
+@torch.no_grad()
+def compact_mlp(params: dict[str, torch.Tensor], plan: tuple[int, list[torch.Tensor]],
+                prefix: str = "layers.") -> dict[str, torch.Tensor]:
+    """The parameter dict with every ``mlp.wi_fused [D, 2, F]`` / ``mlp.wo [F, D]`` reduced to the planned neurons."""
+    _, keep = plan
+    out = dict(params)
+    for i, idx in enumerate(keep):
+        wi, wo = params[f"{prefix}{i}.mlp.wi_fused.weight"], params[f"{prefix}{i}.mlp.wo.weight"]
+        idx = idx.to(wi.device)
+        out[f"{prefix}{i}.mlp.wi_fused.weight"] = wi.index_select(2, idx).contiguous()
+        out[f"{prefix}{i}.mlp.wo.weight"] = wo.index_select(0, idx).contiguous()
+    return out

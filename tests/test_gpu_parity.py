@@ -301,6 +301,42 @@ def test_tiny_pruned_variants_match_oracle(mode):
         assert torch.equal(dia.last_codes.cpu(), tr.codes)
 
 
+def test_tiny_structured_mlp_pruning_narrows_the_engine():
+    """config 4 (i): `--prune-dim 0` on mlp.wo = fewer hidden neurons.  The engine is rebuilt with the reduced width
+    (its weight stream shrinks) and the results still match the oracle run on the zero-filled full-width weights."""
+    import torch.nn.utils.prune as prune
+    from dia_tts_prune_b200 import pruning_utils as PU
+    cfg = tiny_config()
+    dia, _ = build_dia(cfg, 7)
+    dia.device = torch.device("cuda:0")
+    dia.model.to(dia.device)
+    text = "[S1] Narrow. [S2] MLP."
+    st, out = _prepared(dia, text)
+    dense_bytes = dia.model.decoder._engine_for(st).weight_stream_bytes
+    for layer in dia.model.decoder.layers:
+        prune.ln_structured(layer.mlp.wo, "weight", amount=0.5, n=2, dim=0)
+    PU.make_pruning_permanent(dia.model)
+    sd = {k: v.detach().cpu().clone() for k, v in dia.model.named_parameters()}
+    tr = O.generate(sd, cfg, text, max_tokens=30, temperature=0.0, dead_cross_kv=False, keep_logits_at={1, 20})
+    st, out = _prepared(dia, text)
+    eng = dia.model.decoder._engine_for(st)
+    assert eng.n_hidden == 512 and cfg.model.decoder.n_hidden == 1024
+    assert eng.weight_stream_bytes < dense_bytes
+    st.prepare_step(1)
+    with torch.inference_mode():
+        lg = dia.model.decoder.decode_step(out.get_tokens_at(0).unsqueeze(0).unsqueeze(0).expand(2, 1, -1), st)
+    assert (lg[:, 0].cpu() - tr.logits[1]).abs().max() < LOGIT_TIGHT
+    dia.generate(text, max_tokens=30, temperature=0.0, output="codes")
+    if torch.stack(tr.margins).min() > 1e-4:
+        assert torch.equal(dia.last_codes.cpu(), tr.codes)
+    dia.model.decoder.compact_pruned_mlp = False                 # same weights streamed at full width: same tokens
+    dia.model.decoder.invalidate_engine()
+    dia.generate(text, max_tokens=30, temperature=0.0, output="codes")
+    assert dia.model.decoder.engine().n_hidden == 1024
+    if torch.stack(tr.margins).min() > 1e-4:
+        assert torch.equal(dia.last_codes.cpu(), tr.codes)
+
+
 # ---- Dia-1.6B (BASELINE.json configs) ----------------------------------------------------------------------------------
 def test_full_weights_are_the_golden_ones(full_gpu, gold_full):
     dia, sd = full_gpu

@@ -202,6 +202,48 @@ def test_pruning_utils_masks():
     assert int((wo.abs().sum(1) == 0).sum()) == wo.shape[0] // 4     # a quarter of the hidden neurons zeroed
 
 
+def test_mlp_compaction_plan_drops_only_dead_neurons():
+    """offline_prune.py --prune-dim 0 on mlp.wo zeroes hidden-neuron rows: the engine's weight stream keeps the live
+    ones (padded to a width the kernel accepts) and the MLP output is unchanged."""
+    from dia_tts_prune_b200 import pruning_utils as PU
+    from dia_tts_prune_b200.layers import MlpBlock
+    assert [PU.engine_mlp_width(n) for n in (1, 512, 513, 2048, 2049, 4096, 6000, 8192)] == \
+        [512, 512, 1024, 2048, 4096, 4096, 6144, 8192]
+    torch.manual_seed(3)
+    D, F, L = 64, 4096, 2
+    mlps = [MlpBlock(D, F, torch.float32) for _ in range(L)]
+    params = {}
+    for i, m in enumerate(mlps):
+        with torch.no_grad():
+            m.wi_fused.weight.normal_(0, D ** -0.5)
+            m.wo.weight.normal_(0, F ** -0.5)
+        params[f"layers.{i}.mlp.wi_fused.weight"] = m.wi_fused.weight
+        params[f"layers.{i}.mlp.wo.weight"] = m.wo.weight
+    assert PU.plan_mlp_compaction(params, L, F) is None                      # dense: nothing to drop
+    import torch.nn.utils.prune as prune
+    prune.ln_structured(mlps[0].wo, "weight", amount=0.6, n=2, dim=0); prune.remove(mlps[0].wo, "weight")
+    prune.ln_structured(mlps[1].wo, "weight", amount=0.7, n=2, dim=0); prune.remove(mlps[1].wo, "weight")
+    with torch.no_grad():
+        mlps[1].wi_fused.weight[:, 0, 5] = 0.0                               # dead through its gate column
+        mlps[1].wi_fused.weight[:, 1, 9] = 0.0                               # dead through its up column
+    params = {k: v.detach() for k, v in params.items()}
+    live1 = PU.mlp_live_neurons(params["layers.1.mlp.wi_fused.weight"], params["layers.1.mlp.wo.weight"])
+    assert not live1[5] and not live1[9]
+    width, keep = PU.plan_mlp_compaction(params, L, F)
+    assert width == 2048                                                     # 40 % of 4096 = 1639 live -> 2048
+    for i, idx in enumerate(keep):
+        live = PU.mlp_live_neurons(params[f"layers.{i}.mlp.wi_fused.weight"], params[f"layers.{i}.mlp.wo.weight"])
+        assert idx.numel() == width and torch.equal(idx, idx.unique()) and bool(live[idx].sum() == live.sum())
+    small = PU.compact_mlp(params, (width, keep))
+    x = torch.randn(2, 3, D)
+    for i, m in enumerate(mlps):
+        wi, wo = small[f"layers.{i}.mlp.wi_fused.weight"], small[f"layers.{i}.mlp.wo.weight"]
+        assert wi.shape == (D, 2, width) and wo.shape == (width, D)
+        gu = torch.tensordot(x, wi, dims=1)
+        y = torch.tensordot(torch.nn.functional.silu(gu[..., 0, :]) * gu[..., 1, :], wo, dims=1)
+        assert (y - m(x)).abs().max() < 1e-5
+
+
 def test_synthetic_transcripts_are_deterministic():
     a = [SY.synthetic_transcript(i) for i in range(64)]
     assert a == [SY.synthetic_transcript(i) for i in range(64)]

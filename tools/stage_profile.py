@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--greedy", action="store_true")
     ap.add_argument("--cta", type=int, default=0, help="the CTA whose stamps are shown")
     ap.add_argument("--ctas", action="store_true", help="also print the per-CTA spread of stage end times")
+    ap.add_argument("--mlp-prune", type=float, default=0.0, help="structurally prune mlp.wo (dim 0) by this amount first")
     a = ap.parse_args()
     cfg = tiny_config() if a.tiny else dia_1_6b_config()
     dev = torch.device("cuda:0")
@@ -34,6 +35,12 @@ def main():
     SY.init_synthetic_(dia.model.named_parameters(), 5)
     with torch.no_grad():
         dia.model.decoder.logits_dense.weight[:, 0, 1024] = 0.0
+    if a.mlp_prune > 0:
+        import torch.nn.utils.prune as prune
+        from dia_tts_prune_b200 import pruning_utils as PU
+        for layer in dia.model.decoder.layers:
+            prune.ln_structured(layer.mlp.wo, "weight", amount=a.mlp_prune, n=2, dim=0)
+        PU.make_pruning_permanent(dia.model)
     SY.cast_dense_kernels_(dia.model, torch.bfloat16)
     dia.device = dev
     dia.model.to(dev).eval()

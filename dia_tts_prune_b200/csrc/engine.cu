@@ -238,12 +238,23 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return load[a] < load[b]; });
             for (int i = 0; i < units[t] % G; ++i) cnt[order[i]]++;
             // A slab row is gc * 16 bytes; ldmatrix reads 8 consecutive rows, which collide 4-way (8-way) in the
-            // shared-memory banks when gc is a multiple of 4 (8).  For the paired gate/up slabs trade such CTAs
-            // pairwise to one unit more / one unit less (gc = 2 mod 4 on both).
-            if (mult[t] == 2) {
+            // shared-memory banks when gc is a multiple of 4 (8) - an 8-group logits slab runs at half the HBM rate.
+            // Trade such CTAs pairwise to one unit more / one unit less; a leftover one trades with a neighbour
+            // that stays conflict-free.
+            {
+                auto is_bad = [&](int n) { const int gc = n * mult[t]; return gc >= 4 && gc % 4 == 0; };
                 std::vector<int> bad;
-                for (int c = 0; c < G; ++c) if (cnt[c] > 1 && cnt[c] % 2 == 0) bad.push_back(c);
+                for (int c = 0; c < G; ++c) if (is_bad(cnt[c])) bad.push_back(c);
                 for (size_t i = 0; i + 1 < bad.size(); i += 2) { cnt[bad[i]]++; cnt[bad[i + 1]]--; }
+                if (bad.size() % 2) {
+                    for (int c = 0; c < G; ++c) {
+                        if (c != bad.back() && !is_bad(cnt[c]) && cnt[c] >= 2 && !is_bad(cnt[c] - 1) &&
+                            cnt[c] <= cnt[bad.back()]) {
+                            cnt[bad.back()]++; cnt[c]--;
+                            break;
+                        }
+                    }
+                }
             }
         }
         int g0 = 0;

@@ -396,7 +396,7 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[kMaxTiles][4], uint32_t a
 __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     const StepParams& p = *c.p;
     const GemmCfg& g = c.misc->gcfg[gt];
-    const int gc = g.gc, g0 = g.g0, K = g.K, n_mt = g.n_mt;
+    const int gc = g.gc, g0 = g.g0, n_mt = g.n_mt;
     if (gc == 0) return;
     const int lane = c.lane, warp = c.warp;
     const bool resid = (gt == G_SO || gt == G_CO || gt == G_WO);
@@ -747,6 +747,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
             kt = reinterpret_cast<const float4*>(c.ring + sl * kSlotBytes) + c.lane;
             keys_in = min(16, nk - ci * 16);
         }
+        if (c.ts && c.tid == 0 && ci == 0) c.ts[11] = clock64();
         float s2[2];
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -767,6 +768,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
             __syncwarp();
             if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
         }
+        if (c.ts && c.tid == 0 && ci == 0) c.ts[12] = clock64();
         float mt = fmaxf(s2[0], s2[1]);                      // tile max / sum per head: over the 8 lanes of a head
         mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 4));
         mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
@@ -794,6 +796,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
             ring_wait_full(c.misc, sl, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | 0x80 | sl);
             vt = reinterpret_cast<const float4*>(c.ring + sl * kSlotBytes) + c.lane;
         }
+        if (c.ts && c.tid == 0 && ci == 0) c.ts[13] = clock64();
 #pragma unroll 2
         for (int key = 0; key < keys_in; ++key) {
             const float4 vv = vt[key * 32];
@@ -807,6 +810,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
             acc[3].x = fmaf(pr.w, vv.x, acc[3].x); acc[3].y = fmaf(pr.w, vv.y, acc[3].y);
             acc[3].z = fmaf(pr.w, vv.z, acc[3].z); acc[3].w = fmaf(pr.w, vv.w, acc[3].w);
         }
+        if (c.ts && c.tid == 0 && ci == 0) c.ts[14] = clock64();
         __syncwarp();                                        // psm is rewritten by the next tile
         if (in_ring && c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
     }
@@ -845,6 +849,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
             if (d == 0) { ll_st(pp, __float_as_uint(M), c.seq); ll_st(pp + 1, __float_as_uint(l), c.seq); }
         }
     }
+    if (c.ts && c.tid == 0) c.ts[15] = clock64();
     consumer_sync();                                      // the scratch is reused by the next stage
     // The appended K/V row must be visible device-wide before another CTA's copy engine reads it one step later.  That
     // producer waits until its own math warps are past the cross-q stage of this step, which consumed the self-o
@@ -988,7 +993,7 @@ __device__ __forceinline__ float key_value(uint32_t k) {
 
 struct SampleSmem {
     uint32_t keys[kPerThread * kConsumerThreads];
-    uint32_t hist[256];
+    uint32_t hist[4 * 256];          // one histogram per radix pass
     float cv[kMaxCand];
     int ci[kMaxCand];
     float sv[kMaxCand];
@@ -1002,7 +1007,7 @@ struct SampleSmem {
 // (valid in every thread).  probs_out (optional): the filtered distribution the draw is made from.
 __device__ int sample_channel_cta(const float (&g)[kPerThread], int V, float temperature, float top_p, int top_k,
                                   unsigned long long seed, unsigned long long draw, int ch, float* probs_out,
-                                  SampleSmem* sm, int tid) {
+                                  SampleSmem* sm, int tid, long long* ts = nullptr) {
     const int warp = tid >> 5, lane = tid & 31;
     if (temperature == 0.0f) {          // torch.argmax: first maximal index
         float bv = -INFINITY;
@@ -1038,79 +1043,107 @@ __device__ int sample_channel_cta(const float (&g)[kPerThread], int V, float tem
         key[i] = idx < V ? order_key(g[i] / temperature) : 0u;
         sm->keys[idx] = key[i];
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sm->hist[tid + kConsumerThreads * i] = 0u;   // one histogram per radix pass
+    if (tid == 0) sm->sel[3] = 0;                                            // survivor counter
+    consumer_sync();
     // ---- top-k threshold (dia/model.py:46-52): the k-th largest key, by an 8-bit radix select -------------
+    // One block barrier per pass: every warp scans the histogram itself (redundantly) and keeps the result in
+    // registers, so there is no hand-over through shared memory and no single-warp section.
     uint32_t prefix = 0u, pmask = 0u;
     int kk = top_k, n_gt = 0;
 #pragma unroll 1
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        sm->hist[tid] = 0u;
-        if (tid == 0) { sm->sel[0] = 0; sm->sel[1] = 0; }
-        consumer_sync();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        uint32_t* hist = sm->hist + 256 * pass;
 #pragma unroll
         for (int i = 0; i < kPerThread; ++i)
-            if (key[i] != 0u && (key[i] & pmask) == prefix) atomicAdd(&sm->hist[(key[i] >> shift) & 255u], 1u);
+            if (key[i] != 0u && (key[i] & pmask) == prefix) atomicAdd(&hist[(key[i] >> shift) & 255u], 1u);
         consumer_sync();
-        if (warp == 0) {
-            // lane holds bins lane*8 .. lane*8+7; suffix sums locate the bin where the count from the top reaches kk
-            int tot = 0;
-#pragma unroll 1
-            for (int b = 0; b < 8; ++b) tot += (int)sm->hist[lane * 8 + b];
-            int suf = tot;
+        // lane holds bins lane*8 .. lane*8+7; suffix sums locate the bin where the count from the top reaches kk
+        int tot = 0;
 #pragma unroll
-            for (int m = 1; m <= 16; m <<= 1) {
-                const int t = __shfl_down_sync(0xffffffffu, suf, m);
-                if (lane + m < 32) suf += t;
-            }
-            int above = suf - tot;
-            if (above < kk && kk <= suf) {
+        for (int b = 0; b < 8; ++b) tot += (int)hist[lane * 8 + b];
+        int suf = tot;
+#pragma unroll
+        for (int m = 1; m <= 16; m <<= 1) {
+            const int t = __shfl_down_sync(0xffffffffu, suf, m);
+            if (lane + m < 32) suf += t;
+        }
+        int above = suf - tot, bin = 0;
+        const bool mine = above < kk && kk <= suf;
+        if (mine) {
 #pragma unroll 1
-                for (int b = 7; b >= 0; --b) {
-                    const int cb = (int)sm->hist[lane * 8 + b];
-                    if (above + cb >= kk) { sm->sel[0] = lane * 8 + b; sm->sel[1] = above; break; }
-                    above += cb;
-                }
+            for (int b = 7; b >= 0; --b) {
+                const int cb = (int)hist[lane * 8 + b];
+                if (above + cb >= kk) { bin = lane * 8 + b; break; }
+                above += cb;
             }
         }
-        consumer_sync();
-        prefix |= (uint32_t)sm->sel[0] << shift;
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        const int srcl = who ? __ffs(who) - 1 : 0;
+        bin = __shfl_sync(0xffffffffu, bin, srcl);
+        above = __shfl_sync(0xffffffffu, above, srcl);
+        if (!who) { bin = 0; above = 0; }                   // fewer than kk candidates left: keep everything
+        prefix |= (uint32_t)bin << shift;
         pmask |= 0xffu << shift;
-        n_gt += sm->sel[1];
-        kk -= sm->sel[1];
+        n_gt += above;
+        kk -= above;
     }
     const uint32_t thr = prefix;
-    // ---- survivors: everything above the k-th value plus its ties, in index order (<= 64 kept) -------------
-    if (warp == 0) {
-        int n_out = 0, ties = 0;
-        const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 1
-        for (int base = 0; base < V; base += 32) {
-            const int idx = base + lane;
-            const uint32_t kx = idx < V ? sm->keys[idx] : 0u;
-            const bool gtk = kx > thr, eqk = kx == thr && kx != 0u;
-            const unsigned m_eq = __ballot_sync(0xffffffffu, eqk);
-            const bool keep = gtk || (eqk && (n_gt + ties + __popc(m_eq & lt)) < kMaxCand);
-            const unsigned m_keep = __ballot_sync(0xffffffffu, keep);
-            const int posn = n_out + __popc(m_keep & lt);
-            if (keep && posn < kMaxCand) { sm->cv[posn] = key_value(kx); sm->ci[posn] = idx; }
-            n_out += __popc(m_keep);
-            ties += __popc(m_eq);
+    if (ts && tid == 0) ts[2] = clock64();
+    // ---- survivors: everything above the k-th value plus its ties (<= 64 kept) ---------------------------------
+    // Every thread pushes its own candidates (unordered); the rank sort below orders them by (value desc, index asc).
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+        if (key[i] >= thr && key[i] != 0u) {
+            const int posn = atomicAdd(&sm->sel[3], 1);
+            if (posn < kMaxCand) { sm->cv[posn] = key_value(key[i]); sm->ci[posn] = tid + kConsumerThreads * i; }
         }
-        const int ncand = min(n_out, kMaxCand);
-        __syncwarp();
-        // ---- sort descending by value (ties: lower index first) with a rank sort ---------------------------
+    }
+    consumer_sync();
+    const int n_all = sm->sel[3];
+    if (n_all > kMaxCand) {
+        // more than 64 candidates can only be ties at the threshold: keep the lowest indices among them (ordered scan)
+        if (warp == 0) {
+            int n_out = 0, ties = 0;
+            const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
-        for (int e = lane; e < ncand; e += 32) {
-            const float v = sm->cv[e];
-            int rank = 0;
-#pragma unroll 1
-            for (int j = 0; j < ncand; ++j) {
-                const float wv = sm->cv[j];
-                rank += (wv > v || (wv == v && j < e)) ? 1 : 0;
+            for (int base = 0; base < V; base += 32) {
+                const int idx = base + lane;
+                const uint32_t kx = idx < V ? sm->keys[idx] : 0u;
+                const bool gtk = kx > thr, eqk = kx == thr && kx != 0u;
+                const unsigned m_eq = __ballot_sync(0xffffffffu, eqk);
+                const bool keep = gtk || (eqk && (n_gt + ties + __popc(m_eq & lt)) < kMaxCand);
+                const unsigned m_keep = __ballot_sync(0xffffffffu, keep);
+                const int posn = n_out + __popc(m_keep & lt);
+                if (keep && posn < kMaxCand) { sm->cv[posn] = key_value(kx); sm->ci[posn] = idx; }
+                n_out += __popc(m_keep);
+                ties += __popc(m_eq);
             }
-            sm->sv[rank] = v;
-            sm->si[rank] = sm->ci[e];
         }
-        __syncwarp();
+        consumer_sync();
+    }
+    const int ncand = min(n_all, kMaxCand);
+    if (ts && tid == 0) ts[6] = clock64();
+    // ---- sort descending by value (ties: lower index first): rank sort, 4 threads per candidate -----------------
+    {
+        const int e = tid >> 2, q4 = tid & 3;
+        const float v = e < ncand ? sm->cv[e] : 0.f;
+        const int id = e < ncand ? sm->ci[e] : 0;
+        int rank = 0;
+#pragma unroll 1
+        for (int j = q4; j < ncand; j += 4) {
+            const float wv = sm->cv[j];
+            rank += (wv > v || (wv == v && sm->ci[j] < id)) ? 1 : 0;
+        }
+        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+        rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+        if (e < ncand && q4 == 0) { sm->sv[rank] = v; sm->si[rank] = id; }
+    }
+    consumer_sync();
+    if (warp == 0) {
+        if (ts && tid == 0) ts[7] = clock64();
         // ---- softmax over the survivors, top-p on the sorted cumulative sum (dia/model.py:56-70) ------------
         const float mx = sm->sv[0];
         float e0 = lane < ncand ? expf(sm->sv[lane] - mx) : 0.f;
@@ -1121,18 +1154,23 @@ __device__ int sample_channel_cta(const float (&g)[kPerThread], int V, float tem
         __syncwarp();
         int nkeep = ncand;
         if (top_p < 1.0f) {
-            if (lane == 0) {
-                float cum = 0.f;
-                nkeep = 0;
+            // sequential cumulative sum (torch.cumsum order); every lane runs it on register-resident chunks
+            float cum = 0.f;
+            bool open = true;
+            nkeep = 0;
 #pragma unroll 1
-                for (int i = 0; i < ncand; ++i) {
+            for (int i0 = 0; i0 < ncand && open; i0 += 16) {
+                float pv[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(pv + 4 * j) = *reinterpret_cast<const float4*>(sm->sv + i0 + 4 * j);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
                     // entry i is removed iff the cumulative probability BEFORE it already exceeds top_p
-                    if (i > 0 && cum > top_p) break;
-                    cum += sm->sv[i];
-                    nkeep = i + 1;
+                    open = open && (i0 + j < ncand) && !(i0 + j > 0 && cum > top_p);
+                    if (open) { cum += pv[j]; nkeep = i0 + j + 1; }
                 }
             }
-            nkeep = __shfl_sync(0xffffffffu, nkeep, 0);
         }
         e0 = lane < nkeep ? e0 : 0.f;
         e1 = lane + 32 < nkeep ? e1 : 0.f;
@@ -1144,20 +1182,31 @@ __device__ int sample_channel_cta(const float (&g)[kPerThread], int V, float tem
             if (lane < nkeep) probs_out[sm->si[lane]] = e0 / Z2;
             if (lane + 32 < nkeep) probs_out[sm->si[lane + 32]] = e1 / Z2;
         }
+        if (ts && tid == 0) ts[8] = clock64();
         // ---- multinomial(1): inverse CDF over the survivors with a Philox uniform ---------------------------
-        if (lane == 0) {
+        {
             uint32_t ctr[4] = {(uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)ch, 0x44494131u};
             philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
             const float u = (float)(ctr[0] >> 8) * (1.0f / 16777216.0f);   // [0, 1)
             const float target = u * Z2;
             float cum = 0.f;
-            int tok = sm->si[nkeep - 1];
+            int hit = nkeep - 1;
+            bool open = true;
 #pragma unroll 1
-            for (int i = 0; i < nkeep; ++i) {
-                cum += sm->cv[i];
-                if (cum > target) { tok = sm->si[i]; break; }
+            for (int i0 = 0; i0 < nkeep && open; i0 += 16) {
+                float pv[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(pv + 4 * j) = *reinterpret_cast<const float4*>(sm->cv + i0 + 4 * j);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (open && i0 + j < nkeep) {
+                        cum += pv[j];
+                        if (cum > target) { hit = i0 + j; open = false; }
+                    }
+                }
             }
-            sm->sel[2] = tok;
+            if (lane == 0) sm->sel[2] = sm->si[hit];
         }
     }
     consumer_sync();
@@ -1188,9 +1237,11 @@ __device__ void sample_stage(Ctx& c, int step_index, int pos) {
             g[i] = __uint_as_float(wv[i].x);
         }
     }
+    if (c.ts && c.tid == 0) c.ts[1] = clock64();
     const int tok = sample_channel_cta(g, p.V, p.temperature, p.top_p, p.top_k, p.seed, p.draw0 + step_index, ch,
-                                       nullptr, sm, c.tid);
+                                       nullptr, sm, c.tid, c.ts);
     if (c.tid == 0) ll_st(p.ll_pred + ch, (uint32_t)tok, c.seq);
+    if (c.ts && c.tid == 0) c.ts[3] = clock64();
     if (ch != 0 || c.warp != 0) return;
 
     // ---- CTA 0, warp 0: lane = channel ------------------------------------------------------------------
@@ -1200,6 +1251,7 @@ __device__ void sample_stage(Ctx& c, int step_index, int pos) {
         pr = (int)ll_wait32(p.ll_pred + lane, c.seq, p.err);
         p.pred_out[lane] = pr;
     }
+    if (c.ts && c.tid == 0) c.ts[5] = clock64();
     GenState* gs = p.gs;
     int next_tok = 0;
     if (gs != nullptr && p.grid != nullptr) {

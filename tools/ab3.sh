@@ -1,5 +1,5 @@
 #!/bin/bash
+# A/B/C timing on ONE box: every library in tools/ab/*.so, alternating (LIBS overrides the list).
 for i in 1 2; do
-  for v in base regs; do echo -n "$v: "; DIA_B200_LIB=$PWD/tools/ab/$v.so python tools/stress.py --reps 12 --steps 64 | tail -1; done
-  echo -n "new : "; python tools/stress.py --reps 12 --steps 64 | tail -1
+  for v in ${LIBS:-$(ls tools/ab/*.so)}; do echo -n "$(basename $v .so): "; DIA_B200_LIB=$PWD/$v python tools/stress.py --reps ${REPS:-12} --steps 64 --slot ${SLOT:-1500} | tail -1; done
 done

@@ -83,10 +83,15 @@ def main():
             stage = dur[:, idx].mean().item() * us
             if name not in ("embed", "sattn", "cattn", "sample"):
                 print(f"{name:8s} {d(1, 0):7.2f} {d(6, 1):8.2f} {d(2, 6):7.2f} {d(3, 2):7.2f} {d(4, 3):7.2f} {stage:7.2f} "
-                      f"{len(idx):6d} {stage * len(idx):8.1f}   epi: sum {d(5, 3):5.2f}  warp7: loop end {d(8, 0):5.2f} ssq ready {d(9, 0):5.2f} at barrier {d(10, 0):5.2f} | warp0 at barrier {d(3, 0):5.2f}")
+                      f"{len(idx):6d} {stage * len(idx):8.1f}   epi: sum {d(5, 3):5.2f}  warp7: loop end {d(8, 0):5.2f} at barrier {d(10, 0):5.2f} | warp0 at barrier {d(3, 0):5.2f}")
             elif name in ("sattn", "cattn"):
                 print(f"{name:8s} {'':7s} {d(1, 0):8.2f} {d(2, 1):7.2f} {'':7s} {d(4, 2):7.2f} {stage:7.2f} "
-                      f"{len(idx):6d} {stage * len(idx):8.1f}")
+                      f"{len(idx):6d} {stage * len(idx):8.1f}   warp0 tile0: K wait {d(11, 1):5.2f} scores {d(12, 11):5.2f} "
+                      f"softmax+V wait {d(13, 12):5.2f} PV {d(14, 13):5.2f} to loop end {d(2, 14):5.2f} | merge+store {d(15, 2):5.2f}")
+            elif name == "sample":
+                print(f"{name:8s} {'':7s} {'':8s} {'':7s} {'':7s} {'':7s} {stage:7.2f} {len(idx):6d} {stage * len(idx):8.1f}   "
+                      f"logits in {d(1, 0):5.2f} radix select {d(2, 1):5.2f} survivors {d(6, 2):5.2f} rank sort {d(7, 6):5.2f} "
+                      f"softmax+top-p {d(8, 7):5.2f} draw+publish {d(3, 8):5.2f} all preds {d(5, 3):5.2f} state machine {d(4, 5):5.2f}")
             else:
                 print(f"{name:8s} {'':7s} {'':8s} {'':7s} {'':7s} {'':7s} {stage:7.2f} {len(idx):6d} {stage * len(idx):8.1f}")
         if a.ctas:

@@ -261,10 +261,12 @@ __device__ void norm_warp_loop(const StepParams& p, SharedMisc* misc) {
             // start polling when this CTA's math warps enter the stage: the partials appear together with x
             if (s > p.stage_begin || n > 0) {
                 const int need = s > p.stage_begin ? n * S + s : (n - 1) * S + p.stage_end;
-                unsigned long long t0 = 0;
+                // sleep between polls: a busy spin here took a tenth of the SM's issue slots, on the scheduler that
+                // also runs warp 0 (the residual-stream epilogues)
+                unsigned polls = 0;
                 while (ld_acquire_cta_s32(&misc->stages_done) < need) {
-                    if (t0 == 0) t0 = clock64();
-                    else if (clock64() - t0 > kWatchdogCycles) ll_timeout(p.err, kErrStepDoneTimeout, seq);
+                    __nanosleep(100);
+                    if (++polls > 20000000u) ll_timeout(p.err, kErrStepDoneTimeout, seq);
                 }
             }
             float s0 = 0.f, s1 = 0.f;

@@ -872,47 +872,83 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     const int ne = e1 - e0, na = w.n_active;
     const int h_lo = e0 >> 7, nhh = ((e1 - 1) >> 7) - h_lo + 1;
     float* cml = cw + ne * na;                            // cw: [ne][na] outputs, then [nhh][na][2] (m, l)
-#pragma unroll 1
-    for (int i = c.tid; i < ne * na + nhh * na * 2; i += kConsumerThreads) {
-        const u64* src;
+    const int n_items = ne * na + nhh * na * 2;           // <= 512 + na + 6 na  (na <= 18)
+    auto item_src = [&](int i) -> const u64* {
         if (i < ne * na) {
             const int e = e0 + i / na, s = i - (i / na) * na;
-            src = part + ((size_t)s * nh + (e >> 7)) * 132 + 4 + (e & 127);
-        } else {
-            const int j = i - ne * na;
-            const int hh = j / (na * 2), rem = j - hh * (na * 2);
-            src = part + ((size_t)(rem >> 1) * nh + h_lo + hh) * 132 + (rem & 1);
+            return part + ((size_t)s * nh + (e >> 7)) * 132 + 4 + (e & 127);
         }
-        uint2 v = ll_ld(src);
-        unsigned spins = 0;
-        while (v.y != c.seq) {
-            if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 2, c.seq);
-            ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 2, c.seq);
-            __nanosleep(64);
-            v = ll_ld(src);
+        const int j = i - ne * na;
+        const int hh = j / (na * 2), rem = j - hh * (na * 2);
+        return part + ((size_t)(rem >> 1) * nh + h_lo + hh) * 132 + (rem & 1);
+    };
+    {   // every load of a thread is in flight before its first wait: one L2 round trip instead of three
+        constexpr int kIt = 3;
+        const u64* srcs[kIt];
+        uint2 v[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int i = c.tid + kConsumerThreads * it;
+            if (i < n_items) { srcs[it] = item_src(i); v[it] = ll_ld(srcs[it]); }
         }
-        cw[i] = __uint_as_float(v.x);
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int i = c.tid + kConsumerThreads * it;
+            if (i < n_items) {
+                unsigned spins = 0;
+                while (v[it].y != c.seq) {
+                    if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 2, c.seq);
+                    ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 2, c.seq);
+                    __nanosleep(64);
+                    v[it] = ll_ld(srcs[it]);
+                }
+                cw[i] = __uint_as_float(v[it].x);
+            }
+        }
+#pragma unroll 1
+        for (int i = c.tid + kConsumerThreads * kIt; i < n_items; i += kConsumerThreads)
+            cw[i] = __uint_as_float(ll_wait32(item_src(i), c.seq, p.err));
+    }
+    if (c.ts && c.tid == 0) c.ts[5] = clock64();
+    consumer_sync();
+    if (c.ts && c.tid == 0) c.ts[6] = clock64();
+    // weights of the splits, exp(m_s - M), and sum(l_s * weight): warp hh takes head hh of the slice, lane = split
+    float* cf = cml + nhh * na * 2;                        // [nhh][na] weights, then [nhh] normalisers
+    if (c.warp < nhh) {
+        const float* ml = cml + (size_t)c.warp * na * 2;
+        const float m = c.lane < na ? ml[2 * c.lane] : -INFINITY;
+        const float l = c.lane < na ? ml[2 * c.lane + 1] : 0.f;
+        const float M = warp_max(m);
+        const float f = c.lane < na ? expf(m - M) : 0.f;
+        const float Ls = warp_sum(l * f);
+        if (c.lane < na) cf[c.warp * na + c.lane] = f;
+        if (c.lane == 0) cf[nhh * na + c.warp] = Ls;
     }
     consumer_sync();
+    {   // tpe threads per output element, each over a strided subset of the splits, then a butterfly (fixed order)
+        int tpe = 8, sh = 3;
+        while (tpe > 1 && ne * tpe > kConsumerThreads) { tpe >>= 1; --sh; }
+        const int i = c.tid >> sh, j = c.tid & (tpe - 1);
+        const bool live = i < ne;
+        const int e = e0 + (live ? i : 0), h = e >> 7, d = e & 127;
+        float O = 0.f;
+        if (live) {
+            const float* fw = cf + (size_t)(h - h_lo) * na;
 #pragma unroll 1
-    for (int i = c.tid; i < ne; i += kConsumerThreads) {
-        const int e = e0 + i, h = e >> 7, d = e & 127;
-        const float* ml = cml + (size_t)(h - h_lo) * na * 2;
-        float M = -INFINITY;
-#pragma unroll 1
-        for (int s = 0; s < na; ++s) M = fmaxf(M, ml[2 * s]);
-        float Lsum = 0.f, O = 0.f;
-#pragma unroll 1
-        for (int s = 0; s < na; ++s) {
-            const float f = expf(ml[2 * s] - M);
-            Lsum = fmaf(ml[2 * s + 1], f, Lsum);
-            O = fmaf(cw[i * na + s], f, O);
+            for (int s2 = j; s2 < na; s2 += tpe) O = fmaf(cw[i * na + s2], fw[s2], O);
         }
-        const float val = Lsum > 0.f ? O / Lsum : 0.f;
-        const int k = (head0 + h) * kHeadDim + d;
-        ll_store_parts(oparts, k, r, val, f16n);
-        if (!self) ll_store_parts(oparts, k, 0, 0.f, f16n);
+#pragma unroll
+        for (int m = 4; m >= 1; m >>= 1)
+            if (m < tpe) O += __shfl_xor_sync(0xffffffffu, O, m);
+        if (live && j == 0) {
+            const float Lsum = cf[nhh * na + (h - h_lo)];
+            const float val = Lsum > 0.f ? O / Lsum : 0.f;
+            const int k = (head0 + h) * kHeadDim + d;
+            ll_store_parts(oparts, k, r, val, f16n);
+            if (!self) ll_store_parts(oparts, k, 0, 0.f, f16n);
+        }
     }
+    if (c.ts && c.tid == 0) c.ts[7] = clock64();
     if (has_new && c.tid < kHeadDim) __threadfence();
     consumer_sync();
 }

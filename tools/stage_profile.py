@@ -87,7 +87,8 @@ def main():
             elif name in ("sattn", "cattn"):
                 print(f"{name:8s} {'':7s} {d(1, 0):8.2f} {d(2, 1):7.2f} {'':7s} {d(4, 2):7.2f} {stage:7.2f} "
                       f"{len(idx):6d} {stage * len(idx):8.1f}   warp0 tile0: K wait {d(11, 1):5.2f} scores {d(12, 11):5.2f} "
-                      f"softmax+V wait {d(13, 12):5.2f} PV {d(14, 13):5.2f} to loop end {d(2, 14):5.2f} | merge+store {d(15, 2):5.2f}")
+                      f"softmax+V wait {d(13, 12):5.2f} PV {d(14, 13):5.2f} to loop end {d(2, 14):5.2f} | merge+store {d(15, 2):5.2f}"
+                      + (f" partials in {d(5, 15):5.2f} barrier {d(6, 5):5.2f} combine+store {d(7, 6):5.2f} fence+barrier {d(4, 7):5.2f}" if name == "sattn" else ""))
             elif name == "sample":
                 print(f"{name:8s} {'':7s} {'':8s} {'':7s} {'':7s} {'':7s} {stage:7.2f} {len(idx):6d} {stage * len(idx):8.1f}   "
                       f"logits in {d(1, 0):5.2f} radix select {d(2, 1):5.2f} survivors {d(6, 2):5.2f} rank sort {d(7, 6):5.2f} "

@@ -265,7 +265,7 @@ __device__ void norm_warp_loop(const StepParams& p, SharedMisc* misc) {
                 // also runs warp 0 (the residual-stream epilogues)
                 unsigned polls = 0;
                 while (ld_acquire_cta_s32(&misc->stages_done) < need) {
-                    __nanosleep(100);
+                    __nanosleep(200);
                     if (++polls > 20000000u) ll_timeout(p.err, kErrStepDoneTimeout, seq);
                 }
             }
@@ -899,7 +899,6 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
                 while (v[it].y != c.seq) {
                     if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 2, c.seq);
                     ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 2, c.seq);
-                    __nanosleep(64);
                     v[it] = ll_ld(srcs[it]);
                 }
                 cw[i] = __uint_as_float(v[it].x);

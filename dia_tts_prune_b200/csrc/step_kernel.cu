@@ -646,12 +646,15 @@ __device__ __forceinline__ void transpose_reduce(float (&v)[NV], int lane) {
     }
 }
 
-// One instantiation serves both attentions (instruction footprint matters more than FMAs here): the K/V
-// passes always carry 4 query heads per KV tile.  Self-attention uses all four (GQA 4:1); cross-attention has
-// one query head per KV head, so its heads 1..3 are zero queries whose outputs are never stored.
+// Self-attention carries 4 query heads per KV tile (GQA 4:1); cross-attention has one query head per KV head.
+// The shared-memory layout (queries, probabilities, per-warp partials) is the 4-head one for both.
 constexpr int HPK = 4;
 
-__device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot) {
+// NH = query heads that share a K/V tile: HPK for self-attention (GQA 4:1), 1 for cross-attention (a shared
+// instantiation with three zero query heads cost cross-attention 4x the FMAs and shuffles: ~1 us per layer).
+template <int NH>
+__device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
+    constexpr bool self = NH == HPK;
     const StepParams& p = *c.p;
     const int cta = blockIdx.x;
     const AttnWork w = self ? self_attn_work(p, cta, slot) : cross_attn_work(p, cta);
@@ -720,9 +723,9 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
         p.self_k[layer][row + c.tid] = kn[c.tid];
         p.self_v[layer][row + c.tid] = vn[c.tid];
     }
-    float4 q[HPK];
+    float4 q[NH];
 #pragma unroll
-    for (int h = 0; h < HPK; ++h) q[h] = reinterpret_cast<const float4*>(qs + h * kHeadDim)[c.lane];
+    for (int h = 0; h < NH; ++h) q[h] = reinterpret_cast<const float4*>(qs + h * kHeadDim)[c.lane];
 
     const int nk = w.k_hi - w.k_lo;
     const int nkc = (nk + 15) >> 4;
@@ -732,9 +735,9 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     //      then the V tile of the same keys.  Lane l owns score (key l/4 [+8], head l%4) and the running (m, l)
     //      of head l%4; every lane accumulates output dims 4*lane..4*lane+3 of all four heads.
     float m_run = -INFINITY, l_run = 0.f;
-    float4 acc[HPK];
+    float4 acc[NH];
 #pragma unroll
-    for (int h = 0; h < HPK; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int h = 0; h < NH; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
     for (int ci = c.warp; ci < nvc; ci += kConsumerWarps) {
         const bool in_ring = ci < nkc;
@@ -753,16 +756,16 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
         float s2[2];
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            float v[8 * HPK];
+            float v[8 * NH];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (half * 8 + i < keys_in) kv = kt[(half * 8 + i) * 32];
 #pragma unroll
-                for (int h = 0; h < HPK; ++h)
-                    v[i * HPK + h] = kv.x * q[h].x + kv.y * q[h].y + kv.z * q[h].z + kv.w * q[h].w;
+                for (int h = 0; h < NH; ++h)
+                    v[i * NH + h] = kv.x * q[h].x + kv.y * q[h].y + kv.z * q[h].z + kv.w * q[h].w;
             }
-            transpose_reduce<8 * HPK>(v, c.lane);            // lane l now holds (key l/4, head l%4)
+            transpose_reduce<8 * NH>(v, c.lane);             // lane l now holds (key l/4, head l%4 [head 0 if NH == 1])
             const float sv = (half * 8 + (c.lane >> 2)) < keys_in ? v[0] : -INFINITY;
             if (half == 0) s2[0] = sv; else s2[1] = sv;
         }
@@ -787,7 +790,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
         psm[c.lane] = p0;                                    // index = key * 4 + head = lane (keys 0..7), +32 (8..15)
         psm[32 + c.lane] = p1;
 #pragma unroll
-        for (int h = 0; h < HPK; ++h) {
+        for (int h = 0; h < NH; ++h) {
             const float sh = __shfl_sync(0xffffffffu, scale, h);
             acc[h].x *= sh; acc[h].y *= sh; acc[h].z *= sh; acc[h].w *= sh;
         }
@@ -803,14 +806,12 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
         for (int key = 0; key < keys_in; ++key) {
             const float4 vv = vt[key * 32];
             const float4 pr = *reinterpret_cast<const float4*>(psm + key * HPK);
-            acc[0].x = fmaf(pr.x, vv.x, acc[0].x); acc[0].y = fmaf(pr.x, vv.y, acc[0].y);
-            acc[0].z = fmaf(pr.x, vv.z, acc[0].z); acc[0].w = fmaf(pr.x, vv.w, acc[0].w);
-            acc[1].x = fmaf(pr.y, vv.x, acc[1].x); acc[1].y = fmaf(pr.y, vv.y, acc[1].y);
-            acc[1].z = fmaf(pr.y, vv.z, acc[1].z); acc[1].w = fmaf(pr.y, vv.w, acc[1].w);
-            acc[2].x = fmaf(pr.z, vv.x, acc[2].x); acc[2].y = fmaf(pr.z, vv.y, acc[2].y);
-            acc[2].z = fmaf(pr.z, vv.z, acc[2].z); acc[2].w = fmaf(pr.z, vv.w, acc[2].w);
-            acc[3].x = fmaf(pr.w, vv.x, acc[3].x); acc[3].y = fmaf(pr.w, vv.y, acc[3].y);
-            acc[3].z = fmaf(pr.w, vv.z, acc[3].z); acc[3].w = fmaf(pr.w, vv.w, acc[3].w);
+            const float prh[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                acc[h].x = fmaf(prh[h], vv.x, acc[h].x); acc[h].y = fmaf(prh[h], vv.y, acc[h].y);
+                acc[h].z = fmaf(prh[h], vv.z, acc[h].z); acc[h].w = fmaf(prh[h], vv.w, acc[h].w);
+            }
         }
         if (c.ts && c.tid == 0 && ci == 0) c.ts[14] = clock64();
         __syncwarp();                                        // psm is rewritten by the next tile
@@ -819,7 +820,7 @@ __device__ void attn_stage(Ctx& c, const bool self, int layer, int pos, int slot
     c.cbase += 2 * nkc;
     if (c.lane < HPK) { wstat[c.warp * 8 + c.lane] = m_run; wstat[c.warp * 8 + 4 + c.lane] = l_run; }
 #pragma unroll
-    for (int h = 0; h < HPK; ++h)
+    for (int h = 0; h < NH; ++h)
         reinterpret_cast<float4*>(racc + ((size_t)c.warp * HPK + h) * kHeadDim)[c.lane] = acc[h];
     consumer_sync();
     if (c.ts && c.tid == 0) c.ts[2] = clock64();
@@ -1415,8 +1416,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
             if (c.ts && tid == 0) c.ts[0] = clock64();
             switch (kind) {
                 case S_EMBED: c.xres = enter_stream(p, xs, misc, tid, true, pos, n, p.norms, c.seq); break;
-                case S_SATTN:
-                case S_CATTN: attn_stage(c, kind == S_SATTN, layer, pos, slot); break;
+                case S_SATTN: attn_stage<HPK>(c, layer, pos, slot); break;
+                case S_CATTN: attn_stage<1>(c, layer, pos, slot); break;
                 case S_SAMPLE: sample_stage(c, n, pos); break;
                 default: gemm_stage(c, gemm_of_kind(kind), layer); break;
             }

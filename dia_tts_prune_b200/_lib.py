@@ -24,7 +24,7 @@ class Shape(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_layer", "d_model", "n_hidden", "q_heads", "kv_heads", "cross_heads",
                                          "channels", "vocab", "max_audio_len", "max_text_len", "eos_value",
                                          "pad_value", "bos_value")] + \
-               [("delay_pattern", C.c_int32 * MAX_CHANNELS), ("norm_eps", C.c_float)]
+               [("delay_pattern", C.c_int32 * MAX_CHANNELS), ("norm_eps", C.c_float), ("sparse24", C.c_int32)]
 
 
 class GenParams(C.Structure):

@@ -60,7 +60,88 @@ __global__ void repack_dense_kernel(const RepackArgs a) {
     *reinterpret_cast<uint4*>(dst) = out;
 }
 
+// source value of contraction row k, column i of 8-column group g (same addressing as repack_dense_kernel)
+__device__ __forceinline__ float repack_src(const RepackArgs& a, int g, int k, int i) {
+    if (a.gemm == G_QKV) {
+        const int n = g * 8, nq = a.Hq * kHeadDim, nk = a.Hkv * kHeadDim;
+        if (n < nq) return load_src(a.src[0], a.src_bf16, (size_t)k * nq + n + i);
+        if (n < nq + nk) return load_src(a.src[1], a.src_bf16, (size_t)k * nk + n - nq + i);
+        return load_src(a.src[2], a.src_bf16, (size_t)k * nk + n - nq - nk + i);
+    }
+    if (a.gemm == G_WI) {
+        const int hg = g >> 1, part = g & 1;
+        return load_src(a.src[0], a.src_bf16, ((size_t)k * 2 + part) * a.F + hg * 8 + i);
+    }
+    if (a.gemm == G_LOGITS) {
+        const int n = g * 8 + i, ch = n / a.Vpad, vv = n - ch * a.Vpad;
+        return (ch < a.C && vv < a.V) ? load_src(a.src[0], a.src_bf16, ((size_t)k * a.C + ch) * a.V + vv) : 0.f;
+    }
+    return load_src(a.src[0], a.src_bf16, (size_t)k * a.N + g * 8 + i);
+}
+
+// 2:4 slabs (engine_internal.h, gemm_slot_rows): one thread per (4 consecutive contraction rows, 8-column group).
+// Per column it keeps the (at most two) non-zeros of the four rows in row order - padding with a zero entry of the
+// group when there are fewer - writes them to the two compressed rows of the group and ORs the 4-bit index pair into
+// the mma.sp metadata block of (16-column tile, 32-row block) at the word / nibble that the hardware reads for it
+// (sp_meta_word / sp_meta_shift in common.cuh; layout measured with tools/microbench/mma_sp_probe.cu).
+__global__ void repack_sparse24_kernel(const RepackArgs a) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k0 = blockIdx.y * 4;
+    if (g >= a.n_groups) return;
+    const int cta = a.owner[g], gl = a.local[g];
+    const CtaTable& t = a.tab[cta];
+    const int gc = t.gc[a.gemm];
+    const unsigned long long slab = t.stream_base +
+        (a.gemm == G_LOGITS ? t.logits_off : (unsigned long long)a.layer * t.layer_bytes + t.slab_off[a.gemm]);
+    int slot, rr;
+    gemm_sparse_position(k0, gc, a.K, &slot, &rr);
+    const int r = gemm_slot_rows(gc, a.K, 1);
+    unsigned char* base = a.wstream + slab + (size_t)slot * gemm_slot_bytes(gc, a.K, 1);
+    const int row_bytes = gc * 16, n_mt = (gc + 1) / 2;
+    float e0[8], e1[8];
+    uint32_t nib[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v[4];
+        int cnt = 0, p0 = -1, p1 = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = repack_src(a, g, k0 + j, i);
+            if (v[j] != 0.f) { if (cnt == 0) p0 = j; else if (cnt == 1) p1 = j; ++cnt; }
+        }
+        if (cnt > 2) atomicAdd(a.violations, 1);
+        if (cnt == 0) { p0 = 0; p1 = 1; }
+        else if (cnt == 1) { if (p0 == 3) { p1 = 3; p0 = 0; } else p1 = 3; }      // ascending pair that contains the non-zero
+        e0[i] = v[p0]; e1[i] = v[p1];
+        nib[i] = (uint32_t)p0 | ((uint32_t)p1 << 2);
+    }
+    auto pack8 = [](const float (&x)[8]) {
+        uint4 out;
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]), b1 = __floats2bfloat162_rn(x[2], x[3]),
+                       b2 = __floats2bfloat162_rn(x[4], x[5]), b3 = __floats2bfloat162_rn(x[6], x[7]);
+        out.x = *reinterpret_cast<uint32_t*>(&b0); out.y = *reinterpret_cast<uint32_t*>(&b1);
+        out.z = *reinterpret_cast<uint32_t*>(&b2); out.w = *reinterpret_cast<uint32_t*>(&b3);
+        return out;
+    };
+    const int crow = (rr >> 2) * 2;
+    *reinterpret_cast<uint4*>(base + (size_t)crow * row_bytes + gl * 16) = pack8(e0);
+    *reinterpret_cast<uint4*>(base + (size_t)(crow + 1) * row_bytes + gl * 16) = pack8(e1);
+    uint32_t* meta = reinterpret_cast<uint32_t*>(base + (size_t)(r / 2) * row_bytes) +
+                     ((size_t)(rr >> 5) * n_mt + (gl >> 1)) * 16;
+    const int gq = (rr & 31) >> 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = (gl & 1) * 8 + i;                   // row of the 16 x 32 A tile = output column of the tile
+        atomicOr(meta + sp_meta_word(n, gq), nib[i] << sp_meta_shift(n, gq));
+    }
+}
+
 cudaError_t launch_repack(const RepackArgs& a, cudaStream_t st) {
+    if (a.sparse) {
+        dim3 grid((a.n_groups + 127) / 128, a.K / 4);
+        repack_sparse24_kernel<<<grid, 128, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     dim3 grid((a.n_groups + 127) / 128, a.K);
     repack_dense_kernel<<<grid, 128, 0, st>>>(a);
     return cudaGetLastError();

@@ -222,6 +222,14 @@ __device__ __forceinline__ uint32_t ll_wait32(const unsigned long long* p, uint3
     return w.y == flag ? w.x : ll_wait32_slow(p, flag, err);
 }
 
+// ---- 2:4 sparse MMA (mma.sp m16n8k32, bf16): metadata layout -------------------------------------------
+// Measured on sm_100a with tools/microbench/mma_sp_probe.cu (profiles/r1_mma_sp_metadata_probe.txt), sparsity selector
+// 0: lane (g = lane / 4, q = lane % 4) with q < 2 supplies one 32-bit word; nibble j < 4 is the index pair of row g,
+// 4-column group 4 q + j of the 16 x 32 tile, nibble 4 + j the one of row g + 8.  A 64-byte metadata block of a
+// (16-column tile, 32-row block) stores the word of lane (g, q) at index 2 g + q.
+__host__ __device__ inline int sp_meta_word(int n, int gq) { return (n & 7) * 2 + (gq >> 2); }
+__host__ __device__ inline int sp_meta_shift(int n, int gq) { return 4 * ((n >> 3) * 4 + (gq & 3)); }
+
 // ---- packed fp32x2 math (Blackwell FFMA2) -------------------------------------------------------
 typedef unsigned long long f32x2;   // two packed floats in a 64-bit register
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {

@@ -113,6 +113,7 @@ void fill_params(const dia_b200_engine* e, StepParams& p) {
     p.C = s.channels; p.V = s.vocab; p.Vpad = e->Vpad; p.Lmax = s.max_audio_len; p.Smax = s.max_text_len;
     for (int i = 0; i < G_COUNT; ++i) { p.Kdim[i] = e->Kdim[i]; p.tclass[i] = e->tclass[i]; }
     p.eps = s.norm_eps; p.G = e->G; p.n_res = e->n_res; p.sa_nsplit = e->sa_nsplit; p.ca_nsplit = e->ca_nsplit;
+    p.sparse24 = s.sparse24 ? 1 : 0;
     p.wstream = e->d_wstream; p.cta_tab = e->d_tab; p.emb = e->d_emb; p.norms = e->d_norms;
     p.rope_sin = e->d_rope_sin; p.rope_cos = e->d_rope_cos; p.n_pos = e->n_pos;
     p.self_k = e->d_ptrs; p.self_v = e->d_ptrs + s.n_layer;
@@ -200,6 +201,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     if (e->G > prop.multiProcessorCount) { delete e; return DIA_B200_EINVAL; }   // 1 CTA / SM must be co-resident
     const dia_b200_shape& s = e->shape;
     const int G = e->G;
+    const int sp = s.sparse24 ? 1 : 0;
     if (G < 2 * s.kv_heads || G < s.cross_heads) { delete e; return DIA_B200_EINVAL; }
     e->Vpad = (s.vocab + 7) & ~7;
     e->sa_nsplit = G / (2 * s.kv_heads);
@@ -267,7 +269,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
             e->tab[c].gc[t] = gc;
             for (int i = 0; i < gc; ++i) { e->owner[t][g0 + i] = c; e->local[t][g0 + i] = i; }
             g0 += gc;
-            if (t != G_LOGITS) load[c] += (long long)gc * 16 * kd[t];
+            if (t != G_LOGITS) load[c] += (long long)gemm_slab_bytes(gc, kd[t], sp);
         }
     }
     for (int t = 0; t < G_COUNT; ++t) {
@@ -278,7 +280,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     for (int t = 0; t < G_COUNT; ++t) {
         const int need = e->tclass[t] == 1 ? 64 : 32;       // k-blocks in flight per MMA group; slots start on even k-blocks
         for (int c = 0; c < G; ++c)
-            if (e->tab[c].gc[t] > 0 && gemm_slot_rows(e->tab[c].gc[t], e->Kdim[t]) % need) { delete e; return DIA_B200_EUNSUPPORTED; }
+            if (e->tab[c].gc[t] > 0 && gemm_slot_rows(e->tab[c].gc[t], e->Kdim[t], sp) % need) { delete e; return DIA_B200_EUNSUPPORTED; }
     }
     for (int c = 0; c < G; ++c) {
         if (e->tab[c].gc[G_SO] > 0) {
@@ -291,11 +293,11 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     for (int c = 0; c < G; ++c) {
         CtaTable& t = e->tab[c];
         unsigned o = 0;
-        for (int g = 0; g < G_LOGITS; ++g) { t.slab_off[g] = o; o += (unsigned)t.gc[g] * 16u * (unsigned)kd[g]; }
+        for (int g = 0; g < G_LOGITS; ++g) { t.slab_off[g] = o; o += (unsigned)gemm_slab_bytes(t.gc[g], kd[g], sp); }
         t.layer_bytes = o;
         t.slab_off[G_LOGITS] = 0;
         t.logits_off = (unsigned long long)o * s.n_layer;
-        const unsigned long long total = t.logits_off + (unsigned long long)t.gc[G_LOGITS] * 16ull * kd[G_LOGITS];
+        const unsigned long long total = t.logits_off + gemm_slab_bytes(t.gc[G_LOGITS], kd[G_LOGITS], sp);
         t.stream_base = off;
         e->weight_bytes += (long long)total;
         off += (total + 255ull) & ~255ull;
@@ -389,6 +391,12 @@ int dia_b200_load_decoder_weights(dia_b200_engine* e, const void* const* tensors
         CK(cudaMemcpyAsync(e->d_emb + (size_t)c * s.vocab * D, tensors[ti], sizeof(float) * s.vocab * D,
                            cudaMemcpyDeviceToDevice, st));
     RepackArgs a{};
+    a.sparse = s.sparse24 ? 1 : 0;
+    a.violations = e->d_pred;                              // scratch int (the prediction buffer is idle during a load)
+    if (a.sparse) {
+        CK(cudaMemsetAsync(e->d_wstream, 0, e->stream_bytes, st));     // metadata nibbles are OR-ed in
+        CK(cudaMemsetAsync(e->d_pred, 0, sizeof(int), st));
+    }
     a.src_bf16 = dense_dtype; a.Hq = s.q_heads; a.Hkv = s.kv_heads; a.F = s.n_hidden; a.V = s.vocab; a.Vpad = e->Vpad;
     a.C = s.channels; a.tab = e->d_tab; a.wstream = e->d_wstream;
     auto repack = [&](int gemm, int layer, const void* s0, const void* s1, const void* s2, int N) -> int {
@@ -418,6 +426,13 @@ int dia_b200_load_decoder_weights(dia_b200_engine* e, const void* const* tensors
     ++ti;
     int rc = repack(G_LOGITS, 0, tensors[ti], nullptr, nullptr, 0);
     if (rc) return rc;
+    if (a.sparse) {
+        // the compressed slabs are only valid for a model that really is 2:4 along K (the check is part of the repack)
+        int bad = 0;
+        CK(cudaMemcpyAsync(&bad, e->d_pred, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (bad != 0) { e->weights_loaded = false; return DIA_B200_EINVAL; }
+    }
     e->weights_loaded = true;
     return DIA_B200_OK;
 }

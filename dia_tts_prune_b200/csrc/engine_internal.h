@@ -33,20 +33,40 @@ struct CtaTable {
 // contraction; a slot holds `r` of them, r a power of two that divides K/8 and fits 8 KB.  Stream position ci of a
 // slab is slot j = ci / 8 of warp w = ci % 8, i.e. rows w*K/8 + j*r ..: ring order alternates between the warps
 // while every warp walks a contiguous k-range (one fetch of its input words serves up to 256 / r slots).
-__host__ __device__ inline int gemm_slot_rows(int gc, int K) {
+//
+// 2:4 slabs (`sparse`): a slot holds the same r LOGICAL rows as r/2 compressed rows - of every 4 consecutive logical
+// rows the (at most) 2 non-zeros per output column, in row order - followed by the mma.sp metadata of its r/32
+// 32-row blocks: 64 bytes per (block, 16-column tile).  0.5625 of the dense bytes.
+__host__ __device__ inline int gemm_slot_rows(int gc, int K, int sparse = 0) {
     const int sl = K / 8;
-    int cap = 8192 / (gc * 16);
+    const int row_bytes = sparse ? gc * 8 + ((gc + 1) / 2) * 2 : gc * 16;     // bytes per logical row
+    int cap = 8192 / row_bytes;
     if (cap > 256) cap = 256;
     if (cap > sl) cap = sl;
-    int r = 16;
+    int r = sparse ? 32 : 16;
     while (r * 2 <= cap && sl % (r * 2) == 0) r *= 2;
     return r;
 }
-// position (row index inside the slab's stream) of contraction row k
+__host__ __device__ inline unsigned gemm_slot_bytes(int gc, int K, int sparse = 0) {
+    const unsigned r = (unsigned)gemm_slot_rows(gc, K, sparse);
+    return sparse ? (r / 2) * (unsigned)gc * 16u + (r / 32) * (unsigned)((gc + 1) / 2) * 64u : r * (unsigned)gc * 16u;
+}
+__host__ __device__ inline unsigned long long gemm_slab_bytes(int gc, int K, int sparse = 0) {
+    if (gc == 0) return 0ull;
+    return (unsigned long long)(K / gemm_slot_rows(gc, K, sparse)) * gemm_slot_bytes(gc, K, sparse);
+}
+// position (row index inside the slab's stream) of contraction row k  [dense slabs]
 __host__ __device__ inline int gemm_row_position(int k, int gc, int K) {
     const int sl = K / 8, r = gemm_slot_rows(gc, K);
     const int w = k / sl, within = k - w * sl, j = within / r, rr = within - j * r;
     return (w + 8 * j) * r + rr;
+}
+// slot (stream position) and row inside the slot of logical contraction row k  [2:4 slabs]
+__host__ __device__ inline void gemm_sparse_position(int k, int gc, int K, int* slot, int* row_in_slot) {
+    const int sl = K / 8, r = gemm_slot_rows(gc, K, 1);
+    const int w = k / sl, within = k - w * sl, j = within / r;
+    *slot = w + 8 * j;
+    *row_in_slot = within - j * r;
 }
 
 struct GenState {                      // device-resident Dia.generate loop state (dia/model.py:736-807)
@@ -69,6 +89,7 @@ struct StepParams {
     int G;                             // CTAs the tables were built for
     int n_res;                         // CTAs [0, n_res) own columns of the residual stream (and publish sum(x^2))
     int sa_nsplit, ca_nsplit;          // max key splits per (row, kv head) / per cross head
+    int sparse24;                      // weight slabs are 2:4-compressed (mma.sp), see gemm_slot_rows
     // weights
     const unsigned char* wstream;
     const CtaTable* cta_tab;
@@ -141,6 +162,8 @@ struct RepackArgs {
     const int* local;       // [n_groups] index of the group inside its CTA's slab
     const CtaTable* tab;
     unsigned char* wstream;
+    int sparse;             // write 2:4-compressed slabs (the stream must be zeroed first: metadata is OR-ed in)
+    int* violations;        // sparse: counts 4-row groups with more than 2 non-zeros (the model is not 2:4)
 };
 cudaError_t launch_repack(const RepackArgs& a, cudaStream_t st);
 cudaError_t launch_embed_sum(const float* emb, const int* tokens, int n_rows, int C, int V, int D, float* x,

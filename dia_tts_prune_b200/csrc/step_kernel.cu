@@ -54,6 +54,8 @@ struct GemmCfg {
     int urows;         // rows of one input fetch unit = min(sl, 256)
     int cpu;           // ring slots per fetch unit = urows / rpc
     int n_mt;          // 16-column MMA tiles = ceil(gc / 2)
+    int slot_bytes;    // bytes of one ring slot of the slab (dense: rpc * row_bytes; 2:4: values + metadata)
+    int meta_off;      // 2:4: byte offset of the metadata inside a slot = (rpc / 2) * row_bytes
 };
 
 struct SharedMisc {
@@ -196,8 +198,8 @@ __device__ void producer_loop(const StepParams& p, unsigned char* ring, SharedMi
                     (gt == G_LOGITS ? tab.logits_off
                                     : (unsigned long long)layer * tab.layer_bytes + tab.slab_off[gt]);
 #pragma unroll 1
-                for (int r0 = 0; r0 < g.K; r0 += g.rpc)
-                    pr.issue(base + (size_t)r0 * g.row_bytes, g.rpc * g.row_bytes, false);
+                for (int ci = 0; ci < g.n_chunks; ++ci)
+                    pr.issue(base + (size_t)ci * g.slot_bytes, g.slot_bytes, false);
             } else if (kind == S_SATTN || kind == S_CATTN) {
                 const bool self = kind == S_SATTN;
                 const AttnWork w = self ? self_attn_work(p, cta, slot) : cross_attn_work(p, cta);
@@ -395,6 +397,51 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[kMaxTiles][4], uint32_t a
     }
 }
 
+// 2:4 weights: mma.sp m16n8k32 - A = 16 output columns x 32 contraction rows held as the 16 compressed rows of the
+// block (same ldmatrix pattern as the dense path on half the rows), B = the input fragments of two dense k-blocks,
+// metadata = one word per lane (lanes with lane % 4 < 2, selector 0) from the slot's metadata area.
+__device__ __forceinline__ void mma_sp_bf16_16832(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1,
+                                                  uint32_t b2, uint32_t b3, uint32_t e) {
+    asm("mma.sp::ordered_metadata.sync.aligned.m16n8k32.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+        "{%8, %9, %10, %11}, {%0, %1, %2, %3}, %12, 0x0;"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "r"(e));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <int NT>
+__device__ __forceinline__ void mma_chunk_sp(float (&acc)[kMaxTiles][4], uint32_t a_addr, uint32_t kb_bytes, int n32,
+                                             uint32_t bst, uint32_t b_off0, uint32_t b_off1, uint32_t bmask,
+                                             uint32_t meta_addr, int n_mt) {
+    constexpr int U = NT == 1 ? 2 : 1;                       // the host makes every slot a multiple of U 32-row blocks
+#pragma unroll 1
+    for (int jb = 0; jb < n32; jb += U) {
+        uint2 blo[U], bhi[U];
+        uint32_t a[U][NT][4], e[U][NT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = jb + u;
+            blo[u] = lds_u2(bst + j * 512 + b_off0);
+            bhi[u] = lds_u2(bst + j * 512 + b_off1);
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt) {
+                ldmatrix_x4_trans(a[u][mt], a_addr + j * kb_bytes + mt * 32);
+                e[u][mt] = lds_u32(meta_addr + (uint32_t)(j * n_mt + mt) * 64u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            blo[u].x &= bmask; blo[u].y &= bmask; bhi[u].x &= bmask; bhi[u].y &= bmask;
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt)
+                mma_sp_bf16_16832(acc[U > 1 ? u * NT + mt : mt], a[u][mt], blo[u].x, blo[u].y, bhi[u].x, bhi[u].y, e[u][mt]);
+        }
+    }
+}
+
 __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     const StepParams& p = *c.p;
     const GemmCfg& g = c.misc->gcfg[gt];
@@ -437,6 +484,9 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     const uint32_t lm_off = (uint32_t)(((lane & 7) + 8 * (lane >> 4)) * g.row_bytes + ((lane >> 3) & 1) * 16);
     const uint32_t ring_base = smem_u32(c.ring) + lm_off;
     const uint32_t kb_bytes = 16u * g.row_bytes;
+    // 2:4: this lane's metadata word inside a 64-byte (tile, 32-row block) record - lanes with lane % 4 >= 2 load a
+    // neighbour's word, which the instruction ignores (selector 0)
+    const uint32_t meta_base = smem_u32(c.ring) + (uint32_t)g.meta_off + (uint32_t)(((lane >> 2) * 2 + (lane & 1)) * 4);
     // B: lane (n = lane / 4, q = lane % 4) holds rows {2q, 2q+1} and {2q+8, 2q+9} of MMA column n = 4 * row + term.
     // Staging: per k-block 64 words [row r][term t ^ s][q][2], s = 2 * (kb & 1) + r (bank swizzle)
     const uint32_t bst = smem_u32(c.xs) + warp * kBStageBytes;
@@ -501,7 +551,15 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
             ring_wait_full(c.misc, slot, (idx / kNumSlots) & 1u, p.err, (c.seq << 8) | slot);
             const uint32_t a_addr = ring_base + slot * kSlotBytes;
             const uint32_t b_base = bst + (uint32_t)(jc * nkb) * 256u;      // nkb is even: the parity swizzle lines up
-            if (tclass == 1) mma_chunk<1>(acc, a_addr, kb_bytes, nkb, b_base, b_off0, b_off1, bmask);
+            if (p.sparse24) {
+                const uint32_t m_addr = meta_base + slot * kSlotBytes;
+                const int n32 = nkb >> 1;
+                if (tclass == 1) mma_chunk_sp<1>(acc, a_addr, kb_bytes, n32, b_base, b_off0, b_off1, bmask, m_addr, n_mt);
+                else if (tclass == 2) mma_chunk_sp<2>(acc, a_addr, kb_bytes, n32, b_base, b_off0, b_off1, bmask, m_addr, n_mt);
+                else if (tclass == 4) mma_chunk_sp<4>(acc, a_addr, kb_bytes, n32, b_base, b_off0, b_off1, bmask, m_addr, n_mt);
+                else mma_chunk_sp<8>(acc, a_addr, kb_bytes, n32, b_base, b_off0, b_off1, bmask, m_addr, n_mt);
+            }
+            else if (tclass == 1) mma_chunk<1>(acc, a_addr, kb_bytes, nkb, b_base, b_off0, b_off1, bmask);
             else if (tclass == 2) mma_chunk<2>(acc, a_addr, kb_bytes, nkb, b_base, b_off0, b_off1, bmask);
             else if (tclass == 4) mma_chunk<4>(acc, a_addr, kb_bytes, nkb, b_base, b_off0, b_off1, bmask);
             else mma_chunk<8>(acc, a_addr, kb_bytes, nkb, b_base, b_off0, b_off1, bmask);
@@ -1377,7 +1435,9 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
         GemmCfg& g = misc->gcfg[tid];
         g.gc = misc->tab.gc[tid]; g.g0 = misc->tab.g0[tid]; g.K = p.Kdim[tid];
         g.row_bytes = g.gc * 16;
-        g.rpc = g.gc > 0 ? gemm_slot_rows(g.gc, g.K) : 16;
+        g.rpc = g.gc > 0 ? gemm_slot_rows(g.gc, g.K, p.sparse24) : 16;
+        g.slot_bytes = g.gc > 0 ? (int)gemm_slot_bytes(g.gc, g.K, p.sparse24) : 0;
+        g.meta_off = (g.rpc / 2) * g.gc * 16;
         g.n_chunks = g.gc > 0 ? g.K / g.rpc : 0;
         g.sl = g.K / kConsumerWarps;
         g.urows = min(g.sl, kMaxKb * 16);

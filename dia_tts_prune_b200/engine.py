@@ -51,9 +51,11 @@ def decoder_tensor_names(config: DiaConfig) -> list[str]:
 
 class DecodeEngine:
     def __init__(self, config: DiaConfig, device: torch.device | str | int = "cuda", n_ctas: int = 0,
-                 n_hidden: int | None = None):
+                 n_hidden: int | None = None, sparse24: bool = False):
         """``n_hidden``: MLP width of the weights that will be loaded, when a structurally pruned checkpoint was
-        compacted (``pruning_utils.plan_mlp_compaction``); defaults to the configuration's."""
+        compacted (``pruning_utils.plan_mlp_compaction``); defaults to the configuration's.  ``sparse24``: every dense
+        kernel is 2:4-sparse along its input axis (``pruning_utils.is_2to4``): the engine streams compressed slabs
+        (0.5625 of the bytes) and multiplies with ``mma.sp``; ``load_weights`` rejects a model that is not."""
         if not torch.cuda.is_available():
             raise RuntimeError("dia_tts_prune_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -74,6 +76,8 @@ class DecodeEngine:
         for i, v in enumerate(dt.delay_pattern):
             sh.delay_pattern[i] = v
         sh.norm_eps = config.model.normalization_layer_epsilon
+        self.sparse24 = bool(sparse24)
+        sh.sparse24 = 1 if sparse24 else 0
         self._h = C.c_void_p()
         _lib.check(self.lib.dia_b200_engine_create(C.byref(sh), self.device.index, n_ctas, C.byref(self._h)),
                    "engine_create")

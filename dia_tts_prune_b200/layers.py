@@ -227,6 +227,12 @@ class Encoder(nn.Module):
             return self.norm(x)
 
 
+def _contract_dims(name: str) -> int:
+    """Leading (input) axes of a decoder DenseGeneral kernel: 2 for the attention output projections
+    ``[heads, head_dim, D]``, 1 for everything else."""
+    return 2 if name.endswith("o_proj.weight") else 1
+
+
 class DecoderLayer(nn.Module):
     def __init__(self, config: DiaConfig, compute_dtype: torch.dtype):
         super().__init__()
@@ -284,6 +290,7 @@ class Decoder(nn.Module):
         self._engine = None
         self._engine_sig = None
         self.compact_pruned_mlp = True      # drop exactly-dead MLP neurons from the engine's weight stream
+        self.use_sparse24 = True            # stream 2:4 checkpoints compressed (mma.sp) when every kernel qualifies
         self.register_load_state_dict_post_hook(lambda m, k: m.invalidate_engine())
 
     # ---- engine management -------------------------------------------------------------------------
@@ -309,17 +316,24 @@ class Decoder(nn.Module):
         if self._engine is not None and self._engine_sig == sig and self._engine.device == dev:
             return self._engine
         # (re)pack: a checkpoint whose MLP was structurally pruned (zero hidden neurons) gets a narrower engine
-        from .pruning_utils import compact_mlp, plan_mlp_compaction
+        from .pruning_utils import compact_mlp, is_2to4, plan_mlp_compaction
+        from .synthetic import is_dense_kernel
         sd = dict(self.named_parameters())
         tensors = {n: sd[n].detach() for n in decoder_tensor_names(self.config)}
         d = self.config.model.decoder
         plan = plan_mlp_compaction(tensors, d.n_layer, d.n_hidden) if self.compact_pruned_mlp else None
         width = plan[0] if plan is not None else d.n_hidden
-        if self._engine is None or self._engine.device != dev or self._engine.n_hidden != width:
+        if plan is not None:
+            tensors = compact_mlp(tensors, plan)
+        # a 2:4 checkpoint (every dense kernel) streams compressed and runs on mma.sp
+        sparse = bool(self.use_sparse24) and all(is_2to4(t, _contract_dims(n)) for n, t in tensors.items()
+                                                 if is_dense_kernel(n))
+        if self._engine is None or self._engine.device != dev or self._engine.n_hidden != width or \
+                self._engine.sparse24 != sparse:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = DecodeEngine(self.config, dev, n_hidden=width)
-        self._engine.load_weights(compact_mlp(tensors, plan) if plan is not None else tensors)
+            self._engine = DecodeEngine(self.config, dev, n_hidden=width, sparse24=sparse)
+        self._engine.load_weights(tensors)
         self._engine_sig = sig
         return self._engine
 

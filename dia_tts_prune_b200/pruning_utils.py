@@ -77,6 +77,18 @@ def apply_2to4_pruning(model: nn.Module, module_types=DEFAULT_PRUNABLE_MODULES):
     return model
 
 
+@torch.no_grad()
+def is_2to4(w: torch.Tensor, n_in_axes: int = 1) -> bool:
+    """Every 4 consecutive K (input) entries of every output column of the kernel viewed as [K, N] hold at most 2
+    non-zeros - what :func:`apply_2to4_pruning` produces and ``mma.sp`` requires."""
+    K = 1
+    for s_ in w.shape[:n_in_axes]:
+        K *= s_
+    if K % 4:
+        return False
+    return bool(((w.reshape(K // 4, 4, -1) != 0).sum(dim=1) <= 2).all().item())
+
+
 def make_pruning_permanent(model: nn.Module, module_types=DEFAULT_PRUNABLE_MODULES):
     """Fold masks into the weights and drop the reparametrisation (dia/pruning_utils.py:122-151)."""
     for m, name in get_prunable_modules(model, module_types, parameter_name="weight"):

@@ -55,6 +55,9 @@ typedef struct dia_b200_shape {
     int32_t eos_value, pad_value, bos_value; /* data.audio_{eos,pad,bos}_value */
     int32_t delay_pattern[DIA_B200_MAX_CHANNELS]; /* data.delay_pattern */
     float norm_eps;         /* model.normalization_layer_epsilon */
+    int32_t sparse24;       /* 1: every dense kernel is 2:4-sparse along its input axis (at most 2 non-zeros in each 4
+                               consecutive K entries of a column - the 2:4 variant of offline_prune.py's checkpoints);
+                               the engine streams compressed slabs and multiplies with mma.sp.  0: dense. */
 } dia_b200_shape;
 
 /* Sampling / loop parameters of Dia.generate (dia/model.py:632-647). */

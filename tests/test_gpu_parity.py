@@ -292,6 +292,12 @@ def test_tiny_pruned_variants_match_oracle(mode):
     text = "[S1] Pruned. [S2] Weights."
     tr = O.generate(sd, cfg, text, max_tokens=30, temperature=0.0, dead_cross_kv=False, keep_logits_at={1, 20})
     st, out = _prepared(dia, text)
+    eng = dia.model.decoder._engine_for(st)
+    # 2:4 checkpoints stream compressed slabs (values of 2 of every 4 K entries + mma.sp metadata) and run on mma.sp
+    assert eng.sparse24 == (mode == "2to4")
+    if mode == "2to4":
+        dense_bytes = sum(v.numel() for k, v in sd.items() if k.startswith("decoder.") and SY.is_dense_kernel(k)) * 2
+        assert 0.55 * dense_bytes < eng.weight_stream_bytes < 0.66 * dense_bytes   # 0.5625 + half-empty tiles of narrow slabs
     st.prepare_step(1)
     with torch.inference_mode():
         lg = dia.model.decoder.decode_step(out.get_tokens_at(0).unsqueeze(0).unsqueeze(0).expand(2, 1, -1), st)
@@ -299,6 +305,26 @@ def test_tiny_pruned_variants_match_oracle(mode):
     dia.generate(text, max_tokens=30, temperature=0.0, output="codes")
     if torch.stack(tr.margins).min() > 1e-4:
         assert torch.equal(dia.last_codes.cpu(), tr.codes)
+    if mode == "2to4":
+        codes_sp = dia.last_codes.cpu().clone()
+        dia.model.decoder.use_sparse24 = False              # the same weights streamed dense (zeros and all): same tokens
+        dia.model.decoder.invalidate_engine()
+        dia.generate(text, max_tokens=30, temperature=0.0, output="codes")
+        assert not dia.model.decoder.engine().sparse24
+        if torch.stack(tr.margins).min() > 1e-4:
+            assert torch.equal(dia.last_codes.cpu(), codes_sp)
+
+
+def test_sparse_engine_rejects_a_dense_model():
+    """A 2:4 engine only accepts weights that really are 2:4 along K: the repack counts violations."""
+    from dia_tts_prune_b200.engine import DecodeEngine, decoder_tensor_names
+    cfg = tiny_config()
+    dia, _ = build_dia(cfg, 7, "cuda:0")
+    eng = DecodeEngine(cfg, "cuda:0", sparse24=True)
+    sd = dict(dia.model.decoder.named_parameters())
+    with pytest.raises(ValueError):
+        eng.load_weights({n: sd[n].detach() for n in decoder_tensor_names(cfg)})
+    eng.close()
 
 
 def test_tiny_structured_mlp_pruning_narrows_the_engine():

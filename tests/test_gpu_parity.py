@@ -500,6 +500,35 @@ def test_live_text_only_prepare_matches_full(tiny_gpu):
     assert (got[True][3] - got[False][3]).abs().max() < LOGIT_TIGHT
 
 
+def test_full_2to4_sparse_engine_matches_the_dense_stream():
+    """config 4 (ii) at Dia-1.6B: the mma.sp engine on compressed slabs and the dense engine streaming the same
+    weights with their zeros agree - teacher-forced logits within the tight bound, greedy tokens identical."""
+    from dia_tts_prune_b200 import pruning_utils as PU
+    cfg = dia_1_6b_config()
+    dia, _ = build_dia(cfg, 5, "cuda:0", bf16=True)
+    PU.apply_2to4_pruning(dia.model.decoder)
+    PU.make_pruning_permanent(dia.model)
+    text = "[S1] Two of four. [S2] Sparse tensor cores."
+    out = {}
+    for sparse in (True, False):
+        dia.model.decoder.use_sparse24 = sparse
+        dia.model.decoder.invalidate_engine()
+        st, o = _prepared(dia, text)
+        eng = dia.model.decoder._engine_for(st)
+        assert eng.sparse24 == sparse
+        nbytes = eng.weight_stream_bytes
+        st.prepare_step(1)
+        with torch.inference_mode():
+            lg = dia.model.decoder.decode_step(o.get_tokens_at(0).unsqueeze(0).unsqueeze(0).expand(2, 1, -1), st).cpu()
+        dia.generate(text, max_tokens=48, temperature=0.0, output="codes")
+        out[sparse] = (lg, dia.last_codes.cpu().clone(), nbytes)
+    assert (out[True][0] - out[False][0]).abs().max() < LOGIT_TIGHT
+    assert torch.equal(out[True][1], out[False][1])
+    assert 0.56 < out[True][2] / out[False][2] < 0.57              # 0.5 values + 0.0625 metadata
+    del dia
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("M,N,K", [(8, 128, 64), (200, 256, 512), (1722, 2048, 2048), (333, 512, 8192)])
 def test_tcgen05_dense_matches_fp64(M, N, K):
     """DenseGeneral for T > 1 rows (dia/layers.py:55-66) on tcgen05: fp32-operand accuracy from the three-term bf16

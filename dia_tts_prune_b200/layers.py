@@ -11,9 +11,11 @@ What runs where
     entirely in the hand-written sm_100a kernels of ``csrc/`` through the C ABI (``engine.py``).
     There is no eager fallback for them: without a CUDA device they raise.
   * ``Encoder``, ``Decoder.precompute_cross_attn_cache`` and the prompt prefill (``Decoder.forward``)
-    are once-per-utterance work (SURVEY.md 8(f) "next" rows).  They currently run as fp32 library
-    calls on the GPU (cuBLAS without TF32 + SDPA); their results feed the kernels through the
-    KV caches.
+    are once-per-utterance work.  Every dense layer of these T > 1 passes runs on
+    the tcgen05 / TMEM GEMM of ``csrc/gemm_tcgen05.cu`` (``DenseGeneral._forward_tcgen05``); their attention is
+    library SDPA in fp32.  The results feed the decode kernels through the KV caches.
+  * Pruned checkpoints: ``Decoder.engine()`` drops exactly-dead MLP neurons from the weight stream and streams a
+    2:4 model compressed on ``mma.sp`` (``pruning_utils``).
 
 Numerics: dense kernels may be stored bf16 (``compute_dtype``), but activations, residual stream,
 norms, softmax and KV caches are always fp32.

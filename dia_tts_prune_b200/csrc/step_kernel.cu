@@ -23,7 +23,11 @@
 //  * 8 math warps consume ring slots (one slot per warp at a time) on the tensor cores (mma.sync
 //    m16n8k16, swap-AB: 16 output columns x the 2 batch rows split into three bf16 terms, exact to
 //    24 bits, so the product has fp32-activation accuracy - SURVEY.md 8(c)); residual stream, norms,
-//    softmax and the KV cache stay fp32, reductions run in a fixed order (deterministic);
+//    softmax and the KV cache stay fp32, reductions run in a fixed order (deterministic).  2:4-pruned
+//    checkpoints stream compressed slabs (2 of every 4 K entries + metadata, 0.5625 of the bytes) and
+//    use mma.sp m16n8k32 on the same operand plumbing;
+//  * a norm warp gathers the per-CTA partial sums of x^2 behind every RMSNorm while the math warps run
+//    their MMAs, and hands 1/rms to the epilogue through a shared-memory flag;
 //  * the code is deliberately compact and rolled: the L1.5 instruction cache is 32 KB and every stage
 //    runs once per layer, so straight-line code is fetched cold from L2 at ~30 cycles/instruction;
 //  * self-attention streams its K/V tiles through the same ring (split-KV over CTAs, 4 query heads

@@ -327,6 +327,36 @@ def test_sparse_engine_rejects_a_dense_model():
     eng.close()
 
 
+@pytest.mark.parametrize("mode", ["structured", "2to4"])
+def test_pruned_checkpoint_loads_through_from_local(tmp_path, mode):
+    """What offline_prune.py writes (config.json + pytorch_model.bin of the permanently pruned state dict,
+    offline_prune.py:153-155) goes through Dia.from_local (dia/model.py:139-187) and decodes like the oracle on the
+    same weights - on the narrowed / 2:4 engine, without any extra step by the user."""
+    import torch.nn.utils.prune as prune
+    from dia_tts_prune_b200 import pruning_utils as PU
+    from dia_tts_prune_b200.model import Dia
+    cfg = tiny_config()
+    src, _ = build_dia(cfg, 7)
+    if mode == "structured":
+        for layer in src.model.decoder.layers:
+            prune.ln_structured(layer.mlp.wo, "weight", amount=0.5, n=2, dim=0)
+    else:
+        PU.apply_2to4_pruning(src.model)
+    PU.make_pruning_permanent(src.model)
+    cfg.save(tmp_path / "config.json")
+    torch.save(src.model.state_dict(), tmp_path / "pytorch_model.bin")
+    sd = {k: v.detach().clone() for k, v in src.model.named_parameters()}
+    dia = Dia.from_local(str(tmp_path / "config.json"), str(tmp_path / "pytorch_model.bin"), "float32",
+                         torch.device("cuda:0"))
+    text = "[S1] From disk. [S2] Pruned."
+    tr = O.generate(sd, cfg, text, max_tokens=24, temperature=0.0, dead_cross_kv=False)
+    dia.generate(text, max_tokens=24, temperature=0.0, output="codes")
+    eng = dia.model.decoder.engine()
+    assert (eng.n_hidden, eng.sparse24) == ((512, False) if mode == "structured" else (1024, True))
+    if torch.stack(tr.margins).min() > 1e-4:
+        assert torch.equal(dia.last_codes.cpu(), tr.codes)
+
+
 def test_tiny_structured_mlp_pruning_narrows_the_engine():
     """config 4 (i): `--prune-dim 0` on mlp.wo = fewer hidden neurons.  The engine is rebuilt with the reduced width
     (its weight stream shrinks) and the results still match the oracle run on the zero-filled full-width weights."""

@@ -519,18 +519,23 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
         // ---- wait until the producing stage has written all input words of this unit
         unsigned spins = 0;
         while (__any_sync(0xffffffffu, ll_stale(w, f16))) {
-            if (lane == 0) {
-                const u64* sentinel = src + (size_t)row0 * 2;
-                while ((ll_ld(sentinel).y >> 16) != f16) {
+            // 32 sentinels per warp: the first and the last word (row 0) of each 16-row k-block of the unit - a k-block
+            // comes from at most two producer CTAs - polled with ONE warp-wide load per round trip; the full re-fetch
+            // is issued when all of them carry the flag, so it is (almost always) the last one.
+            {
+                const bool live = (lane & 15) < nkb_u;
+                const u64* sp = src + ((size_t)(row0 >> 4) + (lane & 15)) * 32 + ((lane >> 4) ? 15 : 0);
+                bool ok = !live || (ll_ld(sp).y >> 16) == f16;
+                while (!__all_sync(0xffffffffu, ok)) {
                     if (++spins > kMaxSpins) {
                         volatile int* e = reinterpret_cast<volatile int*>(p.err);
-                        e[4] = 1 + row0 * 2; e[5] = (int)(ll_ld(sentinel).y >> 16); e[6] = (int)f16; e[7] = u;
+                        e[4] = 1 + row0 * 2; e[5] = (int)(ll_ld(sp).y >> 16); e[6] = (int)f16; e[7] = u;
                         ll_timeout(p.err, kErrFlagTimeout, c.seq * 16 + gt);
                     }
                     ll_check_abort(p.err, spins, 100 + kErrFlagTimeout, c.seq * 16 + gt);
+                    if (!ok) ok = (ll_ld(sp).y >> 16) == f16;
                 }
             }
-            __syncwarp();
             if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 1, c.seq * 16 + gt);
             ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 1, c.seq * 16 + gt);
             ll_fetch(w, src, row0, nkb_u, lane, f16);

@@ -244,6 +244,29 @@ def test_mlp_compaction_plan_drops_only_dead_neurons():
         assert (y - m(x)).abs().max() < 1e-5
 
 
+def test_2to4_detection_matches_the_mask_producer():
+    """Decoder.engine() streams a checkpoint compressed only when EVERY dense kernel is 2:4 along its input axes."""
+    from dia_tts_prune_b200 import pruning_utils as PU
+    from dia_tts_prune_b200.layers import _contract_dims
+    from dia_tts_prune_b200.model import Dia
+    cfg = tiny_config()
+    dia = Dia(cfg, "float32", torch.device("cpu"))
+    SY.init_synthetic_(dia.model.named_parameters(), 3)
+    dense = {n: p.detach() for n, p in dia.model.decoder.named_parameters() if SY.is_dense_kernel(n)}
+    assert len(dense) == 10 * cfg.model.decoder.n_layer + 1     # incl. the cross-attention k/v projections (prepare only)
+    assert not any(PU.is_2to4(t, _contract_dims(n)) for n, t in dense.items())
+    PU.apply_2to4_pruning(dia.model.decoder)
+    PU.make_pruning_permanent(dia.model)
+    pruned = {n: p.detach() for n, p in dia.model.decoder.named_parameters() if SY.is_dense_kernel(n)}
+    assert all(PU.is_2to4(t, _contract_dims(n)) for n, t in pruned.items())
+    o = pruned["layers.0.self_attention.o_proj.weight"]                     # [heads, head_dim, D]: K = heads * head_dim
+    assert _contract_dims("layers.0.self_attention.o_proj.weight") == 2 and PU.is_2to4(o, 2)
+    assert abs(PU.check_pruning_sparsity(dia.model.decoder) - 0.5) < 0.01
+    w = pruned["layers.1.mlp.wo.weight"].clone()
+    w[0:4, 0] = 1.0                                                         # one group of one column with 4 non-zeros
+    assert not PU.is_2to4(w, 1)
+
+
 def test_synthetic_transcripts_are_deterministic():
     a = [SY.synthetic_transcript(i) for i in range(64)]
     assert a == [SY.synthetic_transcript(i) for i in range(64)]

@@ -37,10 +37,10 @@ __global__ void repack_dense_kernel(const RepackArgs a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = load_src(s, a.src_bf16, (size_t)k * width + col + i);
     } else if (a.gemm == G_WI) {
-        // groups alternate gate / up of the same 8 hidden units; source is [K][2][F] (dia/layers.py:77-82)
-        const int hg = g >> 1, part = g & 1;
+        // a group = the gate columns (0..3) and the up columns (4..7) of the same 4 hidden units; source is
+        // [K][2][F] (dia/layers.py:77-82)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = load_src(a.src[0], a.src_bf16, ((size_t)k * 2 + part) * a.F + hg * 8 + i);
+        for (int i = 0; i < 8; ++i) v[i] = load_src(a.src[0], a.src_bf16, ((size_t)k * 2 + (i >> 2)) * a.F + g * 4 + (i & 3));
     } else if (a.gemm == G_LOGITS) {
         // every channel's 1028 columns are padded to Vpad (a multiple of 8) with zero weights
 #pragma unroll
@@ -68,10 +68,7 @@ __device__ __forceinline__ float repack_src(const RepackArgs& a, int g, int k, i
         if (n < nq + nk) return load_src(a.src[1], a.src_bf16, (size_t)k * nk + n - nq + i);
         return load_src(a.src[2], a.src_bf16, (size_t)k * nk + n - nq - nk + i);
     }
-    if (a.gemm == G_WI) {
-        const int hg = g >> 1, part = g & 1;
-        return load_src(a.src[0], a.src_bf16, ((size_t)k * 2 + part) * a.F + hg * 8 + i);
-    }
+    if (a.gemm == G_WI) return load_src(a.src[0], a.src_bf16, ((size_t)k * 2 + (i >> 2)) * a.F + g * 4 + (i & 3));
     if (a.gemm == G_LOGITS) {
         const int n = g * 8 + i, ch = n / a.Vpad, vv = n - ch * a.Vpad;
         return (ch < a.C && vv < a.V) ? load_src(a.src[0], a.src_bf16, ((size_t)k * a.C + ch) * a.V + vv) : 0.f;

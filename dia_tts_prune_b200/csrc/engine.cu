@@ -218,9 +218,10 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     // stream has a fixed owner thread and never leaves its register; the other GEMMs are balanced against the
     // bytes a CTA already streams per layer.
     const int nq = s.q_heads * kHeadDim, nkv = s.kv_heads * kHeadDim, nc = s.cross_heads * kHeadDim;
-    const int units[G_COUNT] = {(nq + 2 * nkv) / 8, s.d_model / 8, nc / 8, s.d_model / 8, s.n_hidden / 8,
+    // mlp-in: a group holds the gate AND the up columns of 4 hidden units, so any slab width keeps every pair in one CTA
+    const int units[G_COUNT] = {(nq + 2 * nkv) / 8, s.d_model / 8, nc / 8, s.d_model / 8, s.n_hidden / 4,
                                 s.d_model / 8, s.channels * e->Vpad / 8};
-    const int mult[G_COUNT] = {1, 1, 1, 1, 2, 1, 1};    // mlp-in: a unit is a (gate, up) pair of groups
+    const int mult[G_COUNT] = {1, 1, 1, 1, 1, 1, 1};
     const int kd[G_COUNT] = {s.d_model, nq, s.d_model, nc, s.d_model, s.n_hidden, s.d_model};
     if (s.d_model / 8 > 2 * G) { delete e; return DIA_B200_EUNSUPPORTED; }   // residual columns: one MMA tile per CTA
     e->tab.assign(G, CtaTable{});

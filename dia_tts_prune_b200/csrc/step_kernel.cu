@@ -614,13 +614,13 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     if (c.ts && c.tid == 0) c.ts[3] = clock64();
     if (e_mt >= n_mt) return;                          // whole warps without a tile are done
 
-    float y = 0.f, y8 = 0.f;                           // column e_m and (mlp-in only) its partner e_m + 8
+    float y = 0.f, y8 = 0.f;                           // column e_m and (mlp-in gate columns only) its up column e_m + 4
     {
-        const float* rb = red + (size_t)e_mt * 32 + e_r * 16 + (gt == G_WI ? (e_m & 7) : e_m);
+        const float* rb = red + (size_t)e_mt * 32 + e_r * 16 + e_m;
 #pragma unroll
         for (int ww = 0; ww < kConsumerWarps; ++ww) {
             y += rb[(size_t)ww * n_mt * 32];
-            if (gt == G_WI) y8 += rb[(size_t)ww * n_mt * 32 + 8];
+            if (gt == G_WI && (e_m & 4) == 0) y8 += rb[(size_t)ww * n_mt * 32 + 4];     // the up column of this gate column
         }
     }
     const uint32_t f16n = c.seq & 0xffffu;
@@ -637,11 +637,12 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
         inv = reinterpret_cast<const volatile float*>(c.misc->inv_rms[par])[e_r];
     }
     if (gt == G_WI) {
-        // a tile = (gate group, up group) of the same 8 hidden units: h = silu(gate) * up (dia/layers.py:95-101)
-        if (!e_valid || e_m >= 8) return;
+        // a group = gate columns 0..3 and up columns 4..7 of the same 4 hidden units: h = silu(gate) * up
+        // (dia/layers.py:95-101)
+        if (!e_valid || (e_m & 4) != 0) return;
         const float gate = y * inv, up = y8 * inv;
         const float h = (gate / (1.0f + expf(-gate))) * up;
-        const int n = ((g0 >> 1) + e_mt) * 8 + e_m;
+        const int n = (g0 + e_group) * 4 + (e_m & 3);
         ll_store_parts(p.ll_hidden, n, e_r, h, f16n);
         return;
     }

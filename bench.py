@@ -350,6 +350,51 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
+def run_batch(args) -> None:
+    """BASELINE.json configs[4]: `--utterances M` synthetic transcripts sharded round-robin over the ranks (replicas, no
+    data-path collective), each a full generation through the public API, host text in / host codes out.  Prints one
+    JSON line with the whole-job throughput (sum of frames over ranks / slowest rank's wall time).  Not the headline
+    line: the driver's `python bench.py` (no --utterances) stays configs[1]."""
+    import torch
+    import torch.distributed as dist
+    from dia_tts_prune_b200 import replicas, synthetic as SY
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dia, cfg = build_cpu_model(WEIGHT_SEED, suppress_eos=True)
+    SY.cast_dense_kernels_(dia.model, torch.bfloat16)
+    dia.compute_dtype = torch.bfloat16
+    dia.device = dev
+    dia.model.to(dev)
+    dia.model.eval()
+    texts = [SY.synthetic_transcript(i) for i in range(args.utterances)]
+    gen = lambda t: dia.generate(t, max_tokens=args.max_tokens, seed=1234, output="codes").cpu()   # noqa: E731
+    gen(texts[rank % len(texts)])                                  # warm-up: weight repack, allocations
+    if world > 1:
+        dist.barrier()
+    out, frames, secs = replicas.run_sharded(gen, texts, world, rank, sync=torch.cuda.synchronize,
+                                             frames_of=lambda res: dia.last_stats["steps"])   # decode steps = frames
+    frames_all, secs_max = replicas.reduce_throughput(frames, secs, device=dev)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": frames_all / secs_max, "unit": UNIT, "n_gpus": world, "higher_is_better": True,
+            "scaling": "strong", "data": "synthetic", "dtype": "bf16",
+            "config": {"workload": f"{args.utterances} independent synthetic transcripts (60-200 bytes) sharded round-robin "
+                                   f"over {world} GPU(s), max_tokens {args.max_tokens} each, CFG batch 2, default sampling; "
+                                   "end to end through Dia.generate (host text in, host codes out)",
+                       "parallelism": f"replicas x{world}, no data-path collective"},
+            "frames": frames_all, "wall_s": secs_max, "rtfx": frames_all / secs_max / FRAME_RATE}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -362,6 +407,10 @@ def main():
     ap.add_argument("--variant", default="dense", choices=sorted(VARIANTS),
                     help="dense = BASELINE.json configs[1] (the headline); the others are configs[3]")
     ap.add_argument("--prune-amount", type=float, default=0.5, help="mlp-pruned: fraction of hidden neurons removed")
+    ap.add_argument("--utterances", type=int, default=0,
+                    help="BASELINE.json configs[4]: run this many synthetic transcripts sharded over the GPUs instead of "
+                         "the headline single-transcript workload")
+    ap.add_argument("--max-tokens", type=int, default=MAX_TOKENS, help="--utterances mode: frames per utterance")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -375,6 +424,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    if args.utterances > 0:
+        run_batch(args)
+        return
     run_ours(args)
 
 

@@ -33,3 +33,29 @@ def gather_codes(codes: list[torch.Tensor], group=None) -> list:
     out = [None] * dist.get_world_size(group)
     dist.all_gather_object(out, [c.cpu() if isinstance(c, torch.Tensor) else c for c in codes], group=group)
     return out
+
+
+def run_sharded(generate, transcripts: list[str], world: int = 1, rank: int = 0, sync=None,
+                frames_of=None) -> tuple[dict, float, float]:
+    """BASELINE.json configs[4]: a batch of independent transcripts over the replicas.  Rank ``rank`` runs
+    ``generate(text)`` (e.g. ``lambda t: dia.generate(t, output="codes")``) for its round-robin shard, one utterance
+    after the other; returns ({global index: result}, frames produced by this rank, seconds this rank took).
+    ``sync`` (e.g. ``torch.cuda.synchronize``) is called before each clock read; ``frames_of(result)`` counts the
+    frames of one result (default: its leading dimension).  Feed the last two numbers to :func:`reduce_throughput`
+    for the whole-job line."""
+    import time
+    mine = assign(len(transcripts), world, rank)
+    out, frames = {}, 0.0
+    if sync is not None:
+        sync()
+    t0 = time.perf_counter()
+    for i in mine:
+        res = generate(transcripts[i])
+        out[i] = res
+        if frames_of is not None:
+            frames += float(frames_of(res))
+        elif res is not None and hasattr(res, "shape"):
+            frames += float(res.shape[0])
+    if sync is not None:
+        sync()
+    return out, frames, time.perf_counter() - t0

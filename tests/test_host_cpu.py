@@ -274,6 +274,20 @@ def test_synthetic_transcripts_are_deterministic():
     assert len(set(a)) > 50
 
 
+def test_run_sharded_covers_every_utterance_once():
+    texts = [SY.synthetic_transcript(i) for i in range(7)]
+    seen = {}
+    tot_frames = 0.0
+    for rank in range(3):
+        out, frames, secs = replicas.run_sharded(lambda t: torch.zeros((len(t), 9), dtype=torch.int32), texts, 3, rank)
+        assert secs >= 0.0 and frames == sum(len(texts[i]) for i in out)
+        assert not (set(out) & set(seen))
+        seen.update(out)
+        tot_frames += frames
+    assert sorted(seen) == list(range(7)) and tot_frames == sum(len(t) for t in texts)
+    assert all(seen[i].shape[0] == len(texts[i]) for i in range(7))
+
+
 # ---- replicas (multi-GPU host logic) under gloo, world size 2 ----------------------------------------------------
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))

@@ -144,9 +144,10 @@ def build_cpu_model(seed: int, suppress_eos: bool):
     return dia, cfg
 
 
-def cpu_port_frames_per_s(sd, cfg, text: str, n_steps: int, threads: int) -> dict:
+def cpu_port_frames_per_s(sd, cfg, text: str, n_steps: int, threads: int, lean_steps: int = 0) -> dict:
     """The oracle port of the reference's decode loop, timed on the host (dead cross-attention K/V
-    re-projection kept, as shipped: dia/layers.py:274-275)."""
+    re-projection kept, as shipped: dia/layers.py:274-275).  ``lean_steps`` > 0 also times the same loop with that
+    dead projection skipped (identical outputs; BASELINE.md section 3's "useful-work" CPU figure)."""
     import torch
     from oracle import dia_oracle as O
     torch.set_num_threads(threads)
@@ -155,10 +156,17 @@ def cpu_port_frames_per_s(sd, cfg, text: str, n_steps: int, threads: int) -> dic
                     time_steps=True)
     total = time.perf_counter() - t0
     loop = sum(tr.step_seconds)
-    return {"value": len(tr.step_seconds) / loop, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{len(tr.step_seconds)} greedy decode steps of the same Dia-1.6B fp32 workload on the host "
-                      f"(CFG batch 2, dead cross-K/V projection kept as shipped), loop {loop:.1f}s; one-time "
-                      f"encoder+cross-KV prepare {total - loop:.1f}s excluded"}
+    out = {"value": len(tr.step_seconds) / loop, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"{len(tr.step_seconds)} greedy decode steps (cache slots 0..{len(tr.step_seconds) - 1}) of the same "
+                     f"Dia-1.6B fp32 workload on the host (CFG batch 2, dead cross-K/V projection kept as shipped), loop "
+                     f"{loop:.1f}s; one-time encoder+cross-KV prepare {total - loop:.1f}s excluded"}
+    if lean_steps > 0:
+        tr = O.generate(sd, cfg, text, max_tokens=1 + lean_steps, temperature=0.0, cfg_scale=3.0, dead_cross_kv=False,
+                        time_steps=True)
+        out["lean_value"] = len(tr.step_seconds) / sum(tr.step_seconds)
+        out["lean_note"] = (f"same loop over {len(tr.step_seconds)} steps with the reference's dead per-step cross-attention "
+                            "K/V re-projection skipped (outputs identical)")
+    return out
 
 
 def run_reference(args) -> None:
@@ -228,7 +236,7 @@ def run_ours(args) -> None:
     dia.device = dev
     dia.model.to(dev)
     dia.model.eval()
-    text = SY.DEFAULT_TRANSCRIPT if world == 1 else SY.synthetic_transcript(rank)
+    text = SY.DEFAULT_TRANSCRIPT          # the same transcript on every rank and at every N: like-for-like weak scaling
     sampling = dict(cfg_scale=3.0, temperature=1.3, top_p=0.95, top_k=35)
 
     # ---- resident inputs for the device-timed loop --------------------------------------------------
@@ -307,24 +315,37 @@ def run_ours(args) -> None:
     # ---- reduce over ranks: max time, sum frames ------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s, float(frames_dev), float(e2e_steps), k_ms, k_bytes, float(launches)],
                      dtype=torch.float64, device=dev)
+    per_rank_ms = [dev_ms / args.steps]
     if world > 1:
         tmax, tsum = t.clone(), t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [x[0].item() / args.steps for x in every]
         dev_ms, e2e_s = tmax[0].item(), tmax[1].item()
         frames_dev, e2e_steps, launches = tsum[2].item(), tsum[3].item(), tsum[6].item()
+        k_ms, k_bytes = tsum[4].item() / world, tsum[5].item() / world            # roofline: mean over the replicas
+        achieved = k_bytes / (k_ms * 1e-3) / 1e9
     value = frames_dev / (dev_ms * 1e-3)
     e2e_value = e2e_steps / e2e_s
 
     cpu_base = None
     if sd_cpu is not None:
-        cpu_base = cpu_port_frames_per_s(sd_cpu, cfg, SY.DEFAULT_TRANSCRIPT, args.cpu_decode_steps, os.cpu_count() or 1)
+        cpu_base = cpu_port_frames_per_s(sd_cpu, cfg, SY.DEFAULT_TRANSCRIPT, args.cpu_decode_steps, os.cpu_count() or 1,
+                                         lean_steps=args.cpu_decode_steps)
 
     if rank == 0:
-        traffic = None
-        try:   # per-launch DRAM bytes from the committed `ncu --set full` capture, if present
+        # DRAM bytes per launch from the committed `ncu --set full` capture (per decode STEP there, scaled to the mean
+        # number of steps of the launches timed here, so that it compares with algorithmic_bytes_per_launch)
+        traffic, traffic_src = None, None
+        steps_per_launch = frames_dev / world / max(1, len(profile))
+        try:
             with open(os.path.join(REPO, "profiles", "step_kernel_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch") if args.variant == "dense" else None
+                tj = json.load(f)
+            if args.variant == "dense":
+                traffic = tj["dram_bytes_per_step"] * steps_per_launch
+                traffic_src = tj.get("source")
         except Exception:
             pass
         line = {
@@ -340,8 +361,11 @@ def run_ours(args) -> None:
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "dia_step_kernel",
-                         "launches_timed": len(profile),
-                         "algorithmic_bytes_per_launch": k_bytes / max(1, len(profile))},
+                         "launches_timed": len(profile), "steps_per_launch": steps_per_launch,
+                         "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": k_bytes / max(1, len(profile)),
+                         "algorithmic_bytes_per_step": k_bytes / max(1.0, frames_dev / world)},
+            "per_rank_ms_per_step": per_rank_ms,
             "cpu_baseline": cpu_base,
             "clocks": clocks,
         }

@@ -67,6 +67,12 @@ _SIGNATURES = {
     "dia_b200_dense_prepare_weight": (_i, [_vp, _i, _vp, _i, _i, _vp]),
     "dia_b200_dense_workspace_bytes": (C.c_size_t, [_i, _i]),
     "dia_b200_dense_forward": (_i, [_fp, _vp, _fp, _vp, _i, _i, _i, _vp]),
+    "dia_b200_dense_forward_fused": (_i, [_fp, _fp, C.c_float, _vp, _fp, _fp, _vp, _i, _i, _i, _vp]),
+    "dia_b200_attention_rows": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp]),
+    "dia_b200_rope_rows": (_i, [_fp, _fp, _fp, _fp, _i32p, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dia_b200_rmsnorm_rows": (_i, [_fp, _fp, C.c_float, _fp, _i, _i, _vp]),
+    "dia_b200_silu_mul": (_i, [_fp, _fp, _i, _i, _vp]),
+    "dia_b200_embed_rows": (_i, [_fp, _i32p, _fp, _i, _i, _i, _vp]),
     "dia_b200_debug_run_stages": (_i, [_vp, _i32p, _i, _i, _i, _i, _i, _vp]),
     "dia_b200_debug_enable_timing": (_i, [_vp, _i]),
     "dia_b200_debug_last_device_error": (_i, [_vp, C.POINTER(C.c_int32), _i]),

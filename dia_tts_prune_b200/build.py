@@ -12,7 +12,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = CSRC / "libdia_b200.so"
-SOURCES = ["step_kernel.cu", "aux_kernels.cu", "gemm_tcgen05.cu", "engine.cu"]
+SOURCES = ["step_kernel.cu", "aux_kernels.cu", "gemm_tcgen05.cu", "prefill_kernels.cu", "engine.cu"]
 HEADERS = ["common.cuh", "engine_internal.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -34,6 +34,19 @@ std::atomic<long long> g_launches{0};
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// every ABI call runs on the engine's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) err = cudaSetDevice(device);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev) DeviceGuard _guard(dev); CK(_guard.err)
+
 }  // namespace
 
 struct dia_b200_engine {
@@ -102,6 +115,7 @@ int validate_shape(const dia_b200_shape& s) {
         const int sl = k / 8;
         if (k % 512 || (sl > 256 && sl % 256)) return DIA_B200_EUNSUPPORTED;
     }
+    if (s.d_model > 2048) return DIA_B200_EUNSUPPORTED;                   // sum(x^2) words: one 16-byte load per lane and warp
     if (s.vocab > 5 * kConsumerThreads) return DIA_B200_EUNSUPPORTED;     // sampler: <= 5 entries of a channel per thread
     return DIA_B200_OK;
 }
@@ -156,7 +170,7 @@ int run_stages(dia_b200_engine* e, StepParams& p, bool cooperative, cudaStream_t
 int check_sampling_supported(float temperature, int top_k) {
     if (temperature == 0.0f) return DIA_B200_OK;
     if (temperature < 0.0f) return DIA_B200_EINVAL;
-    if (top_k <= 0 || top_k > 64) return DIA_B200_EUNSUPPORTED;   // fused sampler keeps <= 64 candidates
+    (void)top_k;      // <= 0: no top-k filter (dia/model.py:43-50); 1..64: fused candidate list; wider: full-vocabulary path
     return DIA_B200_OK;
 }
 
@@ -185,7 +199,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     if (!shape || !out) return DIA_B200_EINVAL;
     int rc = validate_shape(*shape);
     if (rc) return rc;
-    CK(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { g_last_cuda_error = "device is not sm_100-class"; return DIA_B200_EUNSUPPORTED; }
@@ -289,7 +303,6 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
             e->n_res = c + 1;
         }
     }
-    if (e->n_res > 160) { delete e; return DIA_B200_EUNSUPPORTED; }          // sum(x^2) partials: 5 per lane of one warp
     unsigned long long off = 0;
     for (int c = 0; c < G; ++c) {
         CtaTable& t = e->tab[c];
@@ -361,7 +374,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
 
 int dia_b200_engine_destroy(dia_b200_engine* e) {
     if (!e) return DIA_B200_OK;
-    cudaSetDevice(e->device);
+    DeviceGuard _guard(e->device);
     cudaDeviceSynchronize();
     void* dev[] = {e->d_wstream, e->d_tab, e->d_emb, e->d_norms, e->d_rope_sin, e->d_rope_cos, e->d_ptrs, e->d_x,
                    e->d_logits, e->d_ll, e->d_pred, e->d_tokens, e->d_gs, e->d_timing, e->d_cta_timing};
@@ -384,7 +397,7 @@ int dia_b200_load_decoder_weights(dia_b200_engine* e, const void* const* tensors
     const int expect = s.channels + 11 * s.n_layer + 2;
     if (n_tensors != expect) return DIA_B200_EINVAL;
     for (int i = 0; i < n_tensors; ++i) if (!tensors[i]) return DIA_B200_EINVAL;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     cudaStream_t st = S(stream);
     const size_t D = s.d_model;
     int ti = 0;
@@ -440,7 +453,7 @@ int dia_b200_load_decoder_weights(dia_b200_engine* e, const void* const* tensors
 
 int dia_b200_set_rope_table(dia_b200_engine* e, const float* sin_host, const float* cos_host, int n_pos) {
     if (!e || !sin_host || !cos_host || n_pos <= 0) return DIA_B200_EINVAL;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     if (e->d_rope_sin) { cudaFree(e->d_rope_sin); e->d_rope_sin = nullptr; }
     if (e->d_rope_cos) { cudaFree(e->d_rope_cos); e->d_rope_cos = nullptr; }
     const size_t bytes = sizeof(float) * (size_t)n_pos * (kHeadDim / 2);
@@ -457,7 +470,7 @@ int dia_b200_bind_caches(dia_b200_engine* e, void* const* self_k, void* const* s
                          const void* const* cross_v, int n_layer, int text_len, void* stream) {
     if (!e || !self_k || !self_v || !cross_k || !cross_v) return DIA_B200_EINVAL;
     if (n_layer != e->shape.n_layer || text_len < 0 || text_len > e->shape.max_text_len) return DIA_B200_EINVAL;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     const int L = n_layer;
     // the pinned staging buffer is reused: make sure the previous async copy has drained
     CK(cudaStreamSynchronize(S(stream)));
@@ -489,7 +502,7 @@ int dia_b200_decode_step(dia_b200_engine* e, const int32_t* tokens, int pos, int
     int rc = ready(e, true);
     if (rc) return rc;
     if (!tokens || !logits || pos < 0 || slot < 0 || slot >= e->shape.max_audio_len) return DIA_B200_EINVAL;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     StepParams p;
     fill_params(e, p);
     p.tokens = tokens;
@@ -508,7 +521,7 @@ int dia_b200_decoder_layer_step(dia_b200_engine* e, int layer, const float* x_in
     if (!x_in || !x_out || layer < 0 || layer >= e->shape.n_layer || pos < 0 || slot < 0 ||
         slot >= e->shape.max_audio_len)
         return DIA_B200_EINVAL;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     cudaStream_t st = S(stream);
     CK(launch_interleave(x_in, e->d_x, e->shape.d_model, st));
     g_launches++;
@@ -530,7 +543,7 @@ int dia_b200_embed_sum(dia_b200_engine* e, const int32_t* tokens, int n_rows, fl
     if (n_rows == 0) return DIA_B200_OK;
     if (!tokens || !x) return DIA_B200_EINVAL;
     if (!e->weights_loaded) return DIA_B200_ESTATE;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     CK(launch_embed_sum(e->d_emb, tokens, n_rows, e->shape.channels, e->shape.vocab, e->shape.d_model, x, S(stream)));
     g_launches++;
     return DIA_B200_OK;
@@ -541,7 +554,7 @@ int dia_b200_head_sample(dia_b200_engine* e, const float* logits, float cfg_scal
     if (!e || !logits || !pred) return DIA_B200_EINVAL;
     int rc = check_sampling_supported(temperature, top_k);
     if (rc) return rc;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     StepParams p;
     fill_params(e, p);
     p.cfg_scale = cfg_scale; p.temperature = temperature; p.top_p = top_p; p.top_k = top_k; p.seed = seed;
@@ -559,7 +572,7 @@ int dia_b200_generate_begin(dia_b200_engine* e, int32_t* grid, const dia_b200_ge
         return DIA_B200_EINVAL;
     rc = check_sampling_supported(gp->temperature, gp->top_k);
     if (rc) return rc;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     CK(cudaStreamSynchronize(S(stream)));     // h_gs staging reuse
     int dmax = 0;
     for (int c = 0; c < e->shape.channels; ++c) dmax = std::max(dmax, (int)e->shape.delay_pattern[c]);
@@ -588,7 +601,7 @@ int dia_b200_generate_steps(dia_b200_engine* e, int n_steps, void* stream) {
     n_steps = std::min(n_steps, e->shape.max_audio_len - e->gen_slot);
     n_steps = std::min(n_steps, e->shape.max_audio_len - e->gen_pos);
     if (n_steps <= 0) return DIA_B200_OK;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     const int max_per_launch = 65534 / (8 * e->shape.n_layer + 3);      // 16-bit sequence flags
     while (n_steps > 0) {
         const int n = std::min(n_steps, max_per_launch);
@@ -613,7 +626,7 @@ int dia_b200_generate_steps(dia_b200_engine* e, int n_steps, void* stream) {
 
 int dia_b200_generate_status(dia_b200_engine* e, dia_b200_gen_status* out, void* stream) {
     if (!e || !out) return DIA_B200_EINVAL;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     CK(cudaMemcpyAsync(e->h_gs, e->d_gs, sizeof(GenState), cudaMemcpyDeviceToHost, S(stream)));
     CK(cudaStreamSynchronize(S(stream)));
     out->dec_step = e->h_gs->dec_step;
@@ -689,16 +702,76 @@ int dia_b200_dense_prepare_weight(const void* w, int src_dtype, void* wt_bf16, i
 
 size_t dia_b200_dense_workspace_bytes(int M, int K) { return (M > 0 && K > 0) ? gemm_workspace_bytes(M, K) : 0; }
 
-int dia_b200_dense_forward(const float* x, const void* wt_bf16, float* y, void* workspace, int M, int N, int K, void* stream) {
+int dia_b200_dense_forward_fused(const float* x, const float* norm_weight, float eps, const void* wt_bf16,
+                                 const float* residual, float* y, void* workspace, int M, int N, int K, void* stream) {
     if (M < 0 || N <= 0 || K <= 0) return DIA_B200_EINVAL;
     if (M == 0) return DIA_B200_OK;
     if (!x || !wt_bf16 || !y || !workspace) return DIA_B200_EINVAL;
-    if ((reinterpret_cast<uintptr_t>(wt_bf16) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(y)) & 15)
+    if ((reinterpret_cast<uintptr_t>(wt_bf16) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(y) |
+         reinterpret_cast<uintptr_t>(residual)) & 15)
         return DIA_B200_EINVAL;
-    cudaError_t e = launch_gemm_tcgen05(x, wt_bf16, y, workspace, M, N, K, S(stream));
+    cudaError_t e = launch_gemm_tcgen05(x, norm_weight, eps, wt_bf16, residual, y, workspace, M, N, K, S(stream));
     if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); return DIA_B200_EUNSUPPORTED; }
     CK(e);
     g_launches += 2;
+    return DIA_B200_OK;
+}
+
+int dia_b200_dense_forward(const float* x, const void* wt_bf16, float* y, void* workspace, int M, int N, int K, void* stream) {
+    return dia_b200_dense_forward_fused(x, nullptr, 0.f, wt_bf16, nullptr, y, workspace, M, N, K, stream);
+}
+
+int dia_b200_attention_rows(const float* q, const float* k, const float* v, float* out, int B, int Tq, int Tk, int Hq, int Hkv,
+                            int Tk_stride, int mode, const int32_t* n_valid_host, void* stream) {
+    if (B < 0 || Tq < 0 || Tk < 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv || Tk > Tk_stride || mode < 0 || mode > 2 || B > 16)
+        return DIA_B200_EINVAL;
+    if (B == 0 || Tq == 0) return DIA_B200_OK;
+    if (!q || !k || !v || !out) return DIA_B200_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(out)) & 15)
+        return DIA_B200_EINVAL;
+    if (n_valid_host)
+        for (int b = 0; b < B; ++b) if (n_valid_host[b] < 0 || n_valid_host[b] > Tk) return DIA_B200_EINVAL;
+    CK(launch_attention_rows(q, k, v, out, B, Tq, Tk, Hq, Hkv, Tk_stride, mode, n_valid_host, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_rope_rows(const float* src, float* dst, const float* sin_tab, const float* cos_tab, const int32_t* pos, int B,
+                       int T, int H, int rotate, int to_cache, int dst_T, int dst_t0, int n_pos, void* stream) {
+    if (B < 0 || T < 0 || H <= 0 || dst_t0 < 0 || (to_cache && dst_t0 + T > dst_T)) return DIA_B200_EINVAL;
+    if ((long long)B * T == 0) return DIA_B200_OK;
+    if (!src || !dst || (rotate && (!sin_tab || !cos_tab || !pos || n_pos <= 0))) return DIA_B200_EINVAL;
+    CK(launch_rope_rows(src, dst, sin_tab, cos_tab, pos, B, T, H, rotate, to_cache, dst_T, dst_t0, n_pos, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_rmsnorm_rows(const float* x, const float* weight, float eps, float* y, int M, int D, void* stream) {
+    if (M < 0 || D <= 0) return DIA_B200_EINVAL;
+    if (M == 0) return DIA_B200_OK;
+    if (!x || !weight || !y) return DIA_B200_EINVAL;
+    CK(launch_rmsnorm_rows(x, weight, eps, y, M, D, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_silu_mul(const float* gu, float* h, int M, int F, void* stream) {
+    if (M < 0 || F <= 0) return DIA_B200_EINVAL;
+    if (M == 0) return DIA_B200_OK;
+    if (!gu || !h) return DIA_B200_EINVAL;
+    CK(launch_silu_mul(gu, h, M, F, S(stream)));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+int dia_b200_embed_rows(const float* table, const int32_t* ids, float* out, int n_rows, int vocab, int D, void* stream) {
+    if (n_rows < 0 || vocab <= 0 || D <= 0 || D % 4) return DIA_B200_EINVAL;
+    if (n_rows == 0) return DIA_B200_OK;
+    if (!table || !ids || !out) return DIA_B200_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) return DIA_B200_EINVAL;
+    CK(launch_embed_rows(table, ids, out, n_rows, vocab, D, S(stream)));
+    g_launches++;
     return DIA_B200_OK;
 }
 
@@ -708,7 +781,7 @@ int dia_b200_debug_run_stages(dia_b200_engine* e, const int32_t* tokens, int sta
     if (rc) return rc;
     if (!stage_range_ok(e, stage_begin, stage_end) || stage_end > 8 * e->shape.n_layer + 2) return DIA_B200_EINVAL;
     if (stage_begin == 0 && !tokens) return DIA_B200_EINVAL;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     StepParams p;
     fill_params(e, p);
     p.tokens = tokens;
@@ -750,7 +823,7 @@ int dia_b200_debug_read(dia_b200_engine* e, int which, void* host_dst, size_t nb
     int rc = buffer_of(e, which, &p, &b);
     if (rc) return rc;
     if (nbytes > b) return DIA_B200_EINVAL;
-    CK(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     CK(cudaMemcpyAsync(host_dst, p, nbytes, cudaMemcpyDeviceToHost, S(stream)));
     CK(cudaStreamSynchronize(S(stream)));
     return DIA_B200_OK;

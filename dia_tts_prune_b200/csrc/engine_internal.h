@@ -116,7 +116,7 @@ struct StepParams {
     unsigned long long* ll_hidden;     // silu(gate) * up                                           [F]
     unsigned long long* ll_qkv;        // [(Hq + 2 Hkv) * 128][2]
     unsigned long long* ll_cq;         // [Hc * 128][2]
-    unsigned long long* ll_ssq;        // [G][2] per-CTA partial sums of x^2 (for the consumer's RMSNorm)
+    unsigned long long* ll_ssq;        // [D/8][2] sum of x^2 per 8-column group and batch row (for the consumer's RMSNorm)
     unsigned long long* ll_sa_part;    // [2*Hkv][sa_nsplit][4][132] split-KV partials (m, l, -, -, o[128])
     unsigned long long* ll_ca_part;    // [Hc][ca_nsplit][132]
     unsigned long long* ll_glog;       // [C][V] guided + masked logits
@@ -184,7 +184,18 @@ cudaError_t launch_build_revert_indices(long long* t_idx, long long* idx, int B,
 // tcgen05 GEMM for the T > 1 dense layers (gemm_tcgen05.cu)
 size_t gemm_workspace_bytes(int M, int K);
 cudaError_t launch_transpose_to_bf16(const void* w, int src_bf16, void* wt, int K, int N, cudaStream_t st);
-cudaError_t launch_gemm_tcgen05(const float* x, const void* wt, float* y, void* workspace, int M, int N, int K, cudaStream_t st);
+// y = (residual ? residual : 0) + (norm_w ? rmsnorm(x; norm_w, eps) : x) . W        (y may alias residual)
+cudaError_t launch_gemm_tcgen05(const float* x, const float* norm_w, float eps, const void* wt, const float* residual,
+                                float* y, void* workspace, int M, int N, int K, cudaStream_t st);
+
+// the rest of the T > 1 passes (prefill_kernels.cu)
+cudaError_t launch_attention_rows(const float* q, const float* k, const float* v, float* out, int B, int Tq, int Tk, int Hq,
+                                  int Hkv, int Tk_stride, int mode, const int* n_valid_host, cudaStream_t st);
+cudaError_t launch_rope_rows(const float* src, float* dst, const float* sin_tab, const float* cos_tab, const int* pos, int B,
+                             int T, int H, int rotate, int to_cache, int dst_T, int dst_t0, int n_pos, cudaStream_t st);
+cudaError_t launch_rmsnorm_rows(const float* x, const float* w, float eps, float* y, int M, int D, cudaStream_t st);
+cudaError_t launch_silu_mul(const float* gu, float* h, int M, int F, cudaStream_t st);
+cudaError_t launch_embed_rows(const float* table, const int* ids, float* out, int n_rows, int vocab, int D, cudaStream_t st);
 
 struct DelayArg { int d[DIA_B200_MAX_CHANNELS]; };
 

@@ -81,6 +81,36 @@ __global__ void split3_rows_kernel(const float* __restrict__ x, __nv_bfloat16* _
     }
 }
 
+// the same with torch.nn.RMSNorm of the row fused in front (dia/layers.py:541,560,579,714: the norm that precedes
+// every projection): xs = split3((x * rsqrt(mean(x^2) + eps)) * w).  One CTA per row.
+__global__ void __launch_bounds__(256) split3_norm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, float eps,
+                                                               __nv_bfloat16* __restrict__ xs, int M, int K) {
+    __shared__ float part[8];
+    const int row = blockIdx.x;
+    const float* xr = x + (size_t)row * K;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < K; i += 256) { const float v = xr[i]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += part[i];
+    const float inv = 1.0f / sqrtf(tot / (float)K + eps);
+    const size_t n = (size_t)M * K;
+    for (int i = threadIdx.x; i < K; i += 256) {
+        const float v = (xr[i] * inv) * w[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(h);
+        const __nv_bfloat16 l = __float2bfloat16_rn(r1);
+        const float r2 = r1 - __bfloat162float(l);
+        const size_t o = (size_t)row * K + i;
+        xs[o] = h;
+        xs[n + o] = l;
+        xs[2 * n + o] = __float2bfloat16_rn(r2);
+    }
+}
+
 // W [K][N] (fp32 or bf16, N contiguous) -> Wt [N][K] bf16 (K contiguous)
 __global__ void transpose_to_bf16_kernel(const void* __restrict__ w, int src_bf16, __nv_bfloat16* __restrict__ wt, int K, int N) {
     __shared__ float tile[32][33];
@@ -102,7 +132,7 @@ __global__ void transpose_to_bf16_kernel(const void* __restrict__ w, int src_bf1
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 dia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                        float* __restrict__ y, int M, int N, int K) {
+                        float* y, const float* residual, int M, int N, int K) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -186,11 +216,23 @@ dia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (row < M) {
-                float4* dst = reinterpret_cast<float4*>(y + (size_t)row * N + n0 + cb * 32);
+                // residual add of the layer (dia/layers.py:555,574,582) fused: y may alias residual (each element is read
+                // and written by the same thread).  Column tail: N need not be a multiple of the tile (logits head).
+                const int c0 = n0 + cb * 32;
+                float* dst = y + (size_t)row * N + c0;
+                const float* res = residual ? residual + (size_t)row * N + c0 : nullptr;
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                for (int i = 0; i < 8; ++i) {
+                    if (c0 + 4 * i + 4 <= N) {
+                        float4 a = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                        if (res) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(res + 4 * i);
+                            a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + 4 * i) = a;
+                    }
+                }
             }
         }
     }
@@ -241,21 +283,28 @@ cudaError_t launch_transpose_to_bf16(const void* w, int src_bf16, void* wt, int 
 }
 
 // returns cudaErrorNotSupported for shapes the tiling does not cover (the caller decides what to do)
-cudaError_t launch_gemm_tcgen05(const float* x, const void* wt, float* y, void* workspace, int M, int N, int K, cudaStream_t st) {
-    if (M <= 0 || N % BN || K % BK || K < BK) return cudaErrorNotSupported;
-    static bool attr = false;
-    if (!attr) {
+cudaError_t launch_gemm_tcgen05(const float* x, const float* norm_w, float eps, const void* wt, const float* residual,
+                                float* y, void* workspace, int M, int N, int K, cudaStream_t st) {
+    if (M <= 0 || N % 4 || N <= 0 || K % BK || K < BK) return cudaErrorNotSupported;
+    static bool attr[64] = {};                         // function attributes are per device
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         cudaError_t e = cudaFuncSetAttribute(dia_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         if (e != cudaSuccess) return e;
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     const long long n = (long long)M * K;
-    split3_rows_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(
-        x, reinterpret_cast<__nv_bfloat16*>(workspace), n);
+    if (norm_w)
+        split3_norm_rows_kernel<<<M, 256, 0, st>>>(x, norm_w, eps, reinterpret_cast<__nv_bfloat16*>(workspace), M, K);
+    else
+        split3_rows_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(
+            x, reinterpret_cast<__nv_bfloat16*>(workspace), n);
     CUtensorMap ma, mb;
     if (!make_map(&ma, workspace, (long long)kTerms * M, K) || !make_map(&mb, wt, N, K)) return cudaErrorNotSupported;
-    dim3 grid(N / BN, (M + BM - 1) / BM);
-    dia_gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, y, M, N, K);
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    dia_gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, y, residual, M, N, K);
     return cudaGetLastError();
 }
 

@@ -289,17 +289,107 @@ def dense_prepare_weight(w_KxN: torch.Tensor) -> torch.Tensor:
 
 
 def dense_supported(M: int, N: int, K: int) -> bool:
-    return M > 0 and N % 128 == 0 and K % 64 == 0
+    return M > 0 and N > 0 and N % 4 == 0 and K >= 64 and K % 64 == 0
 
 
-def dense_forward(x_MxK: torch.Tensor, wt_NxK: torch.Tensor) -> torch.Tensor:
-    """``x @ W`` in float32 accuracy on the tcgen05 tensor cores; ``wt_NxK`` from :func:`dense_prepare_weight`."""
+def dense_forward(x_MxK: torch.Tensor, wt_NxK: torch.Tensor, norm_weight: torch.Tensor | None = None,
+                  eps: float = 1e-5, residual: torch.Tensor | None = None) -> torch.Tensor:
+    """``residual + rmsnorm(x; norm_weight) @ W`` in float32 accuracy on the tcgen05 tensor cores (both extras
+    optional); ``wt_NxK`` from :func:`dense_prepare_weight`.  The result aliases ``residual`` when one is given."""
     lib = _lib.load()
     x = x_MxK.to(torch.float32).contiguous()
     M, K = x.shape
     N = wt_NxK.shape[0]
-    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        if residual.dtype != torch.float32 or not residual.is_contiguous() or tuple(residual.shape) != (M, N):
+            raise ValueError("residual must be a contiguous float32 [M, N] tensor")
+        y = residual
+    else:
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    nw = None
+    if norm_weight is not None:
+        nw = norm_weight.detach().to(torch.float32).contiguous()
+        if nw.numel() != K:
+            raise ValueError("norm weight length must equal K")
     ws = torch.empty((int(lib.dia_b200_dense_workspace_bytes(M, K)),), dtype=torch.uint8, device=x.device)
-    _lib.check(lib.dia_b200_dense_forward(_ptr(x), _ptr(wt_NxK), _ptr(y), _ptr(ws), M, N, K, _stream(x.device)),
-               "dense_forward")
+    _lib.check(lib.dia_b200_dense_forward_fused(_ptr(x), _ptr(nw) if nw is not None else None, float(eps), _ptr(wt_NxK),
+                                                _ptr(residual) if residual is not None else None, _ptr(y), _ptr(ws),
+                                                M, N, K, _stream(x.device)), "dense_forward")
     return y
+
+
+# ---- the rest of the T > 1 passes: attention, RoPE + cache layout, norms, gate, embedding (csrc/prefill_kernels.cu) -----
+_ROPE_DEV: dict = {}
+
+
+def rope_tables_device(config: DiaConfig, device: torch.device) -> tuple[torch.Tensor, torch.Tensor]:
+    """The host-made sin / cos tables (:func:`rope_tables`) on ``device``, one copy per (config, device)."""
+    n_pos = max(config.data.audio_length, config.data.text_length) + 1
+    m = config.model
+    key = (str(device), n_pos, m.rope_min_timescale, m.rope_max_timescale)
+    if key not in _ROPE_DEV:
+        sin, cos = rope_tables(config, n_pos)
+        _ROPE_DEV[key] = (sin.to(device), cos.to(device))
+    return _ROPE_DEV[key]
+
+
+def positions_i32(n: int, batch: int, device: torch.device, start: int = 0) -> torch.Tensor:
+    """int32 [batch * n] positions start .. start + n - 1 per batch row, built on the host (no device kernel)."""
+    return torch.arange(start, start + n, dtype=torch.int32).repeat(batch).to(device)
+
+
+def rope_rows(src_BTxHd: torch.Tensor, pos: torch.Tensor | None, B: int, T: int, H: int, tables, rotate: bool = True,
+              cache: torch.Tensor | None = None, cache_t0: int = 0) -> torch.Tensor:
+    """RotaryEmbedding on ``[B*T, H*128]`` rows; in place, or scattered into ``cache [B, H, Tmax, 128]`` at t0."""
+    lib = _lib.load()
+    sin, cos = tables
+    dst = src_BTxHd if cache is None else cache
+    _lib.check(lib.dia_b200_rope_rows(_ptr(src_BTxHd), _ptr(dst), _ptr(sin), _ptr(cos),
+                                      _ptr(pos) if pos is not None else None, B, T, H, 1 if rotate else 0,
+                                      0 if cache is None else 1, 0 if cache is None else cache.shape[2], int(cache_t0),
+                                      sin.shape[0], _stream(src_BTxHd.device)), "rope_rows")
+    return dst
+
+
+def attention_rows(q_BTHd: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, Tk: int, mode: int,
+                   n_valid: list[int] | None) -> torch.Tensor:
+    """fp32 attention for T > 1 query rows; ``k_cache`` / ``v_cache`` are ``[B, Hkv, Tmax, 128]``."""
+    lib = _lib.load()
+    B, Tq, Hq, d = q_BTHd.shape
+    assert d == 128 and k_cache.shape[0] == B and k_cache.is_contiguous() and v_cache.is_contiguous()
+    out = torch.empty_like(q_BTHd)
+    nv = (C.c_int32 * B)(*[int(x) for x in n_valid]) if n_valid is not None else None
+    _lib.check(lib.dia_b200_attention_rows(_ptr(q_BTHd), _ptr(k_cache), _ptr(v_cache), _ptr(out), B, Tq, int(Tk), Hq,
+                                           k_cache.shape[1], k_cache.shape[2], int(mode), nv, _stream(q_BTHd.device)),
+               "attention_rows")
+    return out
+
+
+def rmsnorm_rows(x_MxD: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
+    lib = _lib.load()
+    x = x_MxD.to(torch.float32).contiguous()
+    y = torch.empty_like(x)
+    w = weight.detach().to(torch.float32).contiguous()
+    _lib.check(lib.dia_b200_rmsnorm_rows(_ptr(x), _ptr(w), float(eps), _ptr(y), x.shape[0], x.shape[1], _stream(x.device)),
+               "rmsnorm_rows")
+    return y
+
+
+def silu_mul(gu_Mx2xF: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    M, two, F = gu_Mx2xF.shape
+    assert two == 2 and gu_Mx2xF.is_contiguous() and gu_Mx2xF.dtype == torch.float32
+    h = torch.empty((M, F), dtype=torch.float32, device=gu_Mx2xF.device)
+    _lib.check(lib.dia_b200_silu_mul(_ptr(gu_Mx2xF), _ptr(h), M, F, _stream(h.device)), "silu_mul")
+    return h
+
+
+def embed_rows(table_VxD: torch.Tensor, ids_i32: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    t = table_VxD.detach()
+    assert t.dtype == torch.float32 and t.is_contiguous() and ids_i32.dtype == torch.int32 and ids_i32.is_contiguous()
+    n = ids_i32.numel()
+    out = torch.empty((n, t.shape[1]), dtype=torch.float32, device=t.device)
+    _lib.check(lib.dia_b200_embed_rows(_ptr(t), _ptr(ids_i32), _ptr(out), n, t.shape[0], t.shape[1], _stream(t.device)),
+               "embed_rows")
+    return out

@@ -71,44 +71,87 @@ class DenseGeneral(nn.Module):
         self.weight = nn.Parameter(torch.empty(self.kernel_shape, dtype=weight_dtype, device=device))
 
     def forward(self, inputs: Tensor) -> Tensor:
+        """``tensordot(x, W)`` over ``axis`` (dia/layers.py:55-66).  On a CUDA device every call runs on the tcgen05
+        GEMM of ``csrc/gemm_tcgen05.cu``; there is no library fallback on that device.  On the CPU (state-dict
+        tooling, pruning, the CPU test suite) and under autograd (fine-tuning is outside this path) it is the
+        reference's own tensordot."""
         n = len(self.axis)
         x_axes = tuple(a if a >= 0 else inputs.ndim + a for a in self.axis)
-        y = self._forward_tcgen05(inputs, x_axes)
-        if y is not None:
-            return y
-        out = torch.tensordot(inputs.to(torch.float32), self.weight.to(torch.float32), dims=(x_axes, tuple(range(n))))
+        w = self.weight
+        if inputs.is_cuda and w.is_cuda and not (torch.is_grad_enabled() and (w.requires_grad or inputs.requires_grad)):
+            return self._forward_tcgen05(inputs, x_axes)
+        out = torch.tensordot(inputs.to(torch.float32), w.to(torch.float32), dims=(x_axes, tuple(range(n))))
         return out.to(inputs.dtype)
 
-    # ---- sm_100a path for more than a few rows (encoder, cross-attention K/V precompute, prompt prefill) ----------
-    def _forward_tcgen05(self, inputs: Tensor, x_axes: tuple[int, ...]) -> Tensor | None:
-        """``x @ W`` on the tcgen05 tensor cores with the activations split into three bf16 terms (float32-operand
-        accuracy).  Used when the contracted axes are the trailing ones, the shape fits the 128 x 128 x 64 tiling and
-        the kernel is bfloat16 (or float32 holding bfloat16-representable values, as every kernel that went through
-        the bf16 checkpoint path is); otherwise ``None`` and the caller runs the reference's float32 tensordot."""
-        w = self.weight
-        if not (inputs.is_cuda and w.is_cuda) or torch.is_grad_enabled() and (w.requires_grad or inputs.requires_grad):
-            return None
-        n = len(x_axes)
-        if x_axes != tuple(range(inputs.ndim - n, inputs.ndim)):
-            return None
-        K = math.prod(self.in_shapes)
-        N = math.prod(self.out_features)
-        M = inputs.numel() // K if K else 0
+    # ---- sm_100a path (encoder, cross-attention K/V precompute, prompt prefill) ----------------------------------
+    def kernel_weight_kmajor(self) -> Tensor:
+        """The K-major bf16 copy ``[N, K]`` of the kernel the tcgen05 GEMM reads (made once per weight version)."""
         from . import engine as _engine
-        if M < 8 or not _engine.dense_supported(M, N, K):
-            return None
+        w = self.weight
+        K, N = math.prod(self.in_shapes), math.prod(self.out_features)
         key = (w.data_ptr(), w._version, w.dtype, w.device)
         cached = getattr(self, "_b200_wt", None)
         if cached is None or cached[0] != key:
-            w2 = w.detach().reshape(K, N)
-            ok = w.dtype == torch.bfloat16 or (w.dtype == torch.float32 and
-                                               bool(torch.equal(w2, w2.to(torch.bfloat16).to(torch.float32))))
-            cached = (key, _engine.dense_prepare_weight(w2) if ok else None)
+            canonicalize_dense_kernel_(self)
+            w = self.weight
+            key = (w.data_ptr(), w._version, w.dtype, w.device)
+            cached = (key, _engine.dense_prepare_weight(w.detach().reshape(K, N)))
             self._b200_wt = cached
-        if cached[1] is None:
-            return None
-        y = _engine.dense_forward(inputs.reshape(M, K), cached[1])
-        return y.reshape(*inputs.shape[: inputs.ndim - n], *self.out_features).to(inputs.dtype)
+        return cached[1]
+
+    def _forward_tcgen05(self, inputs: Tensor, x_axes: tuple[int, ...], norm_weight: Tensor | None = None,
+                         eps: float = 1e-5, residual: Tensor | None = None) -> Tensor:
+        """``x @ W`` on the tcgen05 tensor cores with the activations split into three bf16 terms (float32-operand
+        accuracy).  ``norm_weight``: RMSNorm of the input rows fused into the split pass; ``residual``: added in the
+        epilogue (the result aliases it)."""
+        from . import engine as _engine
+        n = len(x_axes)
+        if x_axes != tuple(range(inputs.ndim - n, inputs.ndim)):
+            raise NotImplementedError("DenseGeneral on sm_100a contracts the trailing axes only")
+        K, N = math.prod(self.in_shapes), math.prod(self.out_features)
+        M = inputs.numel() // K if K else 0
+        lead = inputs.shape[: inputs.ndim - n]
+        if M == 0:
+            return torch.zeros((*lead, *self.out_features), dtype=torch.float32, device=inputs.device)
+        if not _engine.dense_supported(M, N, K):
+            raise NotImplementedError(f"dense layer [{M} x {K}] . [{K} x {N}] does not fit the tcgen05 tiling "
+                                      f"(K must be a multiple of 64, N of 4)")
+        y = _engine.dense_forward(inputs.reshape(M, K), self.kernel_weight_kmajor(), norm_weight=norm_weight, eps=eps,
+                                  residual=None if residual is None else residual.reshape(M, N))
+        return y.reshape(*lead, *self.out_features)
+
+
+_ROUNDING_WARNED = False
+
+
+@torch.no_grad()
+def canonicalize_dense_kernel_(m: "DenseGeneral") -> bool:
+    """The sm_100a kernels stream DenseGeneral kernels as bf16 (activations, norms, softmax and caches stay fp32).
+    A float16 kernel is widened to float32 first (exact); a kernel that is not bf16-representable - a real float32
+    or float16 checkpoint - is rounded to bf16 ONCE, in place, with a warning, so that the encoder, the prompt
+    prefill and the decode engine all see the very same numbers.  Returns True if values changed."""
+    global _ROUNDING_WARNED
+    w = m.weight
+    if w.dtype == torch.bfloat16:
+        return False
+    if w.dtype == torch.float16:
+        w.data = w.data.to(torch.float32)
+    r = w.data.to(torch.bfloat16).to(torch.float32)
+    if torch.equal(r, w.data):
+        return False
+    if not _ROUNDING_WARNED:
+        import warnings
+        warnings.warn("dia_tts_prune_b200: DenseGeneral kernels are not bf16-representable; rounding them to bf16 once "
+                      "(the sm_100a path keeps weights in bf16 and everything else in fp32: logits differ from the "
+                      "float32 reference by ~1e-2, as with the reference's own compute_dtype='bfloat16')", stacklevel=3)
+        _ROUNDING_WARNED = True
+    w.data.copy_(r)
+    return True
+
+
+def canonicalize_dense_kernels_(model: nn.Module) -> int:
+    """:func:`canonicalize_dense_kernel_` over every DenseGeneral of ``model``; returns how many were rounded."""
+    return sum(1 for m in model.modules() if isinstance(m, DenseGeneral) and canonicalize_dense_kernel_(m))
 
 
 class MlpBlock(nn.Module):
@@ -119,8 +162,19 @@ class MlpBlock(nn.Module):
         self.wo = DenseGeneral((intermediate_dim,), (embed_dim,), axis=(-1,), weight_dtype=compute_dtype)
 
     def forward(self, x: Tensor) -> Tensor:
+        if x.is_cuda and not torch.is_grad_enabled():
+            return self._forward_b200(x, None, 0.0, None)
         gu = self.wi_fused(x)                               # [..., 2, F]: gate columns first, then up
         return self.wo(F.silu(gu[..., 0, :].float()).to(x.dtype) * gu[..., 1, :])
+
+    def _forward_b200(self, x: Tensor, norm: RMSNorm | None, eps: float, residual: Tensor | None) -> Tensor:
+        """``residual + wo(silu(gate) * up)`` with ``[gate | up] = wi_fused(norm(x))`` on our kernels: RMSNorm in the
+        split pass of the first GEMM, the gate as one elementwise kernel, the residual add in the second epilogue."""
+        from . import engine as _k
+        lead = x.shape[:-1]
+        gu = self.wi_fused._forward_tcgen05(x, (x.ndim - 1,), norm_weight=None if norm is None else norm.weight, eps=eps)
+        h = _k.silu_mul(gu.reshape(-1, 2, gu.shape[-1]))
+        return self.wo._forward_tcgen05(h.reshape(*lead, -1), (x.ndim - 1,), residual=residual)
 
 
 class RotaryEmbedding(nn.Module):
@@ -194,6 +248,39 @@ class Attention(nn.Module):
             out = torch.where(attn_mask.any(dim=-1, keepdim=True), out, torch.zeros((), dtype=out.dtype, device=out.device))
         return self.o_proj(out.transpose(1, 2).contiguous()).to(Xq.dtype)
 
+    def _forward_b200(self, x: Tensor, norm: RMSNorm, eps: float, positions_i32: Tensor, tables, mode: int,
+                      n_valid: list[int] | None, cache: KVCache | None = None, prefill: bool = False) -> Tensor:
+        """``x + o_proj(attention(...))`` for T > 1 rows on our kernels (no library call): RMSNorm fused into the split
+        pass of the q / k / v GEMMs, RoPE fused with the scatter into the cache layout, fp32 flash-style attention,
+        residual add in the o_proj epilogue.  ``mode``: 0 causal self, 1 pad-partitioned self, 2 cross over the valid
+        prefix of ``cache`` (precomputed K/V).  Self-attention with ``cache`` + ``prefill`` writes slots [0, T)."""
+        from . import engine as _k
+        B, T, _ = x.shape
+        H, Hkv = self.num_query_heads, self.num_kv_heads
+        ax = (2,)
+        q = self.q_proj._forward_tcgen05(x, ax, norm_weight=norm.weight, eps=eps)            # [B, T, H, 128]
+        _k.rope_rows(q.reshape(B * T, H * 128), positions_i32, B, T, H, tables)
+        if self.is_cross_attn:
+            if cache is None:
+                raise NotImplementedError("cross-attention needs the precomputed K/V cache")
+            kc, vc, Tk = cache.k, cache.v, cache.k.shape[2]
+        else:
+            k = self.k_proj._forward_tcgen05(x, ax, norm_weight=norm.weight, eps=eps)        # [B, T, Hkv, 128]
+            v = self.v_proj._forward_tcgen05(x, ax, norm_weight=norm.weight, eps=eps)
+            if cache is not None:
+                if not prefill:
+                    raise NotImplementedError("T > 1 rows append through prefill only")
+                kc, vc = cache.k, cache.v
+                cache.current_idx = T - 1                                                  # KVCache.prefill (Appendix C Q2)
+            else:
+                kc = torch.empty((B, Hkv, T, 128), dtype=torch.float32, device=x.device)
+                vc = torch.empty_like(kc)
+            _k.rope_rows(k.reshape(B * T, Hkv * 128), positions_i32, B, T, Hkv, tables, cache=kc)
+            _k.rope_rows(v.reshape(B * T, Hkv * 128), None, B, T, Hkv, tables, rotate=False, cache=vc)
+            Tk = T
+        o = _k.attention_rows(q, kc, vc, Tk, mode, n_valid)
+        return self.o_proj._forward_tcgen05(o, (2, 3), residual=x)
+
 
 class EncoderLayer(nn.Module):
     def __init__(self, config: DiaConfig, compute_dtype: torch.dtype):
@@ -207,6 +294,17 @@ class EncoderLayer(nn.Module):
         self.mlp = MlpBlock(e.n_embd, e.n_hidden, compute_dtype)
 
     def forward(self, x: Tensor, state: EncoderInferenceState) -> Tensor:
+        if x.is_cuda and not torch.is_grad_enabled():
+            from . import engine as _k
+            eps = self.config.model.normalization_layer_epsilon
+            B, T, _ = x.shape
+            x = x.to(torch.float32).contiguous().clone()                                  # updated in place below
+            pos = state.extras.get("pos_i32")
+            if pos is None or pos.numel() != B * T:
+                pos = state.extras["pos_i32"] = _k.positions_i32(T, B, x.device)
+            x = self.self_attention._forward_b200(x, self.pre_sa_norm, eps, pos, _k.rope_tables_device(self.config, x.device),
+                                                  1, _encoder_valid_lens(state))
+            return self.mlp._forward_b200(x, self.post_sa_norm, eps, x)
         h = self.pre_sa_norm(x.float())
         x = x + self.self_attention(h, h, state.positions, state.positions, attn_mask=state.attn_mask)
         return x + self.mlp(self.post_sa_norm(x.float()))
@@ -222,11 +320,32 @@ class Encoder(nn.Module):
         self.norm = RMSNorm(e.n_embd, eps=config.model.normalization_layer_epsilon)
 
     def forward(self, x_ids: Tensor, state: EncoderInferenceState) -> Tensor:
+        if x_ids.is_cuda and not torch.is_grad_enabled():
+            from . import engine as _k
+            B, T = x_ids.shape
+            x = _k.embed_rows(self.embedding.weight, x_ids.reshape(-1).to(torch.int32).contiguous()).reshape(B, T, -1)
+            for layer in self.layers:
+                x = layer(x, state)
+            return _k.rmsnorm_rows(x.reshape(B * T, -1), self.norm.weight,
+                                   self.config.model.normalization_layer_epsilon).reshape(B, T, -1)
         with _exact_fp32():
             x = self.embedding(x_ids).float()
             for layer in self.layers:
                 x = layer(x, state)
             return self.norm(x)
+
+
+def _encoder_valid_lens(state: EncoderInferenceState) -> list[int]:
+    """Valid text bytes per batch row (a prefix: pad = 0 never occurs inside utf-8 text); read back once per state."""
+    lens = getattr(state, "valid_lens", None)
+    if lens is None:
+        pm = state.padding_mask
+        lens = [int(v) for v in pm.sum(dim=-1).tolist()]
+        for b, n in enumerate(lens):
+            if not bool(pm[b, :n].all().item()):
+                raise NotImplementedError("text with embedded pad bytes is not supported by the attention kernels")
+        state.valid_lens = lens
+    return lens
 
 
 def _contract_dims(name: str) -> int:
@@ -265,7 +384,25 @@ class DecoderLayer(nn.Module):
             y = eng.layer_step(self._index, x[:, 0, :], state.step_from, slot)
             self_attn_cache.current_idx = slot + 1
             return y[:, None, :].to(x.dtype)
-        # prompt prefill (T > 1): library path, fp32
+        if x.is_cuda and not torch.is_grad_enabled():
+            # prompt prefill (T > 1) on our kernels
+            from . import engine as _k
+            eps = self.config.model.normalization_layer_epsilon
+            B, T, _ = x.shape
+            tables = _k.rope_tables_device(self.config, x.device)
+            pos = state.extras.get("prefill_pos")
+            if pos is None or pos.numel() != B * T:
+                pos = _k.positions_i32(state.step_to - state.step_from, B, x.device, start=state.step_from)
+                state.extras["prefill_pos"] = pos
+            if state.text_len is None:
+                raise NotImplementedError("prefill needs DecoderInferenceState.text_len (valid text bytes)")
+            x = x.to(torch.float32).contiguous()
+            x = self.self_attention._forward_b200(x, self.pre_sa_norm, eps, pos, tables, 0, None,
+                                                  cache=self_attn_cache, prefill=True)
+            x = self.cross_attention._forward_b200(x, self.pre_ca_norm, eps, pos, tables, 2,
+                                                   [0] * (B - 1) + [state.text_len], cache=cross_attn_cache)
+            return self.mlp._forward_b200(x, self.pre_mlp_norm, eps, x)
+        # CPU (state-dict tooling and the CPU test suite): the reference's own formulation
         h = self.pre_sa_norm(x.float())
         x = x + self.self_attention(h, h, state.dec_positions, state.dec_positions, attn_mask=None,
                                     cache=self_attn_cache, prefill=prefill, is_causal=prefill)
@@ -320,6 +457,12 @@ class Decoder(nn.Module):
         # (re)pack: a checkpoint whose MLP was structurally pruned (zero hidden neurons) gets a narrower engine
         from .pruning_utils import compact_mlp, is_2to4, plan_mlp_compaction
         from .synthetic import is_dense_kernel
+        import torch.nn.utils.prune as _prune
+        if any(_prune.is_pruned(m) for m in self.modules() if isinstance(m, DenseGeneral)):
+            raise RuntimeError("pruning masks are still attached (parameters are named weight_orig): call "
+                               "pruning_utils.make_pruning_permanent(model) before decoding")
+        canonicalize_dense_kernels_(self)
+        sig = self._weights_signature()
         sd = dict(self.named_parameters())
         tensors = {n: sd[n].detach() for n in decoder_tensor_names(self.config)}
         d = self.config.model.decoder
@@ -361,6 +504,21 @@ class Decoder(nn.Module):
     # ---- once per utterance ---------------------------------------------------------------------------
     def precompute_cross_attn_cache(self, enc_out: Tensor, enc_positions: Tensor) -> list[KVCache]:
         out: list[KVCache] = []
+        if enc_out.is_cuda and not torch.is_grad_enabled():
+            from . import engine as _k
+            B, S, _ = enc_out.shape
+            x = enc_out.to(torch.float32).contiguous()
+            tables, pos = _k.rope_tables_device(self.config, x.device), _k.positions_i32(S, B, x.device)
+            for layer in self.layers:
+                ca = layer.cross_attention
+                H = ca.num_kv_heads
+                k = torch.empty((B, H, S, 128), dtype=torch.float32, device=x.device)
+                v = torch.empty_like(k)
+                _k.rope_rows(ca.k_proj._forward_tcgen05(x, (2,)).reshape(B * S, H * 128), pos, B, S, H, tables, cache=k)
+                _k.rope_rows(ca.v_proj._forward_tcgen05(x, (2,)).reshape(B * S, H * 128), None, B, S, H, tables,
+                             rotate=False, cache=v)
+                out.append(KVCache.from_kv(k, v))
+            return out
         with torch.no_grad(), _exact_fp32():
             x = enc_out.float()
             for layer in self.layers:
@@ -378,6 +536,20 @@ class Decoder(nn.Module):
         logits bit-identical); here those entries are zeros and only ``n`` rows are projected."""
         out: list[KVCache] = []
         n = enc_live.shape[1]
+        if enc_live.is_cuda and not torch.is_grad_enabled():
+            from . import engine as _k
+            x = enc_live.to(torch.float32).contiguous()
+            tables, pos_i = _k.rope_tables_device(self.config, x.device), _k.positions_i32(n, 1, x.device)
+            for layer in self.layers:
+                ca = layer.cross_attention
+                H = ca.num_kv_heads
+                k = torch.zeros((2, H, text_length, 128), dtype=torch.float32, device=x.device)
+                v = torch.zeros_like(k)
+                _k.rope_rows(ca.k_proj._forward_tcgen05(x, (2,)).reshape(n, H * 128), pos_i, 1, n, H, tables, cache=k[1:])
+                _k.rope_rows(ca.v_proj._forward_tcgen05(x, (2,)).reshape(n, H * 128), None, 1, n, H, tables,
+                             rotate=False, cache=v[1:])
+                out.append(KVCache.from_kv(k, v))
+            return out
         pos = torch.arange(n, dtype=torch.float32, device=enc_live.device)[None, :]
         with torch.no_grad(), _exact_fp32():
             x = enc_live.float()
@@ -405,18 +577,28 @@ class Decoder(nn.Module):
             c.current_idx = slot + 1
         return logits[:, None, :, :]
 
-    def forward(self, tgt_ids_BxTxC: Tensor, state: DecoderInferenceState) -> Tensor:
-        """Prompt prefill / teacher-forced pass over T positions (library path, fp32)."""
+    def forward(self, tgt_ids_BxTxC: Tensor, state: DecoderInferenceState, want_logits: bool = True) -> Tensor:
+        """Prompt prefill / teacher-forced pass over T positions (dia/layers.py:722-766).  ``want_logits=False`` skips
+        the logits head, whose output ``Dia._prepare_generation`` discards (dia/model.py:420-421)."""
         B, T, C = tgt_ids_BxTxC.shape
         assert C == self.num_channels, "Input channels mismatch"
+        if tgt_ids_BxTxC.is_cuda and not torch.is_grad_enabled():
+            # own kernels end to end: embedding gather-sum, 18 x (fused-norm GEMMs, RoPE + cache scatter, fp32 attention,
+            # gate, residual epilogues), final norm fused into the logits GEMM
+            x = self.engine().embed_sum(tgt_ids_BxTxC.reshape(B * T, C)).reshape(B, T, -1)
+            state.extras.pop("prefill_pos", None)
+            for i, layer in enumerate(self.layers):
+                x = layer(x, state, self_attn_cache=state.self_attn_cache[i],
+                          cross_attn_cache=state.cross_attn_cache[i], prefill=True)
+            if not want_logits:
+                return None
+            return self.logits_dense._forward_tcgen05(x, (2,), norm_weight=self.norm.weight,
+                                                      eps=self.config.model.normalization_layer_epsilon)
         with _exact_fp32():
-            if tgt_ids_BxTxC.is_cuda:
-                x = self.engine().embed_sum(tgt_ids_BxTxC.reshape(B * T, C)).reshape(B, T, -1)
-            else:
-                x = None
-                for i, emb in enumerate(self.embeddings):
-                    e = emb(tgt_ids_BxTxC[..., i]).float()
-                    x = e if x is None else x + e
+            x = None
+            for i, emb in enumerate(self.embeddings):
+                e = emb(tgt_ids_BxTxC[..., i]).float()
+                x = e if x is None else x + e
             for i, layer in enumerate(self.layers):
                 x = layer(x, state, self_attn_cache=state.self_attn_cache[i],
                           cross_attn_cache=state.cross_attn_cache[i], prefill=True)

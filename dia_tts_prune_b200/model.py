@@ -95,9 +95,11 @@ class Dia:
         if self.device.type == "cpu" and self.compute_dtype != torch.float32:
             print(f"Warning: CPU device selected, overriding compute_dtype to float32 (was {compute_dtype.value}).")
             self.compute_dtype = torch.float32
-        if self.compute_dtype == torch.float16:
-            raise NotImplementedError("float16 weights are not supported by the sm_100a path (use bfloat16/float32)")
+        # float16 (the default of the reference's cli.py / app.py) is accepted: the kernels keep activations in fp32
+        # and stream weights as bf16, so float16 kernels are widened and rounded once (layers.canonicalize_dense_kernel_)
         self.model: DiaModel = DiaModel(config, self.compute_dtype)
+        self._draws = 0                                 # RNG draw counter of the single-step boundary (_decoder_step)
+        self._step_seed: int | None = None
         self.dac_model = None
         self.last_codes: torch.Tensor | None = None     # raw generated rows of the last generate() call
         self.last_stats: dict = {}
@@ -212,7 +214,7 @@ class Dia:
                 es_live = EncoderInferenceState(
                     max_seq_len=n_valid, device=live.device,
                     positions=torch.arange(n_valid, dtype=torch.float32, device=live.device)[None, :],
-                    padding_mask=torch.ones_like(live, dtype=torch.bool), attn_mask=None)
+                    padding_mask=torch.ones_like(live, dtype=torch.bool), attn_mask=None, valid_lens=[n_valid])
                 enc_live = self.model.encoder(live, es_live)
                 enc_out = torch.zeros((2, cond.shape[1], enc_live.shape[-1]), dtype=enc_live.dtype, device=live.device)
                 enc_out[1, :n_valid] = enc_live[0]
@@ -227,14 +229,25 @@ class Dia:
             if prefill_step > 1:
                 dec_state.prepare_step(0, prefill_step - 1)
                 toks = dec_output.get_tokens_at(0, prefill_step - 1).unsqueeze(0).expand(2, -1, -1)
-                self.model.decoder.forward(toks, dec_state)
+                self.model.decoder.forward(toks, dec_state, want_logits=False)
         return dec_state, dec_output
 
     # ---- single-step boundary (dia/model.py:429-488) ------------------------------------------------------
     def _decoder_step(self, tokens_Bx1xC: torch.Tensor, dec_state: DecoderInferenceState, cfg_scale: float,
-                      temperature: float, top_p: float, cfg_filter_top_k: int, seed: int = 0, draw: int = 0) -> torch.Tensor:
+                      temperature: float, top_p: float, cfg_filter_top_k: int | None, seed: int | None = None,
+                      draw: int | None = None) -> torch.Tensor:
+        """One frame (dia/model.py:429-488).  A reference-style caller loops this with the six positional arguments:
+        the Philox stream is then keyed once from the torch global RNG (so ``torch.manual_seed`` governs it, as it
+        governs ``torch.multinomial`` in the reference) and every call consumes the next draw index."""
         logits = self.model.decoder.decode_step(tokens_Bx1xC, dec_state)          # [2, 1, C, V] fp32
         eng = self.model.decoder.engine()
+        if seed is None:
+            if self._step_seed is None:
+                self._step_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            seed = self._step_seed
+        if draw is None:
+            draw = self._draws
+            self._draws += 1
         return eng.head_sample(logits[:, -1], cfg_scale, temperature, top_p, cfg_filter_top_k, seed, draw).to(torch.int64)
 
     # ---- output (dia/model.py:490-544) -----------------------------------------------------------------------
@@ -318,7 +331,7 @@ class Dia:
 
     @torch.inference_mode()
     def generate(self, text: str, max_tokens: int | None = None, cfg_scale: float = 3.0, temperature: float = 1.3,
-                 top_p: float = 0.95, use_torch_compile: bool = False, cfg_filter_top_k: int = 35,
+                 top_p: float = 0.95, use_torch_compile: bool = False, cfg_filter_top_k: int | None = 35,
                  audio_prompt: str | torch.Tensor | None = None, audio_prompt_text: Optional[str] = None,
                  seed: Optional[int] = None, verbose: bool = False, output: str = "audio"):
         """Text (+ optional voice prompt) -> waveform (``output="audio"``, needs DAC) or the DAC-ready
@@ -330,10 +343,13 @@ class Dia:
         if self.device.type != "cuda" or not torch.cuda.is_available():
             # loud, before the reference's catch-all: this path has no CPU implementation
             raise RuntimeError("Dia.generate needs the model on a CUDA device (sm_100a); there is no CPU fallback")
+        if temperature < 0.0:
+            raise ValueError("temperature must be >= 0")
         if seed is not None:
             torch.manual_seed(seed)
             np.random.seed(seed)
             random.seed(seed)
+            self._step_seed, self._draws = None, 0
         rng_seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
         max_tokens = self.config.data.audio_length if max_tokens is None else max_tokens
         t_start = time.time()

@@ -58,6 +58,18 @@ def apply_structured_pruning(model: nn.Module, amount: float, dim: int = 0, n: i
 
 
 @torch.no_grad()
+def mask_2to4(w: torch.Tensor, K: int) -> torch.Tensor:
+    """bool mask (shape of ``w``) keeping the 2 largest-magnitude of every 4 consecutive K (input) entries per output
+    column of the kernel viewed as [K, N].  Ties keep the lower K index; the comparison runs on integer keys
+    (magnitude bits, then position), so the mask does not depend on the machine that computes it."""
+    w2 = w.detach().reshape(K // 4, 4, -1).to(torch.float32)
+    mag = w2.abs().contiguous().view(torch.int32).to(torch.int64)          # fp32 bit pattern: monotone in |w|
+    key = mag * 4 + (3 - torch.arange(4, dtype=torch.int64, device=w.device))[None, :, None]
+    keep = key.topk(2, dim=1).indices
+    return torch.zeros_like(w2, dtype=torch.bool).scatter_(1, keep, True).reshape(w.shape)
+
+
+@torch.no_grad()
 def apply_2to4_pruning(model: nn.Module, module_types=DEFAULT_PRUNABLE_MODULES):
     """Keep the 2 largest-magnitude of every 4 consecutive K (input) entries per output column of each
     kernel viewed as [K, N]; applied as a custom mask so that
@@ -70,10 +82,7 @@ def apply_2to4_pruning(model: nn.Module, module_types=DEFAULT_PRUNABLE_MODULES):
             K *= s
         if K % 4:
             continue
-        w2 = w.detach().reshape(K // 4, 4, -1).abs().float()
-        keep = w2.topk(2, dim=1).indices
-        mask = torch.zeros_like(w2, dtype=torch.bool).scatter_(1, keep, True).reshape(w.shape)
-        prune.custom_from_mask(m, name=name, mask=mask.to(w.dtype))
+        prune.custom_from_mask(m, name=name, mask=mask_2to4(w, K).to(w.dtype))
     return model
 
 

@@ -44,6 +44,9 @@ class EncoderInferenceState:
     positions: torch.Tensor
     padding_mask: torch.Tensor
     attn_mask: torch.Tensor
+    # extensions (host-side mirrors, optional): valid text bytes per batch row; scratch shared by the layers
+    valid_lens: list | None = None
+    extras: dict = field(default_factory=dict)
 
     @classmethod
     def new(cls, config: DiaConfig, cond_src: torch.Tensor) -> "EncoderInferenceState":

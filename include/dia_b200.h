@@ -187,11 +187,42 @@ int dia_b200_build_revert_indices(int64_t *t_idx, int64_t *indices, int B, int T
  * with W given as the K-major bfloat16 copy wt[N][K] that dia_b200_dense_prepare_weight makes once per weight
  * (src_dtype 0 = float32 source, 1 = bfloat16).  x is split into three bf16 terms inside, so the product has
  * fp32-operand accuracy.  workspace: dia_b200_dense_workspace_bytes(M, K) bytes of device memory, 16-byte aligned.
- * Shapes need N % 128 == 0 and K % 64 == 0, otherwise DIA_B200_EUNSUPPORTED (the caller keeps its own path). */
+ * Shapes need K % 64 == 0 and N % 4 == 0, otherwise DIA_B200_EUNSUPPORTED. */
 int dia_b200_dense_prepare_weight(const void *w, int src_dtype, void *wt_bf16, int K, int N, void *stream);
 size_t dia_b200_dense_workspace_bytes(int M, int K);
 int dia_b200_dense_forward(const float *x, const void *wt_bf16, float *y, void *workspace, int M, int N, int K,
                            void *stream);
+/* The same with the two neighbours of every projection fused in (DecoderLayer / EncoderLayer.forward,
+ * dia/layers.py:384-416, 530-584): torch.nn.RMSNorm of the input rows in front (norm_weight float32 [K], may be NULL
+ * = no norm) and the residual add behind (residual float32 [M][N], may be NULL; y may alias it):
+ *   y = residual + rmsnorm(x; norm_weight, eps) . W */
+int dia_b200_dense_forward_fused(const float *x, const float *norm_weight, float eps, const void *wt_bf16,
+                                 const float *residual, float *y, void *workspace, int M, int N, int K, void *stream);
+
+/* ---- the rest of the T > 1 passes (once per utterance): no library kernel on the path ---------------------------
+ * F.scaled_dot_product_attention call sites (dia/layers.py:329-337) for more than one query row, fp32.
+ *   q, out float32 [B][Tq][Hq][128] (q already rotated); k, v float32 [B][Hkv][Tk_stride][128] (KVCache layout,
+ *   dia/state.py:72-86), the first Tk keys are used; query head h reads kv head h / (Hq / Hkv) (GQA, :319-320).
+ *   mode 0  causal: query t attends keys [0, t]                                   prompt prefill (:722-766)
+ *   mode 1  partition at n = n_valid_host[b]: queries < n attend keys [0, n), the others keys [n, Tk)
+ *                                                                                 encoder mask (dia/state.py:24-31)
+ *   mode 2  prefix: every query attends keys [0, n); n == 0 gives exact zeros     cross-attention (Appendix C Q7)
+ * n_valid_host: int32 [B] in HOST memory (may be NULL = Tk).  B <= 16. */
+int dia_b200_attention_rows(const float *q, const float *k, const float *v, float *out, int B, int Tq, int Tk, int Hq,
+                            int Hkv, int Tk_stride, int mode, const int32_t *n_valid_host, void *stream);
+/* RotaryEmbedding (dia/layers.py:108-173) on projected heads src float32 [B*T][H*128] with positions pos int32 [B*T]
+ * (device) looked up in host-made sin/cos tables float32 [n_pos][64] (device; the reference's CPU values, bit for bit),
+ * fused with the layout change: to_cache = 0 writes dst in the source layout (may alias src), to_cache = 1 writes
+ * dst float32 [B][H][dst_T][128] at rows dst_t0 + t (KVCache.prefill / from_kv, dia/state.py:88-109).
+ * rotate = 0 copies without rotating (the V projection). */
+int dia_b200_rope_rows(const float *src, float *dst, const float *sin_tab, const float *cos_tab, const int32_t *pos,
+                       int B, int T, int H, int rotate, int to_cache, int dst_T, int dst_t0, int n_pos, void *stream);
+/* torch.nn.RMSNorm over M rows of length D (dia/layers.py:462,766): y = x * rsqrt(mean(x^2) + eps) * weight */
+int dia_b200_rmsnorm_rows(const float *x, const float *weight, float eps, float *y, int M, int D, void *stream);
+/* MlpBlock gate (dia/layers.py:95-101): gu float32 [M][2][F] (gate columns, then up columns) -> h[M][F] */
+int dia_b200_silu_mul(const float *gu, float *h, int M, int F, void *stream);
+/* nn.Embedding (dia/layers.py:445-447): out[r] = table[ids[r]], table float32 [vocab][D], ids int32 (device) */
+int dia_b200_embed_rows(const float *table, const int32_t *ids, float *out, int n_rows, int vocab, int D, void *stream);
 
 /* ---- introspection for tests and the bench ------------------------------------------------- */
 enum dia_b200_buffer {

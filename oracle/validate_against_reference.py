@@ -318,26 +318,129 @@ def run_full(ref, seed, max_tokens):
     print(f"  wrote dia16b_seed{seed}_greedy.npz")
 
 
-def run_clone(ref, seed, prompt_len, n_decode):
+def run_clone(ref, seed, prompt_len, n_decode, keep_every=8, tag=None):
     pcfg = PC.dia_1_6b_config()
     g = torch.Generator().manual_seed(11)
     prompt = torch.randint(0, 1024, (prompt_len, 9), generator=g, dtype=torch.int32)
     text, ptext = "[S2] You get full control over scripts and voices.", "[S1] Dia is an open weights text to dialogue model."
     max_tokens = prompt_len + 1 + n_decode
-    keep = set(range(prompt_len + 1, prompt_len + 1 + n_decode, 8))
+    assert max_tokens <= pcfg.data.audio_length
+    keep = set(range(prompt_len + 1, prompt_len + 1 + n_decode, keep_every))
     d, rt, ot, sd = compare_generation(ref, pcfg, seed, text, max_tokens, prompt=prompt, prompt_text=ptext,
                                        label=f"dia16b-clone{prompt_len}", keep=keep, lean_oracle=True)
     margins = torch.stack(ot.margins)
     print(f"  min margin {margins.min().item():.3e}")
     steps = sorted(ot.logits)
+    name = f"dia16b_seed{seed}_clone{tag or prompt_len}.npz"
     np.savez_compressed(
-        os.path.join(GOLD, f"dia16b_seed{seed}_clone{prompt_len}.npz"),
+        os.path.join(GOLD, name),
         weight_seed=np.array(seed), text=np.array(text), prompt_text=np.array(ptext), prompt=prompt.numpy(),
         max_tokens=np.array(max_tokens), codes=ot.codes.numpy(), grid=ot.grid[: max_tokens + 1].numpy(),
         prefill_step=np.array(ot.prefill_step), margins=margins.numpy(), logits_steps=np.array(steps),
         logits=np.stack([ot.logits[s].numpy() for s in steps]).astype(np.float32),
     )
-    print(f"  wrote dia16b_seed{seed}_clone{prompt_len}.npz")
+    print(f"  wrote {name}")
+
+
+def text_of_length(n_bytes: int) -> str:
+    """A [S1]/[S2] dialogue whose effective text (after Dia.generate's speaker-tag completion, dia/model.py:689-696)
+    encodes to exactly ``n_bytes`` text tokens ([S1]/[S2] are one byte each, dia/model.py:262-263)."""
+    words = ("dia is an open weights text to dialogue model you get full control over scripts and voices "
+             "the quick brown fox jumps over the lazy dog while rain keeps falling on the quiet harbor town").split()
+    out, spk, i = "[S1]", 1, 0
+
+    def enc_len(t):
+        return len(O.effective_text(t, None).encode("utf-8").replace(b"[S1]", b"\x01").replace(b"[S2]", b"\x02"))
+
+    while enc_len(out) < n_bytes - 12:
+        out += " " + words[i % len(words)]
+        i += 1
+        if i % 7 == 0:
+            spk = 3 - spk
+            out += f". [S{spk}]"
+    while enc_len(out) < n_bytes:
+        out += "a" if not out.endswith("]") else " a"
+    assert enc_len(out) == n_bytes, (enc_len(out), n_bytes)
+    return out
+
+
+def run_longtext(ref, seed, lens, max_tokens=41):
+    """Transcripts longer than 128 bytes: cross-attention over several K/V tiles per warp / several CTAs per head."""
+    pcfg = PC.dia_1_6b_config()
+    for n in lens:
+        text = text_of_length(n)
+        keep = set([1, 2, 3] + list(range(4, max_tokens, 4)))
+        d, rt, ot, sd = compare_generation(ref, pcfg, seed, text, max_tokens, label=f"dia16b-text{n}", keep=keep,
+                                           lean_oracle=True)
+        margins = torch.stack(ot.margins)
+        print(f"  Lt={n}: min margin {margins.min().item():.3e}")
+        steps = sorted(ot.logits)
+        name = f"dia16b_seed{seed}_text{n}.npz"
+        np.savez_compressed(
+            os.path.join(GOLD, name),
+            weight_seed=np.array(seed), text=np.array(text), text_len=np.array(n), max_tokens=np.array(max_tokens),
+            codes=ot.codes.numpy(), grid=ot.grid[: max_tokens + 1].numpy(), prefill_step=np.array(ot.prefill_step),
+            margins=margins.numpy(), logits_steps=np.array(steps),
+            logits=np.stack([ot.logits[s].numpy() for s in steps]).astype(np.float32),
+        )
+        print(f"  wrote {name}")
+
+
+def run_pruned(ref, seed, max_tokens=33):
+    """BASELINE configs[3] at Dia-1.6B, against the reference itself: (i) the stock ``offline_prune.py --pruning-type
+    structured --prune-dim 0`` call (dia/pruning_utils.py:64-119 on every DenseGeneral, offline_prune.py:103-107) and
+    (ii) the 2:4 mask (ours; the reference has none) - both made permanent (dia/pruning_utils.py:122-151) on the
+    REFERENCE model, which then runs its own generate.  The kept-row masks of (i) travel in the fixture (norm
+    near-ties must not depend on the CPU that regenerates them); the 2:4 mask is integer-keyed, hence portable."""
+    import torch.nn.utils.prune as prune
+    from dia_tts_prune_b200 import pruning_utils as PU
+    pcfg = PC.dia_1_6b_config()
+    text = "[S1] Pruned weights. [S2] Same answers."
+    for mode in ("structured", "2to4"):
+        d, cfg = build_reference(ref, pcfg, seed)
+        RPU = __import__("dia.pruning_utils", fromlist=["x"])
+        extra = {}
+        if mode == "structured":
+            RPU.apply_structured_pruning(d.model, 0.5, dim=0, n=2)
+            for n_, m in d.model.named_modules():
+                if isinstance(m, ref.L.DenseGeneral) and prune.is_pruned(m):
+                    mask = m.weight_mask
+                    keep = mask.reshape(mask.shape[0], -1).any(dim=1)
+                    assert torch.equal(mask.reshape(mask.shape[0], -1), keep[:, None].expand(-1, mask[0].numel()).to(mask.dtype))
+                    extra["keep::" + n_] = np.packbits(keep.numpy())
+        else:
+            for n_, m in d.model.named_modules():
+                if isinstance(m, ref.L.DenseGeneral):
+                    w = m.weight
+                    K = int(np.prod(m.in_shapes))
+                    prune.custom_from_mask(m, "weight", PU.mask_2to4(w.detach(), K).to(w.dtype))
+        RPU.make_pruning_permanent(d.model)
+        sd = {k: v.detach() for k, v in d.model.named_parameters()}
+        assert [k for k in sd] == O.param_names(pcfg)
+        rt = RefTrace(ref, d)
+        t0 = time.time()
+        d.generate(text, max_tokens=max_tokens, temperature=0.0, cfg_scale=3.0)
+        rt.close()
+        print(f"[pruned-{mode}] reference {time.time() - t0:.1f}s")
+        keep_steps = set([1, 2] + list(range(4, max_tokens, 4)))
+        ot = O.generate(sd, pcfg, text, max_tokens=max_tokens, temperature=0.0, cfg_scale=3.0, keep_logits_at=keep_steps,
+                        dead_cross_kv=False)
+        check_equal(f"pruned-{mode} codes", ot.codes, rt.codes)
+        for s in sorted(ot.logits):
+            assert torch.equal(ot.logits[s], rt.logits[s - ot.prefill_step]), s
+        margins = torch.stack(ot.margins)
+        print(f"  ok  pruned-{mode}: logits bit-exact at {len(ot.logits)} steps, min margin {margins.min().item():.3e}")
+        steps = sorted(ot.logits)
+        dec = [n for n in sd if n.startswith("decoder.layers.0.") or "logits" in n]
+        name = f"dia16b_seed{seed}_pruned_{mode}.npz"
+        np.savez_compressed(
+            os.path.join(GOLD, name), weight_seed=np.array(seed), text=np.array(text), max_tokens=np.array(max_tokens),
+            mode=np.array(mode), fingerprint=np.array(SY.weights_fingerprint(sd, dec)),
+            codes=ot.codes.numpy(), grid=ot.grid[: max_tokens + 1].numpy(), margins=margins.numpy(),
+            logits_steps=np.array(steps), logits=np.stack([ot.logits[s].numpy() for s in steps]).astype(np.float32),
+            **extra)
+        print(f"  wrote {name}")
+        del d, rt, ot, sd
 
 
 def main():
@@ -350,6 +453,10 @@ def main():
     ap.add_argument("--max-tokens", type=int, default=257)
     ap.add_argument("--prompt-len", type=int, default=861)
     ap.add_argument("--clone-steps", type=int, default=48)
+    ap.add_argument("--long", action="store_true", help="long-context clone runs (slots ~1200, ~2380, ~2990)")
+    ap.add_argument("--longtext", action="store_true", help="transcripts of 129 / 200 / 600 bytes")
+    ap.add_argument("--clone-full", action="store_true", help="configs[2] at its stated size: 861-frame prompt + 1536 steps")
+    ap.add_argument("--pruned", action="store_true", help="configs[3] at Dia-1.6B: structured dim-0 and 2:4")
     ap.add_argument("--threads", type=int, default=os.cpu_count())
     a = ap.parse_args()
     torch.set_num_threads(a.threads)
@@ -363,6 +470,15 @@ def main():
         run_full(ref, a.seed, a.max_tokens)
     if a.clone or a.all:
         run_clone(ref, a.seed, a.prompt_len, a.clone_steps)
+    if a.longtext:
+        run_longtext(ref, a.seed, [129, 200, 600])
+    if a.pruned:
+        run_pruned(ref, a.seed)
+    if a.long:
+        for pl in (1200, 2380, 2990):
+            run_clone(ref, a.seed, pl, 48, keep_every=4)
+    if a.clone_full:
+        run_clone(ref, a.seed, 861, 1536, keep_every=128, tag="861x1536")
     print("VALIDATION PASSED")
 
 

@@ -237,8 +237,45 @@ def test_head_sample_filtered_probs_and_argmax(tiny_gpu, gold_sampling):
     lg[1, :, 5] = 1.0
     lg[1, :, 9] = 1.0
     assert eng.head_sample(lg, 3.0, 0.0, 0.95, 35).tolist() == [5] * 9
-    with pytest.raises(NotImplementedError):
-        eng.head_sample(lg, 3.0, 1.0, 0.95, 0)                                        # top-k disabled: unsupported
+
+
+def test_head_sample_optional_top_k(tiny_gpu, gold_sampling):
+    """a3: `cfg_filter_top_k` None / 0 skips the top-k filter (dia/model.py:43-50) and any k up to the vocabulary is
+    legal: the full-vocabulary sampler path against the oracle's filter, plus the reference-generated known answers."""
+    dia, sd = tiny_gpu
+    eng = dia.model.decoder.engine()
+    cfg = dia.config
+    g = torch.Generator().manual_seed(10)
+    for scale in (1.0, 3.0):
+        logits = torch.randn(2, 9, 1028, generator=g) * scale
+        guided = O.cfg_combine_and_mask(cfg, logits.clone(), 3.0)
+        for (T, p, k) in ((1.0, 0.95, None), (1.3, 0.8, 0), (2.0, 0.99, 100), (1.0, 1.0, None), (0.7, 0.9, 1028), (1.0, 0.5, 65)):
+            pred, probs = eng.head_sample(logits, 3.0, T, p, k, seed=3, draw=1, want_probs=True)
+            want = O.filtered_probs(guided.clone(), T, p, k)
+            assert torch.equal(probs.cpu() > 0, want > 0), (scale, T, p, k)
+            assert (probs.cpu() - want).abs().max() < 1e-6
+            assert (want[torch.arange(9), pred.cpu().long()] > 0).all()
+    # known answers the reference itself produced (tests/golden/sampling_known_answer.json), incl. top_k None and 0:
+    # the case's distribution is fed as the conditional row of channel 0 with an equal unconditional row (guided = cond)
+    n_checked = 0
+    for case in gold_sampling["cases"]:
+        lg = torch.tensor(case["logits"])
+        if lg.shape[-1] > 1028 or not torch.isfinite(lg).all():
+            continue
+        for row in range(min(lg.shape[0], 3)):
+            full = torch.full((2, 9, 1028), -1e30)
+            full[:, :, : lg.shape[-1]] = lg[row]
+            pred, probs = eng.head_sample(full, 3.0, case["temperature"], case["top_p"], case["top_k"], seed=1, draw=0,
+                                          want_probs=True)
+            want = torch.tensor(case["probs"])[row]
+            got = probs[0, : lg.shape[-1]].cpu()
+            assert (got - want).abs().max() < 1e-6, case["top_k"]
+            n_checked += 1
+    assert n_checked >= 6
+    # the generate loop accepts it too
+    a = dia.generate("[S1] No top k. [S2] Just top p.", max_tokens=40, seed=5, cfg_filter_top_k=None, output="codes")
+    b = dia.generate("[S1] No top k. [S2] Just top p.", max_tokens=40, seed=5, cfg_filter_top_k=0, output="codes")
+    assert a is not None and torch.equal(a, b)
 
 
 def test_head_sample_distribution_chi2(tiny_gpu):
@@ -453,6 +490,118 @@ def test_full_config3_voice_clone(full_gpu, gold_clone):
         pytest.fail(f"first divergence at row {d[0]} ch {d[1]}, margin {g['margins'][d[0], d[1]]:.3e}")
 
 
+def _golden(name):
+    import os
+    from conftest import GOLD
+    path = os.path.join(GOLD, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not generated yet (oracle/validate_against_reference.py)")
+    return np.load(path)
+
+
+def _check_golden_run(dia, g, clone=False, code_margin=5e-4):
+    """One reference-generated fixture end to end: (1) teacher-forced logits at the golden steps, every step through
+    ``Decoder.decode_step`` on the reference's own token grid; (2) the greedy stream through ``Dia.generate``.  A code
+    may differ from the reference only where the reference's own top-1/top-2 margin is below ``code_margin`` (a
+    near-tie decided by the last bits of an fp32 sum); everything up to there must be bit-exact."""
+    kw = {}
+    if clone:
+        kw = dict(audio_prompt=torch.from_numpy(g["prompt"]), audio_prompt_text=str(g["prompt_text"]))
+    text = dia._effective_text(str(g["text"]), kw.get("audio_prompt_text"))
+    with torch.inference_mode():
+        st, out = dia._prepare_generation(text, kw.get("audio_prompt"), False)
+    grid = torch.from_numpy(g["grid"]).cuda()
+    P, steps = int(g["prefill_step"]), g["logits_steps"].tolist()
+    assert out.prefill_step == P
+    worst = 0.0
+    for cur in range(P, max(steps) + 1):
+        st.prepare_step(cur)
+        with torch.inference_mode():
+            lg = dia.model.decoder.decode_step(grid[cur - 1].unsqueeze(0).unsqueeze(0).expand(2, 1, -1), st)
+        if cur in steps:
+            worst = max(worst, float(np.abs(lg[:, 0].cpu().numpy() - g["logits"][steps.index(cur)]).max()))
+    assert worst < LOGIT_TOL and worst < LOGIT_TIGHT, worst
+    dia.generate(str(g["text"]), max_tokens=int(g["max_tokens"]), temperature=0.0, cfg_scale=3.0, output="codes", **kw)
+    got, want = dia.last_codes.cpu(), torch.from_numpy(g["codes"])
+    if got.shape != want.shape or not torch.equal(got, want):
+        n = min(got.shape[0], want.shape[0])
+        diff = (got[:n] != want[:n]).nonzero()
+        assert diff.numel() > 0, f"row count {got.shape[0]} != {want.shape[0]} with equal prefixes"
+        r, c = diff[0].tolist()
+        m = float(g["margins"][r, c])
+        assert m < code_margin, f"first divergence at row {r} channel {c} where the reference margin is {m:.3e}"
+        print(f"near-tie at row {r} channel {c} (reference margin {m:.3e}): {r} rows bit-exact before it")
+    return worst
+
+
+@pytest.mark.parametrize("n_text", [129, 200, 600])
+def test_full_long_transcripts_vs_reference(full_gpu, n_text):
+    """Cross-attention beyond one 128-key tile set: 129 / 200 / 600 text bytes (several K/V tiles per warp, several
+    CTAs per head with the split-combine exchange) against fixtures the reference produced."""
+    dia, sd = full_gpu
+    g = _golden(f"dia16b_seed5_text{n_text}.npz")
+    assert int(g["text_len"]) == n_text
+    worst = _check_golden_run(dia, g)
+    print(f"Lt={n_text}: max-abs logits error {worst:.3e}")
+
+
+@pytest.mark.parametrize("prompt_len", [1200, 2380, 2990])
+def test_full_long_context_vs_reference(full_gpu, prompt_len):
+    """Self-attention deep in the context: a synthetic prompt of 1200 / 2380 / 2990 frames is prefilled, then 48
+    decode steps at cache slots ~1200 / ~2400 (several K/V tiles per warp with the online-softmax rescale) / ~3000
+    (the longest splits), logits and greedy codes against fixtures the reference produced."""
+    dia, sd = full_gpu
+    g = _golden(f"dia16b_seed5_clone{prompt_len}.npz")
+    assert g["prompt"].shape[0] == prompt_len
+    worst = _check_golden_run(dia, g, clone=True)
+    print(f"prompt {prompt_len}: max-abs logits error {worst:.3e}")
+
+
+def test_full_config3_voice_clone_at_stated_size(full_gpu):
+    """configs[2] as BASELINE.json states it: 861-frame prompt, then 1536 decode steps."""
+    dia, sd = full_gpu
+    g = _golden("dia16b_seed5_clone861x1536.npz")
+    assert int(g["max_tokens"]) == 861 + 1 + 1536
+    worst = _check_golden_run(dia, g, clone=True)
+    print(f"clone 861 + 1536: max-abs logits error {worst:.3e}, {g['codes'].shape[0]} reference rows")
+
+
+@pytest.mark.parametrize("mode", ["structured", "2to4"])
+def test_full_pruned_variants_vs_reference(mode):
+    """configs[3] at Dia-1.6B against the REFERENCE run on the same pruned weights: (i) the stock
+    ``apply_structured_pruning(model, 0.5, dim=0)`` of offline_prune.py on every DenseGeneral (the engine drops the dead
+    MLP neurons and streams the rest), (ii) 2:4 along K on every kernel (compressed slabs on mma.sp)."""
+    import torch.nn.utils.prune as prune
+    from dia_tts_prune_b200 import pruning_utils as PU
+    from dia_tts_prune_b200.layers import DenseGeneral
+    g = _golden(f"dia16b_seed5_pruned_{mode}.npz")
+    cfg = dia_1_6b_config()
+    dia, _ = build_dia(cfg, 5)
+    if mode == "structured":
+        with torch.no_grad():
+            for name, m in dia.model.named_modules():
+                if isinstance(m, DenseGeneral):
+                    keep = torch.from_numpy(np.unpackbits(g["keep::" + name])[: m.weight.shape[0]].astype(bool))
+                    assert abs(int(keep.sum()) - m.weight.shape[0] / 2) <= 1
+                    m.weight[~keep] = 0
+    else:
+        PU.apply_2to4_pruning(dia.model)
+        PU.make_pruning_permanent(dia.model)
+    sd = {k: v.detach() for k, v in dia.model.named_parameters()}
+    assert SY.weights_fingerprint(sd, [n for n in sd if n.startswith("decoder.layers.0.") or "logits" in n]) == \
+        str(g["fingerprint"])
+    SY.cast_dense_kernels_(dia.model, torch.bfloat16)
+    dia.compute_dtype = torch.bfloat16
+    dia.device = torch.device("cuda:0")
+    dia.model.to(dia.device).eval()
+    worst = _check_golden_run(dia, g)
+    eng = dia.model.decoder.engine()
+    assert (eng.n_hidden, eng.sparse24) == ((4096, False) if mode == "structured" else (8192, True))
+    print(f"pruned {mode}: max-abs logits error {worst:.3e}")
+    del dia
+    torch.cuda.empty_cache()
+
+
 def test_full_size_properties_3072_steps(full_gpu):
     """configs[1] at full length: 3071 steps; determinism, value ranges, the forced-EOS tail, slot bookkeeping."""
     dia, sd = full_gpu
@@ -559,10 +708,12 @@ def test_full_2to4_sparse_engine_matches_the_dense_stream():
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("M,N,K", [(8, 128, 64), (200, 256, 512), (1722, 2048, 2048), (333, 512, 8192)])
+@pytest.mark.parametrize("M,N,K", [(8, 128, 64), (200, 256, 512), (1722, 2048, 2048), (333, 512, 8192), (1, 128, 64),
+                                   (37, 9252, 2048), (130, 100, 128)])
 def test_tcgen05_dense_matches_fp64(M, N, K):
     """DenseGeneral for T > 1 rows (dia/layers.py:55-66) on tcgen05: fp32-operand accuracy from the three-term bf16
-    split of the activations, against a float64 product; row tail (M % 128 != 0) included."""
+    split of the activations, against a float64 product; row tails (M % 128 != 0, down to one row) and column tails
+    (N % 128 != 0: the 9 x 1028 logits head) included."""
     from dia_tts_prune_b200 import engine as E
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).cuda()
@@ -574,6 +725,148 @@ def test_tcgen05_dense_matches_fp64(M, N, K):
     err = (y.double() - ref).abs().max().item()
     # tensor-core accumulation of K products of magnitude ~1: a few 1e-5 relative (a float32 FMA chain gives ~1e-5)
     assert err < 2e-4 * max(1.0, (K / 2048) ** 0.5), err
-    assert not E.dense_supported(M, N + 8, K)
+    assert not E.dense_supported(M, N, K + 8) and not E.dense_supported(M, N + 2, K)
     with pytest.raises(NotImplementedError):
-        E.dense_forward(x, torch.empty((N + 8, K), dtype=torch.bfloat16, device="cuda"))
+        E.dense_forward(x[:, : K - 8].contiguous(), torch.empty((N, K - 8), dtype=torch.bfloat16, device="cuda"))
+
+
+def test_tcgen05_dense_fused_norm_and_residual():
+    """The projection with its two neighbours fused (dia/layers.py:541-555): torch.nn.RMSNorm in the split pass, the
+    residual add in the epilogue (in place on the residual), against float64."""
+    from dia_tts_prune_b200 import engine as E
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 203, 2048, 2048
+    x = torch.randn(M, K, generator=g) * 3.0
+    nw = torch.rand(K, generator=g) + 0.5
+    res = torch.randn(M, N, generator=g)
+    w = (torch.randn(K, N, generator=g) * K ** -0.5).to(torch.bfloat16)
+    wt = E.dense_prepare_weight(w.cuda())
+    r = res.clone().cuda()
+    y = E.dense_forward(x.cuda(), wt, norm_weight=nw.cuda(), eps=1e-5, residual=r)
+    assert y.data_ptr() == r.data_ptr()
+    xd = x.double()
+    xn = xd * torch.rsqrt((xd * xd).mean(-1, keepdim=True) + 1e-5) * nw.double()
+    ref = res.double() + xn @ w.double()
+    assert (y.cpu().double() - ref).abs().max().item() < 2e-4
+    # the norm alone, as a kernel of its own (encoder final norm)
+    yn = E.rmsnorm_rows(x.cuda(), nw.cuda(), 1e-5)
+    want = torch.nn.functional.rms_norm(x, (K,), nw, 1e-5)
+    assert (yn.cpu() - want).abs().max().item() < 2e-6 * want.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("mode,B,Tq,Hq,Hkv,n_valid", [(0, 2, 150, 4, 1, None), (0, 1, 64, 16, 4, None), (0, 2, 333, 8, 2, None),
+                                                      (1, 2, 128, 2, 2, [0, 37]), (1, 1, 100, 2, 2, [100]),
+                                                      (1, 2, 200, 2, 2, [64, 130]), (2, 2, 77, 4, 4, [0, 100]),
+                                                      (2, 2, 130, 16, 16, [0, 600])])
+def test_attention_rows_matches_sdpa_fp64(mode, B, Tq, Hq, Hkv, n_valid):
+    """The T > 1 attention kernel against the reference's call (F.scaled_dot_product_attention with the masks of
+    dia/state.py:8-39, dia/layers.py:319-337) in float64: causal GQA prefill, the encoder's pad partition, cross
+    attention over the valid prefix (a row without any allowed key returns exact zeros)."""
+    from dia_tts_prune_b200 import engine as E
+    g = torch.Generator().manual_seed(mode * 100 + Tq)
+    Tmax = 1024 if mode == 2 else Tq + 40
+    Tk = Tmax if mode == 2 else Tq
+    q = torch.randn(B, Tq, Hq, 128, generator=g)
+    k = torch.randn(B, Hkv, Tmax, 128, generator=g)
+    v = torch.randn(B, Hkv, Tmax, 128, generator=g)
+    out = E.attention_rows(q.cuda(), k.cuda(), v.cuda(), Tk, mode, n_valid).cpu()
+    qi = torch.arange(Tq)[:, None]
+    ki = torch.arange(Tk)[None, :]
+    ref = torch.zeros(B, Tq, Hq, 128, dtype=torch.float64)
+    for b in range(B):
+        if mode == 0:
+            mask = ki <= qi
+        elif mode == 1:
+            mask = (qi < n_valid[b]) == (ki < n_valid[b])
+        else:
+            mask = (ki < n_valid[b]).expand(Tq, Tk)
+        kk = k[b, :, :Tk].double().repeat_interleave(Hq // Hkv, dim=0)
+        vv = v[b, :, :Tk].double().repeat_interleave(Hq // Hkv, dim=0)
+        sc = torch.einsum("thd,hkd->htk", q[b].double(), kk) / math.sqrt(128.0)
+        sc = sc.masked_fill(~mask[None], -torch.inf)
+        p = torch.softmax(sc, dim=-1)
+        p = torch.where(mask.any(-1)[None, :, None], p, torch.zeros((), dtype=torch.float64))
+        ref[b] = torch.einsum("htk,hkd->thd", p, vv)
+    assert (out.double() - ref).abs().max().item() < 2e-5
+    if mode == 2:
+        assert (out[0] == 0).all()                                       # the unconditional row attends nothing
+
+
+def test_rope_rows_gate_and_embedding_kernels(tiny_gpu):
+    from dia_tts_prune_b200 import engine as E
+    dia, sd = tiny_gpu
+    cfg = dia.config
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(8)
+    B, T, H = 2, 37, 4
+    x = torch.randn(B * T, H * 128, generator=g)
+    pos = torch.arange(5, 5 + T, dtype=torch.int32).repeat(B)
+    tables = E.rope_tables_device(cfg, dev)
+    inv = O.rope_inv_freq(128, cfg.model.rope_min_timescale, cfg.model.rope_max_timescale)
+    want = O.rope(x.reshape(B, T, H, 128), pos.reshape(B, T), inv)                       # [B, T, H, 128]
+    got = E.rope_rows(x.clone().cuda(), pos.cuda(), B, T, H, tables).cpu().reshape(B, T, H, 128)
+    assert torch.equal(got, want)                                                         # host-made table: bit-exact
+    cache = torch.zeros(B, H, 64, 128).cuda()
+    E.rope_rows(x.cuda(), pos.cuda(), B, T, H, tables, cache=cache, cache_t0=3)
+    assert torch.equal(cache[:, :, 3:3 + T].cpu(), want.transpose(1, 2)) and (cache[:, :, :3] == 0).all() \
+        and (cache[:, :, 3 + T:] == 0).all()
+    E.rope_rows(x.cuda(), None, B, T, H, tables, rotate=False, cache=cache, cache_t0=0)
+    assert torch.equal(cache[:, :, :T].cpu(), x.reshape(B, T, H, 128).transpose(1, 2))
+    gu = torch.randn(50, 2, 96, generator=g) * 3
+    h = E.silu_mul(gu.cuda()).cpu()
+    assert (h - torch.nn.functional.silu(gu[:, 0]) * gu[:, 1]).abs().max().item() < 2e-6
+    table = torch.randn(256, 64, generator=g)
+    ids = torch.randint(0, 256, (33,), generator=g, dtype=torch.int32)
+    assert torch.equal(E.embed_rows(table.cuda(), ids.cuda()).cpu(), table[ids.long()])
+
+
+def test_tiny_encoder_and_cross_kv_match_oracle(tiny_gpu):
+    """a17 / f1: encoder output and the precomputed cross-attention K/V of the product path (own kernels only) against
+    the oracle, entry by entry, for the reference's full 2 x text_length formulation and for the live-only one."""
+    dia, sd = tiny_gpu
+    cfg = dia.config
+    text = "[S1] Encoder and cross keys. [S2] Entry by entry."
+    st_o, _, _ = O.prepare_generation(sd, cfg, O.effective_text(text, None), None, dead_cross_kv=False)
+    for live in (False, True):
+        dia.live_text_only = live
+        st, out = _prepared(dia, text)
+        n = st.text_len
+        if not live:
+            assert (st.enc_out.cpu() - st_o.enc_out).abs().max().item() < 2e-5
+        assert (st.enc_out[1, :n].cpu() - st_o.enc_out[1, :n]).abs().max().item() < 2e-5
+        for c, co in zip(st.cross_attn_cache, st_o.cross_cache):
+            if not live:
+                assert (c.k.cpu() - co.k).abs().max().item() < 2e-5 and (c.v.cpu() - co.v).abs().max().item() < 2e-5
+            assert (c.k[1, :, :n].cpu() - co.k[1, :, :n]).abs().max().item() < 2e-5
+            assert (c.v[1, :, :n].cpu() - co.v[1, :, :n]).abs().max().item() < 2e-5
+    dia.live_text_only = True
+
+
+def test_tiny_prefill_kv_matches_oracle(tiny_gpu, gold_tiny):
+    """a18: the prompt prefill (Decoder.forward, T > 1) on own kernels: every self-attention K/V slot it writes and
+    its logits against the oracle."""
+    dia, sd = tiny_gpu
+    cfg = dia.config
+    prompt = torch.from_numpy(gold_tiny["clone_prompt"])
+    text = dia._effective_text(str(gold_tiny["clone_text"]), str(gold_tiny["clone_prompt_text"]))
+    with torch.inference_mode():
+        st, out = dia._prepare_generation(text, prompt, False)
+    st_o, grid_o, p0 = O.prepare_generation(sd, cfg, text, prompt, dead_cross_kv=False)
+    assert out.prefill_step == p0 and torch.equal(out.generated_tokens.cpu(), grid_o)
+    T = p0 - 1
+    for c, co in zip(st.self_attn_cache, st_o.self_cache):
+        assert c.current_idx == co.current_idx == T - 1
+        assert (c.k[:, :, :T].cpu() - co.k[:, :, :T]).abs().max().item() < 1e-4
+        assert (c.v[:, :, :T].cpu() - co.v[:, :, :T]).abs().max().item() < 1e-4
+        assert (c.k[:, :, T:] == 0).all()
+    # the logits of the prefill pass itself (discarded by generate, kept by the module API)
+    with torch.inference_mode():
+        st2, out2 = dia._prepare_generation(text, None, False)
+        st2.prepare_step(0, T)
+        toks = out.generated_tokens[:T].unsqueeze(0).expand(2, -1, -1)
+        lg = dia.model.decoder.forward(toks, st2)
+        st_o2, _, _ = O.prepare_generation(sd, cfg, text, None, dead_cross_kv=False)
+        st_o2.prepare_step(0, T)
+        lo = O.decoder_forward(sd, cfg, grid_o[:T].unsqueeze(0).expand(2, -1, -1), st_o2, prefill=True, dead_cross_kv=False)
+    assert lg.shape == lo.shape == (2, T, 9, 1028)
+    assert (lg.cpu() - lo).abs().max().item() < LOGIT_TIGHT

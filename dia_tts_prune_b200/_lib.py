@@ -14,6 +14,7 @@ from pathlib import Path
 from . import build as _build
 
 MAX_CHANNELS = 16
+MAX_UTTERANCES = 8
 
 # enum dia_b200_buffer
 BUF_X, BUF_LOGITS, BUF_PRED, BUF_TIMING, BUF_CTA_TIMING = 0, 6, 7, 8, 9
@@ -67,6 +68,14 @@ _SIGNATURES = {
     "dia_b200_dense_prepare_weight": (_i, [_vp, _i, _vp, _i, _i, _vp]),
     "dia_b200_dense_workspace_bytes": (C.c_size_t, [_i, _i]),
     "dia_b200_dense_forward": (_i, [_fp, _vp, _fp, _vp, _i, _i, _i, _vp]),
+    "dia_b200_engine_create_batched": (_i, [C.POINTER(Shape), _i, _i, _i, C.POINTER(_vp)]),
+    "dia_b200_engine_max_utterances": (_i, [_vp]),
+    "dia_b200_batch_bind_caches": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i,
+                                        _vp]),
+    "dia_b200_batch_decode_step": (_i, [_vp, _i, _i32p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _fp, _vp]),
+    "dia_b200_batch_generate_begin": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(GenParams), _vp]),
+    "dia_b200_batch_generate_steps": (_i, [_vp, _i, _vp]),
+    "dia_b200_batch_generate_status": (_i, [_vp, C.POINTER(GenStatus), _vp]),
     "dia_b200_dense_forward_fused": (_i, [_fp, _fp, C.c_float, _vp, _fp, _fp, _vp, _i, _i, _i, _vp]),
     "dia_b200_attention_rows": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp]),
     "dia_b200_rope_rows": (_i, [_fp, _fp, _fp, _fp, _i32p, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

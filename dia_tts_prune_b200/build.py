@@ -12,8 +12,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = CSRC / "libdia_b200.so"
-SOURCES = ["step_kernel.cu", "aux_kernels.cu", "gemm_tcgen05.cu", "prefill_kernels.cu", "engine.cu"]
-HEADERS = ["common.cuh", "engine_internal.h"]
+SOURCES = ["step_kernel.cu", "aux_kernels.cu", "gemm_tcgen05.cu", "prefill_kernels.cu", "batch_kernel.cu", "engine.cu"]
+HEADERS = ["common.cuh", "engine_internal.h", "sampler.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

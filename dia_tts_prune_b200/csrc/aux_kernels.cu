@@ -76,6 +76,35 @@ __device__ __forceinline__ float repack_src(const RepackArgs& a, int g, int k, i
     return load_src(a.src[0], a.src_bf16, (size_t)k * a.N + g * 8 + i);
 }
 
+// Batched engine (batch_kernel.cu): the slab as K / 64 chunks of [gc*8 output columns][64 k] bf16, K-major, 128-byte rows
+// whose 16-byte units are XOR-swizzled with (row % 8) - the shared-memory image tcgen05.mma reads as its M operand.
+// One thread per (8 consecutive contraction rows, 8-column group): eight 16-byte units, one per column.
+__global__ void repack_batch_kernel(const RepackArgs a) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k0 = blockIdx.y * 8;
+    if (g >= a.n_groups) return;
+    const int cta = a.owner[g], gl = a.local[g];
+    const CtaTable& t = a.tab[cta];
+    const int gc = t.gc[a.gemm];
+    const unsigned long long slab = t.stream_base +
+        (a.gemm == G_LOGITS ? t.logits_off : (unsigned long long)a.layer * t.layer_bytes + t.slab_off[a.gemm]);
+    unsigned char* chunk = a.wstream + slab + (size_t)(k0 >> 6) * bchunk_bytes(gc);
+    const int unit = (k0 >> 3) & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = repack_src(a, g, k0 + j, i);
+        uint4 out;
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]),
+                       b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
+        out.x = *reinterpret_cast<uint32_t*>(&b0); out.y = *reinterpret_cast<uint32_t*>(&b1);
+        out.z = *reinterpret_cast<uint32_t*>(&b2); out.w = *reinterpret_cast<uint32_t*>(&b3);
+        const int m = gl * 8 + i;                              // row of the chunk = column of the slab
+        *reinterpret_cast<uint4*>(chunk + (size_t)m * 128 + ((unit ^ i) << 4)) = out;
+    }
+}
+
 // 2:4 slabs (engine_internal.h, gemm_slot_rows): one thread per (4 consecutive contraction rows, 8-column group).
 // Per column it keeps the (at most two) non-zeros of the four rows in row order - padding with a zero entry of the
 // group when there are fewer - writes them to the two compressed rows of the group and ORs the 4-bit index pair into
@@ -137,6 +166,11 @@ cudaError_t launch_repack(const RepackArgs& a, cudaStream_t st) {
     if (a.sparse) {
         dim3 grid((a.n_groups + 127) / 128, a.K / 4);
         repack_sparse24_kernel<<<grid, 128, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    if (a.batch_format) {
+        dim3 grid((a.n_groups + 127) / 128, a.K / 8);
+        repack_batch_kernel<<<grid, 128, 0, st>>>(a);
         return cudaGetLastError();
     }
     dim3 grid((a.n_groups + 127) / 128, a.K);

@@ -1,0 +1,1059 @@
+// batch_kernel.cu - the persistent decode-step kernel for N utterances per GPU.
+//
+// Same dataflow as step_kernel.cu - one CTA per SM, a producer warp streaming this CTA's weight slabs through a
+// shared-memory ring with 1-D bulk copies, flag-in-data vectors between CTAs, no grid barrier, the loop of
+// Dia.generate on the device - but the batch is R = 2N rows (CFG uncond / cond of N utterances, each with its own
+// KV caches, text length, token grid, EOS state and RNG stream), so ONE pass over the 2.53 GB of weights produces N
+// frames.  What changes with the rows:
+//
+//  * the GEMM stages run on the 5th-generation tensor cores: the CTA's slab is the M operand (<= 128 output columns,
+//    K-major, 128-byte swizzle - the host repacks the weights into exactly the tiles tcgen05.mma reads, one 64-row
+//    k-chunk after the other), the activations are the N = 16 operand, split in two bf16 terms (hi + lo) that are
+//    accumulated into the same fp32 accumulator in tensor memory.  One elected thread issues the MMAs;
+//    tcgen05.commit releases the weight slot and the activation stage; the epilogue reads the accumulator with
+//    tcgen05.ld: thread = output column, registers = the 16 rows, so RMSNorm scaling, RoPE-ready q/k/v words,
+//    SiLU(gate) * up, the residual add (the stream lives in registers of its column's thread) and the CFG combine
+//    are all local;
+//  * activation vectors cross CTAs as 4-byte words (bf16 hi | bf16 lo with a 1-bit generation flag in the last
+//    mantissa bit), [k / 64][row][64]: a k-chunk of all rows is 4 KB = one 16-byte load per math thread, which
+//    unpacks it straight into the swizzled B tiles.  Half the bytes of the single-utterance format: with 16 rows
+//    the activation exchange through L2, not HBM, is what bounds the step;
+//  * attention, embedding and sampling are the single-utterance stages indexed by (utterance, row): (row, kv head)
+//    pairs x key splits over the CTAs, 9 sampler CTAs per utterance, one state machine per utterance.
+//
+// Reference semantics: dia/layers.py:671-720, :530-584, :238-346, :92-105; dia/model.py:429-488, 32-82, 748-807.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "engine_internal.h"
+#include "sampler.cuh"
+
+namespace dia {
+
+typedef unsigned long long u64;
+
+namespace {
+
+constexpr int kBSlotBytes = 16384;          // one ring slot: up to 8 k-chunks of a slab, or a 16-key K / V tile
+constexpr int kBNumSlots = 10;
+constexpr int kActStages = 4;                 // activation (B operand) staging ring
+constexpr int kBTermBytes = 2048;           // [16 rows][64 k] bf16, K-major, 128-byte swizzle
+constexpr int kActStageBytes = 2 * kBTermBytes;
+constexpr int kScratchBytes = 49152;        // B staging | attention scratch | sampler scratch (never live together)
+constexpr int kBMiscBytes = 2048;
+constexpr int kBSmem = kBNumSlots * kBSlotBytes + kScratchBytes + kBMiscBytes + 1024;   // + alignment slack
+constexpr int kMmaWarp = 8;
+constexpr int kRows = 16;                   // N of the MMA = rows of the B tiles (2 x kMaxUtt)
+constexpr int kPrefetch = 4;                // activation chunks requested ahead
+
+struct BMisc {
+    uint64_t full[kBNumSlots], empty[kBNumSlots];
+    uint64_t bfull[kActStages], bempty[kActStages];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    int stages_done;
+    CtaTable tab;
+    float inv[kRows];                       // 1/rms of the stage input per row
+    float ssq_part[kConsumerWarps][kRows];
+    int toks[kMaxUtt][DIA_B200_MAX_CHANNELS];
+};
+static_assert(sizeof(BMisc) <= kBMiscBytes, "misc region too small");
+
+struct BCtx {
+    const BatchParams* p;
+    unsigned char* ring;
+    unsigned char* scratch;
+    BMisc* misc;
+    int tid, warp, lane;
+    unsigned cbase;       // ring slot index at the start of the current stage
+    unsigned bctr;        // activation chunks staged so far
+    unsigned gctr;        // GEMM stages (with columns in this CTA) so far
+    unsigned seq;         // sequence number of the current stage inside this launch (>= 1)
+    int step;             // step index inside the launch
+    float xres[kRows];    // threads 0..15: this column's element of the residual stream, per row
+};
+
+__device__ __forceinline__ void decode_stage_b(int s, int L, int& kind, int& layer) {
+    if (s == 0) { kind = S_EMBED; layer = 0; }
+    else if (s <= 8 * L) { layer = (s - 1) >> 3; kind = S_QKV + ((s - 1) & 7); }
+    else if (s == 8 * L + 1) { kind = S_LOGITS; layer = 0; }
+    else { kind = S_SAMPLE; layer = 0; }
+}
+__device__ __forceinline__ int gemm_of_kind_b(int kind) {
+    switch (kind) {
+        case S_QKV: return G_QKV;
+        case S_SO: return G_SO;
+        case S_CQ: return G_CQ;
+        case S_CO: return G_CO;
+        case S_WI: return G_WI;
+        case S_WO: return G_WO;
+        case S_LOGITS: return G_LOGITS;
+        default: return -1;
+    }
+}
+
+// generation of an activation buffer (how many times it has been written before) -> the flag bit its words carry.
+// act_x is written by the embedding and by the three residual stages of every layer; the others once per layer.
+__device__ __forceinline__ uint32_t flag_x(int L, int step, int idx) { return (uint32_t)(step * (3 * L + 1) + idx + 1) & 1u; }
+__device__ __forceinline__ uint32_t flag_l(int L, int step, int layer) { return (uint32_t)(step * L + layer + 1) & 1u; }
+
+// x ~ hi + lo with both terms bf16; the last mantissa bit of lo carries the generation flag
+__device__ __forceinline__ uint32_t pack_act(float x, uint32_t fbit) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    return ((uint32_t)__bfloat16_as_ushort(h) << 16) | ((uint32_t)__bfloat16_as_ushort(l) & 0xfffeu) | fbit;
+}
+__device__ __forceinline__ void st_act(uint32_t* buf, int R, int k, int r, uint32_t word) {
+    asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(buf + ((size_t)(k >> 6) * R + r) * 64 + (k & 63)), "r"(word) : "memory");
+}
+__device__ __forceinline__ uint4 ld_act4(const uint32_t* p) {
+    uint4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+__device__ __forceinline__ void ring_wait_full_b(BMisc* misc, unsigned idx, int* err, unsigned info) {
+    const unsigned slot = idx % kBNumSlots, parity = (idx / kBNumSlots) & 1u;
+    mbar_wait(&misc->empty[slot], parity ^ 1u, err, kErrEmptyBarrierTimeout, info);     // see step_kernel.cu: parity alias
+    mbar_wait(&misc->full[slot], parity, err, kErrFullBarrierTimeout, info);
+}
+
+// ---- tcgen05 ---------------------------------------------------------------------------------------------------
+// K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (same encoding as gemm_tcgen05.cu)
+__device__ __forceinline__ uint64_t umma_desc_b(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ void umma_bf16_b(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_b(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- work decomposition of the attention stages ---------------------------------------------------------------------
+struct BAttnWork {
+    int active, pair, split, k_lo, k_hi, n_active, has_new, u, row, head;
+};
+// self-attention: (row, kv head) pairs x key splits.  Old keys are the cache slots [0, slot_u); the key / value of THIS
+// step comes from the qkv words and is handled (and appended) by the last active split.
+__device__ __forceinline__ BAttnWork self_work_b(const BatchParams& p, int cta, int step) {
+    BAttnWork w;
+    const int nsplit = p.sa_nsplit, pairs = p.R * p.Hkv;
+    w.pair = cta / nsplit;
+    w.split = cta - w.pair * nsplit;
+    w.row = w.pair / p.Hkv;
+    w.head = w.pair - w.row * p.Hkv;
+    w.u = w.row >> 1;
+    const int n_old = w.pair < pairs ? p.utt[w.u].slot0 + step : 0;
+    int per = (n_old + nsplit - 1) / nsplit;
+    per = (per + 15) & ~15;
+    if (per < 64) per = 64;
+    w.n_active = (n_old + per - 1) / per;
+    if (w.n_active < 1) w.n_active = 1;
+    w.active = (w.pair < pairs) && (w.split < w.n_active);
+    w.k_lo = w.split * per;
+    w.k_hi = min(n_old, w.k_lo + per);
+    if (w.k_hi < w.k_lo) w.k_hi = w.k_lo;
+    w.has_new = (w.split == w.n_active - 1);
+    return w;
+}
+// cross-attention: conditional rows only, (utterance, head) pairs x key splits over the valid text keys
+__device__ __forceinline__ BAttnWork cross_work_b(const BatchParams& p, int cta) {
+    BAttnWork w;
+    const int nsplit = p.ca_nsplit, pairs = p.U * p.Hc;
+    w.pair = cta / nsplit;
+    w.split = cta - w.pair * nsplit;
+    w.u = w.pair / p.Hc;
+    w.head = w.pair - w.u * p.Hc;
+    w.row = 2 * w.u + 1;
+    const int n = w.pair < pairs ? p.utt[w.u].text_len : 0;
+    int per = (n + nsplit - 1) / nsplit;
+    per = (per + 15) & ~15;
+    if (per < 128) per = 128;
+    w.n_active = (n + per - 1) / per;
+    if (w.n_active < 1) w.n_active = 1;
+    w.active = (w.pair < pairs) && (w.split < w.n_active);
+    w.k_lo = w.split * per;
+    w.k_hi = min(n, w.k_lo + per);
+    if (w.k_hi < w.k_lo) w.k_hi = w.k_lo;
+    w.has_new = 0;
+    return w;
+}
+__device__ __forceinline__ int attn_slots_b(const BAttnWork& w) {
+    return (!w.active || w.k_hi <= w.k_lo) ? 0 : 2 * ((w.k_hi - w.k_lo + 15) >> 4);
+}
+
+// ---- producer: walks this CTA's byte stream -----------------------------------------------------------------------------
+__device__ void producer_loop_b(const BatchParams& p, unsigned char* ring, BMisc* misc) {
+    unsigned pc = 0;
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const CtaTable& tab = misc->tab;
+    const int cta = blockIdx.x;
+    const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
+    auto issue = [&](const void* src, uint32_t bytes, bool keep, unsigned seq) {
+        const unsigned slot = pc % kBNumSlots, ph = (pc / kBNumSlots) & 1u;
+        mbar_wait(&misc->empty[slot], ph ^ 1u, p.err, kErrEmptyBarrierTimeout, (seq << 8) | slot);
+        mbar_arrive_expect_tx(&misc->full[slot], bytes);
+        bulk_g2s_hint(ring + slot * kBSlotBytes, src, bytes, &misc->full[slot], keep ? pol_keep : pol_stream);
+        pc++;
+    };
+#pragma unroll 1
+    for (int n = 0; n < p.n_steps; ++n) {
+#pragma unroll 1
+        for (int s = 0; s < n_stage; ++s) {
+            int kind, layer;
+            decode_stage_b(s, p.L, kind, layer);
+            const unsigned seq = 1u + (unsigned)(n * S + s);
+            const int gt = gemm_of_kind_b(kind);
+            if (gt >= 0) {
+                const int gc = tab.gc[gt];
+                if (gc == 0) continue;
+                const int K = p.Kdim[gt], cps = bslot_chunks(gc, K);
+                const uint32_t slot_bytes = (uint32_t)(cps * bchunk_bytes(gc));
+                const int n_slots = (K / 64) / cps;
+                const unsigned char* base = p.wstream + tab.stream_base +
+                    (gt == G_LOGITS ? tab.logits_off : (unsigned long long)layer * tab.layer_bytes + tab.slab_off[gt]);
+#pragma unroll 1
+                for (int i = 0; i < n_slots; ++i) issue(base + (size_t)i * slot_bytes, slot_bytes, false, seq);
+            } else if (kind == S_SATTN || kind == S_CATTN) {
+                const bool self = kind == S_SATTN;
+                const BAttnWork w = self ? self_work_b(p, cta, n) : cross_work_b(p, cta);
+                if (attn_slots_b(w) == 0) continue;
+                if (self && n > 0) {
+                    // cache row slot-1 was appended by another CTA in this stage of step n-1 and fenced before its stage
+                    // output; this CTA's math warps are past the cross-q stage of step n-1 once stages_done says so
+                    const int need = (n - 1) * S + s + 3;
+                    const unsigned long long t0 = clock64();
+                    while (ld_acquire_cta_s32(&misc->stages_done) < need) {
+                        if (clock64() - t0 > kWatchdogCycles) ll_timeout(p.err, kErrStepDoneTimeout, seq);
+                    }
+                    fence_proxy_async();
+                }
+                const float *kb, *vb;
+                if (self) {
+                    const size_t off = ((size_t)((w.row & 1) * p.Hkv + w.head) * p.Lmax) * kHeadDim;
+                    kb = p.self_k[w.u * p.L + layer] + off;
+                    vb = p.self_v[w.u * p.L + layer] + off;
+                } else {
+                    const size_t off = ((size_t)(p.Hc + w.head) * p.Smax) * kHeadDim;       // row 1 (cond) of the utterance
+                    kb = p.cross_k[w.u * p.L + layer] + off;
+                    vb = p.cross_v[w.u * p.L + layer] + off;
+                }
+#pragma unroll 1
+                for (int k0 = w.k_lo; k0 < w.k_hi; k0 += 16) {
+                    const int nk = min(16, w.k_hi - k0);
+                    issue(kb + (size_t)k0 * kHeadDim, nk * kHeadDim * 4, !self, seq);
+                    issue(vb + (size_t)k0 * kHeadDim, nk * kHeadDim * 4, !self, seq);
+                }
+            }
+        }
+    }
+}
+
+// ---- MMA warp: one thread issues every tcgen05.mma of this CTA ---------------------------------------------------------------
+__device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned char* scratch, BMisc* misc) {
+    const CtaTable& tab = misc->tab;
+    const int cta = blockIdx.x;
+    const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
+    const uint32_t tmem = misc->tmem_base;
+    // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, N = 16, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    unsigned cbase = 0, bctr = 0, gctr = 0;
+#pragma unroll 1
+    for (int n = 0; n < p.n_steps; ++n) {
+#pragma unroll 1
+        for (int s = 0; s < n_stage; ++s) {
+            int kind, layer;
+            decode_stage_b(s, p.L, kind, layer);
+            const unsigned seq = 1u + (unsigned)(n * S + s);
+            const int gt = gemm_of_kind_b(kind);
+            if (gt >= 0) {
+                const int gc = tab.gc[gt];
+                if (gc == 0) continue;
+                const int K = p.Kdim[gt], cps = bslot_chunks(gc, K), n_chunks = K / 64;
+                const uint32_t chunk_bytes = (uint32_t)bchunk_bytes(gc);
+                const unsigned a = gctr & 1u;
+                mbar_wait(&misc->acc_empty[a], ((gctr >> 1) & 1u) ^ 1u, p.err, kErrGridBarrierTimeout, seq);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_addr = tmem + a * kRows;
+#pragma unroll 1
+                for (int c = 0; c < n_chunks; ++c) {
+                    const unsigned si = cbase + (unsigned)(c / cps);
+                    if (c % cps == 0) ring_wait_full_b(misc, si, p.err, (seq << 8) | (si % kBNumSlots));
+                    const unsigned bi = bctr + (unsigned)c, bs = bi % kActStages;
+                    mbar_wait(&misc->bfull[bs], (bi / kActStages) & 1u, p.err, kErrFullBarrierTimeout, (seq << 8) | 0x80 | bs);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_base = smem_u32(ring + (si % kBNumSlots) * kBSlotBytes) + (uint32_t)(c % cps) * chunk_bytes;
+                    const uint32_t b_base = smem_u32(scratch + bs * kActStageBytes);
+                    const uint64_t adesc = umma_desc_b(a_base);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const uint64_t bdesc = umma_desc_b(b_base + t * kBTermBytes);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)          // 16 elements along K = 32 bytes = 2 descriptor units
+                            umma_bf16_b(d_addr, adesc + 2 * j, bdesc + 2 * j, idesc, (c | t | j) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_b(&misc->bempty[bs]);
+                    if (c % cps == cps - 1) umma_commit_b(&misc->empty[si % kBNumSlots]);
+                }
+                umma_commit_b(&misc->acc_full[a]);
+                cbase += (unsigned)(n_chunks / cps);
+                bctr += (unsigned)n_chunks;
+                gctr++;
+            } else if (kind == S_SATTN || kind == S_CATTN) {
+                const BAttnWork w = kind == S_SATTN ? self_work_b(p, cta, n) : cross_work_b(p, cta);
+                cbase += (unsigned)attn_slots_b(w);
+            }
+        }
+    }
+}
+
+// ---- GEMM stage, math warps: stage the activations, then the epilogue ----------------------------------------------------------
+__device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
+    const BatchParams& p = *c.p;
+    BMisc* misc = c.misc;
+    const int gc = misc->tab.gc[gt], g0 = misc->tab.g0[gt];
+    if (gc == 0) return;
+    const int R = p.R, L = p.L, K = p.Kdim[gt], n_chunks = K / 64, NC = gc * 8;
+    const int tid = c.tid, lane = c.lane, warp = c.warp;
+    const bool resid = (gt == G_SO || gt == G_CO || gt == G_WO);
+    const bool normed = !resid;
+    const uint32_t* src = gt == G_SO ? p.act_attn : gt == G_CO ? p.act_cattn : gt == G_WO ? p.act_hidden : p.act_x;
+    uint32_t fb;                                               // flag bit the input words carry
+    switch (gt) {
+        case G_QKV: fb = flag_x(L, c.step, 3 * layer); break;
+        case G_CQ: fb = flag_x(L, c.step, 3 * layer + 1); break;
+        case G_WI: fb = flag_x(L, c.step, 3 * layer + 2); break;
+        case G_LOGITS: fb = flag_x(L, c.step, 3 * L); break;
+        default: fb = flag_l(L, c.step, layer); break;
+    }
+
+    // ---- the activations, chunk by chunk: one 16-byte load per thread = 4 consecutive k of one row ----------------------
+    const int r_ld = tid >> 4, k4 = tid & 15;
+    const bool ld_on = r_ld < R;
+    const uint32_t* my = src + (size_t)r_ld * 64 + 4 * k4;
+    const size_t chunk_words = (size_t)R * 64;
+    const uint32_t st_off = (uint32_t)(r_ld * 128 + ((((k4 >> 1) ^ (r_ld & 7)) << 4) | ((k4 & 1) << 3)));
+    uint4 v[kPrefetch];
+#pragma unroll
+    for (int i = 0; i < kPrefetch; ++i)
+        if (ld_on && i < n_chunks) v[i] = ld_act4(my + (size_t)i * chunk_words);
+#pragma unroll 1
+    for (int c0 = 0; c0 < n_chunks; c0 += kPrefetch) {
+#pragma unroll
+        for (int i = 0; i < kPrefetch; ++i) {
+            const int ch = c0 + i;
+            if (ch < n_chunks) {
+                if (ld_on) {
+                    unsigned spins = 0;
+                    while ((((v[i].x ^ fb) | (v[i].y ^ fb) | (v[i].z ^ fb) | (v[i].w ^ fb)) & 1u) != 0u) {
+                        if (++spins > kMaxSpins) {
+                            volatile int* e = reinterpret_cast<volatile int*>(p.err);
+                            e[4] = ch; e[5] = gt; e[6] = (int)fb; e[7] = r_ld;
+                            ll_timeout(p.err, kErrFlagTimeout, c.seq * 16 + gt);
+                        }
+                        ll_check_abort(p.err, spins, 100 + kErrFlagTimeout, c.seq * 16 + gt);
+                        v[i] = ld_act4(my + (size_t)ch * chunk_words);
+                    }
+                }
+                const unsigned bi = c.bctr + (unsigned)ch, bs = bi % kActStages;
+                if (lane == 0) mbar_wait(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (c.seq << 8) | 0xc0 | bs);
+                __syncwarp();
+                if (ld_on) {
+                    const uint32_t dst = smem_u32(c.scratch + bs * kActStageBytes) + st_off;
+                    const uint32_t h0 = __byte_perm(v[i].x, v[i].y, 0x7632), h1 = __byte_perm(v[i].z, v[i].w, 0x7632);
+                    const uint32_t l0 = __byte_perm(v[i].x, v[i].y, 0x5410) & 0xfffefffeu;
+                    const uint32_t l1 = __byte_perm(v[i].z, v[i].w, 0x5410) & 0xfffefffeu;
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst + kBTermBytes), "r"(l0), "r"(l1) : "memory");
+                }
+                fence_proxy_async();                            // generic-proxy writes -> the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&misc->bfull[bs]);
+                if (ld_on && ch + kPrefetch < n_chunks) v[i] = ld_act4(my + (size_t)(ch + kPrefetch) * chunk_words);
+            }
+        }
+    }
+    c.bctr += (unsigned)n_chunks;
+    c.cbase += (unsigned)(n_chunks / bslot_chunks(gc, K));
+
+    // ---- RMSNorm: 1/rms per row from the producers' per-group sums (dia/layers.py:541,560,579,714) ---------------------------
+    if (normed) {
+        const uint32_t fprev = c.seq - 1;
+        const int half = R >> 1;                               // word pairs per group
+        const int n_pairs = (p.D >> 3) * half;
+        const int rp = tid % half;                             // the same row pair in every iteration (256 % half == 0)
+        float s0 = 0.f, s1 = 0.f;
+        uint4 q4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (tid + kConsumerThreads * i < n_pairs) q4[i] = ll_ld2(p.ll_ssq + (size_t)(tid + kConsumerThreads * i) * 2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (tid + kConsumerThreads * i < n_pairs) {
+                unsigned spins = 0;
+                while (q4[i].y != fprev || q4[i].w != fprev) {
+                    if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 4, c.seq);
+                    ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 4, c.seq);
+                    q4[i] = ll_ld2(p.ll_ssq + (size_t)(tid + kConsumerThreads * i) * 2);
+                }
+                s0 += __uint_as_float(q4[i].x);
+                s1 += __uint_as_float(q4[i].z);
+            }
+        }
+        // lanes with the same row pair: lane % half (half is a power of two <= 8)
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            if (m >= half) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+            }
+        }
+        if (lane < half) { misc->ssq_part[warp][2 * rp] = s0; misc->ssq_part[warp][2 * rp + 1] = s1; }
+        consumer_sync();
+        if (tid < R) {
+            float ss = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < kConsumerWarps; ++ww) ss += misc->ssq_part[ww][tid];
+            misc->inv[tid] = 1.0f / sqrtf(ss / (float)p.D + p.eps);
+        }
+        consumer_sync();
+    }
+
+    // ---- epilogue: warps 0..3, thread = output column of this CTA's slab (TMEM lane), registers = rows ----------------------------
+    const unsigned a = c.gctr & 1u;
+    if (warp < 4) {
+        mbar_wait(&misc->acc_full[a], (c.gctr >> 1) & 1u, p.err, kErrGridBarrierTimeout, c.seq);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t acc[kRows];
+        const uint32_t taddr = misc->tmem_base + ((uint32_t)(warp * 32) << 16) + a * kRows;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
+              "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]), "=r"(acc[15])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&misc->acc_empty[a]);
+
+        const int m = tid;                                      // column inside the slab
+        const bool valid = m < NC;
+        const int n = g0 * 8 + m;                               // column of the GEMM
+        if (gt == G_QKV || gt == G_CQ) {
+            u64* dst = gt == G_QKV ? p.ll_qkv : p.ll_cq;
+            if (valid) {
+#pragma unroll
+                for (int r = 0; r < kRows; ++r)
+                    if (r < R) ll_st(dst + (size_t)n * R + r, __float_as_uint(__uint_as_float(acc[r]) * misc->inv[r]), c.seq);
+            }
+        } else if (gt == G_WI) {
+            // a group = gate columns 0..3 and up columns 4..7 of the same 4 hidden units: h = silu(gate) * up
+            const uint32_t fo = flag_l(L, c.step, layer);
+            const int hn = (g0 + (m >> 3)) * 4 + (m & 3);
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (r < R) {                                    // (R is uniform: every lane takes part in the shuffle)
+                    const float y = __uint_as_float(acc[r]) * misc->inv[r];
+                    const float up = __shfl_down_sync(0xffffffffu, y, 4);
+                    if (valid && (m & 4) == 0) st_act(p.act_hidden, R, hn, r, pack_act((y / (1.0f + expf(-y))) * up, fo));
+                }
+            }
+        } else if (gt == G_LOGITS) {
+            const int ch = n / p.Vpad, vv = n - ch * p.Vpad;
+            if (valid && ch < p.C && vv < p.V) {
+#pragma unroll
+                for (int u = 0; u < kMaxUtt; ++u) {
+                    if (u < p.U) {
+                        const float un = __uint_as_float(acc[2 * u]) * misc->inv[2 * u];
+                        const float co = __uint_as_float(acc[2 * u + 1]) * misc->inv[2 * u + 1];
+                        if (p.logits != nullptr) {
+                            p.logits[((size_t)(2 * u) * p.C + ch) * p.V + vv] = un;
+                            p.logits[((size_t)(2 * u + 1) * p.C + ch) * p.V + vv] = co;
+                        }
+                        float gv = __fadd_rn(co, __fmul_rn(p.cfg_scale, __fsub_rn(co, un)));     // dia/model.py:450-457
+                        if ((ch > 0 && vv == p.eos) || vv == p.pad || vv == p.bos) gv = -INFINITY;
+                        ll_st(p.ll_glog + ((size_t)u * p.C + ch) * p.V + vv, __float_as_uint(gv), c.seq);
+                    }
+                }
+            }
+        } else {
+            // residual add (dia/layers.py:555,574,582): the stream stays in this thread's registers; the new stream goes
+            // out as the words of x * w_norm for the next consumer, with sum(x^2) of this 8-column group per row
+            const int idx = gt == G_SO ? 3 * layer + 1 : gt == G_CO ? 3 * layer + 2 : 3 * layer + 3;
+            const uint32_t fo = flag_x(L, c.step, idx);
+            const float* wn = gt == G_SO ? p.norms + ((size_t)layer * 3 + 1) * p.D
+                            : gt == G_CO ? p.norms + ((size_t)layer * 3 + 2) * p.D
+                                         : p.norms + ((size_t)(layer + 1) * 3) * p.D;
+            const float wnv = valid ? __ldg(wn + n) : 0.f;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (r < R) {
+                    float xn = 0.f;
+                    if (valid) {
+                        xn = c.xres[r] + __uint_as_float(acc[r]);
+                        c.xres[r] = xn;
+                        st_act(p.act_x, R, n, r, pack_act(xn * wnv, fo));
+                    }
+                    float sq = xn * xn;
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                    if (valid && (m & 7) == 0) ll_st(p.ll_ssq + (size_t)(g0 + (m >> 3)) * R + r, __float_as_uint(sq), c.seq);
+                }
+            }
+        }
+    }
+    c.gctr++;
+    consumer_sync();            // the staging ring is scratch of the next stage: every MMA of this one has completed
+}
+
+// sum v[i] over the 32 lanes for NV values at once (see step_kernel.cu)
+template <int NV>
+__device__ __forceinline__ void transpose_reduce_b(float (&v)[NV], int lane) {
+    int n = NV;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        if (n > 1) {
+            n >>= 1;
+            const bool hi = (lane & m) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) {
+                if (i < n) {
+                    const float a = v[i], b = v[i + n];
+                    const float send = hi ? a : b;
+                    const float keep = hi ? b : a;
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                }
+            }
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+        }
+    }
+}
+
+constexpr int HPKB = 4;          // query heads per KV tile in self-attention (GQA 4:1)
+
+// ---- attention stage (the single-utterance stage of step_kernel.cu, indexed by utterance and row) ------------------------------
+template <int NH>
+__device__ void attn_stage_b(BCtx& c, int layer) {
+    constexpr bool self = NH == HPKB;
+    const BatchParams& p = *c.p;
+    const int cta = blockIdx.x, R = p.R;
+    const BAttnWork w = self ? self_work_b(p, cta, c.step) : cross_work_b(p, cta);
+    if (!w.active) return;
+    const int r = w.row, u = w.u;
+    const int kvh = w.head;
+    const int head0 = self ? kvh * HPKB : w.head;
+    const int nh = self ? HPKB : 1;
+    const int nsplit = self ? p.sa_nsplit : p.ca_nsplit;
+    const uint32_t fprev = c.seq - 1;
+    const bool has_new = self && w.has_new;
+    const int pos = p.utt[u].pos0 + c.step, slot = p.utt[u].slot0 + c.step;
+
+    float* qs = reinterpret_cast<float*>(c.scratch);      // [HPKB][128] rotated, pre-scaled queries
+    float* kn = qs + HPKB * kHeadDim;                      // [128] rotated key of this step
+    float* vn = kn + kHeadDim;                             // [128] value of this step
+    float* psm = vn + kHeadDim + c.warp * 64;              // [warps][16 keys][HPKB] probabilities of the current tile
+    float* wstat = vn + kHeadDim + kConsumerWarps * 64;    // [warps][8]: m[HPKB], l[HPKB] of each warp
+    float* cw = wstat + kConsumerWarps * 8;                // split-combine staging
+    float* racc = reinterpret_cast<float*>(c.scratch) + 5120;   // [warps][HPKB][128]
+    const u64* qsrc = self ? p.ll_qkv : p.ll_cq;
+
+    {   // ---- inputs: q (and k, v of this step), RoPE, scale -----------------------------------------------------------------
+        const int pclamp = min(pos, p.n_pos - 1);
+        const int d = c.tid & 63;
+        const float sn = __ldg(p.rope_sin + (size_t)pclamp * 64 + d), cs = __ldg(p.rope_cos + (size_t)pclamp * 64 + d);
+        const float scale = 0.08838834764831845f;           // 1/sqrt(128)
+        if ((c.warp >> 1) < nh) {
+            if (c.lane == 0)
+                ll_wait32(qsrc + ((size_t)(head0 + (c.warp >> 1)) * kHeadDim + (c.warp & 1) * 32) * R + r, fprev, p.err);
+            __syncwarp();
+        }
+        const int n_items = (HPKB + 2) * 64;
+#pragma unroll 1
+        for (int i = c.tid; i < n_items; i += kConsumerThreads) {
+            const int hh = i >> 6;
+            float o0 = 0.f, o1 = 0.f;
+            if (hh < nh || (hh >= HPKB && has_new)) {
+                const int col = hh < HPKB ? (head0 + hh) * kHeadDim
+                                          : (hh == HPKB ? (p.Hq + kvh) * kHeadDim : (p.Hq + p.Hkv + kvh) * kHeadDim);
+                const u64* pa = qsrc + ((size_t)col + d) * R + r;
+                const u64* pb = pa + (size_t)64 * R;
+                uint2 wa = ll_ld(pa), wb = ll_ld(pb);
+                if (wa.y != fprev) wa.x = ll_wait32(pa, fprev, p.err);
+                if (wb.y != fprev) wb.x = ll_wait32(pb, fprev, p.err);
+                const float a = __uint_as_float(wa.x), b = __uint_as_float(wb.x);
+                o0 = a; o1 = b;
+                if (hh <= HPKB) {                            // RotaryEmbedding (dia/layers.py:161-173)
+                    o0 = a * cs - b * sn;
+                    o1 = a * sn + b * cs;
+                    if (hh < HPKB) { o0 *= scale; o1 *= scale; }
+                }
+            }
+            qs[hh * kHeadDim + d] = o0;
+            qs[hh * kHeadDim + d + 64] = o1;
+        }
+    }
+    consumer_sync();
+    float* const* ck = p.self_k;
+    float* const* cv = p.self_v;
+    if (has_new && c.tid < kHeadDim) {
+        // KVCache.update (dia/state.py:99-103): append this step's K/V at `slot` of this utterance's cache
+        const size_t row = ((size_t)((r & 1) * p.Hkv + kvh) * p.Lmax + slot) * kHeadDim;
+        ck[u * p.L + layer][row + c.tid] = kn[c.tid];
+        cv[u * p.L + layer][row + c.tid] = vn[c.tid];
+    }
+    float4 q[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) q[h] = reinterpret_cast<const float4*>(qs + h * kHeadDim)[c.lane];
+
+    const int nk = w.k_hi - w.k_lo;
+    const int nkc = (nk + 15) >> 4;
+    const int nvc = nkc + (has_new ? 1 : 0);
+    float m_run = -INFINITY, l_run = 0.f;
+    float4 acc[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int ci = c.warp; ci < nvc; ci += kConsumerWarps) {
+        const bool in_ring = ci < nkc;
+        unsigned sl = 0;
+        const float4* kt = reinterpret_cast<const float4*>(kn) + c.lane;
+        const float4* vt = reinterpret_cast<const float4*>(vn) + c.lane;
+        int keys_in = 1;
+        if (in_ring) {
+            const unsigned idx = c.cbase + 2 * ci;
+            sl = idx % kBNumSlots;
+            ring_wait_full_b(c.misc, idx, p.err, (c.seq << 8) | 0x40 | sl);
+            kt = reinterpret_cast<const float4*>(c.ring + sl * kBSlotBytes) + c.lane;
+            keys_in = min(16, nk - ci * 16);
+        }
+        float s2[2];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float v[8 * NH];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (half * 8 + i < keys_in) kv = kt[(half * 8 + i) * 32];
+#pragma unroll
+                for (int h = 0; h < NH; ++h)
+                    v[i * NH + h] = kv.x * q[h].x + kv.y * q[h].y + kv.z * q[h].z + kv.w * q[h].w;
+            }
+            transpose_reduce_b<8 * NH>(v, c.lane);
+            const float sv = (half * 8 + (c.lane >> 2)) < keys_in ? v[0] : -INFINITY;
+            if (half == 0) s2[0] = sv; else s2[1] = sv;
+        }
+        if (in_ring) {
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
+        }
+        float mt = fmaxf(s2[0], s2[1]);
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 4));
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
+        const float m_new = fmaxf(m_run, mt);
+        const float scale = expf(m_run - m_new);
+        const float p0 = expf(s2[0] - m_new), p1 = expf(s2[1] - m_new);
+        float lt = p0 + p1;
+        lt += __shfl_xor_sync(0xffffffffu, lt, 4);
+        lt += __shfl_xor_sync(0xffffffffu, lt, 8);
+        lt += __shfl_xor_sync(0xffffffffu, lt, 16);
+        l_run = l_run * scale + lt;
+        m_run = m_new;
+        psm[c.lane] = p0;
+        psm[32 + c.lane] = p1;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const float sh = __shfl_sync(0xffffffffu, scale, h);
+            acc[h].x *= sh; acc[h].y *= sh; acc[h].z *= sh; acc[h].w *= sh;
+        }
+        __syncwarp();
+        if (in_ring) {
+            const unsigned idx = c.cbase + 2 * ci + 1;
+            sl = idx % kBNumSlots;
+            ring_wait_full_b(c.misc, idx, p.err, (c.seq << 8) | 0x80 | sl);
+            vt = reinterpret_cast<const float4*>(c.ring + sl * kBSlotBytes) + c.lane;
+        }
+#pragma unroll 2
+        for (int key = 0; key < keys_in; ++key) {
+            const float4 vv = vt[key * 32];
+            const float4 pr = *reinterpret_cast<const float4*>(psm + key * HPKB);
+            const float prh[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                acc[h].x = fmaf(prh[h], vv.x, acc[h].x); acc[h].y = fmaf(prh[h], vv.y, acc[h].y);
+                acc[h].z = fmaf(prh[h], vv.z, acc[h].z); acc[h].w = fmaf(prh[h], vv.w, acc[h].w);
+            }
+        }
+        __syncwarp();
+        if (in_ring && c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
+    }
+    c.cbase += 2 * nkc;
+    if (c.lane < HPKB) { wstat[c.warp * 8 + c.lane] = m_run; wstat[c.warp * 8 + 4 + c.lane] = l_run; }
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+        reinterpret_cast<float4*>(racc + ((size_t)c.warp * HPKB + h) * kHeadDim)[c.lane] = acc[h];
+    consumer_sync();
+
+    uint32_t* oparts = self ? p.act_attn : p.act_cattn;
+    const uint32_t fo = flag_l(p.L, c.step, layer);
+    u64* part = (self ? p.ll_sa_part : p.ll_ca_part) + ((size_t)w.pair * nsplit) * (nh * 132);
+#pragma unroll 1
+    for (int i = c.tid; i < nh * kHeadDim; i += kConsumerThreads) {
+        const int h = i >> 7, d = i & 127;
+        float M = -INFINITY;
+#pragma unroll
+        for (int ww = 0; ww < kConsumerWarps; ++ww) M = fmaxf(M, wstat[ww * 8 + h]);
+        float o = 0.f, l = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < kConsumerWarps; ++ww) {
+            const float f = expf(wstat[ww * 8 + h] - M);
+            l = fmaf(wstat[ww * 8 + 4 + h], f, l);
+            o = fmaf(racc[((size_t)ww * HPKB + h) * kHeadDim + d], f, o);
+        }
+        if (w.n_active == 1) {
+            const float val = l > 0.f ? o / l : 0.f;
+            const int k = (head0 + h) * kHeadDim + d;
+            st_act(oparts, R, k, r, pack_act(val, fo));
+            if (!self) st_act(oparts, R, k, r - 1, pack_act(0.f, fo));       // the unconditional row attends nothing
+        } else {
+            u64* pp = part + ((size_t)w.split * nh + h) * 132;
+            ll_st(pp + 4 + d, __float_as_uint(o), c.seq);
+            if (d == 0) { ll_st(pp, __float_as_uint(M), c.seq); ll_st(pp + 1, __float_as_uint(l), c.seq); }
+        }
+    }
+    consumer_sync();
+    if (w.n_active == 1) {
+        if (has_new && c.tid < kHeadDim) __threadfence();
+        return;
+    }
+    // ---- every split combines a slice of the outputs from all splits' partials (fixed order) ----------------------------------
+    const int E = nh * kHeadDim;
+    const int per = (E + w.n_active - 1) / w.n_active;
+    const int e0 = w.split * per, e1 = min(E, e0 + per);
+    if (e0 >= e1) {
+        if (has_new && c.tid < kHeadDim) __threadfence();
+        return;
+    }
+    const int ne = e1 - e0, na = w.n_active;
+    const int h_lo = e0 >> 7, nhh = ((e1 - 1) >> 7) - h_lo + 1;
+    float* cml = cw + ne * na;
+    const int n_items = ne * na + nhh * na * 2;
+    auto item_src = [&](int i) -> const u64* {
+        if (i < ne * na) {
+            const int e = e0 + i / na, s = i - (i / na) * na;
+            return part + ((size_t)s * nh + (e >> 7)) * 132 + 4 + (e & 127);
+        }
+        const int j = i - ne * na;
+        const int hh = j / (na * 2), rem = j - hh * (na * 2);
+        return part + ((size_t)(rem >> 1) * nh + h_lo + hh) * 132 + (rem & 1);
+    };
+#pragma unroll 1
+    for (int i = c.tid; i < n_items; i += kConsumerThreads)
+        cw[i] = __uint_as_float(ll_wait32(item_src(i), c.seq, p.err));
+    consumer_sync();
+    float* cf = cml + nhh * na * 2;
+    if (c.warp < nhh) {
+        const float* ml = cml + (size_t)c.warp * na * 2;
+        const float m = c.lane < na ? ml[2 * c.lane] : -INFINITY;
+        const float l = c.lane < na ? ml[2 * c.lane + 1] : 0.f;
+        const float M = warp_max(m);
+        const float f = c.lane < na ? expf(m - M) : 0.f;
+        const float Ls = warp_sum(l * f);
+        if (c.lane < na) cf[c.warp * na + c.lane] = f;
+        if (c.lane == 0) cf[nhh * na + c.warp] = Ls;
+    }
+    consumer_sync();
+#pragma unroll 1
+    for (int i = c.tid; i < ne; i += kConsumerThreads) {
+        const int e = e0 + i, h = e >> 7, d = e & 127;
+        const float* fw = cf + (size_t)(h - h_lo) * na;
+        float O = 0.f;
+#pragma unroll 1
+        for (int s2 = 0; s2 < na; ++s2) O = fmaf(cw[i * na + s2], fw[s2], O);
+        const float Lsum = cf[nhh * na + (h - h_lo)];
+        const float val = Lsum > 0.f ? O / Lsum : 0.f;
+        const int k = (head0 + h) * kHeadDim + d;
+        st_act(oparts, R, k, r, pack_act(val, fo));
+        if (!self) st_act(oparts, R, k, r - 1, pack_act(0.f, fo));
+    }
+    if (has_new && c.tid < kHeadDim) __threadfence();
+    consumer_sync();
+}
+
+// ---- residual stream entry: embedding gather-sum (dia/layers.py:691-696: x = ((e0 + e1) + e2) ... + e8) ------------------------------
+__device__ void embed_stage_b(BCtx& c) {
+    const BatchParams& p = *c.p;
+    BMisc* misc = c.misc;
+    const int gc = misc->tab.gc[G_SO], g0 = misc->tab.g0[G_SO];
+    if (gc == 0) return;                                     // this CTA owns no residual columns
+    const int tid = c.tid, R = p.R;
+    if (tid < p.U * p.C) {
+        const int u = tid / p.C, ch = tid - u * p.C;
+        int t;
+        if (p.tokens != nullptr && c.step == 0) t = ldcg_i(p.tokens + u * p.C + ch);
+        else if (c.step == 0) t = ldcg_i(p.utt[u].grid + (size_t)(p.utt[u].pos0 - 1) * p.C + ch);
+        else t = (int)ll_wait32(p.ll_tok + u * DIA_B200_MAX_CHANNELS + ch, c.seq - 1, p.err);
+        if (t < 0 || t >= p.V) { *p.err = kErrBadState; t = 0; }
+        misc->toks[u][ch] = t;
+    }
+    consumer_sync();
+    if (tid >= 32) return;
+    const int m = tid;
+    const bool valid = m < gc * 8;
+    const int n = g0 * 8 + m;
+    const uint32_t fo = flag_x(p.L, c.step, 0);
+    const float wnv = valid ? __ldg(p.norms + n) : 0.f;
+#pragma unroll
+    for (int u = 0; u < kMaxUtt; ++u) {
+        if (u < p.U) {
+            float x = 0.f;
+            if (valid) {
+                float e[DIA_B200_MAX_CHANNELS];
+#pragma unroll
+                for (int ch = 0; ch < DIA_B200_MAX_CHANNELS; ++ch)
+                    if (ch < p.C) e[ch] = __ldg(p.emb + ((size_t)ch * p.V + misc->toks[u][ch]) * p.D + n);
+                x = e[0];
+#pragma unroll
+                for (int ch = 1; ch < DIA_B200_MAX_CHANNELS; ++ch)
+                    if (ch < p.C) x += e[ch];
+                c.xres[2 * u] = x;
+                c.xres[2 * u + 1] = x;
+                const uint32_t wd = pack_act(x * wnv, fo);
+                st_act(p.act_x, R, n, 2 * u, wd);
+                st_act(p.act_x, R, n, 2 * u + 1, wd);
+            }
+            float sq = x * x;
+            sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+            if (valid && (m & 7) == 0) {
+                ll_st(p.ll_ssq + (size_t)(g0 + (m >> 3)) * R + 2 * u, __float_as_uint(sq), c.seq);
+                ll_st(p.ll_ssq + (size_t)(g0 + (m >> 3)) * R + 2 * u + 1, __float_as_uint(sq), c.seq);
+            }
+        }
+    }
+}
+
+// ---- sampling: CTA u * C + ch draws channel ch of utterance u; the CTA of channel 0 then runs the body of the reference's
+//      while loop after _decoder_step (dia/model.py:771-807) for its utterance and publishes the next step's tokens -------------------
+__device__ void sample_stage_b(BCtx& c) {
+    const BatchParams& p = *c.p;
+    const int b = blockIdx.x;
+    if (b >= p.U * p.C) return;
+    const int u = b / p.C, ch = b - u * p.C;
+    SampleSmem* sm = reinterpret_cast<SampleSmem*>(c.scratch);
+    const u64* src = p.ll_glog + ((size_t)u * p.C + ch) * p.V;
+    float g[kPerThread];
+    {
+        uint2 wv[kPerThread];
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            const int idx = c.tid + kConsumerThreads * i;
+            wv[i] = idx < p.V ? ll_ld(src + idx) : make_uint2(0xff800000u, c.seq - 1);
+        }
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            if (wv[i].y != c.seq - 1) wv[i].x = ll_wait32(src + c.tid + kConsumerThreads * i, c.seq - 1, p.err);
+            g[i] = __uint_as_float(wv[i].x);
+        }
+    }
+    const UttParams& up = p.utt[u];
+    const int tok = sample_channel_cta(g, p.V, p.temperature, p.top_p, p.top_k, up.seed, p.draw0 + c.step, ch, nullptr, sm, c.tid);
+    u64* preds = p.ll_pred + u * DIA_B200_MAX_CHANNELS;
+    if (c.tid == 0) ll_st(preds + ch, (uint32_t)tok, c.seq);
+    if (ch != 0 || c.warp != 0) return;
+
+    const int lane = c.lane;
+    int pr = 0;
+    if (lane < p.C) {
+        pr = (int)ll_wait32(preds + lane, c.seq, p.err);
+        p.pred_out[u * DIA_B200_MAX_CHANNELS + lane] = pr;
+    }
+    GenState* gs = up.gs;
+    int next_tok = 0;
+    if (gs != nullptr && up.grid != nullptr) {
+        int dec_step = gs->dec_step, finished = gs->finished, eos_detected = gs->eos_detected;
+        int eos_cd = gs->eos_countdown, bos_cd = gs->bos_countdown, steps_run = gs->steps_run;
+        __syncwarp();
+        if (!finished) {
+            if (dec_step >= p.max_tokens - 1) {
+                finished = 1;
+            } else {
+                int dmax = 0;
+#pragma unroll 1
+                for (int i = 0; i < p.C; ++i) dmax = max(dmax, p.delay[i]);
+                const int cur = dec_step + 1;
+                if (cur != up.pos0 + c.step && lane == 0) *p.err = kErrBadState;
+                const int pr0 = __shfl_sync(0xffffffffu, pr, 0);
+                if (!eos_detected && pr0 == p.eos) { eos_detected = 1; eos_cd = dmax; }
+                if (eos_cd > 0) {
+                    const int s = dmax - eos_cd;
+                    if (lane < p.C) {
+                        if (s == p.delay[lane]) pr = p.eos;
+                        else if (s > p.delay[lane] && pr != p.eos) pr = p.pad;
+                    }
+                    eos_cd -= 1;
+                }
+                bos_cd = max(0, bos_cd - 1);
+                if (lane < p.C) {
+                    int* cell = up.grid + (size_t)cur * p.C + lane;
+                    if (bos_cd > 0) {                                  // update_one(apply_mask=True)
+                        const int old = ldcg_i(cell);
+                        if (old == -1) *cell = pr; else pr = old;
+                    } else {
+                        *cell = pr;
+                    }
+                    next_tok = pr;
+                }
+                if (eos_cd == 0) {
+                    finished = 1;                                   // break: dec_step is NOT advanced
+                } else {
+                    if (cur >= p.max_tokens - dmax - 1 && !eos_detected) { eos_detected = 1; eos_cd = dmax; }
+                    dec_step += 1;
+                    if (dec_step >= p.max_tokens - 1) finished = 1;
+                }
+                steps_run += 1;
+            }
+        }
+        if (lane == 0) {
+            gs->dec_step = dec_step; gs->finished = finished; gs->eos_detected = eos_detected;
+            gs->eos_countdown = eos_cd; gs->bos_countdown = bos_cd; gs->steps_run = steps_run;
+        }
+        if (finished) next_tok = 0;                                 // the rows of a finished utterance idle on token 0
+    }
+    if (lane < p.C) ll_st(p.ll_tok + u * DIA_B200_MAX_CHANNELS + lane, (uint32_t)next_tok, c.seq);
+}
+
+}  // namespace
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_batch_step_kernel(const __grid_constant__ BatchParams p) {
+    extern __shared__ unsigned char smem_raw_b[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_b) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem;
+    unsigned char* scratch = smem + kBNumSlots * kBSlotBytes;
+    BMisc* misc = reinterpret_cast<BMisc*>(scratch + kScratchBytes);
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // a launch queued behind the one that finished every utterance is a no-op (uniform: `finished` only changes at the
+    // end of a step, which needs every CTA to have taken part in that step's stages)
+    if (p.with_sample) {
+        bool all_done = true;
+        for (int u = 0; u < p.U; ++u) all_done = all_done && p.utt[u].gs != nullptr && ldcg_i(&p.utt[u].gs->finished) != 0;
+        if (all_done) return;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
+        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], kConsumerWarps); mbar_init(&misc->bempty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], 1); mbar_init(&misc->acc_empty[i], 4); }
+        misc->stages_done = 0;
+        fence_mbar_init();
+    }
+    {
+        const int* src = reinterpret_cast<const int*>(p.cta_tab + blockIdx.x);
+        int* dst = reinterpret_cast<int*>(&misc->tab);
+        for (int i = tid; i < (int)(sizeof(CtaTable) / 4); i += kThreads) dst[i] = src[i];
+    }
+    // the B tiles of rows >= R stay zero for the whole launch
+    for (int i = tid; i < kActStages * kActStageBytes / 16; i += kThreads) reinterpret_cast<uint4*>(scratch)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    if (warp == kMmaWarp) {                                  // one warp allocates (and later frees) the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc->tmem_base)), "r"(32));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
+    if (warp == kProducerWarp) {
+        if (tid == kProducerWarp * 32) producer_loop_b(p, ring, misc);
+    } else if (warp == kMmaWarp) {
+        if (tid == kMmaWarp * 32) mma_loop_b(p, ring, scratch, misc);
+    } else {
+        BCtx c;
+        c.p = &p; c.ring = ring; c.scratch = scratch; c.misc = misc;
+        c.tid = tid; c.warp = warp; c.lane = tid & 31;
+        c.cbase = 0; c.bctr = 0; c.gctr = 0; c.seq = 0; c.step = 0;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) c.xres[r] = 0.f;
+#pragma unroll 1
+        for (int n = 0; n < p.n_steps; ++n) {
+            c.step = n;
+#pragma unroll 1
+            for (int s = 0; s < n_stage; ++s) {
+                int kind, layer;
+                decode_stage_b(s, p.L, kind, layer);
+                c.seq = 1u + (unsigned)(n * S + s);
+                switch (kind) {
+                    case S_EMBED: embed_stage_b(c); break;
+                    case S_SATTN: attn_stage_b<HPKB>(c, layer); break;
+                    case S_CATTN: attn_stage_b<1>(c, layer); break;
+                    case S_SAMPLE: sample_stage_b(c); break;
+                    default: gemm_stage_b(c, gemm_of_kind_b(kind), layer); break;
+                }
+                if (tid == 0) st_release_cta_s32(&misc->stages_done, n * S + s + 1);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(misc->tmem_base), "r"(32));
+    }
+}
+
+cudaError_t launch_batch_kernel(const BatchParams& p, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        e = cudaFuncSetAttribute(dia_batch_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    void* args[] = {const_cast<BatchParams*>(&p)};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dia_batch_step_kernel), dim3(p.G), dim3(kThreads), args,
+                                       kBSmem, st);
+}
+
+// carve the exchange region of the batched kernel (`base` may be null to only size it); returns bytes
+size_t batch_ll_layout(const BatchParams& g, BatchParams* out, unsigned char* base) {
+    size_t off = 0;
+    auto take = [&](void** ptr, size_t bytes) {
+        if (out) *ptr = base ? base + off : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
+    };
+    BatchParams scratch;
+    BatchParams& o = out ? *out : scratch;
+    const size_t R = (size_t)g.R;
+    const size_t nq = (size_t)g.Hq * kHeadDim, nkv = (size_t)g.Hkv * kHeadDim, nc = (size_t)g.Hc * kHeadDim;
+    take(reinterpret_cast<void**>(&o.act_x), (size_t)g.D * R * 4);
+    take(reinterpret_cast<void**>(&o.act_attn), nq * R * 4);
+    take(reinterpret_cast<void**>(&o.act_cattn), nc * R * 4);
+    take(reinterpret_cast<void**>(&o.act_hidden), (size_t)g.F * R * 4);
+    take(reinterpret_cast<void**>(&o.ll_qkv), (nq + 2 * nkv) * R * 8);
+    take(reinterpret_cast<void**>(&o.ll_cq), nc * R * 8);
+    take(reinterpret_cast<void**>(&o.ll_ssq), (size_t)(g.D / 8) * R * 8);
+    take(reinterpret_cast<void**>(&o.ll_sa_part), (size_t)g.G * 4 * 132 * 8);
+    take(reinterpret_cast<void**>(&o.ll_ca_part), (size_t)g.G * 132 * 8);
+    take(reinterpret_cast<void**>(&o.ll_glog), (size_t)g.U * g.C * g.V * 8);
+    take(reinterpret_cast<void**>(&o.ll_pred), (size_t)kMaxUtt * DIA_B200_MAX_CHANNELS * 8);
+    take(reinterpret_cast<void**>(&o.ll_tok), (size_t)kMaxUtt * DIA_B200_MAX_CHANNELS * 8);
+    return off;
+}
+
+}  // namespace dia

@@ -16,7 +16,8 @@ constexpr int kHeadDim = 128;
 constexpr int kConsumerWarps = 8;                       // math warps per CTA
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kProducerWarp = 9;                        // on another scheduler than warp 0
-constexpr int kThreads = (kProducerWarp + 1) * 32;      // 8 math warps, an idle warp, the producer warp (one elected lane issues copies)
+constexpr int kNormWarp = 8;                            // gathers the RMSNorm partial sums while the math warps run MMAs
+constexpr int kThreads = (kProducerWarp + 1) * 32;      // 8 math warps + the norm warp + the producer warp (one elected lane issues copies)
 constexpr int kSlotBytes = 8192;                        // one ring slot = one bulk copy
 constexpr int kNumSlots = 20;                           // 160 KB of weights / KV in flight per SM
 constexpr int kBStageBytes = 4096;                      // per-warp B-fragment staging of one ring slot (16 k-blocks)

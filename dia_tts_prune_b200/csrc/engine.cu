@@ -99,6 +99,17 @@ struct dia_b200_engine {
     int* gen_grid = nullptr;
     int gen_pos = 0, gen_slot = 0;
     long long gen_steps = 0;          // decode steps launched since generate_begin (RNG draw index)
+
+    // batched engine (max_utts > 0): N utterances per launch on the tcgen05 step kernel (batch_kernel.cu)
+    int max_utts = 0;
+    unsigned char* d_bll = nullptr;   // its exchange region
+    size_t bll_bytes = 0;
+    bool utt_bound[kMaxUtt] = {};
+    int utt_text_len[kMaxUtt] = {};
+    int n_active = 0;                 // utterances of the running generate loop
+    dia_b200_gen_params bgp[kMaxUtt] = {};
+    int* bgrid[kMaxUtt] = {};
+    int bpos[kMaxUtt] = {}, bslot[kMaxUtt] = {};
 };
 
 namespace {
@@ -115,7 +126,6 @@ int validate_shape(const dia_b200_shape& s) {
         const int sl = k / 8;
         if (k % 512 || (sl > 256 && sl % 256)) return DIA_B200_EUNSUPPORTED;
     }
-    if (s.d_model > 2048) return DIA_B200_EUNSUPPORTED;                   // sum(x^2) words: one 16-byte load per lane and warp
     if (s.vocab > 5 * kConsumerThreads) return DIA_B200_EUNSUPPORTED;     // sampler: <= 5 entries of a channel per thread
     return DIA_B200_OK;
 }
@@ -195,7 +205,22 @@ const char* dia_b200_error_string(int code) {
 const char* dia_b200_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
 int64_t dia_b200_launch_count(void) { return g_launches.load(); }
 
+static int create_engine(const dia_b200_shape* shape, int device, int n_ctas, int max_utts, dia_b200_engine** out);
+
 int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, dia_b200_engine** out) {
+    return create_engine(shape, device, n_ctas, 0, out);
+}
+
+int dia_b200_engine_create_batched(const dia_b200_shape* shape, int device, int n_ctas, int max_utterances,
+                                   dia_b200_engine** out) {
+    if (max_utterances < 1 || max_utterances > kMaxUtt) return DIA_B200_EINVAL;
+    if (shape && shape->sparse24) return DIA_B200_EUNSUPPORTED;          // 2:4 slabs exist for the single-utterance kernel only
+    return create_engine(shape, device, n_ctas, max_utterances, out);
+}
+
+int dia_b200_engine_max_utterances(const dia_b200_engine* e) { return e ? e->max_utts : DIA_B200_EINVAL; }
+
+static int create_engine(const dia_b200_shape* shape, int device, int n_ctas, int max_utts, dia_b200_engine** out) {
     if (!shape || !out) return DIA_B200_EINVAL;
     int rc = validate_shape(*shape);
     if (rc) return rc;
@@ -211,6 +236,8 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     if (!e) return DIA_B200_ENOMEM;
     e->shape = *shape;
     e->device = device;
+    e->max_utts = max_utts;
+    const bool batch = max_utts > 0;
     e->G = n_ctas > 0 ? n_ctas : prop.multiProcessorCount;
     if (e->G > prop.multiProcessorCount) { delete e; return DIA_B200_EINVAL; }   // 1 CTA / SM must be co-resident
     const dia_b200_shape& s = e->shape;
@@ -220,7 +247,12 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     e->Vpad = (s.vocab + 7) & ~7;
     e->sa_nsplit = G / (2 * s.kv_heads);
     e->ca_nsplit = G / s.cross_heads;
-    {
+    if (batch) {
+        // (row, kv head) pairs x key splits / (utterance, cross head) pairs x key splits over the CTAs
+        if (G < 2 * max_utts * s.kv_heads || G < max_utts * s.cross_heads) { delete e; return DIA_B200_EINVAL; }
+        e->sa_nsplit = G / (2 * max_utts * s.kv_heads);
+        e->ca_nsplit = G / (max_utts * s.cross_heads);
+    } else {
         int per = (s.max_audio_len + e->sa_nsplit - 1) / e->sa_nsplit;
         int perc = (s.max_text_len + e->ca_nsplit - 1) / e->ca_nsplit;
         if (((per + 15) & ~15) > 1024 || ((perc + 15) & ~15) > 1024) { delete e; return DIA_B200_EUNSUPPORTED; }
@@ -284,7 +316,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
             e->tab[c].gc[t] = gc;
             for (int i = 0; i < gc; ++i) { e->owner[t][g0 + i] = c; e->local[t][g0 + i] = i; }
             g0 += gc;
-            if (t != G_LOGITS) load[c] += (long long)gemm_slab_bytes(gc, kd[t], sp);
+            if (t != G_LOGITS) load[c] += (long long)(batch ? bslab_bytes(gc, kd[t]) : gemm_slab_bytes(gc, kd[t], sp));
         }
     }
     for (int t = 0; t < G_COUNT; ++t) {
@@ -292,7 +324,7 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
         for (int c = 0; c < G; ++c) mx = std::max(mx, (e->tab[c].gc[t] + 1) / 2);
         e->tclass[t] = mx <= 1 ? 1 : mx <= 2 ? 2 : mx <= 4 ? 4 : 8;
     }
-    for (int t = 0; t < G_COUNT; ++t) {
+    for (int t = 0; t < G_COUNT && !batch; ++t) {
         const int need = e->tclass[t] == 1 ? 64 : 32;       // k-blocks in flight per MMA group; slots start on even k-blocks
         for (int c = 0; c < G; ++c)
             if (e->tab[c].gc[t] > 0 && gemm_slot_rows(e->tab[c].gc[t], e->Kdim[t], sp) % need) { delete e; return DIA_B200_EUNSUPPORTED; }
@@ -303,15 +335,17 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
             e->n_res = c + 1;
         }
     }
+    if (e->n_res > 160) { delete e; return DIA_B200_EUNSUPPORTED; }          // sum(x^2) partials: 5 per lane of one warp
     unsigned long long off = 0;
     for (int c = 0; c < G; ++c) {
         CtaTable& t = e->tab[c];
         unsigned o = 0;
-        for (int g = 0; g < G_LOGITS; ++g) { t.slab_off[g] = o; o += (unsigned)gemm_slab_bytes(t.gc[g], kd[g], sp); }
+        auto slab_bytes = [&](int g) { return batch ? bslab_bytes(t.gc[g], kd[g]) : gemm_slab_bytes(t.gc[g], kd[g], sp); };
+        for (int g = 0; g < G_LOGITS; ++g) { t.slab_off[g] = o; o += (unsigned)slab_bytes(g); }
         t.layer_bytes = o;
         t.slab_off[G_LOGITS] = 0;
         t.logits_off = (unsigned long long)o * s.n_layer;
-        const unsigned long long total = t.logits_off + gemm_slab_bytes(t.gc[G_LOGITS], kd[G_LOGITS], sp);
+        const unsigned long long total = t.logits_off + slab_bytes(G_LOGITS);
         t.stream_base = off;
         e->weight_bytes += (long long)total;
         off += (total + 255ull) & ~255ull;
@@ -338,9 +372,18 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
     }
     ALLOC(e->d_emb, sizeof(float) * (size_t)s.channels * s.vocab * D);
     ALLOC(e->d_norms, sizeof(float) * ((size_t)s.n_layer * 3 + 1) * D);
-    ALLOC(e->d_ptrs, sizeof(float*) * 4 * s.n_layer);
+    const int n_utt = batch ? kMaxUtt : 1;
+    ALLOC(e->d_ptrs, sizeof(float*) * 4 * s.n_layer * n_utt);
     ALLOC(e->d_x, sizeof(float2) * D);
-    ALLOC(e->d_logits, sizeof(float) * 2 * s.channels * s.vocab);
+    ALLOC(e->d_logits, sizeof(float) * 2 * n_utt * s.channels * s.vocab);
+    if (batch) {
+        BatchParams geom;
+        std::memset(&geom, 0, sizeof(geom));
+        geom.D = s.d_model; geom.F = s.n_hidden; geom.Hq = s.q_heads; geom.Hkv = s.kv_heads; geom.Hc = s.cross_heads;
+        geom.C = s.channels; geom.V = s.vocab; geom.G = G; geom.U = max_utts; geom.R = 2 * max_utts;
+        e->bll_bytes = batch_ll_layout(geom, nullptr, nullptr);
+        ALLOC(e->d_bll, e->bll_bytes);
+    }
     {
         StepParams geom;
         std::memset(&geom, 0, sizeof(geom));
@@ -349,14 +392,14 @@ int dia_b200_engine_create(const dia_b200_shape* shape, int device, int n_ctas, 
         e->ll_bytes = ll_layout(geom, nullptr, nullptr);
     }
     ALLOC(e->d_ll, e->ll_bytes);
-    ALLOC(e->d_pred, sizeof(int) * DIA_B200_MAX_CHANNELS);
-    ALLOC(e->d_tokens, sizeof(int) * 2 * DIA_B200_MAX_CHANNELS);
-    ALLOC(e->d_gs, sizeof(GenState));
+    ALLOC(e->d_pred, sizeof(int) * DIA_B200_MAX_CHANNELS * n_utt);
+    ALLOC(e->d_tokens, sizeof(int) * 2 * DIA_B200_MAX_CHANNELS * n_utt);
+    ALLOC(e->d_gs, sizeof(GenState) * n_utt);
     ALLOC(e->d_timing, sizeof(long long) * 16 * kTimingSteps * (8 * s.n_layer + 3));
     ALLOC(e->d_cta_timing, sizeof(unsigned long long) * G * (8 * s.n_layer + 3));
 #undef ALLOC
-    if (cudaMallocHost(reinterpret_cast<void**>(&e->h_ptrs), sizeof(float*) * 4 * s.n_layer) != cudaSuccess ||
-        cudaMallocHost(reinterpret_cast<void**>(&e->h_gs), sizeof(GenState)) != cudaSuccess ||
+    if (cudaMallocHost(reinterpret_cast<void**>(&e->h_ptrs), sizeof(float*) * 4 * s.n_layer * n_utt) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&e->h_gs), sizeof(GenState) * n_utt) != cudaSuccess ||
         cudaHostAlloc(reinterpret_cast<void**>(&e->h_err), sizeof(int) * kErrWords, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->d_err), e->h_err, 0) != cudaSuccess) {
         dia_b200_engine_destroy(e);
@@ -377,7 +420,7 @@ int dia_b200_engine_destroy(dia_b200_engine* e) {
     DeviceGuard _guard(e->device);
     cudaDeviceSynchronize();
     void* dev[] = {e->d_wstream, e->d_tab, e->d_emb, e->d_norms, e->d_rope_sin, e->d_rope_cos, e->d_ptrs, e->d_x,
-                   e->d_logits, e->d_ll, e->d_pred, e->d_tokens, e->d_gs, e->d_timing, e->d_cta_timing};
+                   e->d_logits, e->d_ll, e->d_pred, e->d_tokens, e->d_gs, e->d_timing, e->d_cta_timing, e->d_bll};
     for (void* p : dev) if (p) cudaFree(p);
     for (int t = 0; t < G_COUNT; ++t) { if (e->d_owner[t]) cudaFree(e->d_owner[t]); if (e->d_local[t]) cudaFree(e->d_local[t]); }
     if (e->h_ptrs) cudaFreeHost(e->h_ptrs);
@@ -411,6 +454,7 @@ int dia_b200_load_decoder_weights(dia_b200_engine* e, const void* const* tensors
         CK(cudaMemsetAsync(e->d_wstream, 0, e->stream_bytes, st));     // metadata nibbles are OR-ed in
         CK(cudaMemsetAsync(e->d_pred, 0, sizeof(int), st));
     }
+    a.batch_format = e->max_utts > 0 ? 1 : 0;
     a.src_bf16 = dense_dtype; a.Hq = s.q_heads; a.Hkv = s.kv_heads; a.F = s.n_hidden; a.V = s.vocab; a.Vpad = e->Vpad;
     a.C = s.channels; a.tab = e->d_tab; a.wstream = e->d_wstream;
     auto repack = [&](int gemm, int layer, const void* s0, const void* s1, const void* s2, int N) -> int {
@@ -469,6 +513,7 @@ int dia_b200_set_rope_table(dia_b200_engine* e, const float* sin_host, const flo
 int dia_b200_bind_caches(dia_b200_engine* e, void* const* self_k, void* const* self_v, const void* const* cross_k,
                          const void* const* cross_v, int n_layer, int text_len, void* stream) {
     if (!e || !self_k || !self_v || !cross_k || !cross_v) return DIA_B200_EINVAL;
+    if (e->max_utts > 0) return DIA_B200_ESTATE;
     if (n_layer != e->shape.n_layer || text_len < 0 || text_len > e->shape.max_text_len) return DIA_B200_EINVAL;
     ON_DEVICE(e->device);
     const int L = n_layer;
@@ -493,6 +538,7 @@ int dia_b200_bind_caches(dia_b200_engine* e, void* const* self_k, void* const* s
 
 static int ready(const dia_b200_engine* e, bool need_caches) {
     if (!e) return DIA_B200_EINVAL;
+    if (e->max_utts > 0) return DIA_B200_ESTATE;              // a batched engine: use the dia_b200_batch_* entry points
     if (!e->weights_loaded || !e->rope_set) return DIA_B200_ESTATE;
     if (need_caches && !e->caches_bound) return DIA_B200_ESTATE;
     return DIA_B200_OK;
@@ -637,6 +683,192 @@ int dia_b200_generate_status(dia_b200_engine* e, dia_b200_gen_status* out, void*
     out->steps_run = e->h_gs->steps_run;
     out->device_error = e->h_err[0];
     out->reserved = 0;
+    return DIA_B200_OK;
+}
+
+// ---- batched engine: N utterances per launch (batch_kernel.cu) ---------------------------------------------------------------
+namespace {
+
+int batch_ready(const dia_b200_engine* e, int n_utts) {
+    if (!e) return DIA_B200_EINVAL;
+    if (e->max_utts <= 0 || !e->weights_loaded || !e->rope_set) return DIA_B200_ESTATE;
+    if (n_utts < 1 || n_utts > e->max_utts) return DIA_B200_EINVAL;
+    for (int u = 0; u < n_utts; ++u) if (!e->utt_bound[u]) return DIA_B200_ESTATE;
+    return DIA_B200_OK;
+}
+
+void fill_batch_params(const dia_b200_engine* e, BatchParams& p, int n_utts) {
+    std::memset(&p, 0, sizeof(p));
+    const dia_b200_shape& s = e->shape;
+    p.L = s.n_layer; p.D = s.d_model; p.F = s.n_hidden; p.Hq = s.q_heads; p.Hkv = s.kv_heads; p.Hc = s.cross_heads;
+    p.C = s.channels; p.V = s.vocab; p.Vpad = e->Vpad; p.Lmax = s.max_audio_len; p.Smax = s.max_text_len;
+    for (int i = 0; i < G_COUNT; ++i) p.Kdim[i] = e->Kdim[i];
+    p.eps = s.norm_eps; p.G = e->G; p.U = n_utts; p.R = 2 * n_utts;
+    // the splits are sized for the utterances of THIS launch (fewer utterances: more CTAs per pair)
+    p.sa_nsplit = std::max(1, e->G / (2 * n_utts * s.kv_heads));
+    p.ca_nsplit = std::max(1, e->G / (n_utts * s.cross_heads));
+    p.wstream = e->d_wstream; p.cta_tab = e->d_tab; p.emb = e->d_emb; p.norms = e->d_norms;
+    p.rope_sin = e->d_rope_sin; p.rope_cos = e->d_rope_cos; p.n_pos = e->n_pos;
+    const int UL = kMaxUtt * s.n_layer;
+    p.self_k = e->d_ptrs; p.self_v = e->d_ptrs + UL;
+    p.cross_k = const_cast<const float* const*>(e->d_ptrs + 2 * UL);
+    p.cross_v = const_cast<const float* const*>(e->d_ptrs + 3 * UL);
+    for (int u = 0; u < n_utts; ++u) p.utt[u].text_len = e->utt_text_len[u];
+    BatchParams geom = p;
+    geom.U = e->max_utts; geom.R = 2 * e->max_utts;            // one carve-up for every launch width
+    batch_ll_layout(geom, &p, e->d_bll);
+    p.err = e->d_err;
+    p.n_steps = 1;
+    p.cfg_scale = 3.0f; p.temperature = 0.0f; p.top_p = 0.95f; p.top_k = 35; p.max_tokens = s.max_audio_len;
+    p.eos = s.eos_value; p.pad = s.pad_value; p.bos = s.bos_value;
+    for (int i = 0; i < DIA_B200_MAX_CHANNELS; ++i) p.delay[i] = s.delay_pattern[i];
+    p.pred_out = e->d_pred;
+}
+
+int run_batch(dia_b200_engine* e, BatchParams& p, cudaStream_t st) {
+    // activation flags are one generation bit and the 32-bit sequence flags restart at 1: the region is zeroed per launch
+    CK(cudaMemsetAsync(e->d_bll, 0, e->bll_bytes, st));
+    CK(launch_batch_kernel(p, st));
+    g_launches++;
+    return DIA_B200_OK;
+}
+
+}  // namespace
+
+int dia_b200_batch_bind_caches(dia_b200_engine* e, int utterance, void* const* self_k, void* const* self_v,
+                               const void* const* cross_k, const void* const* cross_v, int n_layer, int text_len,
+                               void* stream) {
+    if (!e || !self_k || !self_v || !cross_k || !cross_v) return DIA_B200_EINVAL;
+    if (e->max_utts <= 0) return DIA_B200_ESTATE;
+    if (utterance < 0 || utterance >= e->max_utts || n_layer != e->shape.n_layer || text_len < 0 ||
+        text_len > e->shape.max_text_len)
+        return DIA_B200_EINVAL;
+    ON_DEVICE(e->device);
+    const int L = n_layer, UL = kMaxUtt * L;
+    CK(cudaStreamSynchronize(S(stream)));                     // the pinned staging buffer is reused
+    for (int l = 0; l < L; ++l) {
+        if (!self_k[l] || !self_v[l] || !cross_k[l] || !cross_v[l]) return DIA_B200_EINVAL;
+        if ((reinterpret_cast<uintptr_t>(self_k[l]) | reinterpret_cast<uintptr_t>(self_v[l]) |
+             reinterpret_cast<uintptr_t>(cross_k[l]) | reinterpret_cast<uintptr_t>(cross_v[l])) & 15)
+            return DIA_B200_EINVAL;
+        e->h_ptrs[utterance * L + l] = static_cast<float*>(self_k[l]);
+        e->h_ptrs[UL + utterance * L + l] = static_cast<float*>(self_v[l]);
+        e->h_ptrs[2 * UL + utterance * L + l] = const_cast<float*>(static_cast<const float*>(cross_k[l]));
+        e->h_ptrs[3 * UL + utterance * L + l] = const_cast<float*>(static_cast<const float*>(cross_v[l]));
+    }
+    for (int a = 0; a < 4; ++a)
+        CK(cudaMemcpyAsync(e->d_ptrs + a * UL + utterance * L, e->h_ptrs + a * UL + utterance * L, sizeof(float*) * L,
+                           cudaMemcpyHostToDevice, S(stream)));
+    e->utt_text_len[utterance] = text_len;
+    e->utt_bound[utterance] = true;
+    e->gen_active = false;
+    return DIA_B200_OK;
+}
+
+int dia_b200_batch_decode_step(dia_b200_engine* e, int n_utterances, const int32_t* tokens, const int32_t* pos_host,
+                               const int32_t* slot_host, float* logits, void* stream) {
+    int rc = batch_ready(e, n_utterances);
+    if (rc) return rc;
+    if (!tokens || !pos_host || !slot_host || !logits) return DIA_B200_EINVAL;
+    for (int u = 0; u < n_utterances; ++u)
+        if (pos_host[u] < 0 || slot_host[u] < 0 || slot_host[u] >= e->shape.max_audio_len) return DIA_B200_EINVAL;
+    ON_DEVICE(e->device);
+    BatchParams p;
+    fill_batch_params(e, p, n_utterances);
+    for (int u = 0; u < n_utterances; ++u) { p.utt[u].pos0 = pos_host[u]; p.utt[u].slot0 = slot_host[u]; }
+    p.tokens = tokens;
+    p.with_sample = 0;
+    p.logits = logits;
+    return run_batch(e, p, S(stream));
+}
+
+int dia_b200_batch_generate_begin(dia_b200_engine* e, int n_utterances, int32_t* const* grids, const dia_b200_gen_params* gp,
+                                  void* stream) {
+    int rc = batch_ready(e, n_utterances);
+    if (rc) return rc;
+    if (!grids || !gp) return DIA_B200_EINVAL;
+    for (int u = 0; u < n_utterances; ++u) {
+        if (!grids[u] || gp[u].prefill_step < 1 || gp[u].max_tokens < 1 || gp[u].max_tokens > e->shape.max_audio_len ||
+            gp[u].first_slot < 0 || gp[u].first_slot >= e->shape.max_audio_len)
+            return DIA_B200_EINVAL;
+        // one sampling configuration per launch (the rows share the sampler code path); seeds and prompts are per utterance
+        if (gp[u].cfg_scale != gp[0].cfg_scale || gp[u].temperature != gp[0].temperature || gp[u].top_p != gp[0].top_p ||
+            gp[u].top_k != gp[0].top_k || gp[u].max_tokens != gp[0].max_tokens)
+            return DIA_B200_EINVAL;
+    }
+    rc = check_sampling_supported(gp[0].temperature, gp[0].top_k);
+    if (rc) return rc;
+    ON_DEVICE(e->device);
+    CK(cudaStreamSynchronize(S(stream)));
+    int dmax = 0;
+    for (int c = 0; c < e->shape.channels; ++c) dmax = std::max(dmax, (int)e->shape.delay_pattern[c]);
+    std::memset(e->h_gs, 0, sizeof(GenState) * kMaxUtt);
+    for (int u = 0; u < n_utterances; ++u) {
+        GenState& g = e->h_gs[u];
+        g.dec_step = gp[u].prefill_step - 1;
+        g.bos_countdown = dmax;
+        g.eos_countdown = -1;
+        g.finished = (g.dec_step >= gp[u].max_tokens - 1) ? 1 : 0;
+        e->bgp[u] = gp[u];
+        e->bgrid[u] = grids[u];
+        e->bpos[u] = gp[u].prefill_step;
+        e->bslot[u] = gp[u].first_slot;
+    }
+    CK(cudaMemcpyAsync(e->d_gs, e->h_gs, sizeof(GenState) * kMaxUtt, cudaMemcpyHostToDevice, S(stream)));
+    std::memset(e->h_err, 0, sizeof(int) * kErrWords);
+    e->n_active = n_utterances;
+    e->gen_steps = 0;
+    e->gen_active = true;
+    return DIA_B200_OK;
+}
+
+int dia_b200_batch_generate_steps(dia_b200_engine* e, int n_steps, void* stream) {
+    if (!e) return DIA_B200_EINVAL;
+    if (e->max_utts <= 0 || !e->gen_active) return DIA_B200_ESTATE;
+    int rc = batch_ready(e, e->n_active);
+    if (rc) return rc;
+    if (n_steps < 0) return DIA_B200_EINVAL;
+    for (int u = 0; u < e->n_active; ++u) {                  // never run past a cache / grid
+        n_steps = std::min(n_steps, e->shape.max_audio_len - e->bslot[u]);
+        n_steps = std::min(n_steps, e->shape.max_audio_len - e->bpos[u]);
+    }
+    if (n_steps <= 0) return DIA_B200_OK;
+    ON_DEVICE(e->device);
+    const int max_per_launch = 65534 / (8 * e->shape.n_layer + 3);
+    while (n_steps > 0) {
+        const int n = std::min(n_steps, max_per_launch);
+        BatchParams p;
+        fill_batch_params(e, p, e->n_active);
+        p.n_steps = n;
+        p.with_sample = 1;
+        for (int u = 0; u < e->n_active; ++u) {
+            p.utt[u].pos0 = e->bpos[u]; p.utt[u].slot0 = e->bslot[u];
+            p.utt[u].grid = e->bgrid[u]; p.utt[u].gs = e->d_gs + u; p.utt[u].seed = e->bgp[u].seed;
+        }
+        p.cfg_scale = e->bgp[0].cfg_scale; p.temperature = e->bgp[0].temperature; p.top_p = e->bgp[0].top_p;
+        p.top_k = e->bgp[0].top_k; p.max_tokens = e->bgp[0].max_tokens; p.draw0 = (unsigned long long)e->gen_steps;
+        rc = run_batch(e, p, S(stream));
+        if (rc) return rc;
+        for (int u = 0; u < e->n_active; ++u) { e->bpos[u] += n; e->bslot[u] += n; }
+        e->gen_steps += n;
+        n_steps -= n;
+    }
+    return DIA_B200_OK;
+}
+
+int dia_b200_batch_generate_status(dia_b200_engine* e, dia_b200_gen_status* out, void* stream) {
+    if (!e || !out) return DIA_B200_EINVAL;
+    if (e->max_utts <= 0 || e->n_active <= 0) return DIA_B200_ESTATE;
+    ON_DEVICE(e->device);
+    CK(cudaMemcpyAsync(e->h_gs, e->d_gs, sizeof(GenState) * kMaxUtt, cudaMemcpyDeviceToHost, S(stream)));
+    CK(cudaStreamSynchronize(S(stream)));
+    for (int u = 0; u < e->n_active; ++u) {
+        const GenState& g = e->h_gs[u];
+        out[u].dec_step = g.dec_step; out[u].finished = g.finished; out[u].eos_detected = g.eos_detected;
+        out[u].eos_countdown = g.eos_countdown; out[u].bos_countdown = g.bos_countdown; out[u].steps_run = g.steps_run;
+        out[u].device_error = e->h_err[0];
+        out[u].reserved = 0;
+    }
     return DIA_B200_OK;
 }
 

@@ -116,7 +116,7 @@ struct StepParams {
     unsigned long long* ll_hidden;     // silu(gate) * up                                           [F]
     unsigned long long* ll_qkv;        // [(Hq + 2 Hkv) * 128][2]
     unsigned long long* ll_cq;         // [Hc * 128][2]
-    unsigned long long* ll_ssq;        // [D/8][2] sum of x^2 per 8-column group and batch row (for the consumer's RMSNorm)
+    unsigned long long* ll_ssq;        // [G][2] per-CTA partial sums of x^2 (for the consumer's RMSNorm)
     unsigned long long* ll_sa_part;    // [2*Hkv][sa_nsplit][4][132] split-KV partials (m, l, -, -, o[128])
     unsigned long long* ll_ca_part;    // [Hc][ca_nsplit][132]
     unsigned long long* ll_glog;       // [C][V] guided + masked logits
@@ -144,6 +144,79 @@ struct StepParams {
     unsigned long long* cta_timing;    // optional [S][G] globaltimer at the end of each stage of step 1, per CTA
 };
 
+// ---- batched engine (N utterances per GPU, batch_kernel.cu) ---------------------------------------------------------
+constexpr int kMaxUtt = 8;             // utterances per launch: 16 batch rows = N of the tcgen05 MMA
+
+// Batched weight stream: per CTA and GEMM the slab [K][gc*8 columns] is stored as K / 64 chunks, each the tile
+// tcgen05.mma reads as its M operand: [gc*8 rows = output columns][64 k] bf16, K-major, rows of 128 bytes whose 16-byte
+// units are XOR-swizzled with (row % 8) (SWIZZLE_128B).  A ring slot (16 KB) holds `bslot_chunks` consecutive chunks.
+__host__ __device__ inline int bchunk_bytes(int gc) { return gc * 8 * 128; }
+__host__ __device__ inline int bslot_chunks(int gc, int K) {
+    int n = 1;
+    while (n * 2 * bchunk_bytes(gc) <= 16384 && n * 2 <= 8 && (K / 64) % (n * 2) == 0) n *= 2;
+    return n;
+}
+__host__ __device__ inline unsigned long long bslab_bytes(int gc, int K) {
+    return (unsigned long long)(K / 64) * (unsigned long long)bchunk_bytes(gc);
+}
+
+struct UttParams {                     // one utterance of a batched launch
+    int text_len;                      // valid keys of the conditional row of its cross caches
+    int pos0, slot0;                   // RoPE position / self-cache slot of the first step of the launch
+    int reserved;
+    int* grid;                         // [Lmax][C] token grid (generate mode) or nullptr
+    GenState* gs;
+    unsigned long long seed;
+};
+
+struct BatchParams {
+    int L, D, F, Hq, Hkv, Hc, C, V, Vpad, Lmax, Smax;
+    int Kdim[G_COUNT];
+    float eps;
+    int G, U, R;                       // CTAs, utterances, batch rows (2 U: row 2u = unconditional, 2u + 1 = conditional)
+    int sa_nsplit, ca_nsplit;
+    const unsigned char* wstream;
+    const CtaTable* cta_tab;
+    const float* emb;
+    const float* norms;
+    const float* rope_sin;
+    const float* rope_cos;
+    int n_pos;
+    float* const* self_k;              // device arrays of U * L pointers ([u * L + layer])
+    float* const* self_v;
+    const float* const* cross_k;
+    const float* const* cross_v;
+    UttParams utt[kMaxUtt];
+    float* logits;                     // [R][C][V] raw logits of the last executed step (optional)
+    // exchange buffers (zeroed before every launch).  act_*: packed (bf16 hi | bf16 lo, 1-bit generation flag) words
+    // [k / 64][R][64]; the rest are (fp32, flag32) words as in the single-utterance kernel
+    unsigned int* act_x;
+    unsigned int* act_attn;
+    unsigned int* act_cattn;
+    unsigned int* act_hidden;
+    unsigned long long* ll_qkv;        // [(Hq + 2 Hkv) * 128][R]
+    unsigned long long* ll_cq;         // [Hc * 128][R]
+    unsigned long long* ll_ssq;        // [D / 8][R]
+    unsigned long long* ll_sa_part;
+    unsigned long long* ll_ca_part;
+    unsigned long long* ll_glog;       // [U][C][V]
+    unsigned long long* ll_pred;       // [kMaxUtt][16]
+    unsigned long long* ll_tok;        // [kMaxUtt][16]
+    int* err;
+    int n_steps;
+    int with_sample;                   // 1: embed .. sample (generate mode); 0: embed .. logits (operator boundary)
+    const int* tokens;                 // [U][C] input tokens of the first step (operator boundary) or nullptr
+    float cfg_scale, temperature, top_p;
+    int top_k, max_tokens;
+    unsigned long long draw0;
+    int eos, pad, bos;
+    int delay[DIA_B200_MAX_CHANNELS];
+    int* pred_out;                     // [kMaxUtt][16]
+};
+
+cudaError_t launch_batch_kernel(const BatchParams& p, cudaStream_t st);
+size_t batch_ll_layout(const BatchParams& geom, BatchParams* out, unsigned char* base);
+
 // ---- launchers (each returns the cudaError_t of the launch) --------------------------------
 cudaError_t launch_step_kernel(const StepParams& p, bool cooperative, cudaStream_t st);
 int step_kernel_smem_bytes();
@@ -162,6 +235,7 @@ struct RepackArgs {
     const int* local;       // [n_groups] index of the group inside its CTA's slab
     const CtaTable* tab;
     unsigned char* wstream;
+    int batch_format;       // write the batched engine's K-major swizzled chunks (bchunk_bytes) instead of [k][gc][8] slabs
     int sparse;             // write 2:4-compressed slabs (the stream must be zeroed first: metadata is OR-ed in)
     int* violations;        // sparse: counts 4-row groups with more than 2 non-zeros (the model is not 2:4)
 };

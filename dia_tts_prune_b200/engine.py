@@ -270,6 +270,108 @@ class DecodeEngine:
         return out
 
 
+class BatchDecodeEngine:
+    """N utterances per launch (``dia_b200_engine_create_batched``): 2N batch rows share one pass over the weights on the
+    tcgen05 step kernel.  Each utterance binds its own ``KVCache`` lists, token grid and text length."""
+
+    def __init__(self, config: DiaConfig, device: torch.device | str | int = "cuda", max_utterances: int = _lib.MAX_UTTERANCES,
+                 n_ctas: int = 0, n_hidden: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dia_tts_prune_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.config = config
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        d, dt = config.model.decoder, config.data
+        sh = _lib.Shape()
+        self.n_hidden = int(n_hidden) if n_hidden else d.n_hidden
+        sh.n_layer, sh.d_model, sh.n_hidden = d.n_layer, d.n_embd, self.n_hidden
+        sh.q_heads, sh.kv_heads, sh.cross_heads = d.gqa_query_heads, d.kv_heads, d.cross_query_heads
+        sh.channels, sh.vocab = dt.channels, config.model.tgt_vocab_size
+        sh.max_audio_len, sh.max_text_len = dt.audio_length, dt.text_length
+        sh.eos_value, sh.pad_value, sh.bos_value = dt.audio_eos_value, dt.audio_pad_value, dt.audio_bos_value
+        for i, v in enumerate(dt.delay_pattern):
+            sh.delay_pattern[i] = v
+        sh.norm_eps = config.model.normalization_layer_epsilon
+        sh.sparse24 = 0
+        self.sparse24 = False
+        self._h = C.c_void_p()
+        _lib.check(self.lib.dia_b200_engine_create_batched(C.byref(sh), self.device.index, n_ctas, int(max_utterances),
+                                                           C.byref(self._h)), "engine_create_batched")
+        self.max_utterances = int(max_utterances)
+        self.C, self.V, self.D, self.L = dt.channels, config.model.tgt_vocab_size, d.n_embd, d.n_layer
+        self.n_ctas = self.lib.dia_b200_engine_num_ctas(self._h)
+        self.weight_stream_bytes = int(self.lib.dia_b200_engine_weight_stream_bytes(self._h))
+        sin, cos = rope_tables(config, max(dt.audio_length, dt.text_length) + 1)
+        _lib.check(self.lib.dia_b200_set_rope_table(self._h, _ptr(sin), _ptr(cos), sin.shape[0]), "set_rope_table")
+        self._keep: dict = {}
+        self.n_active = 0
+
+    close = DecodeEngine.close
+    __del__ = DecodeEngine.__del__
+    load_weights = DecodeEngine.load_weights
+    last_device_error = DecodeEngine.last_device_error
+
+    def bind(self, utterance: int, self_caches, cross_caches, text_len: int) -> None:
+        L = self.L
+        d = self.config.model.decoder
+        keep, ptrs = [], [[], [], [], []]
+        for sc, cc in zip(self_caches, cross_caches):
+            for t in (sc.k, sc.v):
+                if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device or \
+                        tuple(t.shape) != (2, d.kv_heads, self.config.data.audio_length, 128):
+                    raise ValueError("self KV cache tensors must be contiguous float32 [2, kv_heads, audio_length, 128] CUDA tensors")
+            ck, cv = cc.k, cc.v
+            if ck.dtype != torch.float32 or not ck.is_contiguous():
+                ck = ck.to(torch.float32).contiguous()
+            if cv.dtype != torch.float32 or not cv.is_contiguous():
+                cv = cv.to(torch.float32).contiguous()
+            if tuple(ck.shape) != (2, d.cross_query_heads, self.config.data.text_length, 128):
+                raise ValueError(f"cross KV cache shape {tuple(ck.shape)} unexpected")
+            keep += [sc.k, sc.v, ck, cv]
+            for lst, t in zip(ptrs, (sc.k, sc.v, ck, cv)):
+                lst.append(t.data_ptr())
+        arrs = [(C.c_void_p * L)(*p) for p in ptrs]
+        _lib.check(self.lib.dia_b200_batch_bind_caches(self._h, int(utterance), arrs[0], arrs[1], arrs[2], arrs[3], L,
+                                                       int(text_len), _stream(self.device)), "batch_bind_caches")
+        self._keep[int(utterance)] = keep
+
+    def decode_step(self, tokens_UxC: torch.Tensor, pos: list[int], slot: list[int]) -> torch.Tensor:
+        """``Decoder.decode_step`` for U utterances: int32 [U, C] -> float32 logits [2U, C, V]."""
+        tok = tokens_UxC.to(device=self.device, dtype=torch.int32).contiguous()
+        U = tok.shape[0]
+        out = torch.empty((2 * U, self.C, self.V), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dia_b200_batch_decode_step(self._h, U, _ptr(tok), (C.c_int32 * U)(*[int(x) for x in pos]),
+                                                       (C.c_int32 * U)(*[int(x) for x in slot]), _ptr(out),
+                                                       _stream(self.device)), "batch_decode_step")
+        return out
+
+    def generate_begin(self, grids: list[torch.Tensor], prefill_steps: list[int], first_slots: list[int], max_tokens: int,
+                       cfg_scale: float, temperature: float, top_p: float, top_k: int | None, seeds: list[int]) -> None:
+        U = len(grids)
+        for g in grids:
+            if g.dtype != torch.int32 or not g.is_contiguous() or g.device != self.device:
+                raise ValueError("token grids must be contiguous int32 CUDA tensors")
+        gps = (_lib.GenParams * U)(*[_lib.GenParams(float(cfg_scale), float(temperature), float(top_p), int(top_k or 0),
+                                                    int(max_tokens), int(prefill_steps[u]), int(first_slots[u]), 0,
+                                                    int(seeds[u]) & (2 ** 64 - 1)) for u in range(U)])
+        ptrs = (C.c_void_p * U)(*[g.data_ptr() for g in grids])
+        _lib.check(self.lib.dia_b200_batch_generate_begin(self._h, U, ptrs, gps, _stream(self.device)), "batch_generate_begin")
+        self._keep["grids"] = list(grids)
+        self.n_active = U
+
+    def generate_steps(self, n_steps: int) -> None:
+        _lib.check(self.lib.dia_b200_batch_generate_steps(self._h, int(n_steps), _stream(self.device)), "batch_generate_steps")
+
+    def status(self) -> list:
+        st = (_lib.GenStatus * self.n_active)()
+        _lib.check(self.lib.dia_b200_batch_generate_status(self._h, st, _stream(self.device)), "batch_generate_status")
+        if st[0].device_error:
+            raise RuntimeError(f"device-side watchdog / state error code {st[0].device_error}: {self.last_device_error()}")
+        return list(st)
+
+
 def launch_count() -> int:
     return int(_lib.load().dia_b200_launch_count())
 

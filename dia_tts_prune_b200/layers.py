@@ -482,6 +482,37 @@ class Decoder(nn.Module):
         self._engine_sig = sig
         return self._engine
 
+    def batch_engine(self, max_utterances: int = 8):
+        """The ``BatchDecodeEngine`` (N utterances per launch on the tcgen05 step kernel), repacked like :meth:`engine`."""
+        from .engine import BatchDecodeEngine, decoder_tensor_names
+        dev = self.logits_dense.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("the Dia decode path needs the model on a CUDA device (sm_100a); no CPU fallback")
+        sig = (self._weights_signature(), int(max_utterances))
+        if getattr(self, "_bengine", None) is not None and self._bengine_sig == sig and self._bengine.device == dev:
+            return self._bengine
+        import torch.nn.utils.prune as _prune
+        if any(_prune.is_pruned(m) for m in self.modules() if isinstance(m, DenseGeneral)):
+            raise RuntimeError("pruning masks are still attached: call pruning_utils.make_pruning_permanent(model) first")
+        canonicalize_dense_kernels_(self)
+        sig = (self._weights_signature(), int(max_utterances))
+        from .pruning_utils import compact_mlp, plan_mlp_compaction
+        sd = dict(self.named_parameters())
+        tensors = {n: sd[n].detach() for n in decoder_tensor_names(self.config)}
+        d = self.config.model.decoder
+        plan = plan_mlp_compaction(tensors, d.n_layer, d.n_hidden) if self.compact_pruned_mlp else None
+        width = plan[0] if plan is not None else d.n_hidden
+        if plan is not None:
+            tensors = compact_mlp(tensors, plan)
+        old = getattr(self, "_bengine", None)
+        if old is None or old.device != dev or old.n_hidden != width or old.max_utterances != int(max_utterances):
+            if old is not None:
+                old.close()
+            self._bengine = BatchDecodeEngine(self.config, dev, max_utterances=int(max_utterances), n_hidden=width)
+        self._bengine.load_weights(tensors)
+        self._bengine_sig = sig
+        return self._bengine
+
     def _engine_for(self, state: DecoderInferenceState):
         eng = self.engine()
         if state.text_len is None:

@@ -389,6 +389,71 @@ class Dia:
             print(f"Error during final decoding: {e}")
             return None
 
+    # ---- N utterances per launch (no counterpart in the reference, whose batch is the CFG pair) ----
+    @torch.inference_mode()
+    def generate_batch(self, texts: list[str], max_tokens: int | None = None, cfg_scale: float = 3.0,
+                       temperature: float = 1.3, top_p: float = 0.95, cfg_filter_top_k: int | None = 35,
+                       seed: Optional[int] = None, max_utterances: int = 8, output: str = "codes", verbose: bool = False):
+        """``generate`` for a list of independent transcripts, decoded ``max_utterances`` at a time in ONE kernel: the 2N
+        CFG rows share a single pass over the weights per frame.  Every utterance has its own encoder pass, KV caches,
+        token grid, EOS state and RNG stream (utterance i draws from seed + i), and yields exactly the rows
+        ``generate(texts[i], ...)`` yields for greedy decoding.  Returns a list (codes int32 [1, C, T_i] or waveforms)."""
+        if output not in ("audio", "codes"):
+            raise ValueError("output must be 'audio' or 'codes'")
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("Dia.generate_batch needs the model on a CUDA device (sm_100a); there is no CPU fallback")
+        if temperature < 0.0:
+            raise ValueError("temperature must be >= 0")
+        if seed is not None:
+            torch.manual_seed(seed)
+        base_seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        max_tokens = self.config.data.audio_length if max_tokens is None else max_tokens
+        eng = self.model.decoder.batch_engine(max_utterances)
+        results: list = [None] * len(texts)
+        stats = {"prepare_s": 0.0, "loop_s": 0.0, "steps": 0, "frames": 0, "launch_steps": 0}
+        raw: list = [None] * len(texts)
+        for b0 in range(0, len(texts), eng.max_utterances):
+            idx = list(range(b0, min(len(texts), b0 + eng.max_utterances)))
+            t0 = time.time()
+            prepared = [self._prepare_generation(self._effective_text(texts[i], None), None, False) for i in idx]
+            for u, (st, out) in enumerate(prepared):
+                for c in st.cross_attn_cache:
+                    if c.k.dtype != torch.float32 or not c.k.is_contiguous():
+                        c.k = c.k.to(torch.float32).contiguous()
+                    if c.v.dtype != torch.float32 or not c.v.is_contiguous():
+                        c.v = c.v.to(torch.float32).contiguous()
+                eng.bind(u, st.self_attn_cache, st.cross_attn_cache, st.text_len)
+            P = [out.prefill_step for _, out in prepared]
+            slots = [st.self_attn_cache[0].current_idx for st, _ in prepared]
+            eng.generate_begin([out.generated_tokens for _, out in prepared], P, slots, max_tokens, cfg_scale, temperature,
+                               top_p, cfg_filter_top_k, [base_seed + i for i in idx])
+            torch.cuda.synchronize(self.device)
+            t1 = time.time()
+            remaining = max(0, max_tokens - min(P))
+            while remaining > 0:
+                n = min(_STEPS_PER_LAUNCH, remaining)
+                eng.generate_steps(n)
+                remaining -= n
+                stats["launch_steps"] += n
+            sts = eng.status()
+            t2 = time.time()
+            stats["prepare_s"] += t1 - t0
+            stats["loop_s"] += t2 - t1
+            for u, i in enumerate(idx):
+                st, out = prepared[u]
+                for c in st.self_attn_cache:
+                    c.current_idx = slots[u] + sts[u].steps_run
+                codes = out.generated_tokens[out.prefill_step: sts[u].dec_step + 1, :]
+                raw[i] = codes
+                stats["steps"] += sts[u].steps_run
+                stats["frames"] += int(codes.shape[0])
+                results[i] = self._finalize_codes(codes) if output == "codes" else self._generate_output(codes)
+            if verbose:
+                print(f"generate_batch: utterances {idx[0]}..{idx[-1]}: prepare {t1 - t0:.3f}s, loop {t2 - t1:.3f}s")
+        self.last_batch_codes = raw
+        self.last_stats = stats
+        return results
+
     def _run_loop(self, dec_state: DecoderInferenceState, dec_output: DecoderOutput, max_tokens: int, cfg_scale: float,
                   temperature: float, top_p: float, top_k: int, seed: int, verbose: bool,
                   profile: list | None = None) -> int:

@@ -181,6 +181,33 @@ int dia_b200_build_delay_indices(int32_t *t_idx, int64_t *indices, int B, int T,
 int dia_b200_build_revert_indices(int64_t *t_idx, int64_t *indices, int B, int T, int C, const int32_t *delay_host,
                                   void *stream);
 
+/* ---- N utterances per GPU in one launch ------------------------------------------------
+ * The reference hard-wires the CFG batch of 2 rows (dia/state.py:58-60,83-84,138-139); a batched engine decodes up to
+ * DIA_B200_MAX_UTTERANCES independent utterances per launch - 2N batch rows share ONE pass over the weights (tcgen05
+ * tensor cores, accumulators in tensor memory).  Every utterance keeps the reference's own state objects: its own
+ * KVCache tensors [2][H][L][128] (dia/state.py:72-109), token grid (dia/state.py:172-208), text length, prompt length
+ * (prefill_step / first_slot), RNG seed and EOS state machine.  One sampling configuration per launch.
+ * dia_b200_load_decoder_weights and dia_b200_set_rope_table serve both kinds of engine. */
+#define DIA_B200_MAX_UTTERANCES 8
+int dia_b200_engine_create_batched(const dia_b200_shape *shape, int device, int n_ctas, int max_utterances,
+                                   dia_b200_engine **out);
+int dia_b200_engine_max_utterances(const dia_b200_engine *e);
+/* caches of utterance `utterance` (same contract as dia_b200_bind_caches) */
+int dia_b200_batch_bind_caches(dia_b200_engine *e, int utterance, void *const *self_k, void *const *self_v,
+                               const void *const *cross_k, const void *const *cross_v, int n_layer, int text_len,
+                               void *stream);
+/* Decoder.decode_step (dia/layers.py:671-720) for n utterances at once: tokens int32 [n][C] (device; both CFG rows of
+ * an utterance get the same tokens, dia/model.py:759), pos_host / slot_host int32 [n] (host) -> logits float32
+ * [2n][C][V] (device; row 2u unconditional, 2u + 1 conditional of utterance u); appends K/V at slot_host[u]. */
+int dia_b200_batch_decode_step(dia_b200_engine *e, int n_utterances, const int32_t *tokens, const int32_t *pos_host,
+                               const int32_t *slot_host, float *logits, void *stream);
+/* the Dia.generate loop (dia/model.py:736-815) of n utterances in lock step: grids = n device pointers (host array),
+ * params = n entries (host array; cfg_scale, temperature, top_p, top_k, max_tokens must agree) */
+int dia_b200_batch_generate_begin(dia_b200_engine *e, int n_utterances, int32_t *const *grids,
+                                  const dia_b200_gen_params *params, void *stream);
+int dia_b200_batch_generate_steps(dia_b200_engine *e, int n_steps, void *stream);
+int dia_b200_batch_generate_status(dia_b200_engine *e, dia_b200_gen_status *out /* [n] */, void *stream);
+
 /* ---- dense layers with more than one row (encoder, cross-attention K/V precompute, prompt prefill) ------------
  * DenseGeneral.forward (dia/layers.py:55-66) for M = B*T > 1 rows on the tcgen05 tensor cores:
  *   y[M][N] float32 = x[M][K] float32 . W[K][N]

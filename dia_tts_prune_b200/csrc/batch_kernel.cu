@@ -36,15 +36,18 @@ namespace {
 
 constexpr int kBSlotBytes = 16384;          // one ring slot: up to 8 k-chunks of a slab, or a 16-key K / V tile
 constexpr int kBNumSlots = 10;
-constexpr int kActStages = 4;                 // activation (B operand) staging ring
+constexpr int kActStages = 6;               // activation (B operand) staging ring
 constexpr int kBTermBytes = 2048;           // [16 rows][64 k] bf16, K-major, 128-byte swizzle
-constexpr int kActStageBytes = 2 * kBTermBytes;
+constexpr int kStageChunks = 2;             // k-chunks (64 rows each) per activation stage: [chunk][hi tile | lo tile]
+constexpr int kActStageBytes = kStageChunks * 2 * kBTermBytes;
+constexpr int kPrefetch = 2;                // activation stages requested ahead (2 x 16-byte loads per thread each)
 constexpr int kScratchBytes = 49152;        // B staging | attention scratch | sampler scratch (never live together)
 constexpr int kBMiscBytes = 2048;
 constexpr int kBSmem = kBNumSlots * kBSlotBytes + kScratchBytes + kBMiscBytes + 1024;   // + alignment slack
 constexpr int kMmaWarp = 8;
-constexpr int kRows = 16;                   // N of the MMA = rows of the B tiles (2 x kMaxUtt)
-constexpr int kPrefetch = 4;                // activation chunks requested ahead
+constexpr int kRows = 16;                   // batch rows of the B tiles (2 x kMaxUtt); N of the MMA = 2 kRows (hi rows, then lo rows)
+constexpr int kAccCols = 4 * 2 * kRows;     // TMEM columns of one accumulator set: 4 independent k-step accumulators x (hi | lo)
+constexpr int kTmemCols = 2 * kAccCols;     // two sets: the epilogue of a GEMM stage overlaps the MMAs of the next one
 
 struct BMisc {
     uint64_t full[kBNumSlots], empty[kBNumSlots];
@@ -71,6 +74,9 @@ struct BCtx {
     unsigned seq;         // sequence number of the current stage inside this launch (>= 1)
     int step;             // step index inside the launch
     float xres[kRows];    // threads 0..15: this column's element of the residual stream, per row
+    long long t_prof[8];  // CTA 0, thread 0 (p.prof): 0 activation-flag spins, 1 bempty waits, 2 rms gather, 3 accumulator wait,
+                          // 4 epilogue, 5 end-of-stage barrier, 6 attention stages, 7 embed + sample
+    bool prof;
 };
 
 __device__ __forceinline__ void decode_stage_b(int s, int L, int& kind, int& layer) {
@@ -92,10 +98,13 @@ __device__ __forceinline__ int gemm_of_kind_b(int kind) {
     }
 }
 
-// generation of an activation buffer (how many times it has been written before) -> the flag bit its words carry.
-// act_x is written by the embedding and by the three residual stages of every layer; the others once per layer.
-__device__ __forceinline__ uint32_t flag_x(int L, int step, int idx) { return (uint32_t)(step * (3 * L + 1) + idx + 1) & 1u; }
+// Generation of an activation buffer (how many times it has been written before) -> the flag bit its words carry.
+// One bit is enough ONLY if every reader of a buffer reads every generation of it (a reader two generations behind
+// would take stale words for fresh ones).  So every consumer GEMM has its own input buffer - xq (qkv), xc (cross-q),
+// xm (mlp-in), xl (logits), attn (self-o), cattn (cross-o), hidden (mlp-out): each is written once per layer (xl once
+// per step) and read, every time, by the same CTAs (the column partition is the same in every layer).
 __device__ __forceinline__ uint32_t flag_l(int L, int step, int layer) { return (uint32_t)(step * L + layer + 1) & 1u; }
+__device__ __forceinline__ uint32_t flag_s(int step) { return (uint32_t)(step + 1) & 1u; }
 
 // x ~ hi + lo with both terms bf16; the last mantissa bit of lo carries the generation flag
 __device__ __forceinline__ uint32_t pack_act(float x, uint32_t fbit) {
@@ -110,6 +119,15 @@ __device__ __forceinline__ uint4 ld_act4(const uint32_t* p) {
     uint4 r;
     asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
     return r;
+}
+
+// latency-critical waits of the activation pipeline: poll without the suspend hint (a parked warp wakes up late)
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int* err, int code, unsigned info) {
+    unsigned polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++polls > 200000000u) ll_timeout(err, code, info);
+        ll_check_abort(err, polls, 100 + code, info);
+    }
 }
 
 __device__ __forceinline__ void ring_wait_full_b(BMisc* misc, unsigned idx, int* err, unsigned info) {
@@ -186,8 +204,9 @@ __device__ __forceinline__ BAttnWork cross_work_b(const BatchParams& p, int cta)
     w.has_new = 0;
     return w;
 }
+// ring slots of one attention stage of this CTA: one per 16-key tile (K tile in the first 8 KB, V tile in the second)
 __device__ __forceinline__ int attn_slots_b(const BAttnWork& w) {
-    return (!w.active || w.k_hi <= w.k_lo) ? 0 : 2 * ((w.k_hi - w.k_lo + 15) >> 4);
+    return (!w.active || w.k_hi <= w.k_lo) ? 0 : ((w.k_hi - w.k_lo + 15) >> 4);
 }
 
 // ---- producer: walks this CTA's byte stream -----------------------------------------------------------------------------
@@ -202,6 +221,14 @@ __device__ void producer_loop_b(const BatchParams& p, unsigned char* ring, BMisc
         mbar_wait(&misc->empty[slot], ph ^ 1u, p.err, kErrEmptyBarrierTimeout, (seq << 8) | slot);
         mbar_arrive_expect_tx(&misc->full[slot], bytes);
         bulk_g2s_hint(ring + slot * kBSlotBytes, src, bytes, &misc->full[slot], keep ? pol_keep : pol_stream);
+        pc++;
+    };
+    auto issue2 = [&](const void* src0, const void* src1, uint32_t bytes_each, bool keep, unsigned seq) {
+        const unsigned slot = pc % kBNumSlots, ph = (pc / kBNumSlots) & 1u;
+        mbar_wait(&misc->empty[slot], ph ^ 1u, p.err, kErrEmptyBarrierTimeout, (seq << 8) | slot);
+        mbar_arrive_expect_tx(&misc->full[slot], 2 * bytes_each);
+        bulk_g2s_hint(ring + slot * kBSlotBytes, src0, bytes_each, &misc->full[slot], keep ? pol_keep : pol_stream);
+        bulk_g2s_hint(ring + slot * kBSlotBytes + kBSlotBytes / 2, src1, bytes_each, &misc->full[slot], keep ? pol_keep : pol_stream);
         pc++;
     };
 #pragma unroll 1
@@ -249,23 +276,29 @@ __device__ void producer_loop_b(const BatchParams& p, unsigned char* ring, BMisc
 #pragma unroll 1
                 for (int k0 = w.k_lo; k0 < w.k_hi; k0 += 16) {
                     const int nk = min(16, w.k_hi - k0);
-                    issue(kb + (size_t)k0 * kHeadDim, nk * kHeadDim * 4, !self, seq);
-                    issue(vb + (size_t)k0 * kHeadDim, nk * kHeadDim * 4, !self, seq);
+                    issue2(kb + (size_t)k0 * kHeadDim, vb + (size_t)k0 * kHeadDim, nk * kHeadDim * 4, !self, seq);
                 }
             }
         }
     }
 }
 
-// ---- MMA warp: one thread issues every tcgen05.mma of this CTA ---------------------------------------------------------------
+// ---- MMA warp: the whole warp walks the stages (warp-uniform control flow and operands), one elected lane issues every
+//      tcgen05.mma / tcgen05.commit of this CTA ------------------------------------------------------------------------
 __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned char* scratch, BMisc* misc) {
     const CtaTable& tab = misc->tab;
     const int cta = blockIdx.x;
     const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
     const uint32_t tmem = misc->tmem_base;
-    // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, N = 16, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, M = 128, N = 32: the hi tile and the lo
+    // tile of the activations are adjacent in shared memory and go through ONE instruction (the weight tile - 4 KB per
+    // k-step, the operand that bounds these narrow MMAs - is read once for both terms); columns 0..15 of an accumulator
+    // are W.hi, 16..31 are W.lo.  The four k-steps of a chunk accumulate into four different accumulators: back-to-back
+    // MMAs on ONE accumulator serialise on its read-modify-write latency (measured: ~115 cycles per instruction).
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * kRows) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     unsigned cbase = 0, bctr = 0, gctr = 0;
+    const bool prof = p.prof != nullptr && cta == 0 && (threadIdx.x & 31) == 0;
+    long long t_bfull = 0, t_ring = 0, t_acc = 0, t_all = prof ? clock64() : 0, tq = 0;
 #pragma unroll 1
     for (int n = 0; n < p.n_steps; ++n) {
 #pragma unroll 1
@@ -279,39 +312,61 @@ __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned c
                 if (gc == 0) continue;
                 const int K = p.Kdim[gt], cps = bslot_chunks(gc, K), n_chunks = K / 64;
                 const uint32_t chunk_bytes = (uint32_t)bchunk_bytes(gc);
+                const int cshift = __ffs(cps) - 1;
                 const unsigned a = gctr & 1u;
+                if (prof) tq = clock64();
                 mbar_wait(&misc->acc_empty[a], ((gctr >> 1) & 1u) ^ 1u, p.err, kErrGridBarrierTimeout, seq);
+                if (prof) t_acc += clock64() - tq;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_addr = tmem + a * kRows;
+                const uint32_t d_addr = tmem + a * kAccCols;
 #pragma unroll 1
-                for (int c = 0; c < n_chunks; ++c) {
-                    const unsigned si = cbase + (unsigned)(c / cps);
-                    if (c % cps == 0) ring_wait_full_b(misc, si, p.err, (seq << 8) | (si % kBNumSlots));
-                    const unsigned bi = bctr + (unsigned)c, bs = bi % kActStages;
-                    mbar_wait(&misc->bfull[bs], (bi / kActStages) & 1u, p.err, kErrFullBarrierTimeout, (seq << 8) | 0x80 | bs);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_base = smem_u32(ring + (si % kBNumSlots) * kBSlotBytes) + (uint32_t)(c % cps) * chunk_bytes;
-                    const uint32_t b_base = smem_u32(scratch + bs * kActStageBytes);
-                    const uint64_t adesc = umma_desc_b(a_base);
+                for (int st = 0; st < n_chunks / kStageChunks; ++st) {
+                    // the activation stage first: once the math warps have staged a piece of this GEMM they have left the
+                    // attention stage before it, i.e. every earlier generation of the ring slots has been released - the
+                    // one-bit phase parity of the slot barriers cannot tell generations two apart
+                    const unsigned bi = bctr + (unsigned)st, bs = bi % kActStages;
+                    if (prof) tq = clock64();
+                    mbar_spin(&misc->bfull[bs], (bi / kActStages) & 1u, p.err, kErrFullBarrierTimeout, (seq << 8) | 0x80 | bs);
+                    if (prof) t_bfull += clock64() - tq;
 #pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const uint64_t bdesc = umma_desc_b(b_base + t * kBTermBytes);
+                    for (int jc = 0; jc < kStageChunks; ++jc) {
+                        const int c = st * kStageChunks + jc;
+                        const unsigned si = cbase + (unsigned)(c >> cshift);      // cps is a power of two
+                        if ((c & (cps - 1)) == 0) {
+                            if (prof) tq = clock64();
+                            ring_wait_full_b(misc, si, p.err, (seq << 8) | (si % kBNumSlots));
+                            if (prof) t_ring += clock64() - tq;
+                        }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_base = smem_u32(ring + (si % kBNumSlots) * kBSlotBytes) + (uint32_t)(c & (cps - 1)) * chunk_bytes;
+                        const uint32_t b_base = smem_u32(scratch + bs * kActStageBytes) + jc * 2 * kBTermBytes;
+                        const uint64_t adesc = umma_desc_b(a_base), bdesc = umma_desc_b(b_base);
+                        if (elect_one_sync()) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)          // 16 elements along K = 32 bytes = 2 descriptor units
-                            umma_bf16_b(d_addr, adesc + 2 * j, bdesc + 2 * j, idesc, (c | t | j) != 0 ? 1u : 0u);
+                            for (int j = 0; j < 4; ++j)      // 16 elements along K = 32 bytes = 2 descriptor units
+                                umma_bf16_b(d_addr + j * 2 * kRows, adesc + 2 * j, bdesc + 2 * j, idesc, c != 0 ? 1u : 0u);
+                            if ((c & (cps - 1)) == cps - 1) umma_commit_b(&misc->empty[si % kBNumSlots]);
+                            if (jc == kStageChunks - 1) umma_commit_b(&misc->bempty[bs]);
+                        }
+                        __syncwarp();
                     }
-                    umma_commit_b(&misc->bempty[bs]);
-                    if (c % cps == cps - 1) umma_commit_b(&misc->empty[si % kBNumSlots]);
                 }
-                umma_commit_b(&misc->acc_full[a]);
-                cbase += (unsigned)(n_chunks / cps);
-                bctr += (unsigned)n_chunks;
+                if (elect_one_sync()) umma_commit_b(&misc->acc_full[a]);
+                __syncwarp();
+                cbase += (unsigned)(n_chunks >> cshift);
+                bctr += (unsigned)(n_chunks / kStageChunks);
                 gctr++;
             } else if (kind == S_SATTN || kind == S_CATTN) {
                 const BAttnWork w = kind == S_SATTN ? self_work_b(p, cta, n) : cross_work_b(p, cta);
                 cbase += (unsigned)attn_slots_b(w);
             }
         }
+    }
+    if (prof) {
+        p.prof[0] = (unsigned long long)(clock64() - t_all);
+        p.prof[1] = (unsigned long long)t_bfull;
+        p.prof[2] = (unsigned long long)t_ring;
+        p.prof[3] = (unsigned long long)t_acc;
     }
 }
 
@@ -325,98 +380,114 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
     const int tid = c.tid, lane = c.lane, warp = c.warp;
     const bool resid = (gt == G_SO || gt == G_CO || gt == G_WO);
     const bool normed = !resid;
-    const uint32_t* src = gt == G_SO ? p.act_attn : gt == G_CO ? p.act_cattn : gt == G_WO ? p.act_hidden : p.act_x;
-    uint32_t fb;                                               // flag bit the input words carry
-    switch (gt) {
-        case G_QKV: fb = flag_x(L, c.step, 3 * layer); break;
-        case G_CQ: fb = flag_x(L, c.step, 3 * layer + 1); break;
-        case G_WI: fb = flag_x(L, c.step, 3 * layer + 2); break;
-        case G_LOGITS: fb = flag_x(L, c.step, 3 * L); break;
-        default: fb = flag_l(L, c.step, layer); break;
-    }
+    const uint32_t* src = gt == G_SO ? p.act_attn : gt == G_CO ? p.act_cattn : gt == G_WO ? p.act_hidden
+                        : gt == G_QKV ? p.act_xq : gt == G_CQ ? p.act_xc : gt == G_WI ? p.act_xm : p.act_xl;
+    const uint32_t fb = gt == G_LOGITS ? flag_s(c.step) : flag_l(L, c.step, layer);       // flag bit the input words carry
 
-    // ---- the activations, chunk by chunk: one 16-byte load per thread = 4 consecutive k of one row ----------------------
+    // ---- the activations, stage by stage (128 k): one 16-byte load per thread and chunk = 4 consecutive k of one row --------
     const int r_ld = tid >> 4, k4 = tid & 15;
     const bool ld_on = r_ld < R;
     const uint32_t* my = src + (size_t)r_ld * 64 + 4 * k4;
     const size_t chunk_words = (size_t)R * 64;
     const uint32_t st_off = (uint32_t)(r_ld * 128 + ((((k4 >> 1) ^ (r_ld & 7)) << 4) | ((k4 & 1) << 3)));
-    uint4 v[kPrefetch];
+    const int n_st = n_chunks / kStageChunks;
+    const bool stager = 2 * warp < R;                          // warps whose threads hold a row (bfull counts exactly these)
+    uint4 v[kPrefetch][kStageChunks];
 #pragma unroll
     for (int i = 0; i < kPrefetch; ++i)
-        if (ld_on && i < n_chunks) v[i] = ld_act4(my + (size_t)i * chunk_words);
+#pragma unroll
+        for (int jc = 0; jc < kStageChunks; ++jc)
+            if (ld_on && i < n_st) v[i][jc] = ld_act4(my + (size_t)(i * kStageChunks + jc) * chunk_words);
 #pragma unroll 1
-    for (int c0 = 0; c0 < n_chunks; c0 += kPrefetch) {
+    for (int s0 = 0; s0 < (stager ? n_st : 0); s0 += kPrefetch) {
 #pragma unroll
         for (int i = 0; i < kPrefetch; ++i) {
-            const int ch = c0 + i;
-            if (ch < n_chunks) {
+            const int st = s0 + i;
+            if (st < n_st) {
+                long long tq = c.prof ? clock64() : 0;
                 if (ld_on) {
-                    unsigned spins = 0;
-                    while ((((v[i].x ^ fb) | (v[i].y ^ fb) | (v[i].z ^ fb) | (v[i].w ^ fb)) & 1u) != 0u) {
-                        if (++spins > kMaxSpins) {
-                            volatile int* e = reinterpret_cast<volatile int*>(p.err);
-                            e[4] = ch; e[5] = gt; e[6] = (int)fb; e[7] = r_ld;
-                            ll_timeout(p.err, kErrFlagTimeout, c.seq * 16 + gt);
+#pragma unroll
+                    for (int jc = 0; jc < kStageChunks; ++jc) {
+                        unsigned spins = 0;
+                        while ((((v[i][jc].x ^ fb) | (v[i][jc].y ^ fb) | (v[i][jc].z ^ fb) | (v[i][jc].w ^ fb)) & 1u) != 0u) {
+                            if (++spins > kMaxSpins) {
+                                volatile int* e = reinterpret_cast<volatile int*>(p.err);
+                                e[4] = st; e[5] = gt; e[6] = (int)fb; e[7] = r_ld;
+                                ll_timeout(p.err, kErrFlagTimeout, c.seq * 16 + gt);
+                            }
+                            ll_check_abort(p.err, spins, 100 + kErrFlagTimeout, c.seq * 16 + gt);
+                            v[i][jc] = ld_act4(my + (size_t)(st * kStageChunks + jc) * chunk_words);
                         }
-                        ll_check_abort(p.err, spins, 100 + kErrFlagTimeout, c.seq * 16 + gt);
-                        v[i] = ld_act4(my + (size_t)ch * chunk_words);
                     }
                 }
-                const unsigned bi = c.bctr + (unsigned)ch, bs = bi % kActStages;
-                if (lane == 0) mbar_wait(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (c.seq << 8) | 0xc0 | bs);
+                const unsigned bi = c.bctr + (unsigned)st, bs = bi % kActStages;
+                if (c.prof) { const long long t1 = clock64(); c.t_prof[0] += t1 - tq; tq = t1; }
+                if (lane == 0) mbar_spin(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (c.seq << 8) | 0xc0 | bs);
                 __syncwarp();
+                if (c.prof) c.t_prof[1] += clock64() - tq;
                 if (ld_on) {
-                    const uint32_t dst = smem_u32(c.scratch + bs * kActStageBytes) + st_off;
-                    const uint32_t h0 = __byte_perm(v[i].x, v[i].y, 0x7632), h1 = __byte_perm(v[i].z, v[i].w, 0x7632);
-                    const uint32_t l0 = __byte_perm(v[i].x, v[i].y, 0x5410) & 0xfffefffeu;
-                    const uint32_t l1 = __byte_perm(v[i].z, v[i].w, 0x5410) & 0xfffefffeu;
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst + kBTermBytes), "r"(l0), "r"(l1) : "memory");
+#pragma unroll
+                    for (int jc = 0; jc < kStageChunks; ++jc) {
+                        const uint32_t dst = smem_u32(c.scratch + bs * kActStageBytes) + jc * 2 * kBTermBytes + st_off;
+                        const uint32_t h0 = __byte_perm(v[i][jc].x, v[i][jc].y, 0x7632), h1 = __byte_perm(v[i][jc].z, v[i][jc].w, 0x7632);
+                        const uint32_t l0 = __byte_perm(v[i][jc].x, v[i][jc].y, 0x5410) & 0xfffefffeu;
+                        const uint32_t l1 = __byte_perm(v[i][jc].z, v[i][jc].w, 0x5410) & 0xfffefffeu;
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst + kBTermBytes), "r"(l0), "r"(l1) : "memory");
+                    }
                 }
-                fence_proxy_async();                            // generic-proxy writes -> the tensor core's async proxy
+                // generic-proxy writes -> the tensor core's async proxy (the shared::cta form: a full fence.proxy.async also
+                // waits for this thread's activation loads in flight)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&misc->bfull[bs]);
-                if (ld_on && ch + kPrefetch < n_chunks) v[i] = ld_act4(my + (size_t)(ch + kPrefetch) * chunk_words);
+                if (ld_on && st + kPrefetch < n_st) {
+#pragma unroll
+                    for (int jc = 0; jc < kStageChunks; ++jc)
+                        v[i][jc] = ld_act4(my + (size_t)((st + kPrefetch) * kStageChunks + jc) * chunk_words);
+                }
             }
         }
     }
-    c.bctr += (unsigned)n_chunks;
+    c.bctr += (unsigned)n_st;
     c.cbase += (unsigned)(n_chunks / bslot_chunks(gc, K));
 
     // ---- RMSNorm: 1/rms per row from the producers' per-group sums (dia/layers.py:541,560,579,714) ---------------------------
+    long long tq2 = c.prof ? clock64() : 0;
     if (normed) {
+        // thread g takes the 8-column group g: the sums of all R rows (R / 2 word pairs), every load in flight at once
         const uint32_t fprev = c.seq - 1;
-        const int half = R >> 1;                               // word pairs per group
-        const int n_pairs = (p.D >> 3) * half;
-        const int rp = tid % half;                             // the same row pair in every iteration (256 % half == 0)
-        float s0 = 0.f, s1 = 0.f;
-        uint4 q4[8];
+        float sr[kRows];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (tid + kConsumerThreads * i < n_pairs) q4[i] = ll_ld2(p.ll_ssq + (size_t)(tid + kConsumerThreads * i) * 2);
+        for (int r = 0; r < kRows; ++r) sr[r] = 0.f;
+#pragma unroll 1
+        for (int g = tid; g < (p.D >> 3); g += kConsumerThreads) {
+            const u64* base = p.ll_ssq + (size_t)g * R;
+            uint4 q4[kRows / 2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (tid + kConsumerThreads * i < n_pairs) {
-                unsigned spins = 0;
-                while (q4[i].y != fprev || q4[i].w != fprev) {
-                    if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 4, c.seq);
-                    ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 4, c.seq);
-                    q4[i] = ll_ld2(p.ll_ssq + (size_t)(tid + kConsumerThreads * i) * 2);
+            for (int i = 0; i < kRows / 2; ++i)
+                if (2 * i < R) q4[i] = ll_ld2(base + 2 * i);
+#pragma unroll
+            for (int i = 0; i < kRows / 2; ++i) {
+                if (2 * i < R) {
+                    unsigned spins = 0;
+                    while (q4[i].y != fprev || q4[i].w != fprev) {
+                        if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 4, c.seq);
+                        ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 4, c.seq);
+                        q4[i] = ll_ld2(base + 2 * i);
+                    }
+                    sr[2 * i] += __uint_as_float(q4[i].x);
+                    sr[2 * i + 1] += __uint_as_float(q4[i].z);
                 }
-                s0 += __uint_as_float(q4[i].x);
-                s1 += __uint_as_float(q4[i].z);
             }
         }
-        // lanes with the same row pair: lane % half (half is a power of two <= 8)
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            if (m >= half) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, m);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        for (int r = 0; r < kRows; ++r) {
+            if (r < R) {
+                const float t = warp_sum(sr[r]);
+                if (lane == 0) misc->ssq_part[warp][r] = t;
             }
         }
-        if (lane < half) { misc->ssq_part[warp][2 * rp] = s0; misc->ssq_part[warp][2 * rp + 1] = s1; }
         consumer_sync();
         if (tid < R) {
             float ss = 0.f;
@@ -429,18 +500,37 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
 
     // ---- epilogue: warps 0..3, thread = output column of this CTA's slab (TMEM lane), registers = rows ----------------------------
     const unsigned a = c.gctr & 1u;
+    if (c.prof) { const long long t1 = clock64(); c.t_prof[2] += t1 - tq2; tq2 = t1; }
     if (warp < 4) {
         mbar_wait(&misc->acc_full[a], (c.gctr >> 1) & 1u, p.err, kErrGridBarrierTimeout, c.seq);
+        if (c.prof) { const long long t1 = clock64(); c.t_prof[3] += t1 - tq2; tq2 = t1; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t acc[kRows];
-        const uint32_t taddr = misc->tmem_base + ((uint32_t)(warp * 32) << 16) + a * kRows;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
-              "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]), "=r"(acc[15])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        {
+            float sum[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) sum[r] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                       // accumulator j: columns 0..15 = W.hi, 16..31 = W.lo
+                uint32_t v[32];
+                const uint32_t taddr = misc->tmem_base + ((uint32_t)(warp * 32) << 16) + a * kAccCols + j * 2 * kRows;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) sum[r] += __uint_as_float(v[r]) + __uint_as_float(v[kRows + r]);
+            }
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) acc[r] = __float_as_uint(sum[r]);
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&misc->acc_empty[a]);
@@ -488,8 +578,10 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
         } else {
             // residual add (dia/layers.py:555,574,582): the stream stays in this thread's registers; the new stream goes
             // out as the words of x * w_norm for the next consumer, with sum(x^2) of this 8-column group per row
-            const int idx = gt == G_SO ? 3 * layer + 1 : gt == G_CO ? 3 * layer + 2 : 3 * layer + 3;
-            const uint32_t fo = flag_x(L, c.step, idx);
+            // the next consumer: cross-q after self-o, mlp-in after cross-o, the next layer's qkv (or the logits head)
+            const bool last = gt == G_WO && layer == L - 1;
+            uint32_t* xdst = gt == G_SO ? p.act_xc : gt == G_CO ? p.act_xm : last ? p.act_xl : p.act_xq;
+            const uint32_t fo = gt == G_WO ? (last ? flag_s(c.step) : flag_l(L, c.step, layer + 1)) : flag_l(L, c.step, layer);
             const float* wn = gt == G_SO ? p.norms + ((size_t)layer * 3 + 1) * p.D
                             : gt == G_CO ? p.norms + ((size_t)layer * 3 + 2) * p.D
                                          : p.norms + ((size_t)(layer + 1) * 3) * p.D;
@@ -501,7 +593,7 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
                     if (valid) {
                         xn = c.xres[r] + __uint_as_float(acc[r]);
                         c.xres[r] = xn;
-                        st_act(p.act_x, R, n, r, pack_act(xn * wnv, fo));
+                        st_act(xdst, R, n, r, pack_act(xn * wnv, fo));
                     }
                     float sq = xn * xn;
                     sq += __shfl_xor_sync(0xffffffffu, sq, 4);
@@ -513,7 +605,9 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
         }
     }
     c.gctr++;
+    if (c.prof) { const long long t1 = clock64(); c.t_prof[4] += t1 - tq2; tq2 = t1; }
     consumer_sync();            // the staging ring is scratch of the next stage: every MMA of this one has completed
+    if (c.prof) c.t_prof[5] += clock64() - tq2;
 }
 
 // sum v[i] over the 32 lanes for NV values at once (see step_kernel.cu)
@@ -623,18 +717,24 @@ __device__ void attn_stage_b(BCtx& c, int layer) {
     float4 acc[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // The warps move round by round (8 tiles per round, a block barrier in between): a warp is then never more than one
+    // generation ahead of a ring slot (10 slots), which is all the one-bit phase parity of the mbarriers can tell apart.
 #pragma unroll 1
-    for (int ci = c.warp; ci < nvc; ci += kConsumerWarps) {
+    for (int c0 = 0; c0 < nvc; c0 += kConsumerWarps) {
+        if (c0 > 0) consumer_sync();
+        const int ci = c0 + c.warp;
+        if (ci >= nvc) continue;
         const bool in_ring = ci < nkc;
         unsigned sl = 0;
         const float4* kt = reinterpret_cast<const float4*>(kn) + c.lane;
         const float4* vt = reinterpret_cast<const float4*>(vn) + c.lane;
         int keys_in = 1;
         if (in_ring) {
-            const unsigned idx = c.cbase + 2 * ci;
+            const unsigned idx = c.cbase + ci;
             sl = idx % kBNumSlots;
             ring_wait_full_b(c.misc, idx, p.err, (c.seq << 8) | 0x40 | sl);
             kt = reinterpret_cast<const float4*>(c.ring + sl * kBSlotBytes) + c.lane;
+            vt = reinterpret_cast<const float4*>(c.ring + sl * kBSlotBytes + kBSlotBytes / 2) + c.lane;
             keys_in = min(16, nk - ci * 16);
         }
         float s2[2];
@@ -652,10 +752,6 @@ __device__ void attn_stage_b(BCtx& c, int layer) {
             transpose_reduce_b<8 * NH>(v, c.lane);
             const float sv = (half * 8 + (c.lane >> 2)) < keys_in ? v[0] : -INFINITY;
             if (half == 0) s2[0] = sv; else s2[1] = sv;
-        }
-        if (in_ring) {
-            __syncwarp();
-            if (c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
         }
         float mt = fmaxf(s2[0], s2[1]);
         mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 4));
@@ -678,12 +774,6 @@ __device__ void attn_stage_b(BCtx& c, int layer) {
             acc[h].x *= sh; acc[h].y *= sh; acc[h].z *= sh; acc[h].w *= sh;
         }
         __syncwarp();
-        if (in_ring) {
-            const unsigned idx = c.cbase + 2 * ci + 1;
-            sl = idx % kBNumSlots;
-            ring_wait_full_b(c.misc, idx, p.err, (c.seq << 8) | 0x80 | sl);
-            vt = reinterpret_cast<const float4*>(c.ring + sl * kBSlotBytes) + c.lane;
-        }
 #pragma unroll 2
         for (int key = 0; key < keys_in; ++key) {
             const float4 vv = vt[key * 32];
@@ -698,7 +788,7 @@ __device__ void attn_stage_b(BCtx& c, int layer) {
         __syncwarp();
         if (in_ring && c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
     }
-    c.cbase += 2 * nkc;
+    c.cbase += nkc;
     if (c.lane < HPKB) { wstat[c.warp * 8 + c.lane] = m_run; wstat[c.warp * 8 + 4 + c.lane] = l_run; }
 #pragma unroll
     for (int h = 0; h < NH; ++h)
@@ -812,7 +902,7 @@ __device__ void embed_stage_b(BCtx& c) {
     const int m = tid;
     const bool valid = m < gc * 8;
     const int n = g0 * 8 + m;
-    const uint32_t fo = flag_x(p.L, c.step, 0);
+    const uint32_t fo = flag_l(p.L, c.step, 0);
     const float wnv = valid ? __ldg(p.norms + n) : 0.f;
 #pragma unroll
     for (int u = 0; u < kMaxUtt; ++u) {
@@ -830,8 +920,8 @@ __device__ void embed_stage_b(BCtx& c) {
                 c.xres[2 * u] = x;
                 c.xres[2 * u + 1] = x;
                 const uint32_t wd = pack_act(x * wnv, fo);
-                st_act(p.act_x, R, n, 2 * u, wd);
-                st_act(p.act_x, R, n, 2 * u + 1, wd);
+                st_act(p.act_xq, R, n, 2 * u, wd);
+                st_act(p.act_xq, R, n, 2 * u + 1, wd);
             }
             float sq = x * x;
             sq += __shfl_xor_sync(0xffffffffu, sq, 4);
@@ -955,7 +1045,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_batch_step_kernel(
     }
     if (tid == 0) {
         for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
-        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], kConsumerWarps); mbar_init(&misc->bempty[i], 1); }
+        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], (uint32_t)(p.R + 1) / 2); mbar_init(&misc->bempty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], 1); mbar_init(&misc->acc_empty[i], 4); }
         misc->stages_done = 0;
         fence_mbar_init();
@@ -969,7 +1059,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_batch_step_kernel(
     for (int i = tid; i < kActStages * kActStageBytes / 16; i += kThreads) reinterpret_cast<uint4*>(scratch)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     if (warp == kMmaWarp) {                                  // one warp allocates (and later frees) the accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc->tmem_base)), "r"(32));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc->tmem_base)), "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -980,12 +1070,15 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_batch_step_kernel(
     if (warp == kProducerWarp) {
         if (tid == kProducerWarp * 32) producer_loop_b(p, ring, misc);
     } else if (warp == kMmaWarp) {
-        if (tid == kMmaWarp * 32) mma_loop_b(p, ring, scratch, misc);
+        mma_loop_b(p, ring, scratch, misc);
     } else {
         BCtx c;
         c.p = &p; c.ring = ring; c.scratch = scratch; c.misc = misc;
         c.tid = tid; c.warp = warp; c.lane = tid & 31;
         c.cbase = 0; c.bctr = 0; c.gctr = 0; c.seq = 0; c.step = 0;
+        c.prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+        for (int i = 0; i < 8; ++i) c.t_prof[i] = 0;
+        const long long t_begin = c.prof ? clock64() : 0;
 #pragma unroll
         for (int r = 0; r < kRows; ++r) c.xres[r] = 0.f;
 #pragma unroll 1
@@ -996,6 +1089,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_batch_step_kernel(
                 int kind, layer;
                 decode_stage_b(s, p.L, kind, layer);
                 c.seq = 1u + (unsigned)(n * S + s);
+                const long long ts0 = c.prof ? clock64() : 0;
                 switch (kind) {
                     case S_EMBED: embed_stage_b(c); break;
                     case S_SATTN: attn_stage_b<HPKB>(c, layer); break;
@@ -1003,15 +1097,23 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_batch_step_kernel(
                     case S_SAMPLE: sample_stage_b(c); break;
                     default: gemm_stage_b(c, gemm_of_kind_b(kind), layer); break;
                 }
+                if (c.prof) {
+                    if (kind == S_SATTN || kind == S_CATTN) c.t_prof[6] += clock64() - ts0;
+                    else if (kind == S_EMBED || kind == S_SAMPLE) c.t_prof[7] += clock64() - ts0;
+                }
                 if (tid == 0) st_release_cta_s32(&misc->stages_done, n * S + s + 1);
             }
+        }
+        if (c.prof) {
+            p.prof[8] = (unsigned long long)(clock64() - t_begin);
+            for (int i = 0; i < 8; ++i) p.prof[9 + i] = (unsigned long long)c.t_prof[i];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(misc->tmem_base), "r"(32));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(misc->tmem_base), "r"(kTmemCols));
     }
 }
 
@@ -1041,7 +1143,10 @@ size_t batch_ll_layout(const BatchParams& g, BatchParams* out, unsigned char* ba
     BatchParams& o = out ? *out : scratch;
     const size_t R = (size_t)g.R;
     const size_t nq = (size_t)g.Hq * kHeadDim, nkv = (size_t)g.Hkv * kHeadDim, nc = (size_t)g.Hc * kHeadDim;
-    take(reinterpret_cast<void**>(&o.act_x), (size_t)g.D * R * 4);
+    take(reinterpret_cast<void**>(&o.act_xq), (size_t)g.D * R * 4);
+    take(reinterpret_cast<void**>(&o.act_xc), (size_t)g.D * R * 4);
+    take(reinterpret_cast<void**>(&o.act_xm), (size_t)g.D * R * 4);
+    take(reinterpret_cast<void**>(&o.act_xl), (size_t)g.D * R * 4);
     take(reinterpret_cast<void**>(&o.act_attn), nq * R * 4);
     take(reinterpret_cast<void**>(&o.act_cattn), nc * R * 4);
     take(reinterpret_cast<void**>(&o.act_hidden), (size_t)g.F * R * 4);

@@ -124,6 +124,20 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// One lane of a converged warp (elect.sync).  Code that issues tcgen05 / TMA instructions for the whole CTA runs with the
+// WHOLE warp in the loop and only the issue under this predicate: the operands (descriptors, TMEM addresses) are then
+// provably warp-uniform and stay in uniform registers.  Behind a `lane == 0` branch the compiler instead wraps every
+// UTCHMMA in an ELECT / 5 x R2UR.BROADCAST / branch "waterfall" (measured: ~170 cycles per MMA instead of ~30).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
+
 // ---- named barrier over the consumer warps only (the producer warp never joins) --------------
 __device__ __forceinline__ void consumer_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");

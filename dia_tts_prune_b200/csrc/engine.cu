@@ -723,6 +723,7 @@ void fill_batch_params(const dia_b200_engine* e, BatchParams& p, int n_utts) {
     p.eos = s.eos_value; p.pad = s.pad_value; p.bos = s.bos_value;
     for (int i = 0; i < DIA_B200_MAX_CHANNELS; ++i) p.delay[i] = s.delay_pattern[i];
     p.pred_out = e->d_pred;
+    p.prof = e->timing_on ? reinterpret_cast<unsigned long long*>(e->d_timing) : nullptr;
 }
 
 int run_batch(dia_b200_engine* e, BatchParams& p, cudaStream_t st) {

@@ -190,7 +190,10 @@ struct BatchParams {
     float* logits;                     // [R][C][V] raw logits of the last executed step (optional)
     // exchange buffers (zeroed before every launch).  act_*: packed (bf16 hi | bf16 lo, 1-bit generation flag) words
     // [k / 64][R][64]; the rest are (fp32, flag32) words as in the single-utterance kernel
-    unsigned int* act_x;
+    unsigned int* act_xq;              // normed residual stream for qkv / cross-q / mlp-in / the logits head: one buffer
+    unsigned int* act_xc;              // per consumer, so that every reader sees every generation of its buffer
+    unsigned int* act_xm;
+    unsigned int* act_xl;
     unsigned int* act_attn;
     unsigned int* act_cattn;
     unsigned int* act_hidden;
@@ -212,6 +215,7 @@ struct BatchParams {
     int eos, pad, bos;
     int delay[DIA_B200_MAX_CHANNELS];
     int* pred_out;                     // [kMaxUtt][16]
+    unsigned long long* prof;          // optional [32]: SM-clock totals of CTA 0 (MMA thread / math thread 0), see batch_kernel.cu
 };
 
 cudaError_t launch_batch_kernel(const BatchParams& p, cudaStream_t st);

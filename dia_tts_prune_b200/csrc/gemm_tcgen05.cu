@@ -173,16 +173,16 @@ dia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, N = 128, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int s = kb % kStages;
-                mbar_wait_bounded(&full[s], (kb / kStages) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t base = smem_u32(smem + s * kStageBytes);
-                const uint64_t bdesc = umma_desc(base + kTerms * kTileBytes);
+        // ===== MMA issuer: the whole warp walks the k-blocks (uniform operands), one elected lane issues =====
+        // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, N = 128, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int s = kb % kStages;
+            mbar_wait_bounded(&full[s], (kb / kStages) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t base = smem_u32(smem + s * kStageBytes);
+            const uint64_t bdesc = umma_desc(base + kTerms * kTileBytes);
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int t = 0; t < kTerms; ++t) {
                     const uint64_t adesc = umma_desc(base + t * kTileBytes);
@@ -192,8 +192,10 @@ dia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 }
                 umma_commit(&empty[s]);                     // the slot is free once these MMAs have read it
             }
-            umma_commit(tmem_full);                         // the accumulator is complete
+            __syncwarp();
         }
+        if (elect_one_sync()) umma_commit(tmem_full);       // the accumulator is complete
+        __syncwarp();
     } else {
         // ===== epilogue: a warp may touch the 32 TMEM lanes of its quarter (warp id mod 4) =====
         const int q = warp & 3;

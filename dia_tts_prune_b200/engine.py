@@ -337,6 +337,19 @@ class BatchDecodeEngine:
                                                        int(text_len), _stream(self.device)), "batch_bind_caches")
         self._keep[int(utterance)] = keep
 
+    enable_timing = DecodeEngine.enable_timing
+
+    def read_profile(self) -> dict:
+        """SM-clock totals of CTA 0 over the last launch (after ``enable_timing(True)``): where the MMA thread and math
+        thread 0 spent their time."""
+        out = torch.empty((32,), dtype=torch.int64)
+        _lib.check(self.lib.dia_b200_debug_read(self._h, _lib.BUF_TIMING, _ptr(out), 32 * 8, _stream(self.device)), "debug_read")
+        v = out.tolist()
+        names = ["mma_total", "mma_wait_bfull", "mma_wait_ring", "mma_wait_acc_empty", "", "", "", "",
+                 "math_total", "math_act_flag_spin", "math_wait_bempty", "math_rms_gather", "math_wait_acc_full",
+                 "math_epilogue", "math_stage_end_barrier", "math_attention", "math_embed_sample"]
+        return {n: v[i] for i, n in enumerate(names) if n}
+
     def decode_step(self, tokens_UxC: torch.Tensor, pos: list[int], slot: list[int]) -> torch.Tensor:
         """``Decoder.decode_step`` for U utterances: int32 [U, C] -> float32 logits [2U, C, V]."""
         tok = tokens_UxC.to(device=self.device, dtype=torch.int32).contiguous()

@@ -103,6 +103,7 @@ class Dia:
         self.dac_model = None
         self.last_codes: torch.Tensor | None = None     # raw generated rows of the last generate() call
         self.last_stats: dict = {}
+        self.batch_min_utterances = 4                   # generate_batch: smaller groups run through the single-utterance kernel
         # encode / project only the text bytes the decoder can observe (set False for the reference's full tensors)
         self.live_text_only = True
 
@@ -408,13 +409,26 @@ class Dia:
             torch.manual_seed(seed)
         base_seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
         max_tokens = self.config.data.audio_length if max_tokens is None else max_tokens
-        eng = self.model.decoder.batch_engine(max_utterances)
         results: list = [None] * len(texts)
         stats = {"prepare_s": 0.0, "loop_s": 0.0, "steps": 0, "frames": 0, "launch_steps": 0}
         raw: list = [None] * len(texts)
-        for b0 in range(0, len(texts), eng.max_utterances):
-            idx = list(range(b0, min(len(texts), b0 + eng.max_utterances)))
+        per = max(1, min(int(max_utterances), 8))
+        for b0 in range(0, len(texts), per):
+            idx = list(range(b0, min(len(texts), b0 + per)))
             t0 = time.time()
+            if len(idx) < self.batch_min_utterances:
+                # Below the measured crossover (tools/batch_bench.py: the batched step costs ~2.3 ms for 1..2 utterances and
+                # ~3.3 ms for 8, the single-utterance step 0.75 ms) a short group is faster one utterance after the other
+                for i in idx:
+                    res = self.generate(texts[i], max_tokens=max_tokens, cfg_scale=cfg_scale, temperature=temperature,
+                                        top_p=top_p, cfg_filter_top_k=cfg_filter_top_k, seed=base_seed + i, output=output)
+                    results[i], raw[i] = res, self.last_codes
+                    stats["prepare_s"] += self.last_stats.get("prepare_s", 0.0)
+                    stats["loop_s"] += self.last_stats.get("loop_s", 0.0)
+                    stats["steps"] += self.last_stats.get("steps", 0)
+                    stats["frames"] += self.last_stats.get("frames", 0)
+                continue
+            eng = self.model.decoder.batch_engine(per)
             prepared = [self._prepare_generation(self._effective_text(texts[i], None), None, False) for i in idx]
             for u, (st, out) in enumerate(prepared):
                 for c in st.cross_attn_cache:

@@ -15,6 +15,11 @@ def assign(n_items: int, world: int, rank: int) -> list[int]:
     return list(range(rank, n_items, world))
 
 
+def shard(items: list, world: int, rank: int) -> list:
+    """This rank's round-robin share of ``items`` (utterance i goes to rank i % world)."""
+    return [items[i] for i in assign(len(items), world, rank)]
+
+
 def reduce_throughput(frames: float, seconds: float, device=None, group=None) -> tuple[float, float]:
     """(sum of frames over ranks, max of seconds over ranks); identity when not distributed."""
     if not (dist.is_available() and dist.is_initialized()):

@@ -918,6 +918,7 @@ def test_tiny_generate_batch_equals_single_utterance_streams(tiny_gpu):
     """Greedy ``generate_batch`` yields, per utterance, exactly the rows ``generate`` yields for it alone (and the oracle's),
     including the per-utterance EOS countdown at the end of the budget."""
     dia, sd = tiny_gpu
+    dia.batch_min_utterances = 1                                        # always the batched kernel, also for short groups
     single = []
     for t in BATCH_TEXTS:
         dia.generate(t, max_tokens=40, temperature=0.0, output="codes")
@@ -935,6 +936,10 @@ def test_tiny_generate_batch_equals_single_utterance_streams(tiny_gpu):
     b = dia.generate_batch(BATCH_TEXTS * 2, max_tokens=30, seed=4, max_utterances=4)
     assert len(a) == 6 and all(torch.equal(x, y) for x, y in zip(a, b))
     assert not torch.equal(a[0], a[3])                                  # same text, different RNG stream
+    # the default policy runs groups below the measured crossover through the single-utterance kernel: same greedy rows
+    dia.batch_min_utterances = 4
+    outs2 = dia.generate_batch(BATCH_TEXTS, max_tokens=40, temperature=0.0, max_utterances=4)
+    assert all(torch.equal(x, y) for x, y in zip(outs, outs2))
 
 
 def test_full_generate_batch_vs_reference_goldens(full_gpu, gold_full):
@@ -943,6 +948,7 @@ def test_full_generate_batch_vs_reference_goldens(full_gpu, gold_full):
     dia, sd = full_gpu
     golds = [_golden(f"dia16b_seed5_text{n}.npz") for n in (129, 200, 600)]
     texts = [str(g["text"]) for g in golds] + [str(gold_full["text"])]
+    dia.batch_min_utterances = 1
     dia.generate_batch(texts, max_tokens=41, temperature=0.0, cfg_scale=3.0, max_utterances=4)
     for i, g in enumerate(golds):
         got, want = dia.last_batch_codes[i].cpu(), torch.from_numpy(g["codes"])

@@ -17,6 +17,7 @@ ap.add_argument("--slot", type=int, default=1500)
 ap.add_argument("--steps", type=int, default=64)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--tiny", action="store_true")
+ap.add_argument("--profile", action="store_true", help="print where CTA 0's MMA thread and math thread 0 spend their clocks")
 a = ap.parse_args()
 cfg = tiny_config() if a.tiny else dia_1_6b_config()
 dev = torch.device("cuda:0")
@@ -52,4 +53,13 @@ with torch.inference_mode():
             assert all(s.steps_run == a.steps for s in st), [s.steps_run for s in st]
             us = e0.elapsed_time(e1) * 1000 / a.steps
             best = us if best is None else min(best, us)
+        if a.profile:
+            eng.enable_timing(True)
+            eng.generate_begin([o.generated_tokens for _, o in prepared[:U]], [slot + 1] * U, [slot] * U, cfg.data.audio_length,
+                               3.0, 1.3, 0.95, 35, list(range(U)))
+            eng.generate_steps(a.steps)
+            torch.cuda.synchronize()
+            pr = eng.read_profile()
+            eng.enable_timing(False)
+            print("   profile (us/step): " + "  ".join(f"{k}={v / 1965.0 / a.steps:.1f}" for k, v in pr.items()))
         print(f"N={U}: {best:8.1f} us/step  {U / best * 1e6:9.1f} frames/s per GPU  (slot {slot}, {a.steps} steps/launch, best of {a.reps})")

@@ -28,6 +28,10 @@
 #include "engine_internal.h"
 #include "sampler.cuh"
 
+#ifndef DIA_BATCH_FENCE
+#define DIA_BATCH_FENCE 1      // 1: every writer fences (shipped); 0 / 2: timing experiments only (tools/ab_variants.sh)
+#endif
+
 namespace dia {
 
 typedef unsigned long long u64;
@@ -44,7 +48,9 @@ constexpr int kPrefetch = 2;                // activation stages requested ahead
 constexpr int kScratchBytes = 49152;        // B staging | attention scratch | sampler scratch (never live together)
 constexpr int kBMiscBytes = 2048;
 constexpr int kBSmem = kBNumSlots * kBSlotBytes + kScratchBytes + kBMiscBytes + 1024;   // + alignment slack
-constexpr int kMmaWarp = 8;
+constexpr int kMmaWarp = 8;                 // first MMA warp; the second one is kMmaWarp2 (the producer warp sits between)
+constexpr int kMmaWarp2 = 10;
+constexpr int kBThreads = 12 * 32;          // 8 math warps, MMA warp, producer warp, second MMA warp, (one idle: warps come in fours)
 constexpr int kRows = 16;                   // batch rows of the B tiles (2 x kMaxUtt); N of the MMA = 2 kRows (hi rows, then lo rows)
 constexpr int kAccCols = 4 * 2 * kRows;     // TMEM columns of one accumulator set: 4 independent k-step accumulators x (hi | lo)
 constexpr int kTmemCols = 2 * kAccCols;     // two sets: the epilogue of a GEMM stage overlaps the MMAs of the next one
@@ -119,6 +125,10 @@ __device__ __forceinline__ uint4 ld_act4(const uint32_t* p) {
     uint4 r;
     asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
     return r;
+}
+
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 
 // latency-critical waits of the activation pipeline: poll without the suspend hint (a parked warp wakes up late)
@@ -285,7 +295,10 @@ __device__ void producer_loop_b(const BatchParams& p, unsigned char* ring, BMisc
 
 // ---- MMA warp: the whole warp walks the stages (warp-uniform control flow and operands), one elected lane issues every
 //      tcgen05.mma / tcgen05.commit of this CTA ------------------------------------------------------------------------
-__device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned char* scratch, BMisc* misc) {
+// Two MMA warps share every chunk: warp `which` issues k-steps 2 * which and 2 * which + 1 (each k-step has its own
+// accumulator).  One tcgen05.mma costs its issuing thread ~100 cycles while the tensor pipe is busy for 16 (ncu: the pipe
+// is 5 % active), so two issuers double the rate; every slot / stage / accumulator barrier collects both commits.
+__device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned char* scratch, BMisc* misc, int which) {
     const CtaTable& tab = misc->tab;
     const int cta = blockIdx.x;
     const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
@@ -297,7 +310,7 @@ __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned c
     // MMAs on ONE accumulator serialise on its read-modify-write latency (measured: ~115 cycles per instruction).
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * kRows) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     unsigned cbase = 0, bctr = 0, gctr = 0;
-    const bool prof = p.prof != nullptr && cta == 0 && (threadIdx.x & 31) == 0;
+    const bool prof = p.prof != nullptr && cta == 0 && (threadIdx.x & 31) == 0 && which == 0;
     long long t_bfull = 0, t_ring = 0, t_acc = 0, t_all = prof ? clock64() : 0, tq = 0;
 #pragma unroll 1
     for (int n = 0; n < p.n_steps; ++n) {
@@ -343,8 +356,10 @@ __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned c
                         const uint64_t adesc = umma_desc_b(a_base), bdesc = umma_desc_b(b_base);
                         if (elect_one_sync()) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)      // 16 elements along K = 32 bytes = 2 descriptor units
+                            for (int jj = 0; jj < 2; ++jj) {  // 16 elements along K = 32 bytes = 2 descriptor units
+                                const int j = 2 * which + jj;
                                 umma_bf16_b(d_addr + j * 2 * kRows, adesc + 2 * j, bdesc + 2 * j, idesc, c != 0 ? 1u : 0u);
+                            }
                             if ((c & (cps - 1)) == cps - 1) umma_commit_b(&misc->empty[si % kBNumSlots]);
                             if (jc == kStageChunks - 1) umma_commit_b(&misc->bempty[bs]);
                         }
@@ -438,8 +453,15 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
                 }
                 // generic-proxy writes -> the tensor core's async proxy (the shared::cta form: a full fence.proxy.async also
                 // waits for this thread's activation loads in flight)
+#if DIA_BATCH_FENCE == 1
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
+#elif DIA_BATCH_FENCE == 2
+                __syncwarp();
+                if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#else
+                __syncwarp();
+#endif
                 if (lane == 0) mbar_arrive(&misc->bfull[bs]);
                 if (ld_on && st + kPrefetch < n_st) {
 #pragma unroll
@@ -786,7 +808,7 @@ __device__ void attn_stage_b(BCtx& c, int layer) {
             }
         }
         __syncwarp();
-        if (in_ring && c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
+        if (in_ring && c.lane == 0) mbar_arrive_n(&c.misc->empty[sl], 2);
     }
     c.cbase += nkc;
     if (c.lane < HPKB) { wstat[c.warp * 8 + c.lane] = m_run; wstat[c.warp * 8 + 4 + c.lane] = l_run; }
@@ -1028,7 +1050,7 @@ __device__ void sample_stage_b(BCtx& c) {
 }  // namespace
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_batch_step_kernel(const __grid_constant__ BatchParams p) {
+extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel(const __grid_constant__ BatchParams p) {
     extern __shared__ unsigned char smem_raw_b[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_b) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
@@ -1044,19 +1066,20 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_batch_step_kernel(
         if (all_done) return;
     }
     if (tid == 0) {
-        for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
-        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], (uint32_t)(p.R + 1) / 2); mbar_init(&misc->bempty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], 1); mbar_init(&misc->acc_empty[i], 4); }
+        // slot / stage / accumulator releases collect one commit from each of the two MMA warps
+        for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 2); }
+        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], (uint32_t)(p.R + 1) / 2); mbar_init(&misc->bempty[i], 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], 2); mbar_init(&misc->acc_empty[i], 4); }
         misc->stages_done = 0;
         fence_mbar_init();
     }
     {
         const int* src = reinterpret_cast<const int*>(p.cta_tab + blockIdx.x);
         int* dst = reinterpret_cast<int*>(&misc->tab);
-        for (int i = tid; i < (int)(sizeof(CtaTable) / 4); i += kThreads) dst[i] = src[i];
+        for (int i = tid; i < (int)(sizeof(CtaTable) / 4); i += kBThreads) dst[i] = src[i];
     }
     // the B tiles of rows >= R stay zero for the whole launch
-    for (int i = tid; i < kActStages * kActStageBytes / 16; i += kThreads) reinterpret_cast<uint4*>(scratch)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < kActStages * kActStageBytes / 16; i += kBThreads) reinterpret_cast<uint4*>(scratch)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     if (warp == kMmaWarp) {                                  // one warp allocates (and later frees) the accumulator columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc->tmem_base)), "r"(kTmemCols));
@@ -1069,9 +1092,9 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_batch_step_kernel(
     const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
     if (warp == kProducerWarp) {
         if (tid == kProducerWarp * 32) producer_loop_b(p, ring, misc);
-    } else if (warp == kMmaWarp) {
-        mma_loop_b(p, ring, scratch, misc);
-    } else {
+    } else if (warp == kMmaWarp || warp == kMmaWarp2) {
+        mma_loop_b(p, ring, scratch, misc, warp == kMmaWarp ? 0 : 1);
+    } else if (warp < kConsumerWarps) {
         BCtx c;
         c.p = &p; c.ring = ring; c.scratch = scratch; c.misc = misc;
         c.tid = tid; c.warp = warp; c.lane = tid & 31;
@@ -1128,7 +1151,7 @@ cudaError_t launch_batch_kernel(const BatchParams& p, cudaStream_t st) {
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     void* args[] = {const_cast<BatchParams*>(&p)};
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dia_batch_step_kernel), dim3(p.G), dim3(kThreads), args,
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dia_batch_step_kernel), dim3(p.G), dim3(kBThreads), args,
                                        kBSmem, st);
 }
 

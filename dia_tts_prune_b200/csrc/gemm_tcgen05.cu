@@ -8,11 +8,11 @@
 // (x = hi + lo + lo2, exact to 24 bits) and each k-step issues three tcgen05.mma into the SAME fp32 accumulator in
 // tensor memory: the product has fp32-operand accuracy at bf16 tensor-core speed.
 //
-// Structure (one 128 x 128 output tile per CTA, warp-specialised):
+// Structure (one 128 x 256 output tile per CTA, warp-specialised):
 //   warp 0    one lane: TMA producer - cp.async.bulk.tensor loads of the three A-term tiles [128 x 64] and the B
-//             tile [128 x 64] (both K-major, 128-byte swizzle) into a 3-stage shared-memory ring (64 KB per stage)
-//   warp 1    allocates 128 TMEM columns; one lane issues tcgen05.mma (M = 128, N = 128, K = 16, kind::f16, bf16
-//             inputs, fp32 accumulate) and releases ring slots with tcgen05.commit
+//             tile [256 x 64] (both K-major, 128-byte swizzle) into a 2-stage shared-memory ring (80 KB per stage)
+//   warp 1    allocates 256 TMEM columns; the warp walks the k-blocks and one elected lane issues tcgen05.mma (M = 128,
+//             N = 256, K = 16, kind::f16, bf16 inputs, fp32 accumulate) and releases ring slots with tcgen05.commit
 //   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> registers -> fp32 stores
 // W is kept as a K-major bf16 copy [N][K] made once per weight (transpose_to_bf16_kernel), so that A and B use the
 // same canonical UMMA layout.  Every wait is bounded (a stuck pipeline traps instead of hanging the GPU).
@@ -28,11 +28,15 @@ namespace dia {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
+// BN = 256: the three A-term tiles (48 KB per k-block) are shared by twice as many output columns - the kernel is bound
+// by the operand traffic from L2 (BN = 128 moved 4.3 GB for M = 2048, N = 16384, K = 2048: 13 TB/s at 326 us), and a
+// 256-wide MMA (128-cycle floor) also hides the ~100 cycles one tcgen05.mma takes to issue.
+constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kTerms = 3;
-constexpr int kStages = 3;
+constexpr int kStages = 2;
 constexpr int kTileBytes = BM * BK * 2;                     // 16 KB: one [128 x 64] bf16 tile
-constexpr int kStageBytes = (kTerms + 1) * kTileBytes;      // 64 KB
+constexpr int kBTileBytes = BN * BK * 2;                    // 32 KB: the weight tile
+constexpr int kStageBytes = kTerms * kTileBytes + kBTileBytes;   // 80 KB
 constexpr int kGemmThreads = 192;                           // 6 warps
 constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 
@@ -263,13 +267,13 @@ static EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// a [rows][K] bf16 matrix, K contiguous, read in [128 rows x 64 k] boxes with the 128-byte swizzle
-static bool make_map(CUtensorMap* map, const void* base, long long rows, int K) {
+// a [rows][K] bf16 matrix, K contiguous, read in [box_rows x 64 k] boxes with the 128-byte swizzle
+static bool make_map(CUtensorMap* map, const void* base, long long rows, int K, int box_rows) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -304,7 +308,7 @@ cudaError_t launch_gemm_tcgen05(const float* x, const float* norm_w, float eps, 
         split3_rows_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(
             x, reinterpret_cast<__nv_bfloat16*>(workspace), n);
     CUtensorMap ma, mb;
-    if (!make_map(&ma, workspace, (long long)kTerms * M, K) || !make_map(&mb, wt, N, K)) return cudaErrorNotSupported;
+    if (!make_map(&ma, workspace, (long long)kTerms * M, K, BM) || !make_map(&mb, wt, N, K, BN)) return cudaErrorNotSupported;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     dia_gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, y, residual, M, N, K);
     return cudaGetLastError();

@@ -207,8 +207,8 @@ __global__ void rope_rows_kernel(const float* __restrict__ src, float* __restric
         if (rotate) {
             const int p = min(max(pos[row], 0), n_pos - 1);
             const float sn = sin_tab[(size_t)p * 64 + d], cs = cos_tab[(size_t)p * 64 + d];
-            o0 = a * cs - bb * sn;
-            o1 = a * sn + bb * cs;
+            o0 = __fsub_rn(__fmul_rn(a, cs), __fmul_rn(bb, sn));      // separate roundings, like the reference's
+            o1 = __fadd_rn(__fmul_rn(a, sn), __fmul_rn(bb, cs));      // x1 * cos - x2 * sin (no fused multiply-add)
         }
         float* o = to_cache ? dst + (((size_t)b * H + hh) * dst_T + dst_t0 + t) * kHeadDim
                             : dst + (row * H + hh) * kHeadDim;

@@ -407,7 +407,7 @@ class Dia:
             raise ValueError("temperature must be >= 0")
         if seed is not None:
             torch.manual_seed(seed)
-        base_seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        base_seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 31, (1,)).item())   # + i stays a numpy seed
         max_tokens = self.config.data.audio_length if max_tokens is None else max_tokens
         results: list = [None] * len(texts)
         stats = {"prepare_s": 0.0, "loop_s": 0.0, "steps": 0, "frames": 0, "launch_steps": 0}

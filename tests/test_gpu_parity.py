@@ -973,3 +973,51 @@ def test_full_batched_eight_utterances_smoke(full_gpu):
     # utterance 0 alone gives the same greedy rows
     dia.generate(texts[0], max_tokens=300, temperature=0.0, output="codes")
     assert torch.equal(dia.last_codes.cpu()[:200], dia.last_batch_codes[0].cpu()[:200]) or True   # near-ties may differ late
+
+
+def test_non_representable_fp32_checkpoint_is_rounded_once_and_consistently():
+    """A real float32 (or float16) checkpoint is not bf16-representable.  The sm_100a path streams DenseGeneral kernels as
+    bf16, so such kernels are rounded ONCE, in the module, with a warning - encoder, prompt prefill and decode engine
+    then see the same numbers.  Against the oracle on the UNROUNDED weights the logits differ by the weight rounding
+    (bounded here by 6e-2, the reference's own bf16-regime error); against the oracle on the rounded
+    weights the usual tight bound holds."""
+    import warnings
+    from dia_tts_prune_b200 import layers as LY
+    cfg = tiny_config()
+    dia, _ = build_dia(cfg, 7)
+    g = torch.Generator().manual_seed(21)
+    with torch.no_grad():
+        for n, p_ in dia.model.named_parameters():
+            if SY.is_dense_kernel(n):
+                p_.add_(torch.randn(p_.shape, generator=g) * 2e-4)            # no longer bf16-representable
+    sd_exact = {k: v.detach().clone() for k, v in dia.model.named_parameters()}
+    dia.device = torch.device("cuda:0")
+    dia.model.to(dia.device)
+    text = "[S1] Full precision checkpoint. [S2] Rounded once."
+    LY._ROUNDING_WARNED = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        st, out = _prepared(dia, text)
+        st.prepare_step(1)
+        with torch.inference_mode():
+            lg = dia.model.decoder.decode_step(out.get_tokens_at(0).unsqueeze(0).unsqueeze(0).expand(2, 1, -1), st)[:, 0].cpu()
+    assert any("bf16" in str(x.message) for x in w)
+    sd_round = {k: v.detach().cpu().clone() for k, v in dia.model.named_parameters()}
+    for n in sd_round:
+        if SY.is_dense_kernel(n):
+            assert torch.equal(sd_round[n], sd_round[n].to(torch.bfloat16).to(torch.float32)) and not torch.equal(sd_round[n], sd_exact[n])
+    lo_round = O.generate(sd_round, cfg, text, max_tokens=3, temperature=0.0, dead_cross_kv=False, keep_logits_at={1}).logits[1]
+    lo_exact = O.generate(sd_exact, cfg, text, max_tokens=3, temperature=0.0, dead_cross_kv=False, keep_logits_at={1}).logits[1]
+    assert (lg - lo_round).abs().max().item() < LOGIT_TIGHT
+    err = (lg - lo_exact).abs().max().item()
+    print(f"float32 checkpoint, weights rounded to bf16: max-abs logits error vs the unrounded oracle {err:.3e}")
+    assert err < 6e-2
+    # float16 (the default --compute-dtype of the reference's cli.py) is accepted and handled the same way
+    from dia_tts_prune_b200.model import Dia
+    assert Dia(cfg, "float16", torch.device("cuda:0")).model.decoder.logits_dense.weight.dtype == torch.float16
+    d16, _ = build_dia(cfg, 7)
+    SY.cast_dense_kernels_(d16.model, torch.float16)                   # DenseGeneral kernels float16, norms / embeddings float32
+    d16.compute_dtype, d16.device = torch.float16, torch.device("cuda:0")
+    d16.model.to(d16.device).eval()
+    codes = d16.generate(text, max_tokens=20, temperature=0.0, output="codes")
+    assert codes is not None and codes.shape[1] == 9

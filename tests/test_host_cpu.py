@@ -322,3 +322,33 @@ def test_replicas_world_size_2_gloo():
     assert replicas.reduce_throughput(5, 2) == (5.0, 2.0)           # identity when not distributed
     with pytest.raises(ValueError):
         replicas.assign(3, 2, 2)
+
+
+def test_dia_accepts_every_reference_compute_dtype():
+    """The reference's entry points default to float16 (cli.py --compute-dtype, app.py); every ComputeDtype value must
+    construct (on the CPU the reference itself overrides to float32, dia/model.py:118-121)."""
+    from dia_tts_prune_b200.config import tiny_config
+    from dia_tts_prune_b200.model import ComputeDtype, Dia
+    for dt in ComputeDtype:
+        d = Dia(tiny_config(), dt.value, torch.device("cpu"))
+        assert d.compute_dtype == torch.float32 and d.model is not None
+    for dt in ("float16", "bfloat16", "float32"):
+        from dia_tts_prune_b200.layers import DiaModel
+        m = DiaModel(tiny_config(), {"float16": torch.float16, "bfloat16": torch.bfloat16, "float32": torch.float32}[dt])
+        assert m.decoder.logits_dense.weight.dtype == {"float16": torch.float16, "bfloat16": torch.bfloat16,
+                                                       "float32": torch.float32}[dt]
+
+
+def test_canonicalize_rounds_once_and_widens_float16():
+    import warnings
+    from dia_tts_prune_b200 import layers as LY
+    m = LY.DenseGeneral((64,), (128,), weight_dtype=torch.float16)
+    with torch.no_grad():
+        m.weight.copy_(torch.randn(64, 128) * 0.1)
+    LY._ROUNDING_WARNED = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert LY.canonicalize_dense_kernel_(m) is True
+    assert m.weight.dtype == torch.float32 and len(w) == 1
+    assert torch.equal(m.weight, m.weight.to(torch.bfloat16).to(torch.float32))
+    assert LY.canonicalize_dense_kernel_(m) is False                      # idempotent

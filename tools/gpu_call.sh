@@ -1,3 +1,2 @@
 set -x
-(time timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -25) > gpurun_out/r2_t12_all.log 2>&1; tail -30 gpurun_out/r2_t12_all.log
-timeout 900 python bench.py --steps 2 --warmup 3 > gpurun_out/r2_t12_bench.json 2> gpurun_out/r2_t12_bench.err; tail -c 3000 gpurun_out/r2_t12_bench.json; tail -5 gpurun_out/r2_t12_bench.err
+for v in bf0 bf2; do echo "== $v"; DIA_B200_LIB=$PWD/tools/ab/$v.so timeout 300 python tools/batch_bench.py --utts 1 8 --profile --reps 2 2>&1 | tail -4; done > gpurun_out/r2_t16_fence.log 2>&1; cat gpurun_out/r2_t16_fence.log

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Turn the outputs of tools/ncu_bench.sh (gpurun_out/launches_r1.csv, gpurun_out/step_r1_full.ncu-rep) into the
-committed summaries under profiles/: the launch list (shares), the metrics of the full capture, the executed-instruction
-and stall-sample shares per source function, and step_kernel_traffic.json (read by bench.py for roofline.traffic).
+"""Turn the outputs of tools/ncu_bench.sh (gpurun_out/launches_<tag>.csv, gpurun_out/step_<tag>_full.ncu-rep and, when
+present, batch_<tag>_full.ncu-rep / gemm_<tag>_full.ncu-rep) into the committed summaries under profiles/: the launch list
+(shares), the metrics of the full captures, the executed-instruction and stall-sample shares per source function, and
+step_kernel_traffic.json (read by bench.py for roofline.traffic).
 
-    python tools/summarize_ncu.py [--tag r1]
+    python tools/summarize_ncu.py [--tag r2]
 """
 import argparse
 import collections
@@ -22,13 +23,16 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__inst_issued.avg.pct_of_peak_sustained_active",
            "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+           "sm__inst_executed_pipe_uniform.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
            "launch__block_size", "smsp__inst_executed.sum", "smsp__pcsamp_sample_count"]
 TO_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
 def launch_list(tag):
-    path = os.path.join(OUT, "launches_r1.csv")
+    path = os.path.join(OUT, f"launches_{tag}.csv")
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
     per = collections.defaultdict(lambda: [0, 0.0])
     for r in rows:
@@ -37,15 +41,35 @@ def launch_list(tag):
     total = sum(v[1] for v in per.values())
     with open(os.path.join(PROF, f"{tag}_ncu_launch_list.txt"), "w") as f:
         f.write("# ncu launch list, kernels of libdia_b200.so only (-k regex:dia), of `python bench.py --steps 1 --warmup 1 "
-                "--no-cpu-baseline`\n# (cold-cache, serialised: compare SHARES).  One bench step = one 3071-step generation = "
-                "48 launches of dia_step_kernel;\n# the one-time weight repack (repack_dense_kernel) is outside every timed "
-                f"region.\n# total device time of these launches: {total:.1f} ms\nlaunches  ms_total  share  kernel\n")
+                "--no-cpu-baseline --batch-utterances 8`\n# (cold-cache, serialised: compare SHARES).  One bench step = one "
+                "3071-step generation = 24 launches of dia_step_kernel (128 steps each);\n# the batch field adds 8 utterances "
+                "in one dia_batch_step_kernel stream; the one-time weight repacks are outside every timed\n# region.  "
+                f"Total device time of these launches: {total:.1f} ms\nlaunches  ms_total  share  kernel\n")
         for k, (n, ms) in sorted(per.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{n:8d} {ms:10.2f} {100 * ms / total:6.1f}%  {k}\n")
 
 
+def metrics_only(tag, rep_name, title, out_name):
+    rep = os.path.join(OUT, rep_name)
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    kv = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
+    lines = [title]
+    for m in METRICS:
+        if m in kv:
+            lines.append(f"{m:80s} {kv[m][1]:>16s} {kv[m][0]}")
+    for h in hdr:
+        if h.startswith("smsp__pcsamp_warps_issue_stalled") and not h.endswith("not_issued") and kv[h][1] not in ("0", ""):
+            lines.append(f"{h:80s} {kv[h][1]:>16s} {kv[h][0]}")
+    with open(os.path.join(PROF, out_name), "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
 def full_capture(tag):
-    rep = os.path.join(OUT, "step_r1_full.ncu-rep")
+    rep = os.path.join(OUT, f"step_{tag}_full.ncu-rep")
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -103,7 +127,7 @@ def full_capture(tag):
     with open(os.path.join(PROF, f"{tag}_ncu_step_kernel_full.txt"), "w") as f:
         f.write("\n".join(lines) + "\n")
     with open(os.path.join(PROF, "step_kernel_traffic.json"), "w") as f:
-        json.dump({"dram_bytes_per_launch": rd + wr, "steps_per_launch": 64, "first_slot": 1500,
+        json.dump({"dram_bytes_per_step": (rd + wr) / 64, "captured_steps_per_launch": 64, "first_slot": 1500,
                    "source": f"profiles/{tag}_ncu_step_kernel_full.txt"}, f)
         f.write("\n")
 
@@ -134,8 +158,14 @@ def line_table():
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--tag", default="r1")
+    ap.add_argument("--tag", default="r2")
     a = ap.parse_args()
     launch_list(a.tag)
     full_capture(a.tag)
+    metrics_only(a.tag, f"batch_{a.tag}_full.ncu-rep",
+                 "# ncu --set full --clock-control none, dia_batch_step_kernel, ONE launch of 16 decode steps of 8 utterances "
+                 "from slot 1500 (tools/ncu_bench.sh)", f"{a.tag}_ncu_batch_kernel_full.txt")
+    metrics_only(a.tag, f"gemm_{a.tag}_full.ncu-rep",
+                 "# ncu --set full --clock-control none, dia_gemm_tcgen05_kernel, M = 2048, N = 16384, K = 2048 (tools/gemm_check.py)",
+                 f"{a.tag}_ncu_tcgen05_gemm.txt")
     print("profiles updated")

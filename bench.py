@@ -46,12 +46,14 @@ VARIANTS = {
     "mlp-pruned": "Dia-1.6B with mlp.wo structurally pruned along dim 0 (offline_prune.py --prune-dim 0, L2 norm; "
                   "BASELINE.json configs[3] 'reduced MLP width')",
     "2to4": "Dia-1.6B with every dense kernel 2:4-pruned along K (BASELINE.json configs[3], unstructured-sparse variant)",
+    "structured": "Dia-1.6B after the stock offline_prune.py call: apply_structured_pruning(model, amount, dim=0, n=2) on "
+                  "EVERY DenseGeneral (input rows zeroed; the engine drops them: K-row compaction + reduced MLP width)",
 }
 
 
 def workload_config(text_len: int, world: int, variant: str = "dense", amount: float = 0.0) -> dict:
     """The `config` object both arms print (BASELINE.json configs[1], one utterance per GPU)."""
-    model = VARIANTS[variant] + (f", amount {amount}" if variant == "mlp-pruned" else "")
+    model = VARIANTS[variant] + (f", amount {amount}" if variant in ("mlp-pruned", "structured") else "")
     return {"workload": f"{model} bf16 weights, single transcript per GPU, CFG batch 2, full 3072-token "
                         "generation (3071 decode steps), reference default sampling T=1.3 top_p=0.95 top_k=35",
             "precision": "bf16 weights; fp32 activations, accumulation, softmax and KV cache",
@@ -62,7 +64,7 @@ def workload_config(text_len: int, world: int, variant: str = "dense", amount: f
 
 
 def algorithmic_bytes(cfg, slot: int, text_len: int, kv_elem: int = 4, n_hidden: int | None = None,
-                      weight_scale: float = 1.0) -> int:
+                      weight_scale: float = 1.0, dense_bytes: int | None = None) -> int:
     """bf16 weights of the 18 layers + logits head, fp32 norm weights, 9 embedding rows,
     plus self-KV rows read / appended and the valid cross-KV rows of the conditional row.  Pruned variants:
     ``n_hidden`` = live MLP width of a structurally pruned model; ``weight_scale`` = 0.5625 for 2:4 (half the
@@ -72,6 +74,8 @@ def algorithmic_bytes(cfg, slot: int, text_len: int, kv_elem: int = 4, n_hidden:
     nq, nkv, nc = d.gqa_query_heads * hd, d.kv_heads * hd, d.cross_query_heads * hd
     per_layer = D * (nq + 2 * nkv) + nq * D + D * nc + nc * D + D * 2 * F + F * D
     w = int(2 * weight_scale * (d.n_layer * per_layer + D * cfg.data.channels * cfg.model.tgt_vocab_size))
+    if dense_bytes is not None:        # row-compacted (structurally pruned) model: the live kernels as the engine streams them
+        w = int(dense_bytes)
     w += 4 * (3 * d.n_layer + 1) * D + 4 * cfg.data.channels * D
     kv_row = d.n_layer * 2 * 2 * nkv * kv_elem            # K and V, both CFG rows, all layers, one slot
     cross = d.n_layer * 2 * nc * kv_elem * text_len       # K and V, conditional row only
@@ -224,6 +228,10 @@ def run_ours(args) -> None:
         if args.variant == "mlp-pruned":
             for layer in dia.model.decoder.layers:
                 prune.ln_structured(layer.mlp.wo, "weight", amount=args.prune_amount, n=2, dim=0)
+        elif args.variant == "structured":
+            PU.apply_structured_pruning(dia.model, args.prune_amount, dim=0, n=2)
+            with torch.no_grad():        # keep the zeroed channel-0 EOS column from coming back as the only live one
+                dia.model.decoder.logits_dense.weight[:, 0, cfg.data.audio_eos_value] = 0.0
         else:
             PU.apply_2to4_pruning(dia.model.decoder)
         PU.make_pruning_permanent(dia.model)
@@ -247,6 +255,7 @@ def run_ours(args) -> None:
     text_len = dec_state.text_len
     eng_width = dia.model.decoder.engine().n_hidden           # < n_hidden when dead MLP neurons were dropped
     w_scale = 0.5625 if args.variant == "2to4" else 1.0
+    live_bytes = dia.model.decoder.engine().weight_stream_bytes if args.variant == "structured" else None
 
     def one_generation(profile=None) -> int:
         for c in dec_state.self_attn_cache:
@@ -285,7 +294,7 @@ def run_ours(args) -> None:
     k_bytes = k_ms = 0.0
     for (a, b, slot0, n) in profile:
         k_ms += a.elapsed_time(b)
-        k_bytes += sum(algorithmic_bytes(cfg, slot0 + i, text_len, n_hidden=eng_width, weight_scale=w_scale)
+        k_bytes += sum(algorithmic_bytes(cfg, slot0 + i, text_len, n_hidden=eng_width, weight_scale=w_scale, dense_bytes=live_bytes)
                        for i in range(n))
     peak, peak_src = measured_peak()
     achieved = k_bytes / (k_ms * 1e-3) / 1e9

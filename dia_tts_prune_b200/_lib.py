@@ -25,7 +25,8 @@ class Shape(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_layer", "d_model", "n_hidden", "q_heads", "kv_heads", "cross_heads",
                                          "channels", "vocab", "max_audio_len", "max_text_len", "eos_value",
                                          "pad_value", "bos_value")] + \
-               [("delay_pattern", C.c_int32 * MAX_CHANNELS), ("norm_eps", C.c_float), ("sparse24", C.c_int32)]
+               [("delay_pattern", C.c_int32 * MAX_CHANNELS), ("norm_eps", C.c_float), ("sparse24", C.c_int32),
+                ("k_rows", C.c_int32 * 7)]
 
 
 class GenParams(C.Structure):
@@ -51,6 +52,7 @@ _SIGNATURES = {
     "dia_b200_engine_weight_stream_bytes": (C.c_int64, [_vp]),
     "dia_b200_load_decoder_weights": (_i, [_vp, C.POINTER(_vp), _i, _i, _vp]),
     "dia_b200_set_rope_table": (_i, [_vp, _vp, _vp, _i]),
+    "dia_b200_set_row_map": (_i, [_vp, _i, C.POINTER(C.c_int32), _vp]),
     "dia_b200_bind_caches": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i, _vp]),
     "dia_b200_decode_step": (_i, [_vp, _i32p, _i, _i, _fp, _vp]),
     "dia_b200_decoder_layer_step": (_i, [_vp, _i, _fp, _fp, _i, _i, _vp]),

@@ -116,14 +116,15 @@ def dia_1_6b_config() -> DiaConfig:
     )
 
 
-def tiny_config(n_layer: int = 2, audio_length: int = 256, text_length: int = 128) -> DiaConfig:
+def tiny_config(n_layer: int = 2, audio_length: int = 256, text_length: int = 128, width: int = 1) -> DiaConfig:
     """A small configuration with the same head geometry (head_dim 128, GQA
-    4:1, 9 codebooks of 1028) used by fast parity tests."""
+    4:1, 9 codebooks of 1028) used by fast parity tests.  ``width`` scales the decoder (width 2: d_model 1024, 8 query
+    heads - wide enough for the 512-row granularity of the K-row compaction)."""
     return DiaConfig(
         model=ModelConfig(
             encoder=EncoderConfig(n_layer=2, n_embd=256, n_hidden=512, n_head=2, head_dim=128),
-            decoder=DecoderConfig(n_layer=n_layer, n_embd=512, n_hidden=1024, gqa_query_heads=4, kv_heads=1,
-                                  gqa_head_dim=128, cross_query_heads=4, cross_head_dim=128),
+            decoder=DecoderConfig(n_layer=n_layer, n_embd=512 * width, n_hidden=1024 * width, gqa_query_heads=4 * width,
+                                  kv_heads=width, gqa_head_dim=128, cross_query_heads=4 * width, cross_head_dim=128),
             src_vocab_size=256, tgt_vocab_size=1028),
         data=DataConfig(text_length=text_length, audio_length=audio_length, channels=9),
     )

@@ -28,10 +28,6 @@
 #include "engine_internal.h"
 #include "sampler.cuh"
 
-#ifndef DIA_BATCH_FENCE
-#define DIA_BATCH_FENCE 1      // 1: every writer fences (shipped); 0 / 2: timing experiments only (tools/ab_variants.sh)
-#endif
-
 namespace dia {
 
 typedef unsigned long long u64;
@@ -385,6 +381,30 @@ __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned c
     }
 }
 
+// sum v[i] over the 32 lanes for NV values at once (see step_kernel.cu)
+template <int NV>
+__device__ __forceinline__ void transpose_reduce_b(float (&v)[NV], int lane) {
+    int n = NV;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        if (n > 1) {
+            n >>= 1;
+            const bool hi = (lane & m) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) {
+                if (i < n) {
+                    const float a = v[i], b = v[i + n];
+                    const float send = hi ? a : b;
+                    const float keep = hi ? b : a;
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                }
+            }
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+        }
+    }
+}
+
 // ---- GEMM stage, math warps: stage the activations, then the epilogue ----------------------------------------------------------
 __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
     const BatchParams& p = *c.p;
@@ -399,39 +419,48 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
                         : gt == G_QKV ? p.act_xq : gt == G_CQ ? p.act_xc : gt == G_WI ? p.act_xm : p.act_xl;
     const uint32_t fb = gt == G_LOGITS ? flag_s(c.step) : flag_l(L, c.step, layer);       // flag bit the input words carry
 
-    // ---- the activations, stage by stage (128 k): one 16-byte load per thread and chunk = 4 consecutive k of one row --------
-    const int r_ld = tid >> 4, k4 = tid & 15;
-    const bool ld_on = r_ld < R;
-    const uint32_t* my = src + (size_t)r_ld * 64 + 4 * k4;
+    // ---- the activations, stage by stage (128 k).  The math warps form two groups of four that take the stages alternately
+    //      (two stages in flight per CTA: the chain wait-for-a-free-stage -> store -> fence -> arrive of one stage overlaps the
+    //      other group's).  A stage of all rows is R x 2 x 16 pieces of 16 bytes (4 consecutive k of one row of one chunk);
+    //      thread t of a group takes the pieces t, t + 128, ... ------------------------------------------------------------------
     const size_t chunk_words = (size_t)R * 64;
-    const uint32_t st_off = (uint32_t)(r_ld * 128 + ((((k4 >> 1) ^ (r_ld & 7)) << 4) | ((k4 & 1) << 3)));
     const int n_st = n_chunks / kStageChunks;
-    const bool stager = 2 * warp < R;                          // warps whose threads hold a row (bfull counts exactly these)
-    uint4 v[kPrefetch][kStageChunks];
+    const int grp = warp >> 2, t128 = tid & 127;
+    const int n_pieces = R * kStageChunks * 16;                // per stage; <= 512
+    constexpr int kPc = 4;                                     // pieces per thread and stage (512 / 128)
+    static_assert(kStageChunks == 2, "piece index split assumes two chunks per stage");
+    const int rc16 = R * 16;
+    auto piece_src = [&](int st, int q) -> const uint32_t* {
+        const int jc = q >= rc16 ? 1 : 0, rem = q - jc * rc16, r = rem >> 4, k4 = rem & 15;
+        return src + (size_t)(st * kStageChunks + jc) * chunk_words + (size_t)r * 64 + 4 * k4;
+    };
+    uint4 v[kPrefetch][kPc];
 #pragma unroll
-    for (int i = 0; i < kPrefetch; ++i)
+    for (int i = 0; i < kPrefetch; ++i) {
+        const int st = grp + 2 * i;
 #pragma unroll
-        for (int jc = 0; jc < kStageChunks; ++jc)
-            if (ld_on && i < n_st) v[i][jc] = ld_act4(my + (size_t)(i * kStageChunks + jc) * chunk_words);
+        for (int j = 0; j < kPc; ++j)
+            if (st < n_st && t128 + 128 * j < n_pieces) v[i][j] = ld_act4(piece_src(st, t128 + 128 * j));
+    }
 #pragma unroll 1
-    for (int s0 = 0; s0 < (stager ? n_st : 0); s0 += kPrefetch) {
+    for (int s0 = grp; s0 < n_st; s0 += 2 * kPrefetch) {
 #pragma unroll
         for (int i = 0; i < kPrefetch; ++i) {
-            const int st = s0 + i;
+            const int st = s0 + 2 * i;
             if (st < n_st) {
                 long long tq = c.prof ? clock64() : 0;
-                if (ld_on) {
 #pragma unroll
-                    for (int jc = 0; jc < kStageChunks; ++jc) {
+                for (int j = 0; j < kPc; ++j) {
+                    if (t128 + 128 * j < n_pieces) {
                         unsigned spins = 0;
-                        while ((((v[i][jc].x ^ fb) | (v[i][jc].y ^ fb) | (v[i][jc].z ^ fb) | (v[i][jc].w ^ fb)) & 1u) != 0u) {
+                        while ((((v[i][j].x ^ fb) | (v[i][j].y ^ fb) | (v[i][j].z ^ fb) | (v[i][j].w ^ fb)) & 1u) != 0u) {
                             if (++spins > kMaxSpins) {
                                 volatile int* e = reinterpret_cast<volatile int*>(p.err);
-                                e[4] = st; e[5] = gt; e[6] = (int)fb; e[7] = r_ld;
+                                e[4] = st; e[5] = gt; e[6] = (int)fb; e[7] = j;
                                 ll_timeout(p.err, kErrFlagTimeout, c.seq * 16 + gt);
                             }
                             ll_check_abort(p.err, spins, 100 + kErrFlagTimeout, c.seq * 16 + gt);
-                            v[i][jc] = ld_act4(my + (size_t)(st * kStageChunks + jc) * chunk_words);
+                            v[i][j] = ld_act4(piece_src(st, t128 + 128 * j));
                         }
                     }
                 }
@@ -440,34 +469,29 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
                 if (lane == 0) mbar_spin(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (c.seq << 8) | 0xc0 | bs);
                 __syncwarp();
                 if (c.prof) c.t_prof[1] += clock64() - tq;
-                if (ld_on) {
+                const uint32_t stage = smem_u32(c.scratch + bs * kActStageBytes);
 #pragma unroll
-                    for (int jc = 0; jc < kStageChunks; ++jc) {
-                        const uint32_t dst = smem_u32(c.scratch + bs * kActStageBytes) + jc * 2 * kBTermBytes + st_off;
-                        const uint32_t h0 = __byte_perm(v[i][jc].x, v[i][jc].y, 0x7632), h1 = __byte_perm(v[i][jc].z, v[i][jc].w, 0x7632);
-                        const uint32_t l0 = __byte_perm(v[i][jc].x, v[i][jc].y, 0x5410) & 0xfffefffeu;
-                        const uint32_t l1 = __byte_perm(v[i][jc].z, v[i][jc].w, 0x5410) & 0xfffefffeu;
+                for (int j = 0; j < kPc; ++j) {
+                    const int q = t128 + 128 * j;
+                    if (q < n_pieces) {
+                        const int jc = q >= rc16 ? 1 : 0, rem = q - jc * rc16, r = rem >> 4, k4 = rem & 15;
+                        const uint32_t dst = stage + (uint32_t)(jc * 2 * kBTermBytes + r * 128 + ((((k4 >> 1) ^ (r & 7)) << 4) | ((k4 & 1) << 3)));
+                        const uint32_t h0 = __byte_perm(v[i][j].x, v[i][j].y, 0x7632), h1 = __byte_perm(v[i][j].z, v[i][j].w, 0x7632);
+                        const uint32_t l0 = __byte_perm(v[i][j].x, v[i][j].y, 0x5410) & 0xfffefffeu;
+                        const uint32_t l1 = __byte_perm(v[i][j].z, v[i][j].w, 0x5410) & 0xfffefffeu;
                         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
                         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst + kBTermBytes), "r"(l0), "r"(l1) : "memory");
                     }
                 }
                 // generic-proxy writes -> the tensor core's async proxy (the shared::cta form: a full fence.proxy.async also
                 // waits for this thread's activation loads in flight)
-#if DIA_BATCH_FENCE == 1
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-#elif DIA_BATCH_FENCE == 2
-                __syncwarp();
-                if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#else
-                __syncwarp();
-#endif
                 if (lane == 0) mbar_arrive(&misc->bfull[bs]);
-                if (ld_on && st + kPrefetch < n_st) {
+                const int nx = st + 2 * kPrefetch;
 #pragma unroll
-                    for (int jc = 0; jc < kStageChunks; ++jc)
-                        v[i][jc] = ld_act4(my + (size_t)((st + kPrefetch) * kStageChunks + jc) * chunk_words);
-                }
+                for (int j = 0; j < kPc; ++j)
+                    if (nx < n_st && t128 + 128 * j < n_pieces) v[i][j] = ld_act4(piece_src(nx, t128 + 128 * j));
             }
         }
     }
@@ -503,13 +527,8 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
                 }
             }
         }
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-            if (r < R) {
-                const float t = warp_sum(sr[r]);
-                if (lane == 0) misc->ssq_part[warp][r] = t;
-            }
-        }
+        transpose_reduce_b<kRows>(sr, lane);                  // 31 shuffles instead of 16 x 5: lanes 2r, 2r + 1 hold row r
+        if ((lane & 1) == 0) misc->ssq_part[warp][lane >> 1] = sr[0];
         consumer_sync();
         if (tid < R) {
             float ss = 0.f;
@@ -630,30 +649,6 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
     if (c.prof) { const long long t1 = clock64(); c.t_prof[4] += t1 - tq2; tq2 = t1; }
     consumer_sync();            // the staging ring is scratch of the next stage: every MMA of this one has completed
     if (c.prof) c.t_prof[5] += clock64() - tq2;
-}
-
-// sum v[i] over the 32 lanes for NV values at once (see step_kernel.cu)
-template <int NV>
-__device__ __forceinline__ void transpose_reduce_b(float (&v)[NV], int lane) {
-    int n = NV;
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        if (n > 1) {
-            n >>= 1;
-            const bool hi = (lane & m) != 0;
-#pragma unroll
-            for (int i = 0; i < NV / 2; ++i) {
-                if (i < n) {
-                    const float a = v[i], b = v[i + n];
-                    const float send = hi ? a : b;
-                    const float keep = hi ? b : a;
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-                }
-            }
-        } else {
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
-        }
-    }
 }
 
 constexpr int HPKB = 4;          // query heads per KV tile in self-attention (GQA 4:1)
@@ -1068,7 +1063,7 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
     if (tid == 0) {
         // slot / stage / accumulator releases collect one commit from each of the two MMA warps
         for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 2); }
-        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], (uint32_t)(p.R + 1) / 2); mbar_init(&misc->bempty[i], 2); }
+        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], 4); mbar_init(&misc->bempty[i], 2); }   // 4 warps stage a stage
         for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], 2); mbar_init(&misc->acc_empty[i], 4); }
         misc->stages_done = 0;
         fence_mbar_init();

@@ -100,6 +100,10 @@ struct dia_b200_engine {
     int gen_pos = 0, gen_slot = 0;
     long long gen_steps = 0;          // decode steps launched since generate_begin (RNG draw index)
 
+    int Kfull[G_COUNT]{};             // contraction lengths before K-row compaction
+    int* d_rowmap[G_COUNT]{};         // device maps [L][Kfull] (logits [Kfull]) of the compacted GEMM families
+    bool rowmap_set[G_COUNT]{};
+
     // batched engine (max_utts > 0): N utterances per launch on the tcgen05 step kernel (batch_kernel.cu)
     int max_utts = 0;
     unsigned char* d_bll = nullptr;   // its exchange region
@@ -127,6 +131,16 @@ int validate_shape(const dia_b200_shape& s) {
         if (k % 512 || (sl > 256 && sl % 256)) return DIA_B200_EUNSUPPORTED;
     }
     if (s.vocab > 5 * kConsumerThreads) return DIA_B200_EUNSUPPORTED;     // sampler: <= 5 entries of a channel per thread
+    {
+        const int full[7] = {s.d_model, s.q_heads * kHeadDim, s.d_model, s.cross_heads * kHeadDim, s.d_model, s.n_hidden, s.d_model};
+        for (int t = 0; t < 7; ++t) {
+            const int k = s.k_rows[t];
+            if (k == 0) continue;
+            if (k < 0 || k > full[t] || t == 5) return DIA_B200_EINVAL;                 // mlp-out is compacted through n_hidden
+            if (k % 512 || (k / 8 > 256 && (k / 8) % 256)) return DIA_B200_EUNSUPPORTED;
+            if (s.sparse24) return DIA_B200_EUNSUPPORTED;
+        }
+    }
     return DIA_B200_OK;
 }
 
@@ -138,6 +152,7 @@ void fill_params(const dia_b200_engine* e, StepParams& p) {
     for (int i = 0; i < G_COUNT; ++i) { p.Kdim[i] = e->Kdim[i]; p.tclass[i] = e->tclass[i]; }
     p.eps = s.norm_eps; p.G = e->G; p.n_res = e->n_res; p.sa_nsplit = e->sa_nsplit; p.ca_nsplit = e->ca_nsplit;
     p.sparse24 = s.sparse24 ? 1 : 0;
+    for (int i = 0; i < G_COUNT; ++i) { p.rowmap[i] = e->d_rowmap[i]; p.Kfull[i] = e->Kfull[i]; }
     p.wstream = e->d_wstream; p.cta_tab = e->d_tab; p.emb = e->d_emb; p.norms = e->d_norms;
     p.rope_sin = e->d_rope_sin; p.rope_cos = e->d_rope_cos; p.n_pos = e->n_pos;
     p.self_k = e->d_ptrs; p.self_v = e->d_ptrs + s.n_layer;
@@ -215,6 +230,7 @@ int dia_b200_engine_create_batched(const dia_b200_shape* shape, int device, int 
                                    dia_b200_engine** out) {
     if (max_utterances < 1 || max_utterances > kMaxUtt) return DIA_B200_EINVAL;
     if (shape && shape->sparse24) return DIA_B200_EUNSUPPORTED;          // 2:4 slabs exist for the single-utterance kernel only
+    if (shape) for (int t = 0; t < 7; ++t) if (shape->k_rows[t]) return DIA_B200_EUNSUPPORTED;   // so does K-row compaction
     return create_engine(shape, device, n_ctas, max_utterances, out);
 }
 
@@ -275,7 +291,8 @@ static int create_engine(const dia_b200_shape* shape, int device, int n_ctas, in
     const int order_t[G_COUNT] = {G_SO, G_CO, G_WO, G_WI, G_QKV, G_CQ, G_LOGITS};
     for (int oi = 0; oi < G_COUNT; ++oi) {
         const int t = order_t[oi];
-        e->Kdim[t] = kd[t];
+        e->Kfull[t] = kd[t];
+        e->Kdim[t] = s.k_rows[t] > 0 ? s.k_rows[t] : kd[t];
         e->n_groups[t] = units[t] * mult[t];
         std::vector<int> cnt(G, units[t] / G);
         if (t == G_CO || t == G_WO) {
@@ -316,7 +333,7 @@ static int create_engine(const dia_b200_shape* shape, int device, int n_ctas, in
             e->tab[c].gc[t] = gc;
             for (int i = 0; i < gc; ++i) { e->owner[t][g0 + i] = c; e->local[t][g0 + i] = i; }
             g0 += gc;
-            if (t != G_LOGITS) load[c] += (long long)(batch ? bslab_bytes(gc, kd[t]) : gemm_slab_bytes(gc, kd[t], sp));
+            if (t != G_LOGITS) load[c] += (long long)(batch ? bslab_bytes(gc, e->Kdim[t]) : gemm_slab_bytes(gc, e->Kdim[t], sp));
         }
     }
     for (int t = 0; t < G_COUNT; ++t) {
@@ -340,7 +357,7 @@ static int create_engine(const dia_b200_shape* shape, int device, int n_ctas, in
     for (int c = 0; c < G; ++c) {
         CtaTable& t = e->tab[c];
         unsigned o = 0;
-        auto slab_bytes = [&](int g) { return batch ? bslab_bytes(t.gc[g], kd[g]) : gemm_slab_bytes(t.gc[g], kd[g], sp); };
+        auto slab_bytes = [&](int g) { return batch ? bslab_bytes(t.gc[g], e->Kdim[g]) : gemm_slab_bytes(t.gc[g], e->Kdim[g], sp); };
         for (int g = 0; g < G_LOGITS; ++g) { t.slab_off[g] = o; o += (unsigned)slab_bytes(g); }
         t.layer_bytes = o;
         t.slab_off[G_LOGITS] = 0;
@@ -370,6 +387,8 @@ static int create_engine(const dia_b200_shape* shape, int device, int n_ctas, in
         ALLOC(e->d_owner[t], sizeof(int) * e->n_groups[t]);
         ALLOC(e->d_local[t], sizeof(int) * e->n_groups[t]);
     }
+    for (int t = 0; t < G_COUNT; ++t)
+        if (s.k_rows[t] > 0) ALLOC(e->d_rowmap[t], sizeof(int) * (size_t)(t == G_LOGITS ? 1 : s.n_layer) * e->Kfull[t]);
     ALLOC(e->d_emb, sizeof(float) * (size_t)s.channels * s.vocab * D);
     ALLOC(e->d_norms, sizeof(float) * ((size_t)s.n_layer * 3 + 1) * D);
     const int n_utt = batch ? kMaxUtt : 1;
@@ -422,7 +441,7 @@ int dia_b200_engine_destroy(dia_b200_engine* e) {
     void* dev[] = {e->d_wstream, e->d_tab, e->d_emb, e->d_norms, e->d_rope_sin, e->d_rope_cos, e->d_ptrs, e->d_x,
                    e->d_logits, e->d_ll, e->d_pred, e->d_tokens, e->d_gs, e->d_timing, e->d_cta_timing, e->d_bll};
     for (void* p : dev) if (p) cudaFree(p);
-    for (int t = 0; t < G_COUNT; ++t) { if (e->d_owner[t]) cudaFree(e->d_owner[t]); if (e->d_local[t]) cudaFree(e->d_local[t]); }
+    for (int t = 0; t < G_COUNT; ++t) { if (e->d_owner[t]) cudaFree(e->d_owner[t]); if (e->d_local[t]) cudaFree(e->d_local[t]); if (e->d_rowmap[t]) cudaFree(e->d_rowmap[t]); }
     if (e->h_ptrs) cudaFreeHost(e->h_ptrs);
     if (e->h_gs) cudaFreeHost(e->h_gs);
     if (e->h_err) cudaFreeHost(e->h_err);
@@ -495,6 +514,27 @@ int dia_b200_load_decoder_weights(dia_b200_engine* e, const void* const* tensors
     return DIA_B200_OK;
 }
 
+int dia_b200_set_row_map(dia_b200_engine* e, int gemm, const int32_t* map_host, void* stream) {
+    if (!e || !map_host || gemm < 0 || gemm >= G_COUNT) return DIA_B200_EINVAL;
+    if (!e->d_rowmap[gemm]) return DIA_B200_ESTATE;                      // this GEMM family is not compacted
+    const int L = gemm == G_LOGITS ? 1 : e->shape.n_layer, Kf = e->Kfull[gemm], Kc = e->Kdim[gemm];
+    std::vector<char> hit((size_t)Kc);
+    for (int l = 0; l < L; ++l) {                                        // every compacted row exactly once per layer
+        std::fill(hit.begin(), hit.end(), 0);
+        for (int k = 0; k < Kf; ++k) {
+            const int v = map_host[(size_t)l * Kf + k];
+            if (v < -1 || v >= Kc) return DIA_B200_EINVAL;
+            if (v >= 0) { if (hit[v]) return DIA_B200_EINVAL; hit[v] = 1; }
+        }
+        for (int v = 0; v < Kc; ++v) if (!hit[v]) return DIA_B200_EINVAL;
+    }
+    ON_DEVICE(e->device);
+    CK(cudaMemcpyAsync(e->d_rowmap[gemm], map_host, sizeof(int) * (size_t)L * Kf, cudaMemcpyHostToDevice, S(stream)));
+    CK(cudaStreamSynchronize(S(stream)));
+    e->rowmap_set[gemm] = true;
+    return DIA_B200_OK;
+}
+
 int dia_b200_set_rope_table(dia_b200_engine* e, const float* sin_host, const float* cos_host, int n_pos) {
     if (!e || !sin_host || !cos_host || n_pos <= 0) return DIA_B200_EINVAL;
     ON_DEVICE(e->device);
@@ -540,6 +580,7 @@ static int ready(const dia_b200_engine* e, bool need_caches) {
     if (!e) return DIA_B200_EINVAL;
     if (e->max_utts > 0) return DIA_B200_ESTATE;              // a batched engine: use the dia_b200_batch_* entry points
     if (!e->weights_loaded || !e->rope_set) return DIA_B200_ESTATE;
+    for (int t = 0; t < G_COUNT; ++t) if (e->d_rowmap[t] && !e->rowmap_set[t]) return DIA_B200_ESTATE;
     if (need_caches && !e->caches_bound) return DIA_B200_ESTATE;
     return DIA_B200_OK;
 }

@@ -90,6 +90,10 @@ struct StepParams {
     int n_res;                         // CTAs [0, n_res) own columns of the residual stream (and publish sum(x^2))
     int sa_nsplit, ca_nsplit;          // max key splits per (row, kv head) / per cross head
     int sparse24;                      // weight slabs are 2:4-compressed (mma.sp), see gemm_slot_rows
+    // K-row compaction: rowmap[gt] (device, [L][Kfull[gt]], logits [Kfull]) = position of input element k in the compacted
+    // contraction of GEMM family gt, or -1 (dropped); nullptr = identity.  Producers write their words there.
+    const int* rowmap[G_COUNT];
+    int Kfull[G_COUNT];
     // weights
     const unsigned char* wstream;
     const CtaTable* cta_tab;

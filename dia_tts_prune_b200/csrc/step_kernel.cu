@@ -318,6 +318,12 @@ __device__ __forceinline__ void ll_store_parts(u64* dst, int k, int r, float x, 
     ll_st(dst + (size_t)(k >> 4) * 32 + r * 16 + (k & 15), lo, hi);
 }
 
+// position of input element k in the (K-row compacted) contraction of GEMM family gt in `layer`; -1 = dropped
+__device__ __forceinline__ int row_pos(const StepParams& p, int gt, int layer, int k) {
+    const int* m = p.rowmap[gt];
+    return m == nullptr ? k : __ldg(m + (size_t)(gt == G_LOGITS ? 0 : layer) * p.Kfull[gt] + k);
+}
+
 // ------------------------------------------------------------------------------------------
 // GEMM stage: y[2][N_cta] = x[2][K] . W_slab on the tensor cores (mma.sync m16n8k16, bf16 x bf16 ->
 // fp32).  Swap-AB: the 16 rows of the MMA are 16 OUTPUT COLUMNS (two 8-column groups of the slab,
@@ -471,6 +477,7 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
     const bool e_valid = e_mt < n_mt && e_group < gc;
     const int e_n = (g0 + e_group) * 8 + (e_m & 7);
     float wn_v = 0.f;
+    int x_pos = -1;
     if (resid && e_valid) {
         // weight of the RMSNorm that consumes the new stream: pre_ca / pre_mlp of this layer, or the next
         // layer's pre_sa (the final norm after the last layer) - a cold line, so it is fetched up front
@@ -478,6 +485,10 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
                         : gt == G_CO ? p.norms + ((size_t)layer * 3 + 2) * p.D
                                      : p.norms + ((size_t)(layer + 1) * 3) * p.D;
         wn_v = __ldg(wn + e_n);
+        // ... and where this element sits in the contraction of the consumer (cross-q after self-o, mlp-in after cross-o,
+        // the next layer's qkv or the logits head after mlp-out)
+        const bool last = gt == G_WO && layer == p.L - 1;
+        x_pos = row_pos(p, gt == G_SO ? G_CQ : gt == G_CO ? G_WI : last ? G_LOGITS : G_QKV, gt == G_WO ? layer + 1 : layer, e_n);
     }
 
     float acc[kMaxTiles][4];
@@ -678,7 +689,7 @@ __device__ void gemm_stage(Ctx& c, int gt, int layer) {
         xn = c.xres + y;
         c.xres = xn;
         if (p.want_x) reinterpret_cast<float*>(p.x)[(size_t)e_n * 2 + e_r] = xn;
-        ll_store_parts(p.ll_x, e_n, e_r, xn * wn_v, f16n);
+        if (x_pos >= 0) ll_store_parts(p.ll_x, x_pos, e_r, xn * wn_v, f16n);
     }
     if (c.ts && c.tid == 0) c.ts[7] = clock64();
     float sqv = xn * xn;                                               // half-warps = batch rows
@@ -912,9 +923,11 @@ __device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
         }
         if (w.n_active == 1) {
             const float val = l > 0.f ? o / l : 0.f;
-            const int k = (head0 + h) * kHeadDim + d;
-            ll_store_parts(oparts, k, r, val, f16n);
-            if (!self) ll_store_parts(oparts, k, 0, 0.f, f16n);       // the unconditional row attends nothing
+            const int k = row_pos(p, self ? G_SO : G_CO, layer, (head0 + h) * kHeadDim + d);
+            if (k >= 0) {
+                ll_store_parts(oparts, k, r, val, f16n);
+                if (!self) ll_store_parts(oparts, k, 0, 0.f, f16n);   // the unconditional row attends nothing
+            }
         } else {
             u64* pp = part + ((size_t)w.split * nh + h) * 132;
             ll_st(pp + 4 + d, __float_as_uint(o), c.seq);
@@ -1012,9 +1025,11 @@ __device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
         if (live && j == 0) {
             const float Lsum = cf[nhh * na + (h - h_lo)];
             const float val = Lsum > 0.f ? O / Lsum : 0.f;
-            const int k = (head0 + h) * kHeadDim + d;
-            ll_store_parts(oparts, k, r, val, f16n);
-            if (!self) ll_store_parts(oparts, k, 0, 0.f, f16n);
+            const int k = row_pos(p, self ? G_SO : G_CO, layer, (head0 + h) * kHeadDim + d);
+            if (k >= 0) {
+                ll_store_parts(oparts, k, r, val, f16n);
+                if (!self) ll_store_parts(oparts, k, 0, 0.f, f16n);
+            }
         }
     }
     if (c.ts && c.tid == 0) c.ts[7] = clock64();
@@ -1028,7 +1043,7 @@ __device__ void attn_stage(Ctx& c, int layer, int pos, int slot) {
 // Warp 0 only: lane = row * 16 + column of this CTA's residual columns.
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ float enter_stream(const StepParams& p, unsigned char* xs, const SharedMisc* misc, int tid,
-                                           bool embed, int pos, int step, const float* wnorm, uint32_t seq_out) {
+                                           bool embed, int pos, int step, const float* wnorm, uint32_t seq_out, int layer) {
     const GemmCfg& g = misc->gcfg[G_SO];
     if (g.gc == 0) return 0.f;                                // this CTA owns no residual columns
     const int lane = tid & 31, warp = tid >> 5, e_r = lane >> 4, e_m = lane & 15;
@@ -1063,7 +1078,8 @@ __device__ __noinline__ float enter_stream(const StepParams& p, unsigned char* x
     }
     if (valid) {
         if (p.want_x) reinterpret_cast<float*>(p.x)[(size_t)n * 2 + e_r] = x;
-        ll_store_parts(p.ll_x, n, e_r, x * __ldg(wnorm + n), seq_out & 0xffffu);
+        const int kp = row_pos(p, layer >= p.L ? G_LOGITS : G_QKV, layer, n);   // consumer: qkv of `layer` (or the logits head)
+        if (kp >= 0) ll_store_parts(p.ll_x, kp, e_r, x * __ldg(wnorm + n), seq_out & 0xffffu);
     }
     float sqv = valid ? x * x : 0.f;
 #pragma unroll
@@ -1223,7 +1239,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
         // the stream a previous launch left in p.x, published as if stage_begin - 1 had just produced it
         const int layer = (p.stage_begin - 1) >> 3;
         c.seq = (unsigned)p.stage_begin;
-        c.xres = enter_stream(p, xs, misc, tid, false, 0, 0, p.norms + (size_t)layer * 3 * p.D, c.seq);
+        c.xres = enter_stream(p, xs, misc, tid, false, 0, 0, p.norms + (size_t)layer * 3 * p.D, c.seq, layer);
     }
 #pragma unroll 1
     for (int n = 0; n < p.n_steps; ++n) {
@@ -1236,7 +1252,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dia_step_kernel(const 
             c.ts = (p.timing != nullptr && (int)blockIdx.x == p.timing_cta && (tid == 0 || tid == 224)) ? p.timing + ((size_t)n * S + s) * 16 : nullptr;
             if (c.ts && tid == 0) c.ts[0] = clock64();
             switch (kind) {
-                case S_EMBED: c.xres = enter_stream(p, xs, misc, tid, true, pos, n, p.norms, c.seq); break;
+                case S_EMBED: c.xres = enter_stream(p, xs, misc, tid, true, pos, n, p.norms, c.seq, 0); break;
                 case S_SATTN: attn_stage<HPK>(c, layer, pos, slot); break;
                 case S_CATTN: attn_stage<1>(c, layer, pos, slot); break;
                 case S_SAMPLE: sample_stage(c, n, pos); break;

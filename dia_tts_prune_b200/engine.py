@@ -51,7 +51,7 @@ def decoder_tensor_names(config: DiaConfig) -> list[str]:
 
 class DecodeEngine:
     def __init__(self, config: DiaConfig, device: torch.device | str | int = "cuda", n_ctas: int = 0,
-                 n_hidden: int | None = None, sparse24: bool = False):
+                 n_hidden: int | None = None, sparse24: bool = False, k_rows: dict | None = None):
         """``n_hidden``: MLP width of the weights that will be loaded, when a structurally pruned checkpoint was
         compacted (``pruning_utils.plan_mlp_compaction``); defaults to the configuration's.  ``sparse24``: every dense
         kernel is 2:4-sparse along its input axis (``pruning_utils.is_2to4``): the engine streams compressed slabs
@@ -78,6 +78,10 @@ class DecodeEngine:
         sh.norm_eps = config.model.normalization_layer_epsilon
         self.sparse24 = bool(sparse24)
         sh.sparse24 = 1 if sparse24 else 0
+        # K-row compaction of a structurally pruned checkpoint: {GEMM family: contraction length} (pruning_utils.plan_row_compaction)
+        self.k_rows = {int(k): int(v) for k, v in (k_rows or {}).items()}
+        for fam, kk in self.k_rows.items():
+            sh.k_rows[fam] = kk
         self._h = C.c_void_p()
         _lib.check(self.lib.dia_b200_engine_create(C.byref(sh), self.device.index, n_ctas, C.byref(self._h)),
                    "engine_create")
@@ -121,6 +125,14 @@ class DecodeEngine:
         _lib.check(self.lib.dia_b200_load_decoder_weights(self._h, arr, len(staged), dense_dtype, _stream(self.device)),
                    "load_decoder_weights")
         torch.cuda.current_stream(self.device).synchronize()    # sources may be freed after this
+
+    def set_row_maps(self, maps: dict[int, torch.Tensor]) -> None:
+        """``{GEMM family: int32 [layers, K]}`` from ``pruning_utils.compact_rows`` (position of every input element in
+        the compacted contraction, -1 = dropped)."""
+        for fam, m in maps.items():
+            m = m.to(dtype=torch.int32, device="cpu").contiguous()
+            _lib.check(self.lib.dia_b200_set_row_map(self._h, int(fam), C.cast(m.data_ptr(), C.POINTER(C.c_int32)),
+                                                     _stream(self.device)), "set_row_map")
 
     # ---- per-utterance binding -------------------------------------------------------------------
     def bind(self, self_caches, cross_caches, text_len: int) -> None:

@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import contextlib
 import math
+import os
 import weakref
 from typing import Optional
 
@@ -69,6 +70,23 @@ class DenseGeneral(nn.Module):
         self.in_shapes, self.out_features, self.axis = in_shapes, out_features, axis
         self.kernel_shape = self.in_shapes + self.out_features
         self.weight = nn.Parameter(torch.empty(self.kernel_shape, dtype=weight_dtype, device=device))
+
+    # the K-major bf16 copy the tcgen05 GEMM reads is keyed by (data_ptr, version): drop it whenever the parameter object
+    # is replaced (torch.nn.utils.prune, load_state_dict(assign=True)) or moved (.to / .cpu / .cuda) - a new tensor can
+    # land on the very address the old one had
+    def __setattr__(self, name, value):
+        if name in ("weight", "weight_orig", "weight_mask"):
+            self.__dict__.pop("_b200_wt", None)
+        super().__setattr__(name, value)
+
+    def __delattr__(self, name):
+        if name in ("weight", "weight_orig", "weight_mask"):
+            self.__dict__.pop("_b200_wt", None)
+        super().__delattr__(name)
+
+    def _apply(self, fn, *a, **kw):
+        self.__dict__.pop("_b200_wt", None)
+        return super()._apply(fn, *a, **kw)
 
     def forward(self, inputs: Tensor) -> Tensor:
         """``tensordot(x, W)`` over ``axis`` (dia/layers.py:55-66).  On a CUDA device every call runs on the tcgen05
@@ -429,6 +447,8 @@ class Decoder(nn.Module):
         self._engine = None
         self._engine_sig = None
         self.compact_pruned_mlp = True      # drop exactly-dead MLP neurons from the engine's weight stream
+        # drop all-zero input rows of the other kernels (K-row compaction); DIA_NO_ROW_COMPACTION=1 is the A/B switch of bench.py
+        self.compact_pruned_rows = os.environ.get("DIA_NO_ROW_COMPACTION", "0") != "1"
         self.use_sparse24 = True            # stream 2:4 checkpoints compressed (mma.sp) when every kernel qualifies
         self.register_load_state_dict_post_hook(lambda m, k: m.invalidate_engine())
 
@@ -473,12 +493,21 @@ class Decoder(nn.Module):
         # a 2:4 checkpoint (every dense kernel) streams compressed and runs on mma.sp
         sparse = bool(self.use_sparse24) and all(is_2to4(t, _contract_dims(n)) for n, t in tensors.items()
                                                  if is_dense_kernel(n))
+        # `--prune-dim 0` checkpoints: all-zero INPUT rows of the other kernels are dropped as well (K-row compaction)
+        from .pruning_utils import compact_rows, plan_row_compaction
+        rplan = plan_row_compaction(tensors, d.n_layer) if (self.compact_pruned_rows and not sparse) else {}
+        maps = {}
+        if rplan:
+            tensors, maps = compact_rows(tensors, rplan)
+        k_rows = {fam: w for fam, (w, _) in rplan.items()}
         if self._engine is None or self._engine.device != dev or self._engine.n_hidden != width or \
-                self._engine.sparse24 != sparse:
+                self._engine.sparse24 != sparse or self._engine.k_rows != k_rows:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = DecodeEngine(self.config, dev, n_hidden=width, sparse24=sparse)
+            self._engine = DecodeEngine(self.config, dev, n_hidden=width, sparse24=sparse, k_rows=k_rows)
         self._engine.load_weights(tensors)
+        if maps:
+            self._engine.set_row_maps(maps)
         self._engine_sig = sig
         return self._engine
 

@@ -179,3 +179,79 @@ def compact_mlp(params: dict[str, torch.Tensor], plan: tuple[int, list[torch.Ten
         out[f"{prefix}{i}.mlp.wi_fused.weight"] = wi.index_select(2, idx).contiguous()
         out[f"{prefix}{i}.mlp.wo.weight"] = wo.index_select(0, idx).contiguous()
     return out
+
+
+# ---- K-row compaction: `--prune-dim 0` zeroes whole INPUT rows of a kernel (offline_prune.py:43, dia/pruning_utils.py:64-119) ----
+# GEMM families of the decode engine (csrc/engine_internal.h): the kernels that make up each, viewed as [K, N]
+K_FAMILIES = {0: ("self_attention.q_proj.weight", "self_attention.k_proj.weight", "self_attention.v_proj.weight"),
+              1: ("self_attention.o_proj.weight",), 2: ("cross_attention.q_proj.weight",),
+              3: ("cross_attention.o_proj.weight",), 4: ("mlp.wi_fused.weight",)}
+K_LOGITS = 6
+
+
+def _rows_live(w: torch.Tensor, n_in_axes: int) -> torch.Tensor:
+    K = 1
+    for s_ in w.shape[:n_in_axes]:
+        K *= s_
+    return (w.reshape(K, -1) != 0).any(dim=1)
+
+
+@torch.no_grad()
+def plan_row_compaction(params: dict[str, torch.Tensor], n_layer: int, prefix: str = "layers.") -> dict:
+    """Which all-zero input rows the decode engine can drop, per GEMM family: ``{family: (K_eff, [index tensor per
+    layer])}`` for the families worth compacting (the fused q/k/v projection keeps a row that is live in any of the
+    three).  ``K_eff`` is the common contraction length the kernel accepts (``engine_mlp_width``); layers with fewer live
+    rows are padded with dead ones (zero weights: exact).  mlp-out is handled by :func:`plan_mlp_compaction`."""
+    plan = {}
+    for fam, names in K_FAMILIES.items():
+        n_in = 2 if fam in (1, 3) else 1
+        lives = []
+        for i in range(n_layer):
+            live = None
+            for nm in names:
+                l_ = _rows_live(params[f"{prefix}{i}.{nm}"], n_in)
+                live = l_ if live is None else (live | l_)
+            lives.append(live)
+        K = lives[0].numel()
+        width = engine_mlp_width(max(int(l_.sum().item()) for l_ in lives))
+        if width >= K:
+            continue
+        keep = []
+        for live in lives:
+            a = torch.nonzero(live, as_tuple=False).flatten()
+            b = torch.nonzero(~live, as_tuple=False).flatten()
+            keep.append(torch.sort(torch.cat([a, b[: width - a.numel()]])).values)
+        plan[fam] = (width, keep)
+    live = _rows_live(params["logits_dense.weight"], 1)
+    width = engine_mlp_width(int(live.sum().item()))
+    if width < live.numel():
+        a = torch.nonzero(live, as_tuple=False).flatten()
+        b = torch.nonzero(~live, as_tuple=False).flatten()
+        plan[K_LOGITS] = (width, [torch.sort(torch.cat([a, b[: width - a.numel()]])).values])
+    return plan
+
+
+@torch.no_grad()
+def compact_rows(params: dict[str, torch.Tensor], plan: dict, prefix: str = "layers.") -> tuple[dict, dict]:
+    """(parameter dict with the planned kernels reduced to their kept input rows, ``{family: int32 map [layers, K]}``
+    with the compacted position of every input element or -1) - what ``dia_b200_set_row_map`` takes."""
+    out = dict(params)
+    maps = {}
+    for fam, (width, keep) in plan.items():
+        names = ("logits_dense.weight",) if fam == K_LOGITS else K_FAMILIES[fam]
+        n_in = 2 if fam in (1, 3) else 1
+        rows = []
+        for i, idx in enumerate(keep):
+            for nm in names:
+                key = nm if fam == K_LOGITS else f"{prefix}{i}.{nm}"
+                w = params[key]
+                K = 1
+                for s_ in w.shape[:n_in]:
+                    K *= s_
+                w2 = w.reshape(K, *w.shape[n_in:]).index_select(0, idx.to(w.device)).contiguous()
+                out[key] = w2                                   # [K_eff, out...]: the engine reads it as [K_eff, N]
+            m = torch.full((K,), -1, dtype=torch.int32)
+            m[idx.cpu()] = torch.arange(idx.numel(), dtype=torch.int32)
+            rows.append(m)
+        maps[fam] = torch.stack(rows).contiguous()
+    return out, maps

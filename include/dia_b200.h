@@ -58,6 +58,11 @@ typedef struct dia_b200_shape {
     int32_t sparse24;       /* 1: every dense kernel is 2:4-sparse along its input axis (at most 2 non-zeros in each 4
                                consecutive K entries of a column - the 2:4 variant of offline_prune.py's checkpoints);
                                the engine streams compressed slabs and multiplies with mma.sp.  0: dense. */
+    int32_t k_rows[7];      /* K-row compaction of a structurally pruned checkpoint (offline_prune.py --prune-dim 0 zeroes whole
+                               INPUT rows of a kernel, dia/pruning_utils.py:64-119): contraction length of each GEMM family
+                               (0 qkv, 1 self-o, 2 cross-q, 3 cross-o, 4 mlp-in, 5 mlp-out, 6 logits) after its all-zero rows
+                               were dropped; 0 = not compacted.  The kernels handed to dia_b200_load_decoder_weights then
+                               have that many rows, and dia_b200_set_row_map says where every input element goes. */
 } dia_b200_shape;
 
 /* Sampling / loop parameters of Dia.generate (dia/model.py:632-647). */
@@ -122,6 +127,13 @@ int dia_b200_load_decoder_weights(dia_b200_engine *e, const void *const *tensors
 /* sin/cos of position*inv_freq for positions [0,n_pos), HOST float32 [n_pos][64] each
  * (RotaryEmbedding, dia/layers.py:126-132,161-169; computed by the caller so that it equals
  * the reference's own CPU values bit for bit). */
+/* K-row compaction (shape.k_rows[gemm] > 0): map int32 [n_layer][K_full] (host; the logits head: [K_full]) gives, for every
+ * element k of the input vector of that GEMM family in every layer, its row in the compacted kernel, or -1 if the kernel's
+ * row k was all zeros and has been dropped.  Every row 0 .. k_rows[gemm]-1 must be hit exactly once per layer.  The stage
+ * that PRODUCES the vector writes each element straight to its compacted position, so the consumer streams and multiplies
+ * only the live rows - exact, because the dropped products are zeros. */
+int dia_b200_set_row_map(dia_b200_engine *e, int gemm, const int32_t *map_host, void *stream);
+
 int dia_b200_set_rope_table(dia_b200_engine *e, const float *sin_host, const float *cos_host, int n_pos);
 
 /* Bind one utterance's caches: HOST arrays (n_layer entries) of DEVICE pointers.

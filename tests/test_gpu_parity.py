@@ -1021,3 +1021,54 @@ def test_non_representable_fp32_checkpoint_is_rounded_once_and_consistently():
     d16.model.to(d16.device).eval()
     codes = d16.generate(text, max_tokens=20, temperature=0.0, output="codes")
     assert codes is not None and codes.shape[1] == 9
+
+
+def test_structured_pruning_of_every_kernel_compacts_rows_and_matches_oracle():
+    """f3: the stock `apply_structured_pruning(model, 0.5, dim=0)` of offline_prune.py zeroes input rows of EVERY kernel.
+    The engine drops them (K-row compaction: producers write each element to its compacted position), streams ~half the
+    bytes, and still matches the oracle run on the zero-filled full-size weights."""
+    from dia_tts_prune_b200 import pruning_utils as PU
+    cfg = tiny_config(width=2)
+    dia, _ = build_dia(cfg, 11)
+    dia.device = torch.device("cuda:0")
+    dia.model.to(dia.device)
+    text = "[S1] Rows dropped. [S2] Same logits."
+    st, out = _prepared(dia, text)
+    dense_bytes = dia.model.decoder._engine_for(st).weight_stream_bytes
+    dia.model.cpu()
+    PU.apply_structured_pruning(dia.model, 0.5, dim=0, n=2)
+    PU.make_pruning_permanent(dia.model)
+    sd = {k: v.detach().clone() for k, v in dia.model.named_parameters()}
+    dia.model.to(dia.device)
+    tr = O.generate(sd, cfg, text, max_tokens=30, temperature=0.0, dead_cross_kv=False, keep_logits_at={1, 2, 20})
+    st, out = _prepared(dia, text)
+    eng = dia.model.decoder._engine_for(st)
+    assert eng.k_rows == {1: 512, 2: 512, 3: 512, 4: 512, 6: 512} and eng.n_hidden == 1024
+    assert eng.weight_stream_bytes < 0.62 * dense_bytes
+    grid = tr.grid.cuda()
+    for cur in (1, 2):
+        st.prepare_step(cur)
+        with torch.inference_mode():
+            lg = dia.model.decoder.decode_step(grid[cur - 1].unsqueeze(0).unsqueeze(0).expand(2, 1, -1), st)
+        assert (lg[:, 0].cpu() - tr.logits[cur]).abs().max() < LOGIT_TIGHT
+    # the layer-wise operator boundary hands the stream from launch to launch through the same maps
+    st2, _ = _prepared(dia, text)
+    st_o, _, _ = O.prepare_generation(sd, cfg, O.effective_text(text, None), None, dead_cross_kv=False)
+    st2.prepare_step(1)
+    st_o.prepare_step(1)
+    x = torch.randn(2, 1, cfg.model.decoder.n_embd, generator=torch.Generator().manual_seed(2))
+    xg, xo = x.cuda(), x.clone()
+    with torch.inference_mode():
+        for i, layer in enumerate(dia.model.decoder.layers):
+            xg = layer(xg, st2, self_attn_cache=st2.self_attn_cache[i], cross_attn_cache=st2.cross_attn_cache[i])
+            xo = O.decoder_layer(sd, cfg, i, xo, st_o, prefill=False, dead_cross_kv=False)
+            assert (xg.cpu() - xo).abs().max() < 1e-4, i
+    dia.generate(text, max_tokens=30, temperature=0.0, output="codes")
+    if torch.stack(tr.margins).min() > 1e-4:
+        assert torch.equal(dia.last_codes.cpu(), tr.codes)
+    dia.model.decoder.compact_pruned_rows = False              # the same weights with their zero rows streamed: same tokens
+    dia.model.decoder.invalidate_engine()
+    dia.generate(text, max_tokens=30, temperature=0.0, output="codes")
+    assert dia.model.decoder.engine().k_rows == {}
+    if torch.stack(tr.margins).min() > 1e-4:
+        assert torch.equal(dia.last_codes.cpu(), tr.codes)

@@ -352,3 +352,43 @@ def test_canonicalize_rounds_once_and_widens_float16():
     assert m.weight.dtype == torch.float32 and len(w) == 1
     assert torch.equal(m.weight, m.weight.to(torch.bfloat16).to(torch.float32))
     assert LY.canonicalize_dense_kernel_(m) is False                      # idempotent
+
+
+def test_row_compaction_plan_is_exact():
+    """K-row compaction of a stock `--prune-dim 0` checkpoint: the kept-row lists cover every live row, the maps are
+    partial permutations, and contracting the compacted kernel with the gathered input equals the full product."""
+    from dia_tts_prune_b200 import pruning_utils as PU
+    from dia_tts_prune_b200.engine import decoder_tensor_names
+    from dia_tts_prune_b200.model import Dia
+    cfg = tiny_config(width=2)
+    dia = Dia(cfg, "float32", torch.device("cpu"))
+    SY.init_synthetic_(dia.model.named_parameters(), 3)
+    PU.apply_structured_pruning(dia.model, 0.5, dim=0, n=2)
+    PU.make_pruning_permanent(dia.model)
+    sd = dict(dia.model.decoder.named_parameters())
+    tensors = {n: sd[n].detach() for n in decoder_tensor_names(cfg)}
+    L = cfg.model.decoder.n_layer
+    plan = PU.plan_row_compaction(tensors, L)
+    # cross-q, mlp-in and the logits head lose half of their 1024 input rows, the attention output projections half of
+    # their heads; the fused q/k/v projection keeps a row that is live in any of the three (87.5 %): not worth it
+    assert set(plan) == {1, 2, 3, 4, 6} and all(w == 512 for w, _ in plan.values())
+    compact, maps = PU.compact_rows(tensors, plan)
+    g = torch.Generator().manual_seed(0)
+    for fam, (width, keep) in plan.items():
+        m = maps[fam]
+        assert m.dtype == torch.int32 and m.shape == ((1 if fam == 6 else L), 1024)
+        for l in range(m.shape[0]):
+            pos = m[l][m[l] >= 0]
+            assert sorted(pos.tolist()) == list(range(width))
+        name = "logits_dense.weight" if fam == 6 else f"layers.1.{PU.K_FAMILIES[fam][0]}"
+        w_full, w_c = tensors[name].reshape(1024, -1), compact[name].reshape(width, -1)
+        x = torch.randn(1024, generator=g)
+        row = m[0 if fam == 6 else 1]
+        xc = torch.zeros(width)
+        xc[row[row >= 0].long()] = x[row >= 0]
+        assert torch.allclose(xc @ w_c, x @ w_full, atol=1e-5)
+    # an unpruned model: nothing to compact
+    dia2 = Dia(cfg, "float32", torch.device("cpu"))
+    SY.init_synthetic_(dia2.model.named_parameters(), 3)
+    sd2 = dict(dia2.model.decoder.named_parameters())
+    assert PU.plan_row_compaction({n: sd2[n].detach() for n in decoder_tensor_names(cfg)}, L) == {}

@@ -36,7 +36,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    extra = os.environ.get("DIA_NVCC_EXTRA", "").split()          # e.g. -DDIA_BATCH_TRACE for a bring-up build
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, f"-I{INCLUDE}", "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

@@ -14,10 +14,13 @@
 //    tcgen05.ld: thread = output column, registers = the 16 rows, so RMSNorm scaling, RoPE-ready q/k/v words,
 //    SiLU(gate) * up, the residual add (the stream lives in registers of its column's thread) and the CFG combine
 //    are all local;
-//  * activation vectors cross CTAs as 4-byte words (bf16 hi | bf16 lo with a 1-bit generation flag in the last
-//    mantissa bit), [k / 64][row][64]: a k-chunk of all rows is 4 KB = one 16-byte load per math thread, which
-//    unpacks it straight into the swizzled B tiles.  Half the bytes of the single-utterance format: with 16 rows
-//    the activation exchange through L2, not HBM, is what bounds the step;
+//  * the input vector of a GEMM stage crosses CTAs as the shared-memory image of the N operand itself (per 64-k chunk
+//    a hi tile and a lo tile of [16 rows][64 k] bf16, swizzled): the producing epilogues store 2-byte terms straight
+//    into that image in global memory, every CTA adds to the buffer's arrival counter with release semantics, and a
+//    dedicated lane of each consuming CTA polls the counter (acquire) and then streams the vector into a 6-stage ring
+//    with 8 KB bulk copies (TMA engine) - no register staging, no per-word flags, the math warps are free for the
+//    RMSNorm sums while the MMAs run.  (The first version moved (hi | lo | 1-bit flag) words through registers: 2 608
+//    stage hand-offs per step between the math warps and the MMA warp were 60 % of the step.)
 //  * attention, embedding and sampling are the single-utterance stages indexed by (utterance, row): (row, kv head)
 //    pairs x key splits over the CTAs, 9 sampler CTAs per utterance, one state machine per utterance.
 //
@@ -40,13 +43,13 @@ constexpr int kActStages = 6;               // activation (B operand) staging ri
 constexpr int kBTermBytes = 2048;           // [16 rows][64 k] bf16, K-major, 128-byte swizzle
 constexpr int kStageChunks = 2;             // k-chunks (64 rows each) per activation stage: [chunk][hi tile | lo tile]
 constexpr int kActStageBytes = kStageChunks * 2 * kBTermBytes;
-constexpr int kPrefetch = 2;                // activation stages requested ahead (2 x 16-byte loads per thread each)
 constexpr int kScratchBytes = 49152;        // B staging | attention scratch | sampler scratch (never live together)
 constexpr int kBMiscBytes = 2048;
 constexpr int kBSmem = kBNumSlots * kBSlotBytes + kScratchBytes + kBMiscBytes + 1024;   // + alignment slack
 constexpr int kMmaWarp = 8;                 // first MMA warp; the second one is kMmaWarp2 (the producer warp sits between)
 constexpr int kMmaWarp2 = 10;
-constexpr int kBThreads = 12 * 32;          // 8 math warps, MMA warp, producer warp, second MMA warp, (one idle: warps come in fours)
+constexpr int kActWarp = 11;                // one lane: waits for the input buffer of every GEMM stage, streams it into the B ring
+constexpr int kBThreads = 12 * 32;          // 8 math warps, MMA warp, producer warp, second MMA warp, activation warp
 constexpr int kRows = 16;                   // batch rows of the B tiles (2 x kMaxUtt); N of the MMA = 2 kRows (hi rows, then lo rows)
 constexpr int kAccCols = 4 * 2 * kRows;     // TMEM columns of one accumulator set: 4 independent k-step accumulators x (hi | lo)
 constexpr int kTmemCols = 2 * kAccCols;     // two sets: the epilogue of a GEMM stage overlaps the MMAs of the next one
@@ -57,6 +60,8 @@ struct BMisc {
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     int stages_done;
+    int trace[kConsumerWarps][2];           // bring-up build: (marker, stage) of every math warp
+    int ready_seq;                          // the input buffer of GEMM stage `ready_seq` (and of every earlier one) is complete
     CtaTable tab;
     float inv[kRows];                       // 1/rms of the stage input per row
     float ssq_part[kConsumerWarps][kRows];
@@ -71,12 +76,11 @@ struct BCtx {
     BMisc* misc;
     int tid, warp, lane;
     unsigned cbase;       // ring slot index at the start of the current stage
-    unsigned bctr;        // activation chunks staged so far
     unsigned gctr;        // GEMM stages (with columns in this CTA) so far
     unsigned seq;         // sequence number of the current stage inside this launch (>= 1)
     int step;             // step index inside the launch
     float xres[kRows];    // threads 0..15: this column's element of the residual stream, per row
-    long long t_prof[8];  // CTA 0, thread 0 (p.prof): 0 activation-flag spins, 1 bempty waits, 2 rms gather, 3 accumulator wait,
+    long long t_prof[8];  // CTA 0, thread 0 (p.prof): 0 wait for the stage input, 1 -, 2 rms gather, 3 accumulator wait,
                           // 4 epilogue, 5 end-of-stage barrier, 6 attention stages, 7 embed + sample
     bool prof;
 };
@@ -100,27 +104,55 @@ __device__ __forceinline__ int gemm_of_kind_b(int kind) {
     }
 }
 
-// Generation of an activation buffer (how many times it has been written before) -> the flag bit its words carry.
-// One bit is enough ONLY if every reader of a buffer reads every generation of it (a reader two generations behind
-// would take stale words for fresh ones).  So every consumer GEMM has its own input buffer - xq (qkv), xc (cross-q),
-// xm (mlp-in), xl (logits), attn (self-o), cattn (cross-o), hidden (mlp-out): each is written once per layer (xl once
-// per step) and read, every time, by the same CTAs (the column partition is the same in every layer).
-__device__ __forceinline__ uint32_t flag_l(int L, int step, int layer) { return (uint32_t)(step * L + layer + 1) & 1u; }
-__device__ __forceinline__ uint32_t flag_s(int step) { return (uint32_t)(step + 1) & 1u; }
+// ---- activation buffers -----------------------------------------------------------------------------------------------------
+// Every consumer GEMM has its own input buffer - xq (qkv), xc (cross-q), xm (mlp-in), xl (logits), attn (self-o), cattn
+// (cross-o), hidden (mlp-out); each is written once per layer (xl once per step) and EVERY CTA adds kArrivalsPerCta to the
+// buffer's counter per generation, whether it owns a piece of the vector or not, and only after it has passed every
+// earlier stage.  A consumer of generation g waits for counter >= g * G * kArrivalsPerCta; every CTA waits at every GEMM
+// stage (also one without columns there), so no CTA can arrive for generation g + 1 before all have arrived for g, and a
+// buffer is only rewritten after all its readers have passed a later all-to-all stage.
+__device__ __forceinline__ int act_of_gemm(int gt) {
+    switch (gt) {
+        case G_QKV: return A_XQ;
+        case G_SO: return A_ATTN;
+        case G_CQ: return A_XC;
+        case G_CO: return A_CATTN;
+        case G_WI: return A_XM;
+        case G_WO: return A_HIDDEN;
+        default: return A_XL;
+    }
+}
+__device__ __forceinline__ unsigned act_generation(int gt, int L, int step, int layer) {
+    return gt == G_LOGITS ? (unsigned)(step + 1) : (unsigned)(step * L + layer + 1);
+}
+__device__ __forceinline__ const unsigned char* act_buffer(const BatchParams& p, int a) {
+    switch (a) {
+        case A_XQ: return p.act_xq;
+        case A_XC: return p.act_xc;
+        case A_XM: return p.act_xm;
+        case A_XL: return p.act_xl;
+        case A_ATTN: return p.act_attn;
+        case A_CATTN: return p.act_cattn;
+        default: return p.act_hidden;
+    }
+}
+__device__ __forceinline__ void act_arrive(const BatchParams& p, int a, unsigned n) { red_release_add_u32(p.ctr + a * 32, n); }
 
-// x ~ hi + lo with both terms bf16; the last mantissa bit of lo carries the generation flag
-__device__ __forceinline__ uint32_t pack_act(float x, uint32_t fbit) {
+// x ~ hi + lo, both bf16, stored at the element's place in the swizzled tiles of its 64-k chunk (see engine_internal.h)
+__device__ __forceinline__ void st_act(unsigned char* buf, int k, int r, float x) {
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-    return ((uint32_t)__bfloat16_as_ushort(h) << 16) | ((uint32_t)__bfloat16_as_ushort(l) & 0xfffeu) | fbit;
+    unsigned char* dst = buf + (size_t)(k >> 6) * (2 * kBTermBytes) + r * 128 + (((((k & 63) >> 3) ^ (r & 7)) << 4) | ((k & 7) << 1));
+    asm volatile("st.relaxed.gpu.global.b16 [%0], %1;" ::"l"(dst), "h"(__bfloat16_as_ushort(h)) : "memory");
+    asm volatile("st.relaxed.gpu.global.b16 [%0], %1;" ::"l"(dst + kBTermBytes), "h"(__bfloat16_as_ushort(l)) : "memory");
 }
-__device__ __forceinline__ void st_act(uint32_t* buf, int R, int k, int r, uint32_t word) {
-    asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(buf + ((size_t)(k >> 6) * R + r) * 64 + (k & 63)), "r"(word) : "memory");
-}
-__device__ __forceinline__ uint4 ld_act4(const uint32_t* p) {
-    uint4 r;
-    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+__device__ __forceinline__ float4 ld_gpu_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
     return r;
+}
+__device__ __forceinline__ void st_gpu_f(float* p, float v) {
+    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
 __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
@@ -289,6 +321,74 @@ __device__ void producer_loop_b(const BatchParams& p, unsigned char* ring, BMisc
     }
 }
 
+// ---- activation lane: for every GEMM stage, wait until the stage's input buffer is complete (all CTAs have arrived), tell
+//      the math warps, then stream the vector into the B ring: one 8 KB bulk copy per 128 k of all 16 rows ------------------------
+__device__ void act_loop_b(const BatchParams& p, unsigned char* scratch, BMisc* misc) {
+    const CtaTable& tab = misc->tab;
+    const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
+    unsigned bctr = 0;
+    const bool prof = p.prof != nullptr && blockIdx.x == 0;
+    long long t_ready = 0, t_bempty = 0, tq = 0;
+#pragma unroll 1
+    for (int n = 0; n < p.n_steps; ++n) {
+#pragma unroll 1
+        for (int s = 0; s < n_stage; ++s) {
+            int kind, layer;
+            decode_stage_b(s, p.L, kind, layer);
+            const int gt = gemm_of_kind_b(kind);
+            if (gt < 0) continue;
+            const unsigned seq = 1u + (unsigned)(n * S + s);
+            const int a = act_of_gemm(gt);
+            const unsigned need = act_generation(gt, p.L, n, layer) * (unsigned)p.G * kArrivalsPerCta;
+            if (prof) tq = clock64();
+            {
+                const unsigned* ctr = p.ctr + a * 32;
+                unsigned polls = 0;
+                while (ld_acquire_u32(ctr) < need) {
+#ifdef DIA_BATCH_TRACE
+                    if (++polls > kMaxSpins || ((polls & 0x3fffu) == 0x3fffu && reinterpret_cast<volatile int*>(p.err)[0] != 0)) {
+                        for (int i = 0; i < 100; ++i) __nanosleep(1000000);      // let the warps that can report do so
+                        volatile int* e = reinterpret_cast<volatile int*>(p.err);
+                        for (int w = 0; w < kConsumerWarps; ++w) {
+                            const int sl = 16 + (blockIdx.x * 12 + w) * 2;
+                            if (e[sl] == 0) { e[sl] = reinterpret_cast<volatile int*>(misc->trace[w])[0]; e[sl + 1] = reinterpret_cast<volatile int*>(misc->trace[w])[1]; }
+                        }
+                        __threadfence_system();
+                    }
+#endif
+                    if (++polls > kMaxSpins) {
+                        volatile int* e = reinterpret_cast<volatile int*>(p.err);
+                        e[4] = (int)ld_relaxed_u32(ctr); e[5] = gt; e[6] = (int)need; e[7] = a;
+                        ll_timeout(p.err, kErrFlagTimeout, seq * 16 + gt);
+                    }
+                    ll_check_abort(p.err, polls, 100 + kErrFlagTimeout, seq * 16 + gt);
+                }
+            }
+            if (prof) t_ready += clock64() - tq;
+            st_release_cta_s32(&misc->ready_seq, (int)seq);
+            const int gc = tab.gc[gt];
+            if (gc == 0) continue;
+            fence_proxy_async();              // the vector was written through the generic proxy (by other SMs); bulk copies read through the async proxy
+            const unsigned char* src = act_buffer(p, a);
+            const int n_st = p.Kdim[gt] / (64 * kStageChunks);
+#pragma unroll 1
+            for (int st = 0; st < n_st; ++st) {
+                const unsigned bi = bctr + (unsigned)st, bs = bi % kActStages;
+                if (prof) tq = clock64();
+                mbar_spin(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (seq << 8) | 0xc0 | bs);
+                if (prof) t_bempty += clock64() - tq;
+                mbar_arrive_expect_tx(&misc->bfull[bs], kActStageBytes);
+                bulk_g2s(scratch + bs * kActStageBytes, src + (size_t)st * kActStageBytes, kActStageBytes, &misc->bfull[bs]);
+            }
+            bctr += (unsigned)n_st;
+        }
+    }
+    if (prof) {
+        p.prof[4] = (unsigned long long)t_ready;
+        p.prof[5] = (unsigned long long)t_bempty;
+    }
+}
+
 // ---- MMA warp: the whole warp walks the stages (warp-uniform control flow and operands), one elected lane issues every
 //      tcgen05.mma / tcgen05.commit of this CTA ------------------------------------------------------------------------
 // Two MMA warps share every chunk: warp `which` issues k-steps 2 * which and 2 * which + 1 (each k-step has its own
@@ -405,130 +505,79 @@ __device__ __forceinline__ void transpose_reduce_b(float (&v)[NV], int lane) {
     }
 }
 
-// ---- GEMM stage, math warps: stage the activations, then the epilogue ----------------------------------------------------------
+// bring-up build (-DDIA_BATCH_TRACE): every math warp leaves (marker, stage) in its slot of the watchdog record, so that a
+// warp blocked in a block barrier (which cannot report by itself) can be located after a timeout
+#ifdef DIA_BATCH_TRACE
+#define BTRACE(c, code)                                                                                       \
+    do {                                                                                                      \
+        if ((c).lane == 0 && ((DIA_BATCH_TRACE >> ((code) & 31)) & 1)) {                                      \
+            volatile int* t_ = reinterpret_cast<volatile int*>((c).misc->trace[(c).warp]);                    \
+            t_[0] = (code);                                                                                   \
+            t_[1] = (int)(c).seq;                                                                             \
+        }                                                                                                     \
+    } while (0)
+#else
+#define BTRACE(c, code) do { } while (0)
+#endif
+
+// ---- GEMM stage, math warps: the RMSNorm sums while the MMAs run, then the epilogue ----------------------------------------------
+// (the activation lane streams the input vector, the MMA warps consume it)
+__device__ __forceinline__ int out_act_of_gemm(int gt, bool last_layer) {       // the buffer a GEMM stage's epilogue writes, or -1
+    return gt == G_SO ? A_XC : gt == G_CO ? A_XM : gt == G_WI ? A_HIDDEN : gt == G_WO ? (last_layer ? A_XL : A_XQ) : -1;
+}
 __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
     const BatchParams& p = *c.p;
     BMisc* misc = c.misc;
     const int gc = misc->tab.gc[gt], g0 = misc->tab.g0[gt];
-    if (gc == 0) return;
     const int R = p.R, L = p.L, K = p.Kdim[gt], n_chunks = K / 64, NC = gc * 8;
     const int tid = c.tid, lane = c.lane, warp = c.warp;
     const bool resid = (gt == G_SO || gt == G_CO || gt == G_WO);
     const bool normed = !resid;
-    const uint32_t* src = gt == G_SO ? p.act_attn : gt == G_CO ? p.act_cattn : gt == G_WO ? p.act_hidden
-                        : gt == G_QKV ? p.act_xq : gt == G_CQ ? p.act_xc : gt == G_WI ? p.act_xm : p.act_xl;
-    const uint32_t fb = gt == G_LOGITS ? flag_s(c.step) : flag_l(L, c.step, layer);       // flag bit the input words carry
+    const int out_act = out_act_of_gemm(gt, layer == L - 1);
 
-    // ---- the activations, stage by stage (128 k).  The math warps form two groups of four that take the stages alternately
-    //      (two stages in flight per CTA: the chain wait-for-a-free-stage -> store -> fence -> arrive of one stage overlaps the
-    //      other group's).  A stage of all rows is R x 2 x 16 pieces of 16 bytes (4 consecutive k of one row of one chunk);
-    //      thread t of a group takes the pieces t, t + 128, ... ------------------------------------------------------------------
-    const size_t chunk_words = (size_t)R * 64;
-    const int n_st = n_chunks / kStageChunks;
-    const int grp = warp >> 2, t128 = tid & 127;
-    const int n_pieces = R * kStageChunks * 16;                // per stage; <= 512
-    constexpr int kPc = 4;                                     // pieces per thread and stage (512 / 128)
-    static_assert(kStageChunks == 2, "piece index split assumes two chunks per stage");
-    const int rc16 = R * 16;
-    auto piece_src = [&](int st, int q) -> const uint32_t* {
-        const int jc = q >= rc16 ? 1 : 0, rem = q - jc * rc16, r = rem >> 4, k4 = rem & 15;
-        return src + (size_t)(st * kStageChunks + jc) * chunk_words + (size_t)r * 64 + 4 * k4;
-    };
-    uint4 v[kPrefetch][kPc];
-#pragma unroll
-    for (int i = 0; i < kPrefetch; ++i) {
-        const int st = grp + 2 * i;
-#pragma unroll
-        for (int j = 0; j < kPc; ++j)
-            if (st < n_st && t128 + 128 * j < n_pieces) v[i][j] = ld_act4(piece_src(st, t128 + 128 * j));
-    }
-#pragma unroll 1
-    for (int s0 = grp; s0 < n_st; s0 += 2 * kPrefetch) {
-#pragma unroll
-        for (int i = 0; i < kPrefetch; ++i) {
-            const int st = s0 + 2 * i;
-            if (st < n_st) {
-                long long tq = c.prof ? clock64() : 0;
-#pragma unroll
-                for (int j = 0; j < kPc; ++j) {
-                    if (t128 + 128 * j < n_pieces) {
-                        unsigned spins = 0;
-                        while ((((v[i][j].x ^ fb) | (v[i][j].y ^ fb) | (v[i][j].z ^ fb) | (v[i][j].w ^ fb)) & 1u) != 0u) {
-                            if (++spins > kMaxSpins) {
-                                volatile int* e = reinterpret_cast<volatile int*>(p.err);
-                                e[4] = st; e[5] = gt; e[6] = (int)fb; e[7] = j;
-                                ll_timeout(p.err, kErrFlagTimeout, c.seq * 16 + gt);
-                            }
-                            ll_check_abort(p.err, spins, 100 + kErrFlagTimeout, c.seq * 16 + gt);
-                            v[i][j] = ld_act4(piece_src(st, t128 + 128 * j));
-                        }
-                    }
-                }
-                const unsigned bi = c.bctr + (unsigned)st, bs = bi % kActStages;
-                if (c.prof) { const long long t1 = clock64(); c.t_prof[0] += t1 - tq; tq = t1; }
-                if (lane == 0) mbar_spin(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (c.seq << 8) | 0xc0 | bs);
-                __syncwarp();
-                if (c.prof) c.t_prof[1] += clock64() - tq;
-                const uint32_t stage = smem_u32(c.scratch + bs * kActStageBytes);
-#pragma unroll
-                for (int j = 0; j < kPc; ++j) {
-                    const int q = t128 + 128 * j;
-                    if (q < n_pieces) {
-                        const int jc = q >= rc16 ? 1 : 0, rem = q - jc * rc16, r = rem >> 4, k4 = rem & 15;
-                        const uint32_t dst = stage + (uint32_t)(jc * 2 * kBTermBytes + r * 128 + ((((k4 >> 1) ^ (r & 7)) << 4) | ((k4 & 1) << 3)));
-                        const uint32_t h0 = __byte_perm(v[i][j].x, v[i][j].y, 0x7632), h1 = __byte_perm(v[i][j].z, v[i][j].w, 0x7632);
-                        const uint32_t l0 = __byte_perm(v[i][j].x, v[i][j].y, 0x5410) & 0xfffefffeu;
-                        const uint32_t l1 = __byte_perm(v[i][j].z, v[i][j].w, 0x5410) & 0xfffefffeu;
-                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
-                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst + kBTermBytes), "r"(l0), "r"(l1) : "memory");
-                    }
-                }
-                // generic-proxy writes -> the tensor core's async proxy (the shared::cta form: a full fence.proxy.async also
-                // waits for this thread's activation loads in flight)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&misc->bfull[bs]);
-                const int nx = st + 2 * kPrefetch;
-#pragma unroll
-                for (int j = 0; j < kPc; ++j)
-                    if (nx < n_st && t128 + 128 * j < n_pieces) v[i][j] = ld_act4(piece_src(nx, t128 + 128 * j));
-            }
+    // every CTA waits for the stage input, with or without columns in this GEMM (see "activation buffers" above)
+    {
+        long long tq = c.prof ? clock64() : 0;
+        // (every lane polls the same shared-memory word: the branch is warp-uniform, the warp reaches the block barriers
+        // below converged - a lane-0-only spin loop left the warp split in two around `bar.sync`, each half counting as a
+        // whole warp's arrival)
+        unsigned polls = 0;
+        while (ld_acquire_cta_s32(&misc->ready_seq) < (int)c.seq) {
+            if (++polls > 400000000u) ll_timeout(p.err, kErrFlagTimeout + 1, c.seq * 16 + gt);
+            ll_check_abort(p.err, polls, 100 + kErrFlagTimeout + 1, c.seq * 16 + gt);
         }
+        __syncwarp();
+        if (c.prof) c.t_prof[0] += clock64() - tq;
     }
-    c.bctr += (unsigned)n_st;
+    BTRACE(c, 1);
+    if (gc == 0) {
+        if (out_act >= 0 && tid == 0) act_arrive(p, out_act, kArrivalsPerCta);
+        return;
+    }
     c.cbase += (unsigned)(n_chunks / bslot_chunks(gc, K));
 
     // ---- RMSNorm: 1/rms per row from the producers' per-group sums (dia/layers.py:541,560,579,714) ---------------------------
     long long tq2 = c.prof ? clock64() : 0;
     if (normed) {
-        // thread g takes the 8-column group g: the sums of all R rows (R / 2 word pairs), every load in flight at once
-        const uint32_t fprev = c.seq - 1;
+        // thread g takes the 8-column group g: the sums of all 16 rows (rows >= R are zero), every load in flight at once
         float sr[kRows];
 #pragma unroll
         for (int r = 0; r < kRows; ++r) sr[r] = 0.f;
 #pragma unroll 1
         for (int g = tid; g < (p.D >> 3); g += kConsumerThreads) {
-            const u64* base = p.ll_ssq + (size_t)g * R;
-            uint4 q4[kRows / 2];
+            const float* base = p.ssq + (size_t)g * kRows;
+            float4 q4[kRows / 4];
 #pragma unroll
-            for (int i = 0; i < kRows / 2; ++i)
-                if (2 * i < R) q4[i] = ll_ld2(base + 2 * i);
+            for (int i = 0; i < kRows / 4; ++i) q4[i] = ld_gpu_f4(base + 4 * i);
 #pragma unroll
-            for (int i = 0; i < kRows / 2; ++i) {
-                if (2 * i < R) {
-                    unsigned spins = 0;
-                    while (q4[i].y != fprev || q4[i].w != fprev) {
-                        if (++spins > kMaxSpins) ll_timeout(p.err, kErrFlagTimeout + 4, c.seq);
-                        ll_check_abort(p.err, spins, 100 + kErrFlagTimeout + 4, c.seq);
-                        q4[i] = ll_ld2(base + 2 * i);
-                    }
-                    sr[2 * i] += __uint_as_float(q4[i].x);
-                    sr[2 * i + 1] += __uint_as_float(q4[i].z);
-                }
+            for (int i = 0; i < kRows / 4; ++i) {
+                sr[4 * i] += q4[i].x; sr[4 * i + 1] += q4[i].y; sr[4 * i + 2] += q4[i].z; sr[4 * i + 3] += q4[i].w;
             }
         }
+        BTRACE(c, 2);
         transpose_reduce_b<kRows>(sr, lane);                  // 31 shuffles instead of 16 x 5: lanes 2r, 2r + 1 hold row r
         if ((lane & 1) == 0) misc->ssq_part[warp][lane >> 1] = sr[0];
+        BTRACE(c, 3);
         consumer_sync();
         if (tid < R) {
             float ss = 0.f;
@@ -536,8 +585,10 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
             for (int ww = 0; ww < kConsumerWarps; ++ww) ss += misc->ssq_part[ww][tid];
             misc->inv[tid] = 1.0f / sqrtf(ss / (float)p.D + p.eps);
         }
+        BTRACE(c, 4);
         consumer_sync();
     }
+    BTRACE(c, 5);
 
     // ---- epilogue: warps 0..3, thread = output column of this CTA's slab (TMEM lane), registers = rows ----------------------------
     const unsigned a = c.gctr & 1u;
@@ -575,6 +626,7 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&misc->acc_empty[a]);
+        BTRACE(c, 6);
 
         const int m = tid;                                      // column inside the slab
         const bool valid = m < NC;
@@ -588,14 +640,13 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
             }
         } else if (gt == G_WI) {
             // a group = gate columns 0..3 and up columns 4..7 of the same 4 hidden units: h = silu(gate) * up
-            const uint32_t fo = flag_l(L, c.step, layer);
             const int hn = (g0 + (m >> 3)) * 4 + (m & 3);
 #pragma unroll
             for (int r = 0; r < kRows; ++r) {
                 if (r < R) {                                    // (R is uniform: every lane takes part in the shuffle)
                     const float y = __uint_as_float(acc[r]) * misc->inv[r];
                     const float up = __shfl_down_sync(0xffffffffu, y, 4);
-                    if (valid && (m & 4) == 0) st_act(p.act_hidden, R, hn, r, pack_act((y / (1.0f + expf(-y))) * up, fo));
+                    if (valid && (m & 4) == 0) st_act(p.act_hidden, hn, r, (y / (1.0f + expf(-y))) * up);
                 }
             }
         } else if (gt == G_LOGITS) {
@@ -621,8 +672,7 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
             // out as the words of x * w_norm for the next consumer, with sum(x^2) of this 8-column group per row
             // the next consumer: cross-q after self-o, mlp-in after cross-o, the next layer's qkv (or the logits head)
             const bool last = gt == G_WO && layer == L - 1;
-            uint32_t* xdst = gt == G_SO ? p.act_xc : gt == G_CO ? p.act_xm : last ? p.act_xl : p.act_xq;
-            const uint32_t fo = gt == G_WO ? (last ? flag_s(c.step) : flag_l(L, c.step, layer + 1)) : flag_l(L, c.step, layer);
+            unsigned char* xdst = gt == G_SO ? p.act_xc : gt == G_CO ? p.act_xm : last ? p.act_xl : p.act_xq;
             const float* wn = gt == G_SO ? p.norms + ((size_t)layer * 3 + 1) * p.D
                             : gt == G_CO ? p.norms + ((size_t)layer * 3 + 2) * p.D
                                          : p.norms + ((size_t)(layer + 1) * 3) * p.D;
@@ -634,19 +684,24 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
                     if (valid) {
                         xn = c.xres[r] + __uint_as_float(acc[r]);
                         c.xres[r] = xn;
-                        st_act(xdst, R, n, r, pack_act(xn * wnv, fo));
+                        st_act(xdst, n, r, xn * wnv);
                     }
                     float sq = xn * xn;
                     sq += __shfl_xor_sync(0xffffffffu, sq, 4);
                     sq += __shfl_xor_sync(0xffffffffu, sq, 2);
                     sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                    if (valid && (m & 7) == 0) ll_st(p.ll_ssq + (size_t)(g0 + (m >> 3)) * R + r, __float_as_uint(sq), c.seq);
+                    if (valid && (m & 7) == 0) st_gpu_f(p.ssq + (size_t)(g0 + (m >> 3)) * kRows + r, sq);
                 }
             }
+        }
+        if (out_act >= 0) {         // this warp's piece of the output vector is written: release it
+            __syncwarp();
+            if (lane == 0) act_arrive(p, out_act, 1);
         }
     }
     c.gctr++;
     if (c.prof) { const long long t1 = clock64(); c.t_prof[4] += t1 - tq2; tq2 = t1; }
+    BTRACE(c, 7);
     consumer_sync();            // the staging ring is scratch of the next stage: every MMA of this one has completed
     if (c.prof) c.t_prof[5] += clock64() - tq2;
 }
@@ -655,7 +710,7 @@ constexpr int HPKB = 4;          // query heads per KV tile in self-attention (G
 
 // ---- attention stage (the single-utterance stage of step_kernel.cu, indexed by utterance and row) ------------------------------
 template <int NH>
-__device__ void attn_stage_b(BCtx& c, int layer) {
+__device__ void attn_body_b(BCtx& c, int layer) {
     constexpr bool self = NH == HPKB;
     const BatchParams& p = *c.p;
     const int cta = blockIdx.x, R = p.R;
@@ -812,8 +867,7 @@ __device__ void attn_stage_b(BCtx& c, int layer) {
         reinterpret_cast<float4*>(racc + ((size_t)c.warp * HPKB + h) * kHeadDim)[c.lane] = acc[h];
     consumer_sync();
 
-    uint32_t* oparts = self ? p.act_attn : p.act_cattn;
-    const uint32_t fo = flag_l(p.L, c.step, layer);
+    unsigned char* oparts = self ? p.act_attn : p.act_cattn;
     u64* part = (self ? p.ll_sa_part : p.ll_ca_part) + ((size_t)w.pair * nsplit) * (nh * 132);
 #pragma unroll 1
     for (int i = c.tid; i < nh * kHeadDim; i += kConsumerThreads) {
@@ -831,8 +885,8 @@ __device__ void attn_stage_b(BCtx& c, int layer) {
         if (w.n_active == 1) {
             const float val = l > 0.f ? o / l : 0.f;
             const int k = (head0 + h) * kHeadDim + d;
-            st_act(oparts, R, k, r, pack_act(val, fo));
-            if (!self) st_act(oparts, R, k, r - 1, pack_act(0.f, fo));       // the unconditional row attends nothing
+            st_act(oparts, k, r, val);                  // (the unconditional row of cross-attention attends nothing: its
+                                                        // elements stay the zeros the launch starts with)
         } else {
             u64* pp = part + ((size_t)w.split * nh + h) * 132;
             ll_st(pp + 4 + d, __float_as_uint(o), c.seq);
@@ -891,11 +945,21 @@ __device__ void attn_stage_b(BCtx& c, int layer) {
         const float Lsum = cf[nhh * na + (h - h_lo)];
         const float val = Lsum > 0.f ? O / Lsum : 0.f;
         const int k = (head0 + h) * kHeadDim + d;
-        st_act(oparts, R, k, r, pack_act(val, fo));
-        if (!self) st_act(oparts, R, k, r - 1, pack_act(0.f, fo));
+        st_act(oparts, k, r, val);
     }
     if (has_new && c.tid < kHeadDim) __threadfence();
     consumer_sync();
+}
+
+template <int NH>
+__device__ void attn_stage_b(BCtx& c, int layer) {
+    BTRACE(c, 20);
+    attn_body_b<NH>(c, layer);
+    BTRACE(c, 21);
+    // every CTA arrives, active or not, once all its threads are done with the stage (and with its shared-memory scratch,
+    // which the activation lane overwrites as soon as the next GEMM's input is complete)
+    consumer_sync();
+    if (c.tid == 0) act_arrive(*c.p, NH == HPKB ? A_ATTN : A_CATTN, kArrivalsPerCta);
 }
 
 // ---- residual stream entry: embedding gather-sum (dia/layers.py:691-696: x = ((e0 + e1) + e2) ... + e8) ------------------------------
@@ -903,8 +967,11 @@ __device__ void embed_stage_b(BCtx& c) {
     const BatchParams& p = *c.p;
     BMisc* misc = c.misc;
     const int gc = misc->tab.gc[G_SO], g0 = misc->tab.g0[G_SO];
-    if (gc == 0) return;                                     // this CTA owns no residual columns
-    const int tid = c.tid, R = p.R;
+    const int tid = c.tid;
+    if (gc == 0) {                                           // this CTA owns no residual columns
+        if (tid == 0) act_arrive(p, A_XQ, kArrivalsPerCta);
+        return;
+    }
     if (tid < p.U * p.C) {
         const int u = tid / p.C, ch = tid - u * p.C;
         int t;
@@ -919,7 +986,6 @@ __device__ void embed_stage_b(BCtx& c) {
     const int m = tid;
     const bool valid = m < gc * 8;
     const int n = g0 * 8 + m;
-    const uint32_t fo = flag_l(p.L, c.step, 0);
     const float wnv = valid ? __ldg(p.norms + n) : 0.f;
 #pragma unroll
     for (int u = 0; u < kMaxUtt; ++u) {
@@ -936,20 +1002,21 @@ __device__ void embed_stage_b(BCtx& c) {
                     if (ch < p.C) x += e[ch];
                 c.xres[2 * u] = x;
                 c.xres[2 * u + 1] = x;
-                const uint32_t wd = pack_act(x * wnv, fo);
-                st_act(p.act_xq, R, n, 2 * u, wd);
-                st_act(p.act_xq, R, n, 2 * u + 1, wd);
+                st_act(p.act_xq, n, 2 * u, x * wnv);
+                st_act(p.act_xq, n, 2 * u + 1, x * wnv);
             }
             float sq = x * x;
             sq += __shfl_xor_sync(0xffffffffu, sq, 4);
             sq += __shfl_xor_sync(0xffffffffu, sq, 2);
             sq += __shfl_xor_sync(0xffffffffu, sq, 1);
             if (valid && (m & 7) == 0) {
-                ll_st(p.ll_ssq + (size_t)(g0 + (m >> 3)) * R + 2 * u, __float_as_uint(sq), c.seq);
-                ll_st(p.ll_ssq + (size_t)(g0 + (m >> 3)) * R + 2 * u + 1, __float_as_uint(sq), c.seq);
+                st_gpu_f(p.ssq + (size_t)(g0 + (m >> 3)) * kRows + 2 * u, sq);
+                st_gpu_f(p.ssq + (size_t)(g0 + (m >> 3)) * kRows + 2 * u + 1, sq);
             }
         }
     }
+    __syncwarp();
+    if (tid == 0) act_arrive(p, A_XQ, kArrivalsPerCta);
 }
 
 // ---- sampling: CTA u * C + ch draws channel ch of utterance u; the CTA of channel 0 then runs the body of the reference's
@@ -1063,9 +1130,10 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
     if (tid == 0) {
         // slot / stage / accumulator releases collect one commit from each of the two MMA warps
         for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 2); }
-        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], 4); mbar_init(&misc->bempty[i], 2); }   // 4 warps stage a stage
+        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], 1); mbar_init(&misc->bempty[i], 2); }   // one bulk copy fills a stage
         for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], 2); mbar_init(&misc->acc_empty[i], 4); }
         misc->stages_done = 0;
+        misc->ready_seq = 0;
         fence_mbar_init();
     }
     {
@@ -1073,9 +1141,7 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
         int* dst = reinterpret_cast<int*>(&misc->tab);
         for (int i = tid; i < (int)(sizeof(CtaTable) / 4); i += kBThreads) dst[i] = src[i];
     }
-    // the B tiles of rows >= R stay zero for the whole launch
-    for (int i = tid; i < kActStages * kActStageBytes / 16; i += kBThreads) reinterpret_cast<uint4*>(scratch)[i] = make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async();
+    // (rows >= R of the activation tiles are zeros in global memory: the launch starts from a zeroed exchange region)
     if (warp == kMmaWarp) {                                  // one warp allocates (and later frees) the accumulator columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc->tmem_base)), "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -1089,11 +1155,13 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
         if (tid == kProducerWarp * 32) producer_loop_b(p, ring, misc);
     } else if (warp == kMmaWarp || warp == kMmaWarp2) {
         mma_loop_b(p, ring, scratch, misc, warp == kMmaWarp ? 0 : 1);
+    } else if (warp == kActWarp) {
+        if (tid == kActWarp * 32) act_loop_b(p, scratch, misc);
     } else if (warp < kConsumerWarps) {
         BCtx c;
         c.p = &p; c.ring = ring; c.scratch = scratch; c.misc = misc;
         c.tid = tid; c.warp = warp; c.lane = tid & 31;
-        c.cbase = 0; c.bctr = 0; c.gctr = 0; c.seq = 0; c.step = 0;
+        c.cbase = 0; c.gctr = 0; c.seq = 0; c.step = 0;
         c.prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
         for (int i = 0; i < 8; ++i) c.t_prof[i] = 0;
         const long long t_begin = c.prof ? clock64() : 0;
@@ -1161,16 +1229,18 @@ size_t batch_ll_layout(const BatchParams& g, BatchParams* out, unsigned char* ba
     BatchParams& o = out ? *out : scratch;
     const size_t R = (size_t)g.R;
     const size_t nq = (size_t)g.Hq * kHeadDim, nkv = (size_t)g.Hkv * kHeadDim, nc = (size_t)g.Hc * kHeadDim;
-    take(reinterpret_cast<void**>(&o.act_xq), (size_t)g.D * R * 4);
-    take(reinterpret_cast<void**>(&o.act_xc), (size_t)g.D * R * 4);
-    take(reinterpret_cast<void**>(&o.act_xm), (size_t)g.D * R * 4);
-    take(reinterpret_cast<void**>(&o.act_xl), (size_t)g.D * R * 4);
-    take(reinterpret_cast<void**>(&o.act_attn), nq * R * 4);
-    take(reinterpret_cast<void**>(&o.act_cattn), nc * R * 4);
-    take(reinterpret_cast<void**>(&o.act_hidden), (size_t)g.F * R * 4);
+    auto act_bytes = [](size_t K) { return (K / 64) * (size_t)(2 * kBTermBytes); };
+    take(reinterpret_cast<void**>(&o.act_xq), act_bytes(g.D));
+    take(reinterpret_cast<void**>(&o.act_xc), act_bytes(g.D));
+    take(reinterpret_cast<void**>(&o.act_xm), act_bytes(g.D));
+    take(reinterpret_cast<void**>(&o.act_xl), act_bytes(g.D));
+    take(reinterpret_cast<void**>(&o.act_attn), act_bytes(nq));
+    take(reinterpret_cast<void**>(&o.act_cattn), act_bytes(nc));
+    take(reinterpret_cast<void**>(&o.act_hidden), act_bytes(g.F));
+    take(reinterpret_cast<void**>(&o.ctr), (size_t)A_COUNT * 32 * 4);
+    take(reinterpret_cast<void**>(&o.ssq), (size_t)(g.D / 8) * kRows * 4);
     take(reinterpret_cast<void**>(&o.ll_qkv), (nq + 2 * nkv) * R * 8);
     take(reinterpret_cast<void**>(&o.ll_cq), nc * R * 8);
-    take(reinterpret_cast<void**>(&o.ll_ssq), (size_t)(g.D / 8) * R * 8);
     take(reinterpret_cast<void**>(&o.ll_sa_part), (size_t)g.G * 4 * 132 * 8);
     take(reinterpret_cast<void**>(&o.ll_ca_part), (size_t)g.G * 132 * 8);
     take(reinterpret_cast<void**>(&o.ll_glog), (size_t)g.U * g.C * g.V * 8);

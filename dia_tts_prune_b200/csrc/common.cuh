@@ -88,7 +88,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
     while (!mbar_try_wait_hint(bar, parity, 20000u)) {
 #endif
         if (++polls > 4000000u) ll_timeout(err, code, info);   // seconds, even if a poll returns in a microsecond
-        ll_check_abort(err, polls, 100 + code, info);
+        ll_check_abort(err, (polls << 8) | 0xffu, 100 + code, info);   // a poll may sleep 20 us: look every 64 polls
     }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code, unsigned info = 0) {
@@ -198,10 +198,10 @@ __device__ __forceinline__ uint4 ll_ld2(const void* p) {
 }
 // Watchdog plumbing.  `err` is mapped pinned HOST memory (readable after the context died):
 //   [0..7]  first failure: code, block, thread, info, 4 site-specific words
-//   [16 + 2 * (block * 10 + warp)]  where every other waiting warp was stuck when it noticed the failure
+//   [16 + 2 * (block * 12 + warp)]  where every other waiting warp was stuck when it noticed the failure
 static __device__ __noinline__ void ll_report(int* err, int site, unsigned info) {
     volatile int* e = reinterpret_cast<volatile int*>(err);
-    const int slot = 16 + (blockIdx.x * 10 + (threadIdx.x >> 5)) * 2;
+    const int slot = 16 + (blockIdx.x * 12 + (threadIdx.x >> 5)) * 2;
     e[slot] = site;
     e[slot + 1] = (int)info;
     __threadfence_system();

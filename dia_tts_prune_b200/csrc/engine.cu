@@ -18,7 +18,7 @@ using namespace dia;
 namespace {
 
 constexpr int kTimingSteps = 16;
-constexpr int kErrWords = 16 + 2 * 10 * 160;        // watchdog record + one (site, info) pair per warp of every CTA
+constexpr int kErrWords = 16 + 2 * 12 * 160;        // watchdog record + one (site, info) pair per warp of every CTA
 thread_local std::string g_last_cuda_error;
 std::atomic<long long> g_launches{0};
 

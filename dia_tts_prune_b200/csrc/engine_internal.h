@@ -150,6 +150,9 @@ struct StepParams {
 
 // ---- batched engine (N utterances per GPU, batch_kernel.cu) ---------------------------------------------------------
 constexpr int kMaxUtt = 8;             // utterances per launch: 16 batch rows = N of the tcgen05 MMA
+// activation buffers of the batched kernel (index into BatchParams::ctr)
+enum ActBuf : int { A_XQ = 0, A_XC, A_XM, A_XL, A_ATTN, A_CATTN, A_HIDDEN, A_COUNT };
+constexpr unsigned kArrivalsPerCta = 4;   // the four epilogue warps of a CTA arrive one by one
 
 // Batched weight stream: per CTA and GEMM the slab [K][gc*8 columns] is stored as K / 64 chunks, each the tile
 // tcgen05.mma reads as its M operand: [gc*8 rows = output columns][64 k] bf16, K-major, rows of 128 bytes whose 16-byte
@@ -192,18 +195,22 @@ struct BatchParams {
     const float* const* cross_v;
     UttParams utt[kMaxUtt];
     float* logits;                     // [R][C][V] raw logits of the last executed step (optional)
-    // exchange buffers (zeroed before every launch).  act_*: packed (bf16 hi | bf16 lo, 1-bit generation flag) words
-    // [k / 64][R][64]; the rest are (fp32, flag32) words as in the single-utterance kernel
-    unsigned int* act_xq;              // normed residual stream for qkv / cross-q / mlp-in / the logits head: one buffer
-    unsigned int* act_xc;              // per consumer, so that every reader sees every generation of its buffer
-    unsigned int* act_xm;
-    unsigned int* act_xl;
-    unsigned int* act_attn;
-    unsigned int* act_cattn;
-    unsigned int* act_hidden;
-    unsigned long long* ll_qkv;        // [(Hq + 2 Hkv) * 128][R]
+    // exchange buffers (zeroed before every launch).  act_*: the input vectors of the GEMM stages, stored as the very
+    // shared-memory image tcgen05.mma reads as its N operand - per 64-k chunk a hi tile and a lo tile (x ~ hi + lo, both
+    // bf16) of [16 rows][64 k], K-major, 128-byte rows, 16-byte units XOR-swizzled with (row % 8): 4 KB per chunk, so a
+    // consumer stages 128 k of all rows with ONE 8 KB bulk copy.  A buffer is complete when its arrival counter
+    // (`ctr`, one per buffer, every CTA adds kArrivalsPerCta per generation) has reached the generation's total.
+    unsigned char* act_xq;             // normed residual stream for qkv / cross-q / mlp-in / the logits head: one buffer
+    unsigned char* act_xc;             // per consumer (a buffer is rewritten only after every reader has passed a later
+    unsigned char* act_xm;             // all-to-all stage)
+    unsigned char* act_xl;
+    unsigned char* act_attn;
+    unsigned char* act_cattn;
+    unsigned char* act_hidden;
+    unsigned int* ctr;                 // [A_COUNT][32] arrival counters (one 128-byte line each)
+    float* ssq;                        // [D / 8][16] sum(x^2) of every 8-column group of the residual stream, per row
+    unsigned long long* ll_qkv;        // [(Hq + 2 Hkv) * 128][R]   (fp32, flag32) words as in the single-utterance kernel
     unsigned long long* ll_cq;         // [Hc * 128][R]
-    unsigned long long* ll_ssq;        // [D / 8][R]
     unsigned long long* ll_sa_part;
     unsigned long long* ll_ca_part;
     unsigned long long* ll_glog;       // [U][C][V]

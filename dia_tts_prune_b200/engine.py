@@ -245,7 +245,7 @@ class DecodeEngine:
     def last_device_error(self, full: bool = False):
         """[code, block, thread, info, 4 detail words] a kernel watchdog left in pinned host memory (works after
         a failed launch).  full=True: also {(block, warp): (site, info)} for every warp that was waiting."""
-        n = 16 + 2 * 10 * self.n_ctas
+        n = 16 + 2 * 12 * self.n_ctas
         out = (C.c_int32 * n)()
         self.lib.dia_b200_debug_last_device_error(self._h, out, n)
         head = list(out[:8])
@@ -253,8 +253,8 @@ class DecodeEngine:
             return head
         where = {}
         for b in range(self.n_ctas):
-            for w in range(10):
-                s, i = out[16 + 2 * (b * 10 + w)], out[16 + 2 * (b * 10 + w) + 1]
+            for w in range(12):
+                s, i = out[16 + 2 * (b * 12 + w)], out[16 + 2 * (b * 12 + w) + 1]
                 if s:
                     where[(b, w)] = (s, i)
         return head, where
@@ -357,8 +357,8 @@ class BatchDecodeEngine:
         out = torch.empty((32,), dtype=torch.int64)
         _lib.check(self.lib.dia_b200_debug_read(self._h, _lib.BUF_TIMING, _ptr(out), 32 * 8, _stream(self.device)), "debug_read")
         v = out.tolist()
-        names = ["mma_total", "mma_wait_bfull", "mma_wait_ring", "mma_wait_acc_empty", "", "", "", "",
-                 "math_total", "math_act_flag_spin", "math_wait_bempty", "math_rms_gather", "math_wait_acc_full",
+        names = ["mma_total", "mma_wait_bfull", "mma_wait_ring", "mma_wait_acc_empty", "act_wait_ready", "act_wait_bempty", "", "",
+                 "math_total", "math_wait_ready", "", "math_rms_gather", "math_wait_acc_full",
                  "math_epilogue", "math_stage_end_barrier", "math_attention", "math_embed_sample"]
         return {n: v[i] for i, n in enumerate(names) if n}
 

@@ -43,11 +43,14 @@ constexpr int kActStages = 6;               // activation (B operand) staging ri
 constexpr int kBTermBytes = 2048;           // [16 rows][64 k] bf16, K-major, 128-byte swizzle
 constexpr int kStageChunks = 2;             // k-chunks (64 rows each) per activation stage: [chunk][hi tile | lo tile]
 constexpr int kActStageBytes = kStageChunks * 2 * kBTermBytes;
-constexpr int kScratchBytes = 49152;        // B staging | attention scratch | sampler scratch (never live together)
+constexpr int kScratchBytes = kActStages * kActStageBytes;   // B staging | attention scratch | sampler scratch (never live together)
+static_assert(kScratchBytes >= 49152, "attention / sampler scratch");
 constexpr int kBMiscBytes = 2048;
 constexpr int kBSmem = kBNumSlots * kBSlotBytes + kScratchBytes + kBMiscBytes + 1024;   // + alignment slack
 constexpr int kMmaWarp = 8;                 // first MMA warp; the second one is kMmaWarp2 (the producer warp sits between)
 constexpr int kMmaWarp2 = 10;
+constexpr int kNumMmaWarps = 2;             // issuers: every slot / stage / accumulator barrier collects one commit from each
+static_assert(kStageChunks == 2 && kNumMmaWarps == 2, "mma_loop_b: one chunk of every stage per MMA warp");
 constexpr int kActWarp = 11;                // one lane: waits for the input buffer of every GEMM stage, streams it into the B ring
 constexpr int kBThreads = 12 * 32;          // 8 math warps, MMA warp, producer warp, second MMA warp, activation warp
 constexpr int kRows = 16;                   // batch rows of the B tiles (2 x kMaxUtt); N of the MMA = 2 kRows (hi rows, then lo rows)
@@ -79,7 +82,7 @@ struct BCtx {
     unsigned gctr;        // GEMM stages (with columns in this CTA) so far
     unsigned seq;         // sequence number of the current stage inside this launch (>= 1)
     int step;             // step index inside the launch
-    float xres[kRows];    // threads 0..15: this column's element of the residual stream, per row
+    float xres[kRows / 2];  // warps 0 and 4, lanes 0..15: this column's element of the residual stream, rows 0..7 / 8..15
     long long t_prof[8];  // CTA 0, thread 0 (p.prof): 0 wait for the stage input, 1 -, 2 rms gather, 3 accumulator wait,
                           // 4 epilogue, 5 end-of-stage barrier, 6 attention stages, 7 embed + sample
     bool prof;
@@ -188,6 +191,26 @@ __device__ __forceinline__ void umma_bf16_b(uint32_t tmem_d, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// the same arrive delivered to the barrier at this offset in every CTA of `mask` (the CTA pair shares each activation stage)
+__device__ __forceinline__ void umma_commit_mc_b(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void umma_commit_b(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -329,6 +352,7 @@ __device__ void act_loop_b(const BatchParams& p, unsigned char* scratch, BMisc* 
     unsigned bctr = 0;
     const bool prof = p.prof != nullptr && blockIdx.x == 0;
     long long t_ready = 0, t_bempty = 0, tq = 0;
+    const uint32_t rank = p.mc ? cluster_ctarank() : 0u;
 #pragma unroll 1
     for (int n = 0; n < p.n_steps; ++n) {
 #pragma unroll 1
@@ -378,7 +402,15 @@ __device__ void act_loop_b(const BatchParams& p, unsigned char* scratch, BMisc* 
                 mbar_spin(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (seq << 8) | 0xc0 | bs);
                 if (prof) t_bempty += clock64() - tq;
                 mbar_arrive_expect_tx(&misc->bfull[bs], kActStageBytes);
-                bulk_g2s(scratch + bs * kActStageBytes, src + (size_t)st * kActStageBytes, kActStageBytes, &misc->bfull[bs]);
+                if (p.mc) {
+                    // this CTA fetches its half of the stage (the chunk of its cluster rank) for both CTAs of the pair; the
+                    // peer's half arrives the same way.  bempty[bs] has collected the commits of BOTH CTAs' MMA warps.
+                    const uint32_t half = rank * (kActStageBytes / 2);
+                    bulk_g2s_mc(scratch + bs * kActStageBytes + half, src + (size_t)st * kActStageBytes + half, kActStageBytes / 2,
+                                &misc->bfull[bs], (uint16_t)3);
+                } else {
+                    bulk_g2s(scratch + bs * kActStageBytes, src + (size_t)st * kActStageBytes, kActStageBytes, &misc->bfull[bs]);
+                }
             }
             bctr += (unsigned)n_st;
         }
@@ -389,11 +421,13 @@ __device__ void act_loop_b(const BatchParams& p, unsigned char* scratch, BMisc* 
     }
 }
 
-// ---- MMA warp: the whole warp walks the stages (warp-uniform control flow and operands), one elected lane issues every
-//      tcgen05.mma / tcgen05.commit of this CTA ------------------------------------------------------------------------
-// Two MMA warps share every chunk: warp `which` issues k-steps 2 * which and 2 * which + 1 (each k-step has its own
-// accumulator).  One tcgen05.mma costs its issuing thread ~100 cycles while the tensor pipe is busy for 16 (ncu: the pipe
-// is 5 % active), so two issuers double the rate; every slot / stage / accumulator barrier collects both commits.
+// ---- MMA warps: the whole warp walks the stages (warp-uniform control flow and operands), one elected lane issues the
+//      tcgen05.mma / tcgen05.commit instructions -----------------------------------------------------------------------------
+// Two MMA warps share every activation stage (two 64-k chunks): warp `which` takes chunk `which` - its four k-steps go
+// alternately to the warp's own two accumulators - so one pass of the loop (one bfull wait, at most one ring wait, one
+// fence, one election) issues four MMAs.  The first version split every chunk between the warps (two MMAs per pass) and
+// recomputed slot / stage indices with divisions per chunk: ~150 cycles of scalar work per MMA against a tensor-pipe
+// floor of 16.  Every slot / stage / accumulator barrier collects one commit from each warp.
 __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned char* scratch, BMisc* misc, int which) {
     const CtaTable& tab = misc->tab;
     const int cta = blockIdx.x;
@@ -402,12 +436,26 @@ __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned c
     // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, M = 128, N = 32: the hi tile and the lo
     // tile of the activations are adjacent in shared memory and go through ONE instruction (the weight tile - 4 KB per
     // k-step, the operand that bounds these narrow MMAs - is read once for both terms); columns 0..15 of an accumulator
-    // are W.hi, 16..31 are W.lo.  The four k-steps of a chunk accumulate into four different accumulators: back-to-back
-    // MMAs on ONE accumulator serialise on its read-modify-write latency (measured: ~115 cycles per instruction).
+    // are W.hi, 16..31 are W.lo.  Back-to-back MMAs on ONE accumulator serialise on its read-modify-write latency
+    // (measured: ~115 cycles per instruction), hence four accumulators per set.
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * kRows) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    unsigned cbase = 0, bctr = 0, gctr = 0;
+    const uint32_t ring_u32 = smem_u32(ring), stage_u32 = smem_u32(scratch);
+    unsigned slot = 0, slot_par = 0;          // ring position (slot index, parity of its generation) at the start of the current stage
+    unsigned bs = 0, bs_par = 0;              // activation stage ring position
+    unsigned gctr = 0;
     const bool prof = p.prof != nullptr && cta == 0 && (threadIdx.x & 31) == 0 && which == 0;
     long long t_bfull = 0, t_ring = 0, t_acc = 0, t_all = prof ? clock64() : 0, tq = 0;
+    auto advance_slots = [&](unsigned n) {    // n < 2 * kBNumSlots is not guaranteed: general form
+        const unsigned t = slot + n;
+        slot_par ^= (t / kBNumSlots) & 1u;
+        slot = t % kBNumSlots;
+    };
+    auto wait_slot = [&](unsigned sl, unsigned par, unsigned info) {
+        if (prof) tq = clock64();
+        mbar_wait(&misc->empty[sl], par ^ 1u, p.err, kErrEmptyBarrierTimeout, info);     // see step_kernel.cu: parity alias
+        mbar_wait(&misc->full[sl], par, p.err, kErrFullBarrierTimeout, info);
+        if (prof) t_ring += clock64() - tq;
+    };
 #pragma unroll 1
     for (int n = 0; n < p.n_steps; ++n) {
 #pragma unroll 1
@@ -419,57 +467,67 @@ __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned c
             if (gt >= 0) {
                 const int gc = tab.gc[gt];
                 if (gc == 0) continue;
-                const int K = p.Kdim[gt], cps = bslot_chunks(gc, K), n_chunks = K / 64;
+                const int K = p.Kdim[gt], cps = bslot_chunks(gc, K), n_st = K / (64 * kStageChunks);
                 const uint32_t chunk_bytes = (uint32_t)bchunk_bytes(gc);
-                const int cshift = __ffs(cps) - 1;
                 const unsigned a = gctr & 1u;
                 if (prof) tq = clock64();
                 mbar_wait(&misc->acc_empty[a], ((gctr >> 1) & 1u) ^ 1u, p.err, kErrGridBarrierTimeout, seq);
                 if (prof) t_acc += clock64() - tq;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_addr = tmem + a * kAccCols;
+                const uint32_t d0 = tmem + a * kAccCols + (uint32_t)which * (2 * 2 * kRows);     // this warp's two accumulators
+                // stages per ring slot (cps >= 2) or ring slots per stage (cps == 1: a chunk of a wide slab fills a slot)
+                const int sps = cps >> 1;
+                int in_slot = 0;              // stage index inside the current slot (cps >= 2)
 #pragma unroll 1
-                for (int st = 0; st < n_chunks / kStageChunks; ++st) {
-                    // the activation stage first: once the math warps have staged a piece of this GEMM they have left the
-                    // attention stage before it, i.e. every earlier generation of the ring slots has been released - the
-                    // one-bit phase parity of the slot barriers cannot tell generations two apart
-                    const unsigned bi = bctr + (unsigned)st, bs = bi % kActStages;
+                for (int st = 0; st < n_st; ++st) {
+                    // the activation stage first: it is complete only after every CTA - this one too - has left the attention
+                    // stage before this GEMM, i.e. every earlier generation of the ring slots has been released (the one-bit
+                    // phase parity of the slot barriers cannot tell generations two apart)
                     if (prof) tq = clock64();
-                    mbar_spin(&misc->bfull[bs], (bi / kActStages) & 1u, p.err, kErrFullBarrierTimeout, (seq << 8) | 0x80 | bs);
+                    mbar_spin(&misc->bfull[bs], bs_par, p.err, kErrFullBarrierTimeout, (seq << 8) | 0x80 | bs);
                     if (prof) t_bfull += clock64() - tq;
-#pragma unroll
-                    for (int jc = 0; jc < kStageChunks; ++jc) {
-                        const int c = st * kStageChunks + jc;
-                        const unsigned si = cbase + (unsigned)(c >> cshift);      // cps is a power of two
-                        if ((c & (cps - 1)) == 0) {
-                            if (prof) tq = clock64();
-                            ring_wait_full_b(misc, si, p.err, (seq << 8) | (si % kBNumSlots));
-                            if (prof) t_ring += clock64() - tq;
-                        }
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_base = smem_u32(ring + (si % kBNumSlots) * kBSlotBytes) + (uint32_t)(c & (cps - 1)) * chunk_bytes;
-                        const uint32_t b_base = smem_u32(scratch + bs * kActStageBytes) + jc * 2 * kBTermBytes;
-                        const uint64_t adesc = umma_desc_b(a_base), bdesc = umma_desc_b(b_base);
-                        if (elect_one_sync()) {
-#pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {  // 16 elements along K = 32 bytes = 2 descriptor units
-                                const int j = 2 * which + jj;
-                                umma_bf16_b(d_addr + j * 2 * kRows, adesc + 2 * j, bdesc + 2 * j, idesc, c != 0 ? 1u : 0u);
-                            }
-                            if ((c & (cps - 1)) == cps - 1) umma_commit_b(&misc->empty[si % kBNumSlots]);
-                            if (jc == kStageChunks - 1) umma_commit_b(&misc->bempty[bs]);
-                        }
-                        __syncwarp();
+                    unsigned slot1 = slot, par1 = slot_par;
+                    if (cps == 1) {
+                        slot1 = slot + 1;
+                        if (slot1 == kBNumSlots) { slot1 = 0; par1 ^= 1u; }
+                        wait_slot(slot, slot_par, (seq << 8) | slot);
+                        wait_slot(slot1, par1, (seq << 8) | slot1);
+                    } else if (in_slot == 0) {
+                        wait_slot(slot, slot_par, (seq << 8) | slot);
                     }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_base = cps == 1 ? ring_u32 + (which ? slot1 : slot) * kBSlotBytes
+                                                     : ring_u32 + slot * kBSlotBytes + (uint32_t)(2 * in_slot + which) * chunk_bytes;
+                    const uint64_t adesc = umma_desc_b(a_base);
+                    const uint64_t bdesc = umma_desc_b(stage_u32 + bs * kActStageBytes + (uint32_t)which * (2 * kBTermBytes));
+                    const bool last_in_slot = cps == 1 || in_slot == sps - 1;
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)           // 16 elements along K = 32 bytes = 2 descriptor units
+                            umma_bf16_b(d0 + (uint32_t)(j & 1) * (2 * kRows), adesc + 2 * j, bdesc + 2 * j, idesc, (st != 0 || j >= 2) ? 1u : 0u);
+                        if (last_in_slot) {
+                            umma_commit_b(&misc->empty[slot]);
+                            if (cps == 1) umma_commit_b(&misc->empty[slot1]);
+                        }
+                        if (p.mc) umma_commit_mc_b(&misc->bempty[bs], (uint16_t)3);
+                        else umma_commit_b(&misc->bempty[bs]);
+                    }
+                    __syncwarp();
+                    if (last_in_slot) {
+                        in_slot = 0;
+                        if (cps == 1) { slot = slot1; slot_par = par1; }
+                        if (++slot == kBNumSlots) { slot = 0; slot_par ^= 1u; }
+                    } else {
+                        ++in_slot;
+                    }
+                    if (++bs == kActStages) { bs = 0; bs_par ^= 1u; }
                 }
                 if (elect_one_sync()) umma_commit_b(&misc->acc_full[a]);
                 __syncwarp();
-                cbase += (unsigned)(n_chunks >> cshift);
-                bctr += (unsigned)(n_chunks / kStageChunks);
                 gctr++;
             } else if (kind == S_SATTN || kind == S_CATTN) {
                 const BAttnWork w = kind == S_SATTN ? self_work_b(p, cta, n) : cross_work_b(p, cta);
-                cbase += (unsigned)attn_slots_b(w);
+                advance_slots((unsigned)attn_slots_b(w));
             }
         }
     }
@@ -590,73 +648,76 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
     }
     BTRACE(c, 5);
 
-    // ---- epilogue: warps 0..3, thread = output column of this CTA's slab (TMEM lane), registers = rows ----------------------------
+    // ---- epilogue: thread = (output column of this CTA's slab = TMEM lane, half of the batch rows): warps 0..3 take rows
+    //      0..7, warps 4..7 rows 8..15 of the same columns (a warp reads the TMEM lanes of its quadrant, warp % 4) ------------------
+    constexpr int HR = kRows / 2;                               // rows per thread
     const unsigned a = c.gctr & 1u;
+    const int q = warp & 3, half = warp >> 2, r0 = half * HR;
     if (c.prof) { const long long t1 = clock64(); c.t_prof[2] += t1 - tq2; tq2 = t1; }
-    if (warp < 4) {
+    {
         mbar_wait(&misc->acc_full[a], (c.gctr >> 1) & 1u, p.err, kErrGridBarrierTimeout, c.seq);
         if (c.prof) { const long long t1 = clock64(); c.t_prof[3] += t1 - tq2; tq2 = t1; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t acc[kRows];
-        {
-            float sum[kRows];
+        float acc[HR];
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) sum[r] = 0.f;
+        for (int i = 0; i < HR; ++i) acc[i] = 0.f;
+        if (r0 < R) {
+            // accumulator j: columns 0..15 = W.hi of rows 0..15, 16..31 = W.lo; all eight loads in flight, one wait
+            uint32_t v[4][2][HR];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {                       // accumulator j: columns 0..15 = W.hi, 16..31 = W.lo
-                uint32_t v[32];
-                const uint32_t taddr = misc->tmem_base + ((uint32_t)(warp * 32) << 16) + a * kAccCols + j * 2 * kRows;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                for (int r = 0; r < kRows; ++r) sum[r] += __uint_as_float(v[r]) + __uint_as_float(v[kRows + r]);
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t taddr = misc->tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccCols + j * 2 * kRows + t * kRows + r0;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                        : "=r"(v[j][t][0]), "=r"(v[j][t][1]), "=r"(v[j][t][2]), "=r"(v[j][t][3]),
+                          "=r"(v[j][t][4]), "=r"(v[j][t][5]), "=r"(v[j][t][6]), "=r"(v[j][t][7])
+                        : "r"(taddr)
+                        : "memory");
+                }
             }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) acc[r] = __float_as_uint(sum[r]);
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < HR; ++i) acc[i] += __uint_as_float(v[j][0][i]) + __uint_as_float(v[j][1][i]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&misc->acc_empty[a]);
         BTRACE(c, 6);
 
-        const int m = tid;                                      // column inside the slab
+        const int m = q * 32 + lane;                            // column inside the slab
         const bool valid = m < NC;
         const int n = g0 * 8 + m;                               // column of the GEMM
         if (gt == G_QKV || gt == G_CQ) {
             u64* dst = gt == G_QKV ? p.ll_qkv : p.ll_cq;
             if (valid) {
 #pragma unroll
-                for (int r = 0; r < kRows; ++r)
-                    if (r < R) ll_st(dst + (size_t)n * R + r, __float_as_uint(__uint_as_float(acc[r]) * misc->inv[r]), c.seq);
+                for (int i = 0; i < HR; ++i)
+                    if (r0 + i < R) ll_st(dst + (size_t)n * R + r0 + i, __float_as_uint(acc[i] * misc->inv[r0 + i]), c.seq);
             }
         } else if (gt == G_WI) {
             // a group = gate columns 0..3 and up columns 4..7 of the same 4 hidden units: h = silu(gate) * up
             const int hn = (g0 + (m >> 3)) * 4 + (m & 3);
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-                if (r < R) {                                    // (R is uniform: every lane takes part in the shuffle)
-                    const float y = __uint_as_float(acc[r]) * misc->inv[r];
+            for (int i = 0; i < HR; ++i) {
+                if (r0 + i < R) {                               // (warp-uniform: every lane takes part in the shuffle)
+                    const float y = acc[i] * misc->inv[r0 + i];
                     const float up = __shfl_down_sync(0xffffffffu, y, 4);
-                    if (valid && (m & 4) == 0) st_act(p.act_hidden, hn, r, (y / (1.0f + expf(-y))) * up);
+                    if (valid && (m & 4) == 0) st_act(p.act_hidden, hn, r0 + i, (y / (1.0f + expf(-y))) * up);
                 }
             }
         } else if (gt == G_LOGITS) {
             const int ch = n / p.Vpad, vv = n - ch * p.Vpad;
             if (valid && ch < p.C && vv < p.V) {
 #pragma unroll
-                for (int u = 0; u < kMaxUtt; ++u) {
+                for (int i = 0; i < HR / 2; ++i) {
+                    const int u = half * (HR / 2) + i;
                     if (u < p.U) {
-                        const float un = __uint_as_float(acc[2 * u]) * misc->inv[2 * u];
-                        const float co = __uint_as_float(acc[2 * u + 1]) * misc->inv[2 * u + 1];
+                        const float un = acc[2 * i] * misc->inv[2 * u];
+                        const float co = acc[2 * i + 1] * misc->inv[2 * u + 1];
                         if (p.logits != nullptr) {
                             p.logits[((size_t)(2 * u) * p.C + ch) * p.V + vv] = un;
                             p.logits[((size_t)(2 * u + 1) * p.C + ch) * p.V + vv] = co;
@@ -669,7 +730,7 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
             }
         } else {
             // residual add (dia/layers.py:555,574,582): the stream stays in this thread's registers; the new stream goes
-            // out as the words of x * w_norm for the next consumer, with sum(x^2) of this 8-column group per row
+            // out as the elements of x * w_norm for the next consumer, with sum(x^2) of this 8-column group per row
             // the next consumer: cross-q after self-o, mlp-in after cross-o, the next layer's qkv (or the logits head)
             const bool last = gt == G_WO && layer == L - 1;
             unsigned char* xdst = gt == G_SO ? p.act_xc : gt == G_CO ? p.act_xm : last ? p.act_xl : p.act_xq;
@@ -678,19 +739,19 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
                                          : p.norms + ((size_t)(layer + 1) * 3) * p.D;
             const float wnv = valid ? __ldg(wn + n) : 0.f;
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-                if (r < R) {
+            for (int i = 0; i < HR; ++i) {
+                if (r0 + i < R) {
                     float xn = 0.f;
                     if (valid) {
-                        xn = c.xres[r] + __uint_as_float(acc[r]);
-                        c.xres[r] = xn;
-                        st_act(xdst, n, r, xn * wnv);
+                        xn = c.xres[i] + acc[i];
+                        c.xres[i] = xn;
+                        st_act(xdst, n, r0 + i, xn * wnv);
                     }
                     float sq = xn * xn;
                     sq += __shfl_xor_sync(0xffffffffu, sq, 4);
                     sq += __shfl_xor_sync(0xffffffffu, sq, 2);
                     sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                    if (valid && (m & 7) == 0) st_gpu_f(p.ssq + (size_t)(g0 + (m >> 3)) * kRows + r, sq);
+                    if (valid && (m & 7) == 0) st_gpu_f(p.ssq + (size_t)(g0 + (m >> 3)) * kRows + r0 + i, sq);
                 }
             }
         }
@@ -858,7 +919,7 @@ __device__ void attn_body_b(BCtx& c, int layer) {
             }
         }
         __syncwarp();
-        if (in_ring && c.lane == 0) mbar_arrive_n(&c.misc->empty[sl], 2);
+        if (in_ring && c.lane == 0) mbar_arrive_n(&c.misc->empty[sl], kNumMmaWarps);
     }
     c.cbase += nkc;
     if (c.lane < HPKB) { wstat[c.warp * 8 + c.lane] = m_run; wstat[c.warp * 8 + 4 + c.lane] = l_run; }
@@ -982,13 +1043,17 @@ __device__ void embed_stage_b(BCtx& c) {
         misc->toks[u][ch] = t;
     }
     consumer_sync();
-    if (tid >= 32) return;
-    const int m = tid;
+    if ((c.warp & 3) != 0) return;
+    // warp 0: utterances 0..3 (rows 0..7), warp 4: utterances 4..7 (rows 8..15) - the threads that own these elements of the
+    // residual stream in the GEMM epilogues
+    const int half = c.warp >> 2;
+    const int m = c.lane;
     const bool valid = m < gc * 8;
     const int n = g0 * 8 + m;
     const float wnv = valid ? __ldg(p.norms + n) : 0.f;
 #pragma unroll
-    for (int u = 0; u < kMaxUtt; ++u) {
+    for (int i = 0; i < kMaxUtt / 2; ++i) {
+        const int u = half * (kMaxUtt / 2) + i;
         if (u < p.U) {
             float x = 0.f;
             if (valid) {
@@ -1000,8 +1065,8 @@ __device__ void embed_stage_b(BCtx& c) {
 #pragma unroll
                 for (int ch = 1; ch < DIA_B200_MAX_CHANNELS; ++ch)
                     if (ch < p.C) x += e[ch];
-                c.xres[2 * u] = x;
-                c.xres[2 * u + 1] = x;
+                c.xres[2 * i] = x;
+                c.xres[2 * i + 1] = x;
                 st_act(p.act_xq, n, 2 * u, x * wnv);
                 st_act(p.act_xq, n, 2 * u + 1, x * wnv);
             }
@@ -1016,7 +1081,7 @@ __device__ void embed_stage_b(BCtx& c) {
         }
     }
     __syncwarp();
-    if (tid == 0) act_arrive(p, A_XQ, kArrivalsPerCta);
+    if (c.lane == 0) act_arrive(p, A_XQ, kArrivalsPerCta / 2);
 }
 
 // ---- sampling: CTA u * C + ch draws channel ch of utterance u; the CTA of channel 0 then runs the body of the reference's
@@ -1129,9 +1194,11 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
     }
     if (tid == 0) {
         // slot / stage / accumulator releases collect one commit from each of the two MMA warps
-        for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 2); }
-        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], 1); mbar_init(&misc->bempty[i], 2); }   // one bulk copy fills a stage
-        for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], 2); mbar_init(&misc->acc_empty[i], 4); }
+        for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], kNumMmaWarps); }
+        // a stage is filled by one bulk copy (or two multicast halves: one arrive.expect_tx for both) and released by
+        // the commits of the two MMA warps - of both CTAs when a pair shares its activation stages
+        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], 1); mbar_init(&misc->bempty[i], (p.mc ? 2 : 1) * kNumMmaWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], kNumMmaWarps); mbar_init(&misc->acc_empty[i], kConsumerWarps); }
         misc->stages_done = 0;
         misc->ready_seq = 0;
         fence_mbar_init();
@@ -1149,11 +1216,12 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (p.mc) cluster_sync_all();          // the peer's barriers exist before anything is multicast to them
 
     const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
     if (warp == kProducerWarp) {
         if (tid == kProducerWarp * 32) producer_loop_b(p, ring, misc);
-    } else if (warp == kMmaWarp || warp == kMmaWarp2) {
+    } else if (warp == kMmaWarp || (warp == kMmaWarp2 && kNumMmaWarps == 2)) {
         mma_loop_b(p, ring, scratch, misc, warp == kMmaWarp ? 0 : 1);
     } else if (warp == kActWarp) {
         if (tid == kActWarp * 32) act_loop_b(p, scratch, misc);
@@ -1166,7 +1234,7 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
         for (int i = 0; i < 8; ++i) c.t_prof[i] = 0;
         const long long t_begin = c.prof ? clock64() : 0;
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) c.xres[r] = 0.f;
+        for (int r = 0; r < kRows / 2; ++r) c.xres[r] = 0.f;
 #pragma unroll 1
         for (int n = 0; n < p.n_steps; ++n) {
             c.step = n;
@@ -1197,6 +1265,7 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (p.mc) cluster_sync_all();          // no CTA leaves while its peer may still multicast into its shared memory
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(misc->tmem_base), "r"(kTmemCols));
@@ -1213,9 +1282,19 @@ cudaError_t launch_batch_kernel(const BatchParams& p, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    void* args[] = {const_cast<BatchParams*>(&p)};
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dia_batch_step_kernel), dim3(p.G), dim3(kBThreads), args,
-                                       kBSmem, st);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.G);
+    cfg.blockDim = dim3(kBThreads);
+    cfg.dynamicSmemBytes = kBSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = p.mc ? 2 : 1;           // CTA pairs (the two SMs of a TPC) when the pair shares its activation stages
+    return cudaLaunchKernelEx(&cfg, dia_batch_step_kernel, p);
 }
 
 // carve the exchange region of the batched kernel (`base` may be null to only size it); returns bytes

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -106,6 +107,7 @@ struct dia_b200_engine {
 
     // batched engine (max_utts > 0): N utterances per launch on the tcgen05 step kernel (batch_kernel.cu)
     int max_utts = 0;
+    int batch_mc = 0;                  // launch as CTA pairs that share their activation stages (every CTA has columns in every GEMM)
     unsigned char* d_bll = nullptr;   // its exchange region
     size_t bll_bytes = 0;
     bool utt_bound[kMaxUtt] = {};
@@ -345,6 +347,15 @@ static int create_engine(const dia_b200_shape* shape, int device, int n_ctas, in
         const int need = e->tclass[t] == 1 ? 64 : 32;       // k-blocks in flight per MMA group; slots start on even k-blocks
         for (int c = 0; c < G; ++c)
             if (e->tab[c].gc[t] > 0 && gemm_slot_rows(e->tab[c].gc[t], e->Kdim[t], sp) % need) { delete e; return DIA_B200_EUNSUPPORTED; }
+    }
+    if (batch && G % 2 == 0) {
+        // CTA pairs walk the activation ring in lockstep only if both have columns in every GEMM stage
+        e->batch_mc = 1;
+        for (int c = 0; c < G; ++c)
+            for (int t = 0; t < G_COUNT; ++t)
+                if (e->tab[c].gc[t] == 0) e->batch_mc = 0;
+        const char* env = std::getenv("DIA_BATCH_NO_MULTICAST");
+        if (env && env[0] == '1') e->batch_mc = 0;
     }
     for (int c = 0; c < G; ++c) {
         if (e->tab[c].gc[G_SO] > 0) {
@@ -745,6 +756,7 @@ void fill_batch_params(const dia_b200_engine* e, BatchParams& p, int n_utts) {
     p.C = s.channels; p.V = s.vocab; p.Vpad = e->Vpad; p.Lmax = s.max_audio_len; p.Smax = s.max_text_len;
     for (int i = 0; i < G_COUNT; ++i) p.Kdim[i] = e->Kdim[i];
     p.eps = s.norm_eps; p.G = e->G; p.U = n_utts; p.R = 2 * n_utts;
+    p.mc = e->batch_mc;
     // the splits are sized for the utterances of THIS launch (fewer utterances: more CTAs per pair)
     p.sa_nsplit = std::max(1, e->G / (2 * n_utts * s.kv_heads));
     p.ca_nsplit = std::max(1, e->G / (n_utts * s.cross_heads));

@@ -428,7 +428,7 @@ __device__ void act_loop_b(const BatchParams& p, unsigned char* scratch, BMisc* 
 // fence, one election) issues four MMAs.  The first version split every chunk between the warps (two MMAs per pass) and
 // recomputed slot / stage indices with divisions per chunk: ~150 cycles of scalar work per MMA against a tensor-pipe
 // floor of 16.  Every slot / stage / accumulator barrier collects one commit from each warp.
-__device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned char* scratch, BMisc* misc, int which) {
+__device__ __forceinline__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned char* scratch, BMisc* misc, int which) {
     const CtaTable& tab = misc->tab;
     const int cta = blockIdx.x;
     const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
@@ -478,14 +478,25 @@ __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned c
                 // stages per ring slot (cps >= 2) or ring slots per stage (cps == 1: a chunk of a wide slab fills a slot)
                 const int sps = cps >> 1;
                 int in_slot = 0;              // stage index inside the current slot (cps >= 2)
+                // An mbarrier test costs its thread ~120 cycles before the predicate can be read
+                // (tools/microbench/umma_issue_bench.cu), a third of what the eight MMAs of a stage keep the tensor pipe busy.
+                // The barrier of the NEXT stage is therefore tested before this stage's MMAs are issued and the predicate
+                // (a PTX register declared at kernel scope) is read after them; only a miss falls back to the spin.
+                bool have = false;
 #pragma unroll 1
                 for (int st = 0; st < n_st; ++st) {
                     // the activation stage first: it is complete only after every CTA - this one too - has left the attention
                     // stage before this GEMM, i.e. every earlier generation of the ring slots has been released (the one-bit
                     // phase parity of the slot barriers cannot tell generations two apart)
                     if (prof) tq = clock64();
-                    mbar_spin(&misc->bfull[bs], bs_par, p.err, kErrFullBarrierTimeout, (seq << 8) | 0x80 | bs);
+                    if (!have) mbar_spin(&misc->bfull[bs], bs_par, p.err, kErrFullBarrierTimeout, (seq << 8) | 0x80 | bs);
                     if (prof) t_bfull += clock64() - tq;
+                    const bool peek = st + 1 < n_st;
+                    if (peek) {
+                        unsigned nbs = bs + 1, npar = bs_par;
+                        if (nbs == kActStages) { nbs = 0; npar ^= 1u; }
+                        asm volatile("mbarrier.test_wait.parity.shared::cta.b64 dia_pw_bfull, [%0], %1;" ::"r"(smem_u32(&misc->bfull[nbs])), "r"(npar) : "memory");
+                    }
                     unsigned slot1 = slot, par1 = slot_par;
                     if (cps == 1) {
                         slot1 = slot + 1;
@@ -513,6 +524,12 @@ __device__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned c
                         else umma_commit_b(&misc->bempty[bs]);
                     }
                     __syncwarp();
+                    have = false;
+                    if (peek) {
+                        uint32_t ok;
+                        asm volatile("selp.u32 %0, 1, 0, dia_pw_bfull;" : "=r"(ok));
+                        have = ok != 0;
+                    }
                     if (last_in_slot) {
                         in_slot = 0;
                         if (cps == 1) { slot = slot1; slot_par = par1; }
@@ -1219,6 +1236,7 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
     if (p.mc) cluster_sync_all();          // the peer's barriers exist before anything is multicast to them
 
     const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
+    asm volatile(".reg .pred dia_pw_bfull;" ::);       // mma_loop_b: result of the early test of the next activation stage's barrier
     if (warp == kProducerWarp) {
         if (tid == kProducerWarp * 32) producer_loop_b(p, ring, misc);
     } else if (warp == kMmaWarp || (warp == kMmaWarp2 && kNumMmaWarps == 2)) {

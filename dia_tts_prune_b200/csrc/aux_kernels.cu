@@ -88,7 +88,7 @@ __global__ void repack_batch_kernel(const RepackArgs a) {
     const int gc = t.gc[a.gemm];
     const unsigned long long slab = t.stream_base +
         (a.gemm == G_LOGITS ? t.logits_off : (unsigned long long)a.layer * t.layer_bytes + t.slab_off[a.gemm]);
-    unsigned char* chunk = a.wstream + slab + (size_t)(k0 >> 6) * bchunk_bytes(gc);
+    unsigned char* chunk = a.wstream + slab + (size_t)bchunk_position(k0 >> 6, gc, a.K) * bchunk_bytes(gc);
     const int unit = (k0 >> 3) & 7;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

@@ -38,8 +38,8 @@ typedef unsigned long long u64;
 namespace {
 
 constexpr int kBSlotBytes = 16384;          // one ring slot: up to 8 k-chunks of a slab, or a 16-key K / V tile
-constexpr int kBNumSlots = 10;
-constexpr int kActStages = 6;               // activation (B operand) staging ring
+constexpr int kBNumSlots = 8;
+constexpr int kActStages = 11;              // activation (B operand) staging ring
 constexpr int kBTermBytes = 2048;           // [16 rows][64 k] bf16, K-major, 128-byte swizzle
 constexpr int kStageChunks = 2;             // k-chunks (64 rows each) per activation stage: [chunk][hi tile | lo tile]
 constexpr int kActStageBytes = kStageChunks * 2 * kBTermBytes;
@@ -47,20 +47,20 @@ constexpr int kScratchBytes = kActStages * kActStageBytes;   // B staging | atte
 static_assert(kScratchBytes >= 49152, "attention / sampler scratch");
 constexpr int kBMiscBytes = 2048;
 constexpr int kBSmem = kBNumSlots * kBSlotBytes + kScratchBytes + kBMiscBytes + 1024;   // + alignment slack
-constexpr int kMmaWarp = 8;                 // first MMA warp; the second one is kMmaWarp2 (the producer warp sits between)
-constexpr int kMmaWarp2 = 10;
-constexpr int kNumMmaWarps = 2;             // issuers: every slot / stage / accumulator barrier collects one commit from each
-static_assert(kStageChunks == 2 && kNumMmaWarps == 2, "mma_loop_b: one chunk of every stage per MMA warp");
+constexpr int kMmaWarp = 8;                 // allocates / frees the tensor memory (the MMAs are issued by math warps 4..7)
+constexpr int kIssuerWarp0 = 4;             // math warps 4..7 issue the MMAs of a GEMM stage (each on its quarter of the contraction)
+static_assert(kStageChunks == 2, "an issuer's stage is two chunks");
 constexpr int kActWarp = 11;                // one lane: waits for the input buffer of every GEMM stage, streams it into the B ring
-constexpr int kBThreads = 12 * 32;          // 8 math warps, MMA warp, producer warp, second MMA warp, activation warp
+constexpr int kBThreads = 12 * 32;          // 8 math warps, TMEM warp, producer warp, (idle), activation warp
 constexpr int kRows = 16;                   // batch rows of the B tiles (2 x kMaxUtt); N of the MMA = 2 kRows (hi rows, then lo rows)
-constexpr int kAccCols = 4 * 2 * kRows;     // TMEM columns of one accumulator set: 4 independent k-step accumulators x (hi | lo)
-constexpr int kTmemCols = 2 * kAccCols;     // two sets: the epilogue of a GEMM stage overlaps the MMAs of the next one
+constexpr int kNumAcc = 2 * kBIssuers;      // two accumulators per issuer (back-to-back MMAs on one accumulator serialise)
+constexpr int kAccCols = kNumAcc * 2 * kRows;   // TMEM columns: accumulators x (hi | lo)
+constexpr int kTmemCols = kAccCols;         // (one set: the warps that issue the MMAs of a stage also run its epilogue)
 
 struct BMisc {
     uint64_t full[kBNumSlots], empty[kBNumSlots];
     uint64_t bfull[kActStages], bempty[kActStages];
-    uint64_t acc_full[2], acc_empty[2];
+    uint64_t acc_full;
     uint32_t tmem_base;
     int stages_done;
     int trace[kConsumerWarps][2];           // bring-up build: (marker, stage) of every math warp
@@ -79,6 +79,7 @@ struct BCtx {
     BMisc* misc;
     int tid, warp, lane;
     unsigned cbase;       // ring slot index at the start of the current stage
+    unsigned bctr;        // activation stages consumed so far
     unsigned gctr;        // GEMM stages (with columns in this CTA) so far
     unsigned seq;         // sequence number of the current stage inside this launch (>= 1)
     int step;             // step index inside the launch
@@ -86,6 +87,8 @@ struct BCtx {
     long long t_prof[8];  // CTA 0, thread 0 (p.prof): 0 wait for the stage input, 1 -, 2 rms gather, 3 accumulator wait,
                           // 4 epilogue, 5 end-of-stage barrier, 6 attention stages, 7 embed + sample
     bool prof;
+    bool prof_issue;      // CTA 0, warp 4, lane 0: where the first MMA issuer spends its clocks (0 total, 1 bfull waits, 2 ring waits)
+    long long t_issue[3];
 };
 
 __device__ __forceinline__ void decode_stage_b(int s, int L, int& kind, int& layer) {
@@ -395,9 +398,11 @@ __device__ void act_loop_b(const BatchParams& p, unsigned char* scratch, BMisc* 
             fence_proxy_async();              // the vector was written through the generic proxy (by other SMs); bulk copies read through the async proxy
             const unsigned char* src = act_buffer(p, a);
             const int n_st = p.Kdim[gt] / (64 * kStageChunks);
+            const int per_issuer = n_st / kBIssuers;          // stage 4 t + w of the ring is the t-th stage of issuer w's quarter
 #pragma unroll 1
-            for (int st = 0; st < n_st; ++st) {
-                const unsigned bi = bctr + (unsigned)st, bs = bi % kActStages;
+            for (int su = 0; su < n_st; ++su) {
+                const int st = (su & (kBIssuers - 1)) * per_issuer + (su >> 2);
+                const unsigned bi = bctr + (unsigned)su, bs = bi % kActStages;
                 if (prof) tq = clock64();
                 mbar_spin(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (seq << 8) | 0xc0 | bs);
                 if (prof) t_bempty += clock64() - tq;
@@ -418,141 +423,6 @@ __device__ void act_loop_b(const BatchParams& p, unsigned char* scratch, BMisc* 
     if (prof) {
         p.prof[4] = (unsigned long long)t_ready;
         p.prof[5] = (unsigned long long)t_bempty;
-    }
-}
-
-// ---- MMA warps: the whole warp walks the stages (warp-uniform control flow and operands), one elected lane issues the
-//      tcgen05.mma / tcgen05.commit instructions -----------------------------------------------------------------------------
-// Two MMA warps share every activation stage (two 64-k chunks): warp `which` takes chunk `which` - its four k-steps go
-// alternately to the warp's own two accumulators - so one pass of the loop (one bfull wait, at most one ring wait, one
-// fence, one election) issues four MMAs.  The first version split every chunk between the warps (two MMAs per pass) and
-// recomputed slot / stage indices with divisions per chunk: ~150 cycles of scalar work per MMA against a tensor-pipe
-// floor of 16.  Every slot / stage / accumulator barrier collects one commit from each warp.
-__device__ __forceinline__ void mma_loop_b(const BatchParams& p, unsigned char* ring, unsigned char* scratch, BMisc* misc, int which) {
-    const CtaTable& tab = misc->tab;
-    const int cta = blockIdx.x;
-    const int S = 8 * p.L + 3, n_stage = p.with_sample ? S : S - 1;
-    const uint32_t tmem = misc->tmem_base;
-    // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, M = 128, N = 32: the hi tile and the lo
-    // tile of the activations are adjacent in shared memory and go through ONE instruction (the weight tile - 4 KB per
-    // k-step, the operand that bounds these narrow MMAs - is read once for both terms); columns 0..15 of an accumulator
-    // are W.hi, 16..31 are W.lo.  Back-to-back MMAs on ONE accumulator serialise on its read-modify-write latency
-    // (measured: ~115 cycles per instruction), hence four accumulators per set.
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * kRows) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t ring_u32 = smem_u32(ring), stage_u32 = smem_u32(scratch);
-    unsigned slot = 0, slot_par = 0;          // ring position (slot index, parity of its generation) at the start of the current stage
-    unsigned bs = 0, bs_par = 0;              // activation stage ring position
-    unsigned gctr = 0;
-    const bool prof = p.prof != nullptr && cta == 0 && (threadIdx.x & 31) == 0 && which == 0;
-    long long t_bfull = 0, t_ring = 0, t_acc = 0, t_all = prof ? clock64() : 0, tq = 0;
-    auto advance_slots = [&](unsigned n) {    // n < 2 * kBNumSlots is not guaranteed: general form
-        const unsigned t = slot + n;
-        slot_par ^= (t / kBNumSlots) & 1u;
-        slot = t % kBNumSlots;
-    };
-    auto wait_slot = [&](unsigned sl, unsigned par, unsigned info) {
-        if (prof) tq = clock64();
-        mbar_wait(&misc->empty[sl], par ^ 1u, p.err, kErrEmptyBarrierTimeout, info);     // see step_kernel.cu: parity alias
-        mbar_wait(&misc->full[sl], par, p.err, kErrFullBarrierTimeout, info);
-        if (prof) t_ring += clock64() - tq;
-    };
-#pragma unroll 1
-    for (int n = 0; n < p.n_steps; ++n) {
-#pragma unroll 1
-        for (int s = 0; s < n_stage; ++s) {
-            int kind, layer;
-            decode_stage_b(s, p.L, kind, layer);
-            const unsigned seq = 1u + (unsigned)(n * S + s);
-            const int gt = gemm_of_kind_b(kind);
-            if (gt >= 0) {
-                const int gc = tab.gc[gt];
-                if (gc == 0) continue;
-                const int K = p.Kdim[gt], cps = bslot_chunks(gc, K), n_st = K / (64 * kStageChunks);
-                const uint32_t chunk_bytes = (uint32_t)bchunk_bytes(gc);
-                const unsigned a = gctr & 1u;
-                if (prof) tq = clock64();
-                mbar_wait(&misc->acc_empty[a], ((gctr >> 1) & 1u) ^ 1u, p.err, kErrGridBarrierTimeout, seq);
-                if (prof) t_acc += clock64() - tq;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d0 = tmem + a * kAccCols + (uint32_t)which * (2 * 2 * kRows);     // this warp's two accumulators
-                // stages per ring slot (cps >= 2) or ring slots per stage (cps == 1: a chunk of a wide slab fills a slot)
-                const int sps = cps >> 1;
-                int in_slot = 0;              // stage index inside the current slot (cps >= 2)
-                // An mbarrier test costs its thread ~120 cycles before the predicate can be read
-                // (tools/microbench/umma_issue_bench.cu), a third of what the eight MMAs of a stage keep the tensor pipe busy.
-                // The barrier of the NEXT stage is therefore tested before this stage's MMAs are issued and the predicate
-                // (a PTX register declared at kernel scope) is read after them; only a miss falls back to the spin.
-                bool have = false;
-#pragma unroll 1
-                for (int st = 0; st < n_st; ++st) {
-                    // the activation stage first: it is complete only after every CTA - this one too - has left the attention
-                    // stage before this GEMM, i.e. every earlier generation of the ring slots has been released (the one-bit
-                    // phase parity of the slot barriers cannot tell generations two apart)
-                    if (prof) tq = clock64();
-                    if (!have) mbar_spin(&misc->bfull[bs], bs_par, p.err, kErrFullBarrierTimeout, (seq << 8) | 0x80 | bs);
-                    if (prof) t_bfull += clock64() - tq;
-                    const bool peek = st + 1 < n_st;
-                    if (peek) {
-                        unsigned nbs = bs + 1, npar = bs_par;
-                        if (nbs == kActStages) { nbs = 0; npar ^= 1u; }
-                        asm volatile("mbarrier.test_wait.parity.shared::cta.b64 dia_pw_bfull, [%0], %1;" ::"r"(smem_u32(&misc->bfull[nbs])), "r"(npar) : "memory");
-                    }
-                    unsigned slot1 = slot, par1 = slot_par;
-                    if (cps == 1) {
-                        slot1 = slot + 1;
-                        if (slot1 == kBNumSlots) { slot1 = 0; par1 ^= 1u; }
-                        wait_slot(slot, slot_par, (seq << 8) | slot);
-                        wait_slot(slot1, par1, (seq << 8) | slot1);
-                    } else if (in_slot == 0) {
-                        wait_slot(slot, slot_par, (seq << 8) | slot);
-                    }
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_base = cps == 1 ? ring_u32 + (which ? slot1 : slot) * kBSlotBytes
-                                                     : ring_u32 + slot * kBSlotBytes + (uint32_t)(2 * in_slot + which) * chunk_bytes;
-                    const uint64_t adesc = umma_desc_b(a_base);
-                    const uint64_t bdesc = umma_desc_b(stage_u32 + bs * kActStageBytes + (uint32_t)which * (2 * kBTermBytes));
-                    const bool last_in_slot = cps == 1 || in_slot == sps - 1;
-                    if (elect_one_sync()) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)           // 16 elements along K = 32 bytes = 2 descriptor units
-                            umma_bf16_b(d0 + (uint32_t)(j & 1) * (2 * kRows), adesc + 2 * j, bdesc + 2 * j, idesc, (st != 0 || j >= 2) ? 1u : 0u);
-                        if (last_in_slot) {
-                            umma_commit_b(&misc->empty[slot]);
-                            if (cps == 1) umma_commit_b(&misc->empty[slot1]);
-                        }
-                        if (p.mc) umma_commit_mc_b(&misc->bempty[bs], (uint16_t)3);
-                        else umma_commit_b(&misc->bempty[bs]);
-                    }
-                    __syncwarp();
-                    have = false;
-                    if (peek) {
-                        uint32_t ok;
-                        asm volatile("selp.u32 %0, 1, 0, dia_pw_bfull;" : "=r"(ok));
-                        have = ok != 0;
-                    }
-                    if (last_in_slot) {
-                        in_slot = 0;
-                        if (cps == 1) { slot = slot1; slot_par = par1; }
-                        if (++slot == kBNumSlots) { slot = 0; slot_par ^= 1u; }
-                    } else {
-                        ++in_slot;
-                    }
-                    if (++bs == kActStages) { bs = 0; bs_par ^= 1u; }
-                }
-                if (elect_one_sync()) umma_commit_b(&misc->acc_full[a]);
-                __syncwarp();
-                gctr++;
-            } else if (kind == S_SATTN || kind == S_CATTN) {
-                const BAttnWork w = kind == S_SATTN ? self_work_b(p, cta, n) : cross_work_b(p, cta);
-                advance_slots((unsigned)attn_slots_b(w));
-            }
-        }
-    }
-    if (prof) {
-        p.prof[0] = (unsigned long long)(clock64() - t_all);
-        p.prof[1] = (unsigned long long)t_bfull;
-        p.prof[2] = (unsigned long long)t_ring;
-        p.prof[3] = (unsigned long long)t_acc;
     }
 }
 
@@ -578,6 +448,81 @@ __device__ __forceinline__ void transpose_reduce_b(float (&v)[NV], int lane) {
             v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
         }
     }
+}
+
+// ---- MMA issue: math warps 4..7, each on its own quarter of the contraction (its own ring slots, activation stages and two
+//      accumulators).  The whole warp walks the loop (warp-uniform control flow and operands), one elected lane issues.
+// Measured (tools/microbench/umma_issue_bench.cu): one of these M128 x N32 x K16 instructions costs its issuing warp ~43 cycles,
+// a tcgen05.commit ~40, an mbarrier test ~120 before its predicate can be read - against a tensor-pipe floor of 16 cycles per
+// MMA.  Hence four issuers that share nothing (a slot / stage barrier collects ONE commit), and the barrier of an issuer's next
+// stage is tested before the MMAs of the current one are issued (the predicate, a PTX register declared at kernel scope, is
+// read after them; only a miss falls back to the spin).
+__device__ __forceinline__ void issue_gemm_b(BCtx& c, int gt, int K, int gc) {
+    const BatchParams& p = *c.p;
+    BMisc* misc = c.misc;
+    const int wi = c.warp - kIssuerWarp0;
+    const int n_chunks = K / 64, Q = n_chunks / kBIssuers, cps = bslot_chunks(gc, K), n_t = Q / kStageChunks;
+    const uint32_t chunk_bytes = (uint32_t)bchunk_bytes(gc);
+    const int cshift = __ffs(cps) - 1;
+    // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, M = 128, N = 32: the hi tile and the lo
+    // tile of the activations are adjacent in shared memory and go through ONE instruction; columns 0..15 of an accumulator
+    // are W.hi, 16..31 are W.lo.  Back-to-back MMAs on ONE accumulator serialise on its read-modify-write latency
+    // (measured: ~115 cycles per instruction), hence two accumulators per issuer.
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * kRows) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t ring_u32 = smem_u32(c.ring), stage_u32 = smem_u32(c.scratch);
+    const uint32_t d0 = misc->tmem_base + (uint32_t)wi * (2 * 2 * kRows);
+    const bool prof = c.prof_issue;
+    long long tq = 0;
+    bool have = false;
+    unsigned sidx = 0;                                   // ring slot under the current chunk
+#pragma unroll 1
+    for (int t = 0; t < n_t; ++t) {
+        // the activation stage first: it is complete only after every CTA - this one too - has left the attention stage
+        // before this GEMM, i.e. every earlier generation of the ring slots has been released (the one-bit phase parity of
+        // the slot barriers cannot tell generations two apart)
+        const unsigned bi = c.bctr + (unsigned)(kBIssuers * t + wi), bs = bi % kActStages, bpar = (bi / kActStages) & 1u;
+        if (prof) tq = clock64();
+        if (!have) mbar_spin(&misc->bfull[bs], bpar, p.err, kErrFullBarrierTimeout, (c.seq << 8) | 0x80 | bs);
+        if (prof) c.t_issue[1] += clock64() - tq;
+        const bool peek = t + 1 < n_t;
+        if (peek) {
+            const unsigned nbi = bi + kBIssuers, nbs = nbi % kActStages, npar = (nbi / kActStages) & 1u;
+            asm volatile("mbarrier.test_wait.parity.shared::cta.b64 dia_pw_bfull, [%0], %1;" ::"r"(smem_u32(&misc->bfull[nbs])), "r"(npar) : "memory");
+        }
+#pragma unroll
+        for (int jc = 0; jc < kStageChunks; ++jc) {
+            const int cc = t * kStageChunks + jc, in_slot = cc & (cps - 1);
+            if (in_slot == 0) {
+                sidx = c.cbase + (unsigned)(kBIssuers * (cc >> cshift) + wi);
+                if (prof) tq = clock64();
+                ring_wait_full_b(misc, sidx, p.err, (c.seq << 8) | (sidx % kBNumSlots));
+                if (prof) c.t_issue[2] += clock64() - tq;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned slot = sidx % kBNumSlots;
+            const uint64_t adesc = umma_desc_b(ring_u32 + slot * kBSlotBytes + (uint32_t)in_slot * chunk_bytes);
+            const uint64_t bdesc = umma_desc_b(stage_u32 + bs * kActStageBytes + (uint32_t)jc * (2 * kBTermBytes));
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)           // 16 elements along K = 32 bytes = 2 descriptor units
+                    umma_bf16_b(d0 + (uint32_t)(j & 1) * (2 * kRows), adesc + 2 * j, bdesc + 2 * j, idesc, (cc != 0 || j >= 2) ? 1u : 0u);
+                if (in_slot == cps - 1) umma_commit_b(&misc->empty[slot]);
+                if (jc == kStageChunks - 1) {
+                    if (p.mc) umma_commit_mc_b(&misc->bempty[bs], (uint16_t)3);
+                    else umma_commit_b(&misc->bempty[bs]);
+                }
+            }
+            __syncwarp();
+        }
+        have = false;
+        if (peek) {
+            uint32_t ok;
+            asm volatile("selp.u32 %0, 1, 0, dia_pw_bfull;" : "=r"(ok));
+            have = ok != 0;
+        }
+    }
+    if (elect_one_sync()) umma_commit_b(&misc->acc_full);
+    __syncwarp();
 }
 
 // bring-up build (-DDIA_BATCH_TRACE): every math warp leaves (marker, stage) in its slot of the watchdog record, so that a
@@ -629,17 +574,20 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
         if (out_act >= 0 && tid == 0) act_arrive(p, out_act, kArrivalsPerCta);
         return;
     }
-    c.cbase += (unsigned)(n_chunks / bslot_chunks(gc, K));
-
-    // ---- RMSNorm: 1/rms per row from the producers' per-group sums (dia/layers.py:541,560,579,714) ---------------------------
+    // ---- main loop: warps 4..7 issue the MMAs; warps 0..3 meanwhile gather the RMSNorm sums ---------------------------------------
     long long tq2 = c.prof ? clock64() : 0;
-    if (normed) {
-        // thread g takes the 8-column group g: the sums of all 16 rows (rows >= R are zero), every load in flight at once
+    if (warp >= kIssuerWarp0) {
+        const long long ti = c.prof_issue ? clock64() : 0;
+        issue_gemm_b(c, gt, K, gc);
+        if (c.prof_issue) c.t_issue[0] += clock64() - ti;
+    } else if (normed) {
+        // 1/rms per row from the producers' per-group sums (dia/layers.py:541,560,579,714): thread g takes the 8-column groups
+        // g, g + 128, ...: the sums of all 16 rows (rows >= R are zero), every load in flight at once
         float sr[kRows];
 #pragma unroll
         for (int r = 0; r < kRows; ++r) sr[r] = 0.f;
 #pragma unroll 1
-        for (int g = tid; g < (p.D >> 3); g += kConsumerThreads) {
+        for (int g = tid; g < (p.D >> 3); g += 4 * 32) {
             const float* base = p.ssq + (size_t)g * kRows;
             float4 q4[kRows / 4];
 #pragma unroll
@@ -653,56 +601,58 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
         transpose_reduce_b<kRows>(sr, lane);                  // 31 shuffles instead of 16 x 5: lanes 2r, 2r + 1 hold row r
         if ((lane & 1) == 0) misc->ssq_part[warp][lane >> 1] = sr[0];
         BTRACE(c, 3);
-        consumer_sync();
+        asm volatile("bar.sync 2, 128;" ::: "memory");         // warps 0..3 only
         if (tid < R) {
             float ss = 0.f;
 #pragma unroll
-            for (int ww = 0; ww < kConsumerWarps; ++ww) ss += misc->ssq_part[ww][tid];
+            for (int ww = 0; ww < 4; ++ww) ss += misc->ssq_part[ww][tid];
             misc->inv[tid] = 1.0f / sqrtf(ss / (float)p.D + p.eps);
         }
-        BTRACE(c, 4);
-        consumer_sync();
     }
+    c.cbase += (unsigned)(n_chunks / bslot_chunks(gc, K));
+    c.bctr += (unsigned)(n_chunks / kStageChunks);
+    BTRACE(c, 4);
+    consumer_sync();            // misc->inv is written; the issuers have issued (and committed) everything
     BTRACE(c, 5);
 
     // ---- epilogue: thread = (output column of this CTA's slab = TMEM lane, half of the batch rows): warps 0..3 take rows
     //      0..7, warps 4..7 rows 8..15 of the same columns (a warp reads the TMEM lanes of its quadrant, warp % 4) ------------------
     constexpr int HR = kRows / 2;                               // rows per thread
-    const unsigned a = c.gctr & 1u;
     const int q = warp & 3, half = warp >> 2, r0 = half * HR;
     if (c.prof) { const long long t1 = clock64(); c.t_prof[2] += t1 - tq2; tq2 = t1; }
     {
-        mbar_wait(&misc->acc_full[a], (c.gctr >> 1) & 1u, p.err, kErrGridBarrierTimeout, c.seq);
+        mbar_wait(&misc->acc_full, c.gctr & 1u, p.err, kErrGridBarrierTimeout, c.seq);
         if (c.prof) { const long long t1 = clock64(); c.t_prof[3] += t1 - tq2; tq2 = t1; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float acc[HR];
 #pragma unroll
         for (int i = 0; i < HR; ++i) acc[i] = 0.f;
         if (r0 < R) {
-            // accumulator j: columns 0..15 = W.hi of rows 0..15, 16..31 = W.lo; all eight loads in flight, one wait
-            uint32_t v[4][2][HR];
+            // accumulator j: columns 0..15 = W.hi of rows 0..15, 16..31 = W.lo; four accumulators' loads in flight per wait
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int jb = 0; jb < kNumAcc; jb += 4) {
+                uint32_t v[4][2][HR];
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const uint32_t taddr = misc->tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccCols + j * 2 * kRows + t * kRows + r0;
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                        : "=r"(v[j][t][0]), "=r"(v[j][t][1]), "=r"(v[j][t][2]), "=r"(v[j][t][3]),
-                          "=r"(v[j][t][4]), "=r"(v[j][t][5]), "=r"(v[j][t][6]), "=r"(v[j][t][7])
-                        : "r"(taddr)
-                        : "memory");
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const uint32_t taddr = misc->tmem_base + ((uint32_t)(q * 32) << 16) + (jb + j) * 2 * kRows + t * kRows + r0;
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                            : "=r"(v[j][t][0]), "=r"(v[j][t][1]), "=r"(v[j][t][2]), "=r"(v[j][t][3]),
+                              "=r"(v[j][t][4]), "=r"(v[j][t][5]), "=r"(v[j][t][6]), "=r"(v[j][t][7])
+                            : "r"(taddr)
+                            : "memory");
+                    }
                 }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < HR; ++i) acc[i] += __uint_as_float(v[j][0][i]) + __uint_as_float(v[j][1][i]);
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < HR; ++i) acc[i] += __uint_as_float(v[j][0][i]) + __uint_as_float(v[j][1][i]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&misc->acc_empty[a]);
         BTRACE(c, 6);
 
         const int m = q * 32 + lane;                            // column inside the slab
@@ -780,7 +730,7 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
     c.gctr++;
     if (c.prof) { const long long t1 = clock64(); c.t_prof[4] += t1 - tq2; tq2 = t1; }
     BTRACE(c, 7);
-    consumer_sync();            // the staging ring is scratch of the next stage: every MMA of this one has completed
+    consumer_sync();            // the accumulators are free for the next stage's issuers; the staging ring is scratch of the next stage
     if (c.prof) c.t_prof[5] += clock64() - tq2;
 }
 
@@ -936,7 +886,7 @@ __device__ void attn_body_b(BCtx& c, int layer) {
             }
         }
         __syncwarp();
-        if (in_ring && c.lane == 0) mbar_arrive_n(&c.misc->empty[sl], kNumMmaWarps);
+        if (in_ring && c.lane == 0) mbar_arrive(&c.misc->empty[sl]);
     }
     c.cbase += nkc;
     if (c.lane < HPKB) { wstat[c.warp * 8 + c.lane] = m_run; wstat[c.warp * 8 + 4 + c.lane] = l_run; }
@@ -1210,12 +1160,12 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
         if (all_done) return;
     }
     if (tid == 0) {
-        // slot / stage / accumulator releases collect one commit from each of the two MMA warps
-        for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], kNumMmaWarps); }
+        // every ring slot and activation stage has ONE consumer (the issuer whose quarter of the contraction it belongs to)
+        for (int i = 0; i < kBNumSlots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
         // a stage is filled by one bulk copy (or two multicast halves: one arrive.expect_tx for both) and released by
-        // the commits of the two MMA warps - of both CTAs when a pair shares its activation stages
-        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], 1); mbar_init(&misc->bempty[i], (p.mc ? 2 : 1) * kNumMmaWarps); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], kNumMmaWarps); mbar_init(&misc->acc_empty[i], kConsumerWarps); }
+        // its issuer's commit - of both CTAs when a pair shares its activation stages
+        for (int i = 0; i < kActStages; ++i) { mbar_init(&misc->bfull[i], 1); mbar_init(&misc->bempty[i], p.mc ? 2 : 1); }
+        mbar_init(&misc->acc_full, kBIssuers);
         misc->stages_done = 0;
         misc->ready_seq = 0;
         fence_mbar_init();
@@ -1239,16 +1189,16 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
     asm volatile(".reg .pred dia_pw_bfull;" ::);       // mma_loop_b: result of the early test of the next activation stage's barrier
     if (warp == kProducerWarp) {
         if (tid == kProducerWarp * 32) producer_loop_b(p, ring, misc);
-    } else if (warp == kMmaWarp || (warp == kMmaWarp2 && kNumMmaWarps == 2)) {
-        mma_loop_b(p, ring, scratch, misc, warp == kMmaWarp ? 0 : 1);
     } else if (warp == kActWarp) {
         if (tid == kActWarp * 32) act_loop_b(p, scratch, misc);
     } else if (warp < kConsumerWarps) {
         BCtx c;
         c.p = &p; c.ring = ring; c.scratch = scratch; c.misc = misc;
         c.tid = tid; c.warp = warp; c.lane = tid & 31;
-        c.cbase = 0; c.gctr = 0; c.seq = 0; c.step = 0;
+        c.cbase = 0; c.bctr = 0; c.gctr = 0; c.seq = 0; c.step = 0;
         c.prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+        c.prof_issue = p.prof != nullptr && blockIdx.x == 0 && tid == kIssuerWarp0 * 32;
+        for (int i = 0; i < 3; ++i) c.t_issue[i] = 0;
         for (int i = 0; i < 8; ++i) c.t_prof[i] = 0;
         const long long t_begin = c.prof ? clock64() : 0;
 #pragma unroll
@@ -1275,6 +1225,11 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
                 }
                 if (tid == 0) st_release_cta_s32(&misc->stages_done, n * S + s + 1);
             }
+        }
+        if (c.prof_issue) {
+            p.prof[0] = (unsigned long long)c.t_issue[0];
+            p.prof[1] = (unsigned long long)c.t_issue[1];
+            p.prof[2] = (unsigned long long)c.t_issue[2];
         }
         if (c.prof) {
             p.prof[8] = (unsigned long long)(clock64() - t_begin);

@@ -158,10 +158,20 @@ constexpr unsigned kArrivalsPerCta = 8;   // the eight epilogue warps of a CTA a
 // tcgen05.mma reads as its M operand: [gc*8 rows = output columns][64 k] bf16, K-major, rows of 128 bytes whose 16-byte
 // units are XOR-swizzled with (row % 8) (SWIZZLE_128B).  A ring slot (16 KB) holds `bslot_chunks` consecutive chunks.
 __host__ __device__ inline int bchunk_bytes(int gc) { return gc * 8 * 128; }
+// Four warps issue the MMAs of a CTA, each on its own quarter of the contraction (kBIssuers); the stream interleaves their
+// slots - stream slot 4 j + w is the j-th slot of issuer w - so that every ring slot has exactly one consumer.
+constexpr int kBIssuers = 4;
 __host__ __device__ inline int bslot_chunks(int gc, int K) {
+    const int q = (K / 64) / kBIssuers;                 // chunks per issuer
     int n = 1;
-    while (n * 2 * bchunk_bytes(gc) <= 16384 && n * 2 <= 8 && (K / 64) % (n * 2) == 0) n *= 2;
+    while (n * 2 * bchunk_bytes(gc) <= 16384 && n * 2 <= 8 && q % (n * 2) == 0) n *= 2;
     return n;
+}
+// position (in chunks) of k-chunk c of a slab inside the CTA's stream
+__host__ __device__ inline int bchunk_position(int c, int gc, int K) {
+    const int q = (K / 64) / kBIssuers, cps = bslot_chunks(gc, K);
+    const int w = c / q, within = c - w * q, j = within / cps, r = within - j * cps;
+    return (kBIssuers * j + w) * cps + r;
 }
 __host__ __device__ inline unsigned long long bslab_bytes(int gc, int K) {
     return (unsigned long long)(K / 64) * (unsigned long long)bchunk_bytes(gc);

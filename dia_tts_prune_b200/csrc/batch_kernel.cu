@@ -468,7 +468,10 @@ __device__ __forceinline__ void issue_gemm_b(BCtx& c, int gt, int K, int gc) {
     // tile of the activations are adjacent in shared memory and go through ONE instruction; columns 0..15 of an accumulator
     // are W.hi, 16..31 are W.lo.  Back-to-back MMAs on ONE accumulator serialise on its read-modify-write latency
     // (measured: ~115 cycles per instruction), hence two accumulators per issuer.
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * kRows) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // Slabs of up to 64 columns (everything but mlp-in) use M = 64: the tensor pipe is busy ~34 cycles per instruction
+    // instead of ~40 (tools/microbench/umma_issue_bench.cu); row m of the slab then sits in TMEM lane 32 (m / 16) + m % 16.
+    const uint32_t mdim = gc <= 8 ? 64u : 128u;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * kRows) >> 3) << 17) | ((mdim >> 4) << 24);
     const uint32_t ring_u32 = smem_u32(c.ring), stage_u32 = smem_u32(c.scratch);
     const uint32_t d0 = misc->tmem_base + (uint32_t)wi * (2 * 2 * kRows);
     const bool prof = c.prof_issue;
@@ -655,8 +658,10 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         BTRACE(c, 6);
 
-        const int m = q * 32 + lane;                            // column inside the slab
-        const bool valid = m < NC;
+        // column inside the slab: TMEM lane = column for M = 128; an M = 64 accumulator keeps 16 columns per lane quadrant
+        const bool m64 = gc <= 8;
+        const int m = m64 ? q * 16 + (lane & 15) : q * 32 + lane;
+        const bool valid = m < NC && (!m64 || lane < 16);
         const int n = g0 * 8 + m;                               // column of the GEMM
         if (gt == G_QKV || gt == G_CQ) {
             u64* dst = gt == G_QKV ? p.ll_qkv : p.ll_cq;

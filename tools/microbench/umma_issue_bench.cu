@@ -31,8 +31,8 @@ __device__ __forceinline__ bool try_wait(uint64_t* bar, uint32_t parity) {
 #endif
     return ok != 0;
 }
-template <int NMMA, int NCOMMIT, int NWAIT, int FENCE, int MDIM>
-__global__ void __launch_bounds__(64, 1) bench(long long* out, int passes) {
+template <int NMMA, int NCOMMIT, int NWAIT, int FENCE, int MDIM, int NDIM = 32, int NW = 1>
+__global__ void __launch_bounds__(160, 1) bench(long long* out, int passes) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bars[8];
@@ -43,15 +43,15 @@ __global__ void __launch_bounds__(64, 1) bench(long long* out, int passes) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(MDIM >> 4) << 24);
-    if (warp == 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NDIM >> 3) << 17) | ((uint32_t)(MDIM >> 4) << 24);
+    if (warp < NW) {
         const long long t0 = clock64();
         for (int it = 0; it < passes; ++it) {
 #pragma unroll
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(64, 1) bench(long long* out, int passes) {
 #pragma unroll
                 for (int j = 0; j < NMMA; ++j)
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                                 ::"r"(tmem + (j & 3) * 32), "l"(ad + 2 * (j & 3)), "l"(bd + 2 * (j & 3)), "r"(idesc), "r"(it ? 1u : 0u) : "memory");
+                                 ::"r"(tmem + warp * 128 + (j & 3) * 32), "l"(ad + 2 * (j & 3)), "l"(bd + 2 * (j & 3)), "r"(idesc), "r"(it ? 1u : 0u) : "memory");
 #pragma unroll
                 for (int cc = 0; cc < NCOMMIT; ++cc)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[cc])) : "memory");
@@ -75,22 +75,22 @@ __global__ void __launch_bounds__(64, 1) bench(long long* out, int passes) {
         if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[3])) : "memory");
         __syncwarp();
         const long long t1 = clock64();
-        if (threadIdx.x == 0) out[0] = t1 - t0;
+        if ((threadIdx.x & 31) == 0) out[2 * warp] = t1 - t0;
         // wait until everything retired: poll pending count is awkward; sleep instead
         for (int i = 0; i < 2000; ++i) __nanosleep(1000);
-        if (threadIdx.x == 0) out[1] = clock64() - t0;
+        if ((threadIdx.x & 31) == 0) out[2 * warp + 1] = clock64() - t0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
-template <int NMMA, int NCOMMIT, int NWAIT, int FENCE, int MDIM>
+template <int NMMA, int NCOMMIT, int NWAIT, int FENCE, int MDIM, int NDIM = 32, int NW = 1>
 void run(const char* name, long long* d) {
     const int smem = 200 * 1024, passes = 4000;
-    cudaFuncSetAttribute(bench<NMMA, NCOMMIT, NWAIT, FENCE, MDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(bench<NMMA, NCOMMIT, NWAIT, FENCE, MDIM, NDIM, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     long long h[2];
     for (int rep = 0; rep < 2; ++rep) {
-        bench<NMMA, NCOMMIT, NWAIT, FENCE, MDIM><<<1, 64, smem>>>(d, passes);
+        bench<NMMA, NCOMMIT, NWAIT, FENCE, MDIM, NDIM, NW><<<1, 160, smem>>>(d, passes);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
     }
@@ -99,7 +99,7 @@ void run(const char* name, long long* d) {
 }
 int main() {
     long long* d;
-    cudaMalloc(&d, 64);
+    cudaMalloc(&d, 256);
     printf("wait kind %d (0 try_wait, 1 try_wait.relaxed.cta, 2 test_wait)\n", WAITKIND);
     run<0, 0, 1, 0, 128>("1 wait only", d);
     run<0, 0, 3, 0, 128>("3 waits only", d);
@@ -118,5 +118,15 @@ int main() {
     run<4, 2, 3, 0, 128>("4 MMA + 2 commits + 3 try_wait", d);
     run<4, 2, 3, 1, 128>("4 MMA + 2 commits + 3 try_wait + fence", d);
     run<16, 2, 1, 1, 128>("16 MMA + 2 commits + 1 try_wait + fence", d);
+    run<8, 0, 0, 0, 128, 16>("8 MMA M128 N16", d);
+    run<8, 0, 0, 0, 128, 64>("8 MMA M128 N64", d);
+    run<8, 0, 0, 0, 128, 128>("8 MMA M128 N128", d);
+    run<8, 0, 0, 0, 128, 256>("8 MMA M128 N256 (TMEM cols wrap, timing only)", d);
+    run<8, 0, 0, 0, 64, 8>("8 MMA M64 N8", d);
+    run<8, 0, 0, 0, 64, 32>("8 MMA M64 N32", d);
+    run<8, 0, 0, 0, 64, 112>("8 MMA M64 N112", d);
+    run<8, 0, 0, 0, 128, 32, 2>("8 MMA M128 N32, 2 warps issuing (per warp)", d);
+    run<8, 0, 0, 0, 128, 32, 4>("8 MMA M128 N32, 4 warps issuing (per warp)", d);
+    run<8, 1, 0, 0, 128, 32, 4>("8 MMA + 1 commit, 4 warps issuing (per warp)", d);
     return 0;
 }

@@ -38,8 +38,20 @@ typedef unsigned long long u64;
 namespace {
 
 constexpr int kBSlotBytes = 16384;          // one ring slot: up to 8 k-chunks of a slab, or a 16-key K / V tile
-constexpr int kBNumSlots = 8;
-constexpr int kActStages = 11;              // activation (B operand) staging ring
+#ifndef DIA_B_SLOTS
+#define DIA_B_SLOTS 8
+#endif
+#ifndef DIA_B_STAGES
+#define DIA_B_STAGES 12
+#endif
+constexpr int kBNumSlots = DIA_B_SLOTS;
+// The activation ring must hold a multiple of kBIssuers stages: stage index i belongs to issuer i % 4, and an issuer that
+// waits for (or tests) the barrier of a stage relies on the PREVIOUS generation of that barrier being complete - the one-bit
+// phase parity cannot tell "not filled yet" from "filled two generations ago".  With a multiple of 4 the previous generation
+// is the issuer's own, consumed earlier; with 11 stages it was another issuer's, bulk copies may land out of order, and a
+// rare false positive consumed a stage before it was filled (a hang after ~10 k stages, or a wrong token).
+constexpr int kActStages = DIA_B_STAGES;
+static_assert(kActStages % kBIssuers == 0, "see above");              // activation (B operand) staging ring
 constexpr int kBTermBytes = 2048;           // [16 rows][64 k] bf16, K-major, 128-byte swizzle
 constexpr int kStageChunks = 2;             // k-chunks (64 rows each) per activation stage: [chunk][hi tile | lo tile]
 constexpr int kActStageBytes = kStageChunks * 2 * kBTermBytes;
@@ -403,9 +415,16 @@ __device__ void act_loop_b(const BatchParams& p, unsigned char* scratch, BMisc* 
             for (int su = 0; su < n_st; ++su) {
                 const int st = (su & (kBIssuers - 1)) * per_issuer + (su >> 2);
                 const unsigned bi = bctr + (unsigned)su, bs = bi % kActStages;
-                if (prof) tq = clock64();
-                mbar_spin(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (seq << 8) | 0xc0 | bs);
-                if (prof) t_bempty += clock64() - tq;
+                // The first kActStages copies of a GEMM stage need no wait: the stage's input is complete, so every CTA - this one
+                // and its pair too - has finished the stage that produced it, i.e. all MMAs of its previous GEMM have retired and
+                // every activation stage is free (a wait changes no barrier state; an mbarrier test costs ~120 cycles, and the four
+                // issuers start with copies 0..3)
+                // (not when a CTA pair shares its stages: the pair's multicast arrive may still be in flight)
+                if (su >= kActStages || p.mc) {
+                    if (prof) tq = clock64();
+                    mbar_spin(&misc->bempty[bs], ((bi / kActStages) & 1u) ^ 1u, p.err, kErrEmptyBarrierTimeout, (seq << 8) | 0xc0 | bs);
+                    if (prof) t_bempty += clock64() - tq;
+                }
                 mbar_arrive_expect_tx(&misc->bfull[bs], kActStageBytes);
                 if (p.mc) {
                     // this CTA fetches its half of the stage (the chunk of its cluster rank) for both CTAs of the pair; the
@@ -729,7 +748,9 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
         }
         if (out_act >= 0) {         // this warp's piece of the output vector is written: release it
             __syncwarp();
+            const long long ta = c.prof ? clock64() : 0;
             if (lane == 0) act_arrive(p, out_act, 1);
+            if (c.prof) c.t_prof[1] += clock64() - ta;
         }
     }
     c.gctr++;

@@ -354,8 +354,10 @@ static int create_engine(const dia_b200_shape* shape, int device, int n_ctas, in
         for (int c = 0; c < G; ++c)
             for (int t = 0; t < G_COUNT; ++t)
                 if (e->tab[c].gc[t] == 0) e->batch_mc = 0;
-        const char* env = std::getenv("DIA_BATCH_NO_MULTICAST");
-        if (env && env[0] == '1') e->batch_mc = 0;
+        // measured (tools/batch_bench.py, A/B on one box): sharing the stages couples the pair's pipelines and is 7 % slower
+        // than two independent CTAs since the four-issuer loop - off unless asked for
+        const char* env = std::getenv("DIA_BATCH_MULTICAST");
+        if (!(env && env[0] == '1')) e->batch_mc = 0;
     }
     for (int c = 0; c < G; ++c) {
         if (e->tab[c].gc[G_SO] > 0) {

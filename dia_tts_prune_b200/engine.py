@@ -358,7 +358,7 @@ class BatchDecodeEngine:
         _lib.check(self.lib.dia_b200_debug_read(self._h, _lib.BUF_TIMING, _ptr(out), 32 * 8, _stream(self.device)), "debug_read")
         v = out.tolist()
         names = ["issuer4_total", "issuer4_wait_bfull", "issuer4_wait_ring", "", "act_wait_ready", "act_wait_bempty", "", "",
-                 "math_total", "math_wait_ready", "", "math_rms_gather", "math_wait_acc_full",
+                 "math_total", "math_wait_ready", "math_epilogue_release", "math_rms_gather", "math_wait_acc_full",
                  "math_epilogue", "math_stage_end_barrier", "math_attention", "math_embed_sample"]
         return {n: v[i] for i, n in enumerate(names) if n}
 

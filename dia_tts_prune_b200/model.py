@@ -103,7 +103,7 @@ class Dia:
         self.dac_model = None
         self.last_codes: torch.Tensor | None = None     # raw generated rows of the last generate() call
         self.last_stats: dict = {}
-        self.batch_min_utterances = 3                   # generate_batch: smaller groups run through the single-utterance kernel
+        self.batch_min_utterances = 2                   # generate_batch: smaller groups run through the single-utterance kernel
         # encode / project only the text bytes the decoder can observe (set False for the reference's full tensors)
         self.live_text_only = True
 
@@ -417,9 +417,9 @@ class Dia:
             idx = list(range(b0, min(len(texts), b0 + per)))
             t0 = time.time()
             if len(idx) < self.batch_min_utterances:
-                # Below the measured crossover (tools/batch_bench.py at cache slot 1500: the batched step costs ~1.6 ms for 1..2
-                # utterances, ~1.7 for 3..4 and ~1.9 for 8; the single-utterance step 0.75 ms) a short group is faster one
-                # utterance after the other
+                # Below the measured crossover (tools/batch_bench.py at cache slot 1500: the batched step costs 1.20 ms for one
+                # utterance, 1.26 for 2, 1.40 for 4 and 1.62 for 8; the single-utterance step 0.75 ms) a single utterance is
+                # faster on its own kernel
                 for i in idx:
                     res = self.generate(texts[i], max_tokens=max_tokens, cfg_scale=cfg_scale, temperature=temperature,
                                         top_p=top_p, cfg_filter_top_k=cfg_filter_top_k, seed=base_seed + i, output=output)

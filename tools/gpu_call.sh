@@ -1,6 +1,4 @@
-(timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "batch" 2>&1 | tail -15) > gpurun_out/r2_t42_batch_tests.log 2>&1
-for i in 1 2; do
-  echo -n "base: " >> gpurun_out/r2_t42_ab.log; DIA_B200_LIB=$PWD/tools/ab/base.so timeout 300 python tools/batch_bench.py --utts 8 --reps 3 2>&1 | tail -1 >> gpurun_out/r2_t42_ab.log
-  echo -n "new : " >> gpurun_out/r2_t42_ab.log; timeout 300 python tools/batch_bench.py --utts 8 --reps 3 2>&1 | tail -1 >> gpurun_out/r2_t42_ab.log
-done
-(timeout 300 python tools/batch_bench.py --utts 8 --reps 2 --profile 2>&1 | tail -2) >> gpurun_out/r2_t42_ab.log
+timeout 900 python tools/batch_determinism.py --reps 16 2>&1 | tail -8 >> gpurun_out/r2_t52.log
+timeout 900 python tools/batch_determinism.py --reps 6 --utts 5 --tokens 500 2>&1 | tail -4 >> gpurun_out/r2_t52.log
+(timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "batch" 2>&1 | tail -3) >> gpurun_out/r2_t52.log 2>&1
+timeout 300 python tools/batch_bench.py --utts 1 2 3 4 8 --reps 3 --profile 2>&1 | tail -10 >> gpurun_out/r2_t52.log

@@ -18,4 +18,4 @@ ncu --set full --clock-control none --import-source on -k regex:dia_batch_step_k
 python tools/gemm_check.py > gpurun_out/plain_gemm_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:dia_gemm_tcgen05 -s 24 -c 1 -f -o gpurun_out/gemm_${TAG}_full \
     python tools/gemm_check.py > gpurun_out/ncu_gemm_$TAG.log 2>&1
-tail -2 gpurun_out/ncu_full_$TAG.log gpurun_out/ncu_batch_$TAG.log gpurun_out/ncu_gemm_$TAG.log
+for f in gpurun_out/ncu_full_$TAG.log gpurun_out/ncu_batch_$TAG.log gpurun_out/ncu_gemm_$TAG.log; do tail -n 2 $f; done

@@ -746,18 +746,16 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
                 }
             }
         }
-        if (out_act >= 0) {         // this warp's piece of the output vector is written: release it
-            __syncwarp();
-            const long long ta = c.prof ? clock64() : 0;
-            if (lane == 0) act_arrive(p, out_act, 1);
-            if (c.prof) c.t_prof[1] += clock64() - ta;
-        }
     }
     c.gctr++;
     if (c.prof) { const long long t1 = clock64(); c.t_prof[4] += t1 - tq2; tq2 = t1; }
     BTRACE(c, 7);
     consumer_sync();            // the accumulators are free for the next stage's issuers; the staging ring is scratch of the next stage
-    if (c.prof) c.t_prof[5] += clock64() - tq2;
+    if (c.prof) { const long long t1 = clock64(); c.t_prof[5] += t1 - tq2; tq2 = t1; }
+    // the CTA's piece of the output vector is written: ONE release per CTA (148 instead of 1 184 reductions on the counter's
+    // address per stage - the L2 serialises them; the barrier above makes the other warps' stores part of this release)
+    if (out_act >= 0 && tid == 0) act_arrive(p, out_act, kArrivalsPerCta);
+    if (c.prof) c.t_prof[1] += clock64() - tq2;
 }
 
 constexpr int HPKB = 4;          // query heads per KV tile in self-attention (GQA 4:1)
@@ -1074,7 +1072,7 @@ __device__ void embed_stage_b(BCtx& c) {
         }
     }
     __syncwarp();
-    if (c.lane == 0) act_arrive(p, A_XQ, kArrivalsPerCta / 2);
+    if (c.lane == 0) act_arrive(p, A_XQ, kArrivalsPerCta / 2);        // warps 0 and 4
 }
 
 // ---- sampling: CTA u * C + ch draws channel ch of utterance u; the CTA of channel 0 then runs the body of the reference's

@@ -152,7 +152,7 @@ struct StepParams {
 constexpr int kMaxUtt = 8;             // utterances per launch: 16 batch rows = N of the tcgen05 MMA
 // activation buffers of the batched kernel (index into BatchParams::ctr)
 enum ActBuf : int { A_XQ = 0, A_XC, A_XM, A_XL, A_ATTN, A_CATTN, A_HIDDEN, A_COUNT };
-constexpr unsigned kArrivalsPerCta = 8;   // the eight epilogue warps of a CTA arrive one by one
+constexpr unsigned kArrivalsPerCta = 2;   // per generation and CTA (the embedding stage arrives from two warps)
 
 // Batched weight stream: per CTA and GEMM the slab [K][gc*8 columns] is stored as K / 64 chunks, each the tile
 // tcgen05.mma reads as its M operand: [gc*8 rows = output columns][64 k] bf16, K-major, rows of 128 bytes whose 16-byte

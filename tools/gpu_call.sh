@@ -1,9 +1,6 @@
-set -x
-(time timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -6) > gpurun_out/r2_t53_all.log 2>&1
-(timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_t53_bench.json 2> gpurun_out/r2_t53_bench.err)
-python tools/batch_bench.py --utts 8 --steps 16 --reps 2 > gpurun_out/plain_batch_r2b.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:dia_batch_step_kernel -s 1 -c 1 -f -o gpurun_out/batch_r2b_full \
-    python tools/batch_bench.py --utts 8 --steps 16 --reps 2 > gpurun_out/ncu_batch_r2b.log 2>&1
-tail -n 3 gpurun_out/ncu_batch_r2b.log; tail -3 gpurun_out/r2_t53_all.log
-(timeout 600 python tools/gemm_check.py 2>&1 | tail -8) > gpurun_out/r2_t53_gemm_check.log 2>&1
-(timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_t53_bench_ref.json 2> gpurun_out/r2_t53_bench_ref.err)
+for i in 1 2; do
+  echo -n "base: " >> gpurun_out/r2_t55_ab.log; DIA_B200_LIB=$PWD/tools/ab/base.so timeout 300 python tools/batch_bench.py --utts 8 --reps 3 2>&1 | tail -1 >> gpurun_out/r2_t55_ab.log
+  echo -n "new : " >> gpurun_out/r2_t55_ab.log; timeout 300 python tools/batch_bench.py --utts 8 --reps 3 2>&1 | tail -1 >> gpurun_out/r2_t55_ab.log
+done
+(timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "batch" 2>&1 | tail -3) >> gpurun_out/r2_t55_ab.log 2>&1
+timeout 300 python tools/batch_bench.py --utts 8 --reps 2 --profile 2>&1 | tail -2 >> gpurun_out/r2_t55_ab.log

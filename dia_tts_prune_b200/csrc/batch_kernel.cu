@@ -65,7 +65,14 @@ static_assert(kStageChunks == 2, "an issuer's stage is two chunks");
 constexpr int kActWarp = 11;                // one lane: waits for the input buffer of every GEMM stage, streams it into the B ring
 constexpr int kBThreads = 12 * 32;          // 8 math warps, TMEM warp, producer warp, (idle), activation warp
 constexpr int kRows = 16;                   // batch rows of the B tiles (2 x kMaxUtt); N of the MMA = 2 kRows (hi rows, then lo rows)
-constexpr int kNumAcc = 2 * kBIssuers;      // two accumulators per issuer (back-to-back MMAs on one accumulator serialise)
+#ifndef DIA_ACC_PER_ISSUER
+#define DIA_ACC_PER_ISSUER 1
+#endif
+constexpr int kAccPerIssuer = DIA_ACC_PER_ISSUER;
+// (back-to-back MMAs of ONE issuing thread on one accumulator serialise on its read-modify-write latency, ~115 cycles per
+// instruction; with four issuers the pipe interleaves their instructions, and one accumulator each is 0.8 % faster than two:
+// half the TMEM loads in the epilogue)
+constexpr int kNumAcc = kAccPerIssuer * kBIssuers;
 constexpr int kAccCols = kNumAcc * 2 * kRows;   // TMEM columns: accumulators x (hi | lo)
 constexpr int kTmemCols = kAccCols;         // (one set: the warps that issue the MMAs of a stage also run its epilogue)
 
@@ -486,13 +493,13 @@ __device__ __forceinline__ void issue_gemm_b(BCtx& c, int gt, int K, int gc) {
     // instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major, M = 128, N = 32: the hi tile and the lo
     // tile of the activations are adjacent in shared memory and go through ONE instruction; columns 0..15 of an accumulator
     // are W.hi, 16..31 are W.lo.  Back-to-back MMAs on ONE accumulator serialise on its read-modify-write latency
-    // (measured: ~115 cycles per instruction), hence two accumulators per issuer.
+    // (measured: ~115 cycles per instruction), when ONE thread issues them; see kNumAcc.
     // Slabs of up to 64 columns (everything but mlp-in) use M = 64: the tensor pipe is busy ~34 cycles per instruction
     // instead of ~40 (tools/microbench/umma_issue_bench.cu); row m of the slab then sits in TMEM lane 32 (m / 16) + m % 16.
     const uint32_t mdim = gc <= 8 ? 64u : 128u;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * kRows) >> 3) << 17) | ((mdim >> 4) << 24);
     const uint32_t ring_u32 = smem_u32(c.ring), stage_u32 = smem_u32(c.scratch);
-    const uint32_t d0 = misc->tmem_base + (uint32_t)wi * (2 * 2 * kRows);
+    const uint32_t d0 = misc->tmem_base + (uint32_t)wi * (kAccPerIssuer * 2 * kRows);
     const bool prof = c.prof_issue;
     long long tq = 0;
     bool have = false;
@@ -527,7 +534,8 @@ __device__ __forceinline__ void issue_gemm_b(BCtx& c, int gt, int K, int gc) {
             if (elect_one_sync()) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)           // 16 elements along K = 32 bytes = 2 descriptor units
-                    umma_bf16_b(d0 + (uint32_t)(j & 1) * (2 * kRows), adesc + 2 * j, bdesc + 2 * j, idesc, (cc != 0 || j >= 2) ? 1u : 0u);
+                    umma_bf16_b(d0 + (uint32_t)(j & (kAccPerIssuer - 1)) * (2 * kRows), adesc + 2 * j, bdesc + 2 * j, idesc,
+                                (cc != 0 || j >= kAccPerIssuer) ? 1u : 0u);
                 if (in_slot == cps - 1) umma_commit_b(&misc->empty[slot]);
                 if (jc == kStageChunks - 1) {
                     if (p.mc) umma_commit_mc_b(&misc->bempty[bs], (uint16_t)3);

@@ -967,12 +967,20 @@ def test_full_batched_eight_utterances_smoke(full_gpu):
     dia, sd = full_gpu
     texts = [SY.synthetic_transcript(i) for i in range(8)]
     a = dia.generate_batch(texts, max_tokens=300, temperature=0.0)
-    b = dia.generate_batch(texts, max_tokens=300, temperature=0.0)
-    for x, y in zip(a, b):
-        assert torch.equal(x, y) and x.shape[1] == 9 and ((x >= 0) & (x <= 1023)).all()
-    # utterance 0 alone gives the same greedy rows
-    dia.generate(texts[0], max_tokens=300, temperature=0.0, output="codes")
-    assert torch.equal(dia.last_codes.cpu()[:200], dia.last_batch_codes[0].cpu()[:200]) or True   # near-ties may differ late
+    first = [c.cpu().clone() for c in dia.last_batch_codes]
+    for rep in range(3):
+        b = dia.generate_batch(texts, max_tokens=300, temperature=0.0)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y) and x.shape[1] == 9 and ((x >= 0) & (x <= 1023)).all()
+        for x, y in zip(first, dia.last_batch_codes):
+            assert torch.equal(x, y.cpu()), "the batched kernel is deterministic: a difference between two runs is a race"
+    # every utterance alone (single-utterance kernel, three-term activations) gives the same first greedy rows: rows 8..15 of
+    # the batch (utterances 4..7) go through the second half of the epilogue warps and of the embedding stage
+    same = 0
+    for u in range(8):
+        dia.generate(texts[u], max_tokens=80, temperature=0.0, output="codes")
+        same += int(torch.equal(dia.last_codes.cpu()[:40], first[u][:40]))
+    assert same >= 7, f"only {same} of 8 utterances reproduce their single-utterance stream over 40 frames"
 
 
 def test_non_representable_fp32_checkpoint_is_rounded_once_and_consistently():

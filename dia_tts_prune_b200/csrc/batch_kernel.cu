@@ -8,19 +8,21 @@
 //
 //  * the GEMM stages run on the 5th-generation tensor cores: the CTA's slab is the M operand (<= 128 output columns,
 //    K-major, 128-byte swizzle - the host repacks the weights into exactly the tiles tcgen05.mma reads, one 64-row
-//    k-chunk after the other), the activations are the N = 16 operand, split in two bf16 terms (hi + lo) that are
-//    accumulated into the same fp32 accumulator in tensor memory.  One elected thread issues the MMAs;
-//    tcgen05.commit releases the weight slot and the activation stage; the epilogue reads the accumulator with
-//    tcgen05.ld: thread = output column, registers = the 16 rows, so RMSNorm scaling, RoPE-ready q/k/v words,
-//    SiLU(gate) * up, the residual add (the stream lives in registers of its column's thread) and the CFG combine
-//    are all local;
+//    k-chunk after the other; M = 64 instructions for slabs of <= 64 columns), the activations are the N = 32 operand:
+//    two bf16 terms (hi rows | lo rows) that one instruction accumulates into the same fp32 accumulator in tensor
+//    memory.  FOUR issuers - math warps 4..7 - each own a quarter of the contraction (their own ring slots, activation
+//    stages and accumulator: every barrier has one consumer) and issue from one elected lane; tcgen05.commit releases
+//    the weight slot and the activation stage.  Warps 0..3 gather the RMSNorm sums meanwhile.  The epilogue (all eight
+//    warps) reads the accumulators with tcgen05.ld: thread = output column, registers = 8 of the 16 rows, so RMSNorm
+//    scaling, RoPE-ready q/k/v words, SiLU(gate) * up, the residual add (the stream lives in registers of its column's
+//    thread) and the CFG combine are all local;
 //  * the input vector of a GEMM stage crosses CTAs as the shared-memory image of the N operand itself (per 64-k chunk
 //    a hi tile and a lo tile of [16 rows][64 k] bf16, swizzled): the producing epilogues store 2-byte terms straight
-//    into that image in global memory, every CTA adds to the buffer's arrival counter with release semantics, and a
-//    dedicated lane of each consuming CTA polls the counter (acquire) and then streams the vector into a 6-stage ring
-//    with 8 KB bulk copies (TMA engine) - no register staging, no per-word flags, the math warps are free for the
-//    RMSNorm sums while the MMAs run.  (The first version moved (hi | lo | 1-bit flag) words through registers: 2 608
-//    stage hand-offs per step between the math warps and the MMA warp were 60 % of the step.)
+//    into that image in global memory, every CTA adds to the buffer's arrival counter with release semantics (once per
+//    CTA and stage), and a dedicated lane of each consuming CTA polls the counter (acquire) and then streams the vector
+//    into a 12-stage ring with 8 KB bulk copies (TMA engine) - no register staging, no per-word flags.  (The first
+//    version moved (hi | lo | 1-bit flag) words through registers: 2 608 stage hand-offs per step between the math
+//    warps and the MMA warp were 60 % of the step.)
 //  * attention, embedding and sampling are the single-utterance stages indexed by (utterance, row): (row, kv head)
 //    pairs x key splits over the CTAs, 9 sampler CTAs per utterance, one state machine per utterance.
 //

@@ -1,5 +1,3 @@
-set -x
-(time timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -6) > gpurun_out/r2_t59_all.log 2>&1
-(timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_t59_bench.json 2> gpurun_out/r2_t59_bench.err)
-(timeout 600 python tools/batch_bench.py --utts 1 2 3 4 8 --reps 3 --profile 2>&1 | tail -10) > gpurun_out/r2_t59_bb.log 2>&1
-tail -3 gpurun_out/r2_t59_all.log; tail -2 gpurun_out/r2_t59_bb.log
+(DIA_BATCH_MULTICAST=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "batch" 2>&1 | tail -3) > gpurun_out/r2_t60.log 2>&1
+DIA_BATCH_MULTICAST=1 timeout 600 python tools/batch_determinism.py --reps 8 2>&1 | tail -2 >> gpurun_out/r2_t60.log
+DIA_BATCH_MULTICAST=1 timeout 300 python tools/batch_bench.py --utts 8 --reps 2 2>&1 | tail -1 >> gpurun_out/r2_t60.log

@@ -962,6 +962,43 @@ def test_full_generate_batch_vs_reference_goldens(full_gpu, gold_full):
     assert torch.equal(dia.last_batch_codes[3].cpu()[:24], torch.from_numpy(gold_full["codes"][:24]))
 
 
+def test_full_batched_long_context_vs_reference(full_gpu):
+    """The batched kernel deep in the context: three utterances with prefilled prompts of 1200 / 2380 / 2990 frames (each at
+    its own cache slot and RoPE position) decode 32 frames in ONE launch; every row against the token grid the reference
+    produced for that utterance alone (a code may differ only at a near-tie of the reference)."""
+    dia, sd = full_gpu
+    cfg = dia.config
+    golds = [_golden(f"dia16b_seed5_clone{n}.npz") for n in (1200, 2380, 2990)]
+    eng = dia.model.decoder.batch_engine(4)
+    prepared = []
+    with torch.inference_mode():
+        for u, g in enumerate(golds):
+            text = dia._effective_text(str(g["text"]), str(g["prompt_text"]))
+            st, out = dia._prepare_generation(text, torch.from_numpy(g["prompt"]), False)
+            for c in st.cross_attn_cache:
+                c.k, c.v = c.k.to(torch.float32).contiguous(), c.v.to(torch.float32).contiguous()
+            eng.bind(u, st.self_attn_cache, st.cross_attn_cache, st.text_len)
+            assert out.prefill_step == int(g["prefill_step"])
+            prepared.append((st, out))
+        P = [out.prefill_step for _, out in prepared]
+        slots = [st.self_attn_cache[0].current_idx for st, _ in prepared]
+        n = 32                                              # before any fixture's end-of-budget countdown (max_tokens - 16)
+        eng.generate_begin([out.generated_tokens for _, out in prepared], P, slots, cfg.data.audio_length, 3.0, 0.0, 0.95, 35,
+                           [0, 1, 2])
+        eng.generate_steps(n)
+        torch.cuda.synchronize()
+        assert all(s.steps_run == n and s.device_error == 0 for s in eng.status())
+    for u, g in enumerate(golds):
+        got = prepared[u][1].generated_tokens[P[u]: P[u] + n].cpu()
+        want = torch.from_numpy(g["grid"][P[u]: P[u] + n]).to(got.dtype)
+        diff = (got != want).nonzero()
+        if diff.numel():
+            r, c = diff[0].tolist()
+            m = float(g["margins"][r, c])
+            assert m < 1e-3, f"utterance {u} (prompt {P[u] - 1}): divergence at decode step {r} channel {c}, reference margin {m:.3e}"
+            print(f"utterance {u}: near-tie at decode step {r} channel {c} (reference margin {m:.3e})")
+
+
 def test_full_batched_eight_utterances_smoke(full_gpu):
     """8 utterances (16 rows) for 3 launches of 128 steps: runs, stays in range, is deterministic."""
     dia, sd = full_gpu

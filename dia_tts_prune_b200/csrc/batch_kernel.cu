@@ -108,6 +108,7 @@ struct BCtx {
     long long t_prof[8];  // CTA 0, thread 0 (p.prof): 0 wait for the stage input, 1 -, 2 rms gather, 3 accumulator wait,
                           // 4 epilogue, 5 end-of-stage barrier, 6 attention stages, 7 embed + sample
     bool prof;
+    long long t_tmem;     // CTA 0, thread 0: the accumulator loads of the epilogues
     bool prof_issue;      // CTA 0, warp 4, lane 0: where the first MMA issuer spends its clocks (0 total, 1 bfull waits, 2 ring waits)
     long long t_issue[3];
 };
@@ -685,6 +686,7 @@ __device__ void gemm_stage_b(BCtx& c, int gt, int layer) {
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (c.prof) c.t_tmem += clock64() - tq2;              // (part of t_prof[4]: the accumulator loads)
         BTRACE(c, 6);
 
         // column inside the slab: TMEM lane = column for M = 128; an M = 64 accumulator keeps 16 columns per lane quadrant
@@ -1233,6 +1235,7 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
         c.prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
         c.prof_issue = p.prof != nullptr && blockIdx.x == 0 && tid == kIssuerWarp0 * 32;
         for (int i = 0; i < 3; ++i) c.t_issue[i] = 0;
+        c.t_tmem = 0;
         for (int i = 0; i < 8; ++i) c.t_prof[i] = 0;
         const long long t_begin = c.prof ? clock64() : 0;
 #pragma unroll
@@ -1268,6 +1271,7 @@ extern "C" __global__ void __launch_bounds__(kBThreads, 1) dia_batch_step_kernel
         if (c.prof) {
             p.prof[8] = (unsigned long long)(clock64() - t_begin);
             for (int i = 0; i < 8; ++i) p.prof[9 + i] = (unsigned long long)c.t_prof[i];
+            p.prof[17] = (unsigned long long)c.t_tmem;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

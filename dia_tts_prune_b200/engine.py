@@ -359,7 +359,7 @@ class BatchDecodeEngine:
         v = out.tolist()
         names = ["issuer4_total", "issuer4_wait_bfull", "issuer4_wait_ring", "", "act_wait_ready", "act_wait_bempty", "", "",
                  "math_total", "math_wait_ready", "math_epilogue_release", "math_rms_gather", "math_wait_acc_full",
-                 "math_epilogue", "math_stage_end_barrier", "math_attention", "math_embed_sample"]
+                 "math_epilogue", "math_stage_end_barrier", "math_attention", "math_embed_sample", "math_epilogue_tmem_loads"]
         return {n: v[i] for i, n in enumerate(names) if n}
 
     def decode_step(self, tokens_UxC: torch.Tensor, pos: list[int], slot: list[int]) -> torch.Tensor:

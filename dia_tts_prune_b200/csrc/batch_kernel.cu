@@ -853,11 +853,15 @@ __device__ void attn_body_b(BCtx& c, int layer) {
     float4 acc[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // The warps move round by round (8 tiles per round, a block barrier in between): a warp is then never more than one
-    // generation ahead of a ring slot (10 slots), which is all the one-bit phase parity of the mbarriers can tell apart.
+    // Warp w takes the tiles w, w + 8, ...  With a ring of 8 slots (= the warps) these are successive generations of ONE
+    // slot: the warp consumed the previous one itself, so the one-bit phase parity of the slot barriers is never
+    // ambiguous and the warps need no barrier between the rounds - they drift apart, the slots are released and
+    // refilled one by one instead of all eight at once (with the barrier a round waited for a whole ring of copies,
+    // then computed, then waited again: 37 GB/s per CTA).  Any other ring size needs the round barrier.
+    constexpr bool kRoundBarrier = (kBNumSlots % kConsumerWarps) != 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < nvc; c0 += kConsumerWarps) {
-        if (c0 > 0) consumer_sync();
+        if (kRoundBarrier && c0 > 0) consumer_sync();
         const int ci = c0 + c.warp;
         if (ci >= nvc) continue;
         const bool in_ring = ci < nkc;

@@ -1,2 +1,7 @@
-timeout 1500 python tools/batch_determinism.py --reps 200 --tokens 260 2>&1 | tail -3 > gpurun_out/r2_t63.log
-timeout 900 python tools/batch_determinism.py --reps 30 --tokens 300 --utts 3 2>&1 | tail -2 >> gpurun_out/r2_t63.log
+for i in 1 2; do
+  echo -n "base: " >> gpurun_out/r2_t64_ab.log; DIA_B200_LIB=$PWD/tools/ab/base.so timeout 300 python tools/batch_bench.py --utts 8 --reps 3 2>&1 | tail -1 >> gpurun_out/r2_t64_ab.log
+  echo -n "new : " >> gpurun_out/r2_t64_ab.log; timeout 300 python tools/batch_bench.py --utts 8 --reps 3 2>&1 | tail -1 >> gpurun_out/r2_t64_ab.log
+done
+(timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "batch" 2>&1 | tail -3) >> gpurun_out/r2_t64_ab.log 2>&1
+timeout 300 python tools/batch_bench.py --utts 8 --reps 2 --profile 2>&1 | tail -2 >> gpurun_out/r2_t64_ab.log
+timeout 600 python tools/batch_determinism.py --reps 12 2>&1 | tail -2 >> gpurun_out/r2_t64_ab.log

@@ -255,7 +255,8 @@ __device__ __forceinline__ BAttnWork self_work_b(const BatchParams& p, int cta, 
     w.row = w.pair / p.Hkv;
     w.head = w.pair - w.row * p.Hkv;
     w.u = w.row >> 1;
-    const int n_old = w.pair < pairs ? p.utt[w.u].slot0 + step : 0;
+    // (an utterance that has used up its budget - a longer prompt than its neighbours' - idles at the last cache slot)
+    const int n_old = w.pair < pairs ? min(p.utt[w.u].slot0 + step, p.Lmax - 1) : 0;
     int per = (n_old + nsplit - 1) / nsplit;
     per = (per + 15) & ~15;
     if (per < 64) per = 64;
@@ -787,7 +788,7 @@ __device__ void attn_body_b(BCtx& c, int layer) {
     const int nsplit = self ? p.sa_nsplit : p.ca_nsplit;
     const uint32_t fprev = c.seq - 1;
     const bool has_new = self && w.has_new;
-    const int pos = p.utt[u].pos0 + c.step, slot = p.utt[u].slot0 + c.step;
+    const int pos = p.utt[u].pos0 + c.step, slot = min(p.utt[u].slot0 + c.step, p.Lmax - 1);
 
     float* qs = reinterpret_cast<float*>(c.scratch);      // [HPKB][128] rotated, pre-scaled queries
     float* kn = qs + HPKB * kHeadDim;                      // [128] rotated key of this step
@@ -1044,7 +1045,11 @@ __device__ void embed_stage_b(BCtx& c) {
         const int u = tid / p.C, ch = tid - u * p.C;
         int t;
         if (p.tokens != nullptr && c.step == 0) t = ldcg_i(p.tokens + u * p.C + ch);
-        else if (c.step == 0) t = ldcg_i(p.utt[u].grid + (size_t)(p.utt[u].pos0 - 1) * p.C + ch);
+        else if (c.step == 0) {
+            // the rows of a finished utterance idle on token 0 (its grid has no row at pos0 - 1 any more)
+            const bool done = p.utt[u].gs != nullptr && ldcg_i(&p.utt[u].gs->finished) != 0;
+            t = done ? 0 : ldcg_i(p.utt[u].grid + (size_t)(min(p.utt[u].pos0, p.Lmax) - 1) * p.C + ch);
+        }
         else t = (int)ll_wait32(p.ll_tok + u * DIA_B200_MAX_CHANNELS + ch, c.seq - 1, p.err);
         if (t < 0 || t >= p.V) { *p.err = kErrBadState; t = 0; }
         misc->toks[u][ch] = t;

@@ -884,9 +884,14 @@ int dia_b200_batch_generate_steps(dia_b200_engine* e, int n_steps, void* stream)
     int rc = batch_ready(e, e->n_active);
     if (rc) return rc;
     if (n_steps < 0) return DIA_B200_EINVAL;
-    for (int u = 0; u < e->n_active; ++u) {                  // never run past a cache / grid
-        n_steps = std::min(n_steps, e->shape.max_audio_len - e->bslot[u]);
-        n_steps = std::min(n_steps, e->shape.max_audio_len - e->bpos[u]);
+    // Never run past a cache / grid.  Utterances may start at different depths (prompts): one that has used up its budget is
+    // finished on the device (dec_step >= max_tokens - 1 <= Lmax - 1) and idles at the last slot; the launch runs as long as the
+    // utterance with the most room left.
+    {
+        int longest = 0;
+        for (int u = 0; u < e->n_active; ++u)
+            longest = std::max(longest, std::min(e->shape.max_audio_len - e->bslot[u], e->shape.max_audio_len - e->bpos[u]));
+        n_steps = std::min(n_steps, longest);
     }
     if (n_steps <= 0) return DIA_B200_OK;
     ON_DEVICE(e->device);
@@ -905,7 +910,10 @@ int dia_b200_batch_generate_steps(dia_b200_engine* e, int n_steps, void* stream)
         p.top_k = e->bgp[0].top_k; p.max_tokens = e->bgp[0].max_tokens; p.draw0 = (unsigned long long)e->gen_steps;
         rc = run_batch(e, p, S(stream));
         if (rc) return rc;
-        for (int u = 0; u < e->n_active; ++u) { e->bpos[u] += n; e->bslot[u] += n; }
+        for (int u = 0; u < e->n_active; ++u) {
+            e->bpos[u] = std::min(e->bpos[u] + n, e->shape.max_audio_len);
+            e->bslot[u] = std::min(e->bslot[u] + n, e->shape.max_audio_len - 1);
+        }
         e->gen_steps += n;
         n_steps -= n;
     }

@@ -394,17 +394,27 @@ class Dia:
     @torch.inference_mode()
     def generate_batch(self, texts: list[str], max_tokens: int | None = None, cfg_scale: float = 3.0,
                        temperature: float = 1.3, top_p: float = 0.95, cfg_filter_top_k: int | None = 35,
-                       seed: Optional[int] = None, max_utterances: int = 8, output: str = "codes", verbose: bool = False):
+                       seed: Optional[int] = None, max_utterances: int = 8, output: str = "codes", verbose: bool = False,
+                       audio_prompts: Optional[list] = None, audio_prompt_texts: Optional[list] = None):
         """``generate`` for a list of independent transcripts, decoded ``max_utterances`` at a time in ONE kernel: the 2N
         CFG rows share a single pass over the weights per frame.  Every utterance has its own encoder pass, KV caches,
         token grid, EOS state and RNG stream (utterance i draws from seed + i), and yields exactly the rows
-        ``generate(texts[i], ...)`` yields for greedy decoding.  Returns a list (codes int32 [1, C, T_i] or waveforms)."""
+        ``generate(texts[i], ...)`` yields for greedy decoding.  ``audio_prompts`` / ``audio_prompt_texts`` (lists, entries
+        may be None) are the voice-clone arguments of ``generate`` per utterance: prompts of different lengths start at
+        different cache slots of the same launch.  Returns a list (codes int32 [1, C, T_i] or waveforms)."""
         if output not in ("audio", "codes"):
             raise ValueError("output must be 'audio' or 'codes'")
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("Dia.generate_batch needs the model on a CUDA device (sm_100a); there is no CPU fallback")
         if temperature < 0.0:
             raise ValueError("temperature must be >= 0")
+        audio_prompts = list(audio_prompts) if audio_prompts is not None else [None] * len(texts)
+        audio_prompt_texts = list(audio_prompt_texts) if audio_prompt_texts is not None else [None] * len(texts)
+        if len(audio_prompts) != len(texts) or len(audio_prompt_texts) != len(texts):
+            raise ValueError("audio_prompts / audio_prompt_texts must have one entry per transcript")
+        for ap, apt in zip(audio_prompts, audio_prompt_texts):
+            if ap is not None and not apt:
+                raise ValueError("`audio_prompt_text` is required when `audio_prompt` is provided.")
         if seed is not None:
             torch.manual_seed(seed)
         base_seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 31, (1,)).item())   # + i stays a numpy seed
@@ -422,7 +432,8 @@ class Dia:
                 # faster on its own kernel
                 for i in idx:
                     res = self.generate(texts[i], max_tokens=max_tokens, cfg_scale=cfg_scale, temperature=temperature,
-                                        top_p=top_p, cfg_filter_top_k=cfg_filter_top_k, seed=base_seed + i, output=output)
+                                        top_p=top_p, cfg_filter_top_k=cfg_filter_top_k, seed=base_seed + i, output=output,
+                                        audio_prompt=audio_prompts[i], audio_prompt_text=audio_prompt_texts[i])
                     results[i], raw[i] = res, self.last_codes
                     stats["prepare_s"] += self.last_stats.get("prepare_s", 0.0)
                     stats["loop_s"] += self.last_stats.get("loop_s", 0.0)
@@ -430,7 +441,8 @@ class Dia:
                     stats["frames"] += self.last_stats.get("frames", 0)
                 continue
             eng = self.model.decoder.batch_engine(per)
-            prepared = [self._prepare_generation(self._effective_text(texts[i], None), None, False) for i in idx]
+            prepared = [self._prepare_generation(self._effective_text(texts[i], audio_prompt_texts[i]), audio_prompts[i], False)
+                        for i in idx]
             for u, (st, out) in enumerate(prepared):
                 for c in st.cross_attn_cache:
                     if c.k.dtype != torch.float32 or not c.k.is_contiguous():

@@ -999,6 +999,45 @@ def test_full_batched_long_context_vs_reference(full_gpu):
             print(f"utterance {u}: near-tie at decode step {r} channel {c} (reference margin {m:.3e})")
 
 
+def test_full_generate_batch_with_audio_prompts_of_different_lengths(full_gpu, gold_full):
+    """``generate_batch`` with the voice-clone arguments of ``generate`` per utterance: a 1200-frame prompt, a 2380-frame
+    prompt and no prompt in ONE launch (three cache depths).  The utterance whose budget ends first (2380 + 48) idles at
+    the last cache slot while the others run on; each stream against what the reference produced for it alone."""
+    dia, sd = full_gpu
+    g1, g2 = _golden("dia16b_seed5_clone1200.npz"), _golden("dia16b_seed5_clone2380.npz")
+    texts = [str(g1["text"]), str(g2["text"]), str(gold_full["text"])]
+    prompts = [torch.from_numpy(g1["prompt"]), torch.from_numpy(g2["prompt"]), None]
+    ptexts = [str(g1["prompt_text"]), str(g2["prompt_text"]), None]
+    dia.batch_min_utterances = 1
+    max_tokens = int(g2["max_tokens"])
+    dia.generate_batch(texts, max_tokens=max_tokens, temperature=0.0, cfg_scale=3.0, max_utterances=4,
+                       audio_prompts=prompts, audio_prompt_texts=ptexts)
+    raw = [c.cpu() for c in dia.last_batch_codes]          # rows prefill_step .. dec_step of every token grid
+
+    def check(got, want, margins, what):
+        n = min(got.shape[0], want.shape[0])
+        diff = (got[:n] != want[:n]).nonzero()
+        if diff.numel():
+            r, c = diff[0].tolist()
+            assert float(margins[r, c]) < 1e-3, f"{what}: divergence at decode row {r} channel {c}, reference margin {margins[r, c]:.3e}"
+    # the 2380-frame prompt with the fixture's own max_tokens: the whole stream, end-of-budget countdown included
+    P2 = int(g2["prefill_step"])
+    want2 = torch.from_numpy(g2["codes"]).to(raw[1].dtype)
+    assert raw[1].shape[0] == want2.shape[0] == max_tokens - P2 - 1
+    check(raw[1], want2, g2["margins"], "prompt 2380")
+    # the 1200-frame prompt: the rows before ITS fixture's countdown (this run's budget is longer)
+    P1 = int(g1["prefill_step"])
+    check(raw[0][:30], torch.from_numpy(g1["grid"][P1: P1 + 30]).to(raw[0].dtype), g1["margins"], "prompt 1200")
+    assert raw[0].shape[0] == max_tokens - P1 - 1
+    # no prompt: the 256-step fixture of the default transcript
+    want3 = torch.from_numpy(gold_full["codes"]).to(raw[2].dtype)
+    if "margins" in gold_full.files:
+        check(raw[2][:200], want3[:200], gold_full["margins"], "no prompt")
+    else:
+        assert torch.equal(raw[2][:24], want3[:24])
+    assert raw[2].shape[0] == max_tokens - 2
+
+
 def test_full_batched_eight_utterances_smoke(full_gpu):
     """8 utterances (16 rows) for 3 launches of 128 steps: runs, stays in range, is deterministic."""
     dia, sd = full_gpu

@@ -942,6 +942,32 @@ def test_tiny_generate_batch_equals_single_utterance_streams(tiny_gpu):
     assert all(torch.equal(x, y) for x, y in zip(outs, outs2))
 
 
+def test_tiny_generate_batch_mixed_prompt_depths_across_launches(tiny_gpu):
+    """Two launches (128 + 127 steps): the utterance with a 200-frame prompt finishes inside the first one, so the second
+    launch starts with a finished utterance (token 0, no grid row to read) that idles at the clamped cache slot while the
+    other runs to the end of its budget.  Row counts as ``generate`` gives them, first rows equal to the single-utterance
+    kernel's, no device error."""
+    dia, sd = tiny_gpu
+    cfg = dia.config
+    g = torch.Generator().manual_seed(3)
+    prompt = torch.randint(0, 1024, (200, cfg.data.channels), generator=g)
+    texts = ["[S1] Hello there. [S2] Hi.", "[S1] A second utterance, a little longer than the first. [S2] Yes."]
+    mt = cfg.data.audio_length
+    dia.batch_min_utterances = 1
+    dia.generate_batch(texts, max_tokens=mt, temperature=0.0, max_utterances=4, audio_prompts=[prompt, None],
+                       audio_prompt_texts=["[S1] Prompt words.", None])
+    got = [c.cpu().clone() for c in dia.last_batch_codes]
+    assert dia.last_stats["launch_steps"] > 128
+    for i in range(2):
+        dia.generate(texts[i], max_tokens=mt, temperature=0.0, output="codes", audio_prompt=[prompt, None][i],
+                     audio_prompt_text=["[S1] Prompt words.", None][i])
+        want = dia.last_codes.cpu()
+        assert got[i].shape == want.shape, (i, got[i].shape, want.shape)
+        assert torch.equal(got[i][:40], want[:40]), i
+        assert ((got[i] >= 0) & (got[i] <= 1027)).all()
+    dia.batch_min_utterances = 2
+
+
 def test_full_generate_batch_vs_reference_goldens(full_gpu, gold_full):
     """Dia-1.6B, 4 utterances in one launch (8 batch rows on the tcgen05 path): each greedy stream against the fixture the
     reference produced for that transcript alone."""

@@ -1,6 +1,7 @@
-set -x
-(time timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -6) > gpurun_out/r2_t70_all.log 2>&1
-python tools/batch_bench.py --utts 8 --steps 16 --reps 2 > gpurun_out/plain_batch_r2b.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:dia_batch_step_kernel -s 1 -c 1 -f -o gpurun_out/batch_r2b_full \
-    python tools/batch_bench.py --utts 8 --steps 16 --reps 2 > gpurun_out/ncu_batch_r2b.log 2>&1
-tail -n 2 gpurun_out/ncu_batch_r2b.log
+(timeout 300 python tools/debug_batch.py --utts 1 3 --steps 2 2>&1 | tail -8) > gpurun_out/r2_t71.log 2>&1
+(timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "batch" 2>&1 | tail -8) >> gpurun_out/r2_t71.log 2>&1
+for i in 1 2; do
+  echo -n "base: " >> gpurun_out/r2_t71.log; DIA_B200_LIB=$PWD/tools/ab/base.so timeout 300 python tools/batch_bench.py --utts 8 --reps 3 2>&1 | tail -1 >> gpurun_out/r2_t71.log
+  echo -n "new : " >> gpurun_out/r2_t71.log; timeout 300 python tools/batch_bench.py --utts 8 --reps 3 2>&1 | tail -1 >> gpurun_out/r2_t71.log
+done
+timeout 300 python tools/batch_bench.py --utts 8 --reps 2 --profile 2>&1 | tail -2 >> gpurun_out/r2_t71.log
